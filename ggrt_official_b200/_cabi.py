@@ -1,0 +1,99 @@
+"""ctypes binding of libggrt_raster.so (include/ggrt_raster.h).
+
+There is no CPU fallback: if the library is missing or a CUDA device is not present the
+calls raise.  The library is built in-tree by ggrt_official_b200.build (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from . import build as _build
+
+ABI_VERSION = 1
+_lib = None
+
+
+class Settings(C.Structure):
+    """struct GgrtRasterSettings"""
+
+    _fields_ = [
+        ("image_height", C.c_int32),
+        ("image_width", C.c_int32),
+        ("tanfovx", C.c_float),
+        ("tanfovy", C.c_float),
+        ("scale_modifier", C.c_float),
+        ("sh_degree", C.c_int32),
+        ("prefiltered", C.c_int32),
+        ("debug", C.c_int32),
+        ("viewmatrix", C.c_void_p),
+        ("projmatrix", C.c_void_p),
+        ("campos", C.c_void_p),
+        ("bg", C.c_void_p),
+    ]
+
+
+class Layout(C.Structure):
+    """struct GgrtRasterLayout"""
+
+    _fields_ = [(n, C.c_size_t) for n in (
+        "geom_rec0", "geom_rec1", "geom_rec2", "geom_rect", "geom_tiles", "geom_flags", "geom_bytes",
+        "img_counts", "img_starts", "img_cursor", "img_header", "img_final_T", "img_ncontrib", "img_bytes",
+        "bin_keys", "bin_points", "bin_bytes")]
+
+
+EXPORTS = (
+    "ggrt_raster_abi_version",
+    "ggrt_raster_last_error",
+    "ggrt_raster_layout",
+    "ggrt_raster_geom_bytes",
+    "ggrt_raster_image_bytes",
+    "ggrt_raster_binning_bytes",
+    "ggrt_raster_forward_prepare",
+    "ggrt_raster_forward_render",
+    "ggrt_raster_backward",
+    "ggrt_raster_mark_visible",
+)
+
+
+def library_path() -> Path:
+    return _build.LIB
+
+
+def lib():
+    """Load (building if the sources are newer) the shared library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    L = C.CDLL(str(path))
+    vp, i32, i64, u32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_size_t
+    L.ggrt_raster_abi_version.restype = C.c_int
+    L.ggrt_raster_last_error.restype = C.c_char_p
+    L.ggrt_raster_layout.argtypes = [i32, i32, i32, i64, C.POINTER(Layout)]
+    L.ggrt_raster_geom_bytes.argtypes = [i32]
+    L.ggrt_raster_geom_bytes.restype = sz
+    L.ggrt_raster_image_bytes.argtypes = [i32, i32]
+    L.ggrt_raster_image_bytes.restype = sz
+    L.ggrt_raster_binning_bytes.argtypes = [i64]
+    L.ggrt_raster_binning_bytes.restype = sz
+    L.ggrt_raster_forward_prepare.argtypes = [C.POINTER(Settings), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ggrt_raster_forward_render.argtypes = [C.POINTER(Settings), i32, i64, u32, vp, vp, vp, vp, vp, vp]
+    L.ggrt_raster_backward.argtypes = [C.POINTER(Settings), i32, i64] + [vp] * 16
+    L.ggrt_raster_mark_visible.argtypes = [i32, vp, vp, vp, vp]
+    if L.ggrt_raster_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libggrt_raster ABI {L.ggrt_raster_abi_version()} != expected {ABI_VERSION}")
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().ggrt_raster_last_error().decode(errors="replace")
+        raise RuntimeError(f"libggrt_raster {what} failed (code {rc}): {msg}")
+
+
+def layout(P: int, H: int, W: int, N: int) -> Layout:
+    out = Layout()
+    check(lib().ggrt_raster_layout(P, H, W, N, C.byref(out)), "layout")
+    return out

@@ -1,0 +1,292 @@
+// extern "C" entry points of libggrt_raster.so (include/ggrt_raster.h) and buffer layout.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace ggrt {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what, int debug, cudaStream_t s) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && debug) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return GGRT_ERR_CUDA;
+    }
+    return GGRT_OK;
+}
+
+void compute_layout(int P, int H, int W, long long N, GgrtRasterLayout* L) {
+    memset(L, 0, sizeof(*L));
+    const size_t p = (size_t)(P > 0 ? P : 0);
+    size_t off = 0;
+    L->geom_rec0 = off; off = align_up(off + p * sizeof(float4));
+    L->geom_rec1 = off; off = align_up(off + p * sizeof(float4));
+    L->geom_rec2 = off; off = align_up(off + p * sizeof(float4));
+    L->geom_rect = off; off = align_up(off + p * sizeof(ushort4));
+    L->geom_tiles = off; off = align_up(off + p * sizeof(uint32_t));
+    L->geom_flags = off; off = align_up(off + p * sizeof(uint8_t));
+    L->geom_bytes = off > 0 ? off : 256;
+
+    const size_t gx = (size_t)(W + TILE - 1) / TILE, gy = (size_t)(H + TILE - 1) / TILE, T = gx * gy;
+    const size_t px = (size_t)H * W;
+    off = 0;
+    L->img_counts = off; off = align_up(off + T * sizeof(uint32_t));
+    L->img_starts = off; off = align_up(off + (T + 1) * sizeof(uint32_t));
+    L->img_cursor = off; off = align_up(off + T * sizeof(uint32_t));
+    L->img_header = off; off = align_up(off + 4 * sizeof(uint32_t));
+    L->img_final_T = off; off = align_up(off + px * sizeof(float));
+    L->img_ncontrib = off; off = align_up(off + px * sizeof(uint32_t));
+    L->img_bytes = off;
+
+    const size_t n = (size_t)(N > 0 ? N : 0);
+    off = 0;
+    L->bin_keys = off; off = align_up(off + n * sizeof(unsigned long long));
+    L->bin_points = off; off = align_up(off + n * sizeof(uint32_t));
+    L->bin_bytes = off > 0 ? off : 256;
+}
+
+GeomPtrs geom_ptrs(void* base, int P) {
+    GgrtRasterLayout L;
+    compute_layout(P, 0, 0, 0, &L);
+    char* b = static_cast<char*>(base);
+    GeomPtrs g;
+    g.rec0 = reinterpret_cast<float4*>(b + L.geom_rec0);
+    g.rec1 = reinterpret_cast<float4*>(b + L.geom_rec1);
+    g.rec2 = reinterpret_cast<float4*>(b + L.geom_rec2);
+    g.rect = reinterpret_cast<ushort4*>(b + L.geom_rect);
+    g.tiles = reinterpret_cast<uint32_t*>(b + L.geom_tiles);
+    g.flags = reinterpret_cast<uint8_t*>(b + L.geom_flags);
+    return g;
+}
+
+ImagePtrs image_ptrs(void* base, int H, int W) {
+    GgrtRasterLayout L;
+    compute_layout(0, H, W, 0, &L);
+    char* b = static_cast<char*>(base);
+    ImagePtrs im;
+    im.counts = reinterpret_cast<uint32_t*>(b + L.img_counts);
+    im.starts = reinterpret_cast<uint32_t*>(b + L.img_starts);
+    im.cursor = reinterpret_cast<uint32_t*>(b + L.img_cursor);
+    im.header = reinterpret_cast<uint32_t*>(b + L.img_header);
+    im.final_T = reinterpret_cast<float*>(b + L.img_final_T);
+    im.n_contrib = reinterpret_cast<uint32_t*>(b + L.img_ncontrib);
+    return im;
+}
+
+BinPtrs bin_ptrs(void* base, long long N) {
+    GgrtRasterLayout L;
+    compute_layout(0, 0, 0, N, &L);
+    char* b = static_cast<char*>(base);
+    BinPtrs p;
+    p.keys = reinterpret_cast<unsigned long long*>(b + L.bin_keys);
+    p.points = reinterpret_cast<uint32_t*>(b + L.bin_points);
+    return p;
+}
+
+static int make_view(const GgrtRasterSettings* s, int P, View* v) {
+    if (s == nullptr) {
+        set_error("settings is NULL");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    if (P < 0 || s->image_height <= 0 || s->image_width <= 0) {
+        set_error("bad sizes: P=%d H=%d W=%d", P, s->image_height, s->image_width);
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    if (s->sh_degree < 0 || s->sh_degree > 4) {
+        set_error("sh_degree %d outside 0..4", s->sh_degree);
+        return GGRT_ERR_UNSUPPORTED;
+    }
+    if (!(s->tanfovx > 0.f) || !(s->tanfovy > 0.f)) {
+        set_error("tanfov must be positive");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    if (!s->viewmatrix || !s->projmatrix || !s->campos || !s->bg) {
+        set_error("viewmatrix / projmatrix / campos / bg must be device pointers");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    v->W = s->image_width;
+    v->H = s->image_height;
+    v->gx = (v->W + TILE - 1) / TILE;
+    v->gy = (v->H + TILE - 1) / TILE;
+    if (v->gx > 65535 || v->gy > 65535) {
+        set_error("image too large");
+        return GGRT_ERR_UNSUPPORTED;
+    }
+    v->P = P;
+    v->deg = s->sh_degree;
+    v->K = (s->sh_degree + 1) * (s->sh_degree + 1);
+    v->tanfovx = s->tanfovx;
+    v->tanfovy = s->tanfovy;
+    v->fx = (float)v->W / (2.0f * s->tanfovx);  // same float expression as the oracle
+    v->fy = (float)v->H / (2.0f * s->tanfovy);
+    v->view = s->viewmatrix;
+    v->proj = s->projmatrix;
+    v->campos = s->campos;
+    v->bg = s->bg;
+    return GGRT_OK;
+}
+
+}  // namespace ggrt
+
+using namespace ggrt;
+
+#define GGRT_TRY(expr)                    \
+    do {                                  \
+        const int rc_ = (expr);           \
+        if (rc_ != GGRT_OK) return rc_;   \
+    } while (0)
+
+extern "C" {
+
+int ggrt_raster_abi_version(void) { return GGRT_RASTER_ABI_VERSION; }
+
+const char* ggrt_raster_last_error(void) { return g_err; }
+
+int ggrt_raster_layout(int32_t P, int32_t H, int32_t W, int64_t N, GgrtRasterLayout* out) {
+    if (!out || P < 0 || H < 0 || W < 0 || N < 0) {
+        set_error("ggrt_raster_layout: bad argument");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    compute_layout(P, H, W, N, out);
+    return GGRT_OK;
+}
+
+size_t ggrt_raster_geom_bytes(int32_t P) {
+    GgrtRasterLayout L;
+    compute_layout(P, 0, 0, 0, &L);
+    return L.geom_bytes;
+}
+
+size_t ggrt_raster_image_bytes(int32_t H, int32_t W) {
+    GgrtRasterLayout L;
+    compute_layout(0, H, W, 0, &L);
+    return L.img_bytes;
+}
+
+size_t ggrt_raster_binning_bytes(int64_t N) {
+    GgrtRasterLayout L;
+    compute_layout(0, 0, 0, N, &L);
+    return L.bin_bytes;
+}
+
+int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, int32_t P, const float* means3D,
+                                const float* cov3D_precomp, const float* opacities, const float* shs,
+                                const float* colors_precomp, int32_t* radii, void* geom_buffer, void* image_buffer,
+                                uint32_t* counts_host, ggrt_stream_t stream) {
+    View v;
+    GGRT_TRY(make_view(settings, P, &v));
+    if ((shs == nullptr) == (colors_precomp == nullptr)) {
+        set_error("exactly one of shs / colors_precomp must be given");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    if (!geom_buffer || !image_buffer || (P > 0 && (!means3D || !cov3D_precomp || !opacities || !radii))) {
+        set_error("forward_prepare: NULL buffer");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int dbg = settings->debug;
+    GeomPtrs g = geom_ptrs(geom_buffer, P);
+    ImagePtrs im = image_ptrs(image_buffer, v.H, v.W);
+    if (cudaMemsetAsync(im.counts, 0, (size_t)v.gx * v.gy * sizeof(uint32_t), s) != cudaSuccess)
+        return check_launch("memset tile counts", 0, s);
+    launch_geometry(v, means3D, cov3D_precomp, opacities, radii, g, im, s);
+    GGRT_TRY(check_launch("geometry", dbg, s));
+    launch_scan_tiles(v, im, s);
+    GGRT_TRY(check_launch("scan_tiles", dbg, s));
+    if (counts_host) {
+        if (cudaMemcpyAsync(counts_host, im.header, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+            return check_launch("copy pair counts", 0, s);
+    }
+    // colour evaluation does not depend on N: it runs while the host waits for the counts
+    launch_color(v, means3D, shs, colors_precomp, radii, g, s);
+    GGRT_TRY(check_launch("color", dbg, s));
+    return GGRT_OK;
+}
+
+int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, int64_t num_rendered,
+                               uint32_t max_tile_pairs, const void* geom_buffer, void* binning_buffer,
+                               void* image_buffer, float* out_color, float* out_depth, ggrt_stream_t stream) {
+    View v;
+    GGRT_TRY(make_view(settings, P, &v));
+    if (!geom_buffer || !image_buffer || !out_color || !out_depth || num_rendered < 0 ||
+        (num_rendered > 0 && !binning_buffer)) {
+        set_error("forward_render: bad argument");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    if (num_rendered > 0xffffffffLL) {
+        set_error("more than 2^32 tile-Gaussian pairs");
+        return GGRT_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int dbg = settings->debug;
+    GeomPtrs g = geom_ptrs(const_cast<void*>(geom_buffer), P);
+    ImagePtrs im = image_ptrs(image_buffer, v.H, v.W);
+    BinPtrs b = bin_ptrs(binning_buffer, num_rendered);
+    if (num_rendered > 0) {
+        launch_emit(v, nullptr, g, im, b, s);
+        GGRT_TRY(check_launch("emit", dbg, s));
+        launch_sort_tiles(v, im, b, max_tile_pairs, s);
+        GGRT_TRY(check_launch("sort_tiles", dbg, s));
+    }
+    launch_render_forward(v, g, im, b, out_color, out_depth, s);
+    GGRT_TRY(check_launch("render_forward", dbg, s));
+    return GGRT_OK;
+}
+
+int ggrt_raster_backward(const GgrtRasterSettings* settings, int32_t P, int64_t num_rendered, const float* means3D,
+                         const float* cov3D_precomp, const float* shs, const int32_t* radii, const void* geom_buffer,
+                         const void* binning_buffer, const void* image_buffer, const float* dL_dout_color,
+                         float* grad_scratch, float* dL_dmeans2D, float* dL_dopacity, float* dL_dmeans3D,
+                         float* dL_dcov3D, float* dL_dsh, float* dL_dcolors, ggrt_stream_t stream) {
+    View v;
+    GGRT_TRY(make_view(settings, P, &v));
+    if (P == 0) return GGRT_OK;
+    if (!means3D || !cov3D_precomp || !radii || !geom_buffer || !image_buffer || !dL_dout_color || !grad_scratch ||
+        !dL_dmeans2D || !dL_dopacity || !dL_dmeans3D || !dL_dcov3D || (num_rendered > 0 && !binning_buffer)) {
+        set_error("backward: NULL buffer");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    if ((shs != nullptr) != (dL_dsh != nullptr) || (shs == nullptr) != (dL_dcolors != nullptr)) {
+        set_error("backward: pass dL_dsh with shs, dL_dcolors without");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int dbg = settings->debug;
+    GeomPtrs g = geom_ptrs(const_cast<void*>(geom_buffer), P);
+    ImagePtrs im = image_ptrs(const_cast<void*>(image_buffer), v.H, v.W);
+    BinPtrs b = bin_ptrs(const_cast<void*>(binning_buffer), num_rendered);
+    if (cudaMemsetAsync(grad_scratch, 0, (size_t)P * GRAD_STRIDE * sizeof(float), s) != cudaSuccess)
+        return check_launch("memset grad scratch", 0, s);
+    if (num_rendered > 0) {
+        launch_render_backward(v, g, im, b, dL_dout_color, grad_scratch, s);
+        GGRT_TRY(check_launch("render_backward", dbg, s));
+    }
+    launch_preprocess_backward(v, means3D, cov3D_precomp, shs, radii, g, grad_scratch, dL_dmeans2D, dL_dopacity,
+                               dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dcolors, s);
+    GGRT_TRY(check_launch("preprocess_backward", dbg, s));
+    return GGRT_OK;
+}
+
+int ggrt_raster_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present,
+                             ggrt_stream_t stream) {
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) {
+        set_error("mark_visible: bad argument");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    launch_mark_visible(P, means3D, viewmatrix, present, s);
+    return check_launch("mark_visible", 0, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+// Internal declarations shared by the kernels of libggrt_raster.so (sm_100a only).
+// Algorithm spec: SURVEY.md Appendix A; call site cuda_splatting.py:101-125.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ggrt_raster.h"
+
+namespace ggrt {
+
+constexpr int TILE = GGRT_RASTER_TILE;
+constexpr int TILE_PIXELS = TILE * TILE;
+constexpr float NEAR_CULL = 0.2f;   // A.1 in_frustum threshold (stock 3DGS value)
+constexpr float LOWPASS = 0.3f;     // A.1 screen-space dilation
+constexpr float ALPHA_MIN = 1.0f / 255.0f;
+constexpr float ALPHA_MAX = 0.99f;
+constexpr float T_EPS = 0.0001f;
+constexpr float RADIUS_CAP = 1.0e6f;
+constexpr int GRAD_STRIDE = 12;     // floats per Gaussian in the backward scratch
+
+// grad_scratch slot meaning (A.4): NDC-mean x,y | conic A, B(half convention), C | opacity | colour r,g,b
+enum GradSlot { G_MX = 0, G_MY = 1, G_CA = 2, G_CB = 3, G_CC = 4, G_OP = 5, G_R = 6, G_G = 7, G_B = 8 };
+
+struct View {  // kernel-side copy of the per-call scalars (matrices stay in device memory)
+    int W, H, gx, gy, P, deg, K;
+    float tanfovx, tanfovy, fx, fy;
+    const float* view;
+    const float* proj;
+    const float* campos;
+    const float* bg;
+};
+
+struct GeomPtrs {
+    float4* rec0;      // {pix_x, pix_y, extent_x, extent_y}
+    float4* rec1;      // {conic A, B, C, opacity}
+    float4* rec2;      // {r, g, b, depth}
+    ushort4* rect;     // tile rect
+    uint32_t* tiles;   // tiles touched
+    uint8_t* flags;    // clamp bits
+};
+
+struct ImagePtrs {
+    uint32_t* counts;
+    uint32_t* starts;
+    uint32_t* cursor;
+    uint32_t* header;
+    float* final_T;
+    uint32_t* n_contrib;
+};
+
+struct BinPtrs {
+    unsigned long long* keys;
+    uint32_t* points;
+};
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+void compute_layout(int P, int H, int W, long long N, GgrtRasterLayout* L);
+GeomPtrs geom_ptrs(void* base, int P);
+ImagePtrs image_ptrs(void* base, int H, int W);
+BinPtrs bin_ptrs(void* base, long long N);
+
+// kernel launchers (each in its own translation unit)
+void launch_geometry(const View& v, const float* means, const float* cov3d, const float* opac, int* radii,
+                     GeomPtrs g, ImagePtrs im, cudaStream_t s);
+void launch_scan_tiles(const View& v, ImagePtrs im, cudaStream_t s);
+void launch_color(const View& v, const float* means, const float* shs, const float* colors, const int* radii,
+                  GeomPtrs g, cudaStream_t s);
+void launch_emit(const View& v, const int* radii_or_null, GeomPtrs g, ImagePtrs im, BinPtrs b, cudaStream_t s);
+void launch_sort_tiles(const View& v, ImagePtrs im, BinPtrs b, uint32_t max_tile_pairs, cudaStream_t s);
+void launch_render_forward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, float* out_color, float* out_depth,
+                           cudaStream_t s);
+void launch_render_backward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, const float* dL_dout, float* scratch,
+                            cudaStream_t s);
+void launch_preprocess_backward(const View& v, const float* means, const float* cov3d, const float* shs,
+                                const int* radii, GeomPtrs g, const float* scratch, float* dmeans2D, float* dopacity,
+                                float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, cudaStream_t s);
+void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------
+// Exactly-rounded float helpers.  The geometry path (cull, cov2D, radius, tile rect,
+// depth key) must be bit-identical to the CPU oracle, which is compiled without FMA
+// contraction; these intrinsics are never fused by the compiler.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+// (a*b + c*d) + e*f with separate roundings, left to right
+__device__ __forceinline__ float dot3(float a, float b, float c, float d, float e, float f) {
+    return fadd(fadd(fmul(a, b), fmul(c, d)), fmul(e, f));
+}
+
+struct Geo {
+    float tx, ty, tz, cx, cy, txtz, tytz, hx, hy, hw, pw;
+    float Tm[2][3];
+    float a, b, c, det;
+};
+
+// A.1 geometric core; returns false if culled.  Same operation order as oracle/raster_oracle.c:geometry().
+__device__ __forceinline__ bool geometry(const View& v, const float* __restrict__ V, const float* __restrict__ M,
+                                         float px, float py, float pz, const float cv[6], Geo& g) {
+    g.tx = fadd(dot3(V[0], px, V[4], py, V[8], pz), V[12]);
+    g.ty = fadd(dot3(V[1], px, V[5], py, V[9], pz), V[13]);
+    g.tz = fadd(dot3(V[2], px, V[6], py, V[10], pz), V[14]);
+    if (!(g.tz > NEAR_CULL)) return false;
+    g.hx = fadd(dot3(M[0], px, M[4], py, M[8], pz), M[12]);
+    g.hy = fadd(dot3(M[1], px, M[5], py, M[9], pz), M[13]);
+    g.hw = fadd(dot3(M[3], px, M[7], py, M[11], pz), M[15]);
+    g.pw = fdiv(1.0f, fadd(g.hw, 0.0000001f));
+    const float limx = fmul(1.3f, v.tanfovx), limy = fmul(1.3f, v.tanfovy);
+    g.txtz = fdiv(g.tx, g.tz);
+    g.tytz = fdiv(g.ty, g.tz);
+    g.cx = fmul(fminf(limx, fmaxf(-limx, g.txtz)), g.tz);
+    g.cy = fmul(fminf(limy, fmaxf(-limy, g.tytz)), g.tz);
+    const float tz2 = fmul(g.tz, g.tz);
+    const float J00 = fdiv(v.fx, g.tz), J02 = fdiv(-fmul(v.fx, g.cx), tz2);
+    const float J11 = fdiv(v.fy, g.tz), J12 = fdiv(-fmul(v.fy, g.cy), tz2);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float r0 = V[4 * k + 0], r1 = V[4 * k + 1], r2 = V[4 * k + 2];
+        g.Tm[0][k] = fadd(fmul(J00, r0), fmul(J02, r2));
+        g.Tm[1][k] = fadd(fmul(J11, r1), fmul(J12, r2));
+    }
+    const float s00 = cv[0], s01 = cv[1], s02 = cv[2], s11 = cv[3], s12 = cv[4], s22 = cv[5];
+    const float* t0 = g.Tm[0];
+    const float* t1 = g.Tm[1];
+    const float v00 = dot3(s00, t0[0], s01, t0[1], s02, t0[2]);
+    const float v01 = dot3(s01, t0[0], s11, t0[1], s12, t0[2]);
+    const float v02 = dot3(s02, t0[0], s12, t0[1], s22, t0[2]);
+    const float v10 = dot3(s00, t1[0], s01, t1[1], s02, t1[2]);
+    const float v11 = dot3(s01, t1[0], s11, t1[1], s12, t1[2]);
+    const float v12 = dot3(s02, t1[0], s12, t1[1], s22, t1[2]);
+    g.a = fadd(dot3(t0[0], v00, t0[1], v01, t0[2], v02), LOWPASS);
+    g.b = dot3(t1[0], v00, t1[1], v01, t1[2], v02);
+    g.c = fadd(dot3(t1[0], v10, t1[1], v11, t1[2], v12), LOWPASS);
+    g.det = fsub(fmul(g.a, g.c), fmul(g.b, g.b));
+    if (!(g.det > 0.0f) && !(g.det < 0.0f)) return false;  // det == 0 (A.1) or NaN
+    return true;
+}
+
+__device__ __forceinline__ int f2i_sat(float x) {
+    x = fmaxf(x, -1.0f);
+    x = fminf(x, 65536.0f);
+    return (int)x;
+}
+
+// SH constants (A.1)
+#define GGRT_SH_C0 0.28209479177387814f
+#define GGRT_SH_C1 0.4886025119029199f
+#define GGRT_SH_C2_0 1.0925484305920792f
+#define GGRT_SH_C2_1 -1.0925484305920792f
+#define GGRT_SH_C2_2 0.31539156525252005f
+#define GGRT_SH_C2_3 -1.0925484305920792f
+#define GGRT_SH_C2_4 0.5462742152960396f
+#define GGRT_SH_C3_0 -0.5900435899266435f
+#define GGRT_SH_C3_1 2.890611442640554f
+#define GGRT_SH_C3_2 -0.4570457994644658f
+#define GGRT_SH_C3_3 0.3731763325901154f
+#define GGRT_SH_C3_4 -0.4570457994644658f
+#define GGRT_SH_C3_5 1.445305721320277f
+#define GGRT_SH_C3_6 -0.5900435899266435f
+#define GGRT_SH_C4_0 2.5033429417967046f
+#define GGRT_SH_C4_1 -1.7701307697799304f
+#define GGRT_SH_C4_2 0.9461746957575601f
+#define GGRT_SH_C4_3 -0.6690465435572892f
+#define GGRT_SH_C4_4 0.10578554691520431f
+#define GGRT_SH_C4_5 -0.6690465435572892f
+#define GGRT_SH_C4_6 0.47308734787878004f
+#define GGRT_SH_C4_7 -1.7701307697799304f
+#define GGRT_SH_C4_8 0.6258357354491761f
+
+// Real SH basis of degree `deg` at unit direction (x,y,z) -> b[0..K)
+__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float* b) {
+    b[0] = GGRT_SH_C0;
+    if (deg < 1) return;
+    b[1] = -GGRT_SH_C1 * y;
+    b[2] = GGRT_SH_C1 * z;
+    b[3] = -GGRT_SH_C1 * x;
+    if (deg < 2) return;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    b[4] = GGRT_SH_C2_0 * xy;
+    b[5] = GGRT_SH_C2_1 * yz;
+    b[6] = GGRT_SH_C2_2 * (2.0f * zz - xx - yy);
+    b[7] = GGRT_SH_C2_3 * xz;
+    b[8] = GGRT_SH_C2_4 * (xx - yy);
+    if (deg < 3) return;
+    b[9] = GGRT_SH_C3_0 * y * (3.0f * xx - yy);
+    b[10] = GGRT_SH_C3_1 * xy * z;
+    b[11] = GGRT_SH_C3_2 * y * (4.0f * zz - xx - yy);
+    b[12] = GGRT_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+    b[13] = GGRT_SH_C3_4 * x * (4.0f * zz - xx - yy);
+    b[14] = GGRT_SH_C3_5 * z * (xx - yy);
+    b[15] = GGRT_SH_C3_6 * x * (xx - 3.0f * yy);
+    if (deg < 4) return;
+    b[16] = GGRT_SH_C4_0 * xy * (xx - yy);
+    b[17] = GGRT_SH_C4_1 * yz * (3.0f * xx - yy);
+    b[18] = GGRT_SH_C4_2 * xy * (7.0f * zz - 1.0f);
+    b[19] = GGRT_SH_C4_3 * yz * (7.0f * zz - 3.0f);
+    b[20] = GGRT_SH_C4_4 * (zz * (35.0f * zz - 30.0f) + 3.0f);
+    b[21] = GGRT_SH_C4_5 * xz * (7.0f * zz - 3.0f);
+    b[22] = GGRT_SH_C4_6 * (xx - yy) * (7.0f * zz - 1.0f);
+    b[23] = GGRT_SH_C4_7 * xz * (xx - 3.0f * yy);
+    b[24] = GGRT_SH_C4_8 * (xx * (xx - 3.0f * yy) - yy * (3.0f * xx - yy));
+}
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what, int debug, cudaStream_t s);
+
+}  // namespace ggrt

@@ -1,0 +1,243 @@
+// Forward per-Gaussian kernels: geometry (A.1 cull / project / cov2D / radius / tile
+// rect + per-tile pair counting), tile scan, SH colour evaluation, mark_visible.
+// Replaces upstream preprocessCUDA + the scan of tiles_touched.
+#include "common.cuh"
+
+namespace ggrt {
+
+constexpr int GEO_THREADS = 256;
+constexpr int COLOR_THREADS = 128;
+
+// ---------------------------------------------------------------------------------------
+// geometry: one thread per Gaussian.  Reads 40 B, writes 2 records + rect + radius.
+// Pair counting goes straight into the per-tile counters (no per-Gaussian prefix sum:
+// tile segments are allocated per tile, see binning.cu).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEO_THREADS)
+geometry_kernel(View v, const float* __restrict__ means, const float* __restrict__ cov3d,
+                const float* __restrict__ opac, int* __restrict__ radii, GeomPtrs g, uint32_t* __restrict__ counts) {
+    __shared__ float sV[16], sM[16];
+    if (threadIdx.x < 16) sV[threadIdx.x] = v.view[threadIdx.x];
+    else if (threadIdx.x < 32) sM[threadIdx.x - 16] = v.proj[threadIdx.x - 16];
+    __syncthreads();
+    const int i = blockIdx.x * GEO_THREADS + threadIdx.x;
+    if (i >= v.P) return;
+
+    const float px = means[3 * i], py = means[3 * i + 1], pz = means[3 * i + 2];
+    float cv[6];
+    {
+        const float2* c2 = reinterpret_cast<const float2*>(cov3d) + 3 * (size_t)i;  // 24 B rows: 8 B aligned
+        if ((reinterpret_cast<uintptr_t>(cov3d) & 7) == 0) {
+            const float2 a = c2[0], b = c2[1], c = c2[2];
+            cv[0] = a.x; cv[1] = a.y; cv[2] = b.x; cv[3] = b.y; cv[4] = c.x; cv[5] = c.y;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) cv[k] = cov3d[6 * (size_t)i + k];
+        }
+    }
+    const float o = opac[i];
+
+    int radius = 0;
+    uint32_t tiles = 0;
+    ushort4 rect = make_ushort4(0, 0, 0, 0);
+    float4 r0 = make_float4(0.f, 0.f, -1.0e30f, -1.0e30f);
+    float4 r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float depth = 0.f;
+
+    Geo q;
+    if (geometry(v, sV, sM, px, py, pz, cv, q)) {
+        const float dinv = fdiv(1.0f, q.det);
+        const float cA = fmul(q.c, dinv), cB = fmul(-q.b, dinv), cC = fmul(q.a, dinv);
+        const float mid = fmul(0.5f, fadd(q.a, q.c));
+        const float sq = fsqrt(fmaxf(0.1f, fsub(fmul(mid, mid), q.det)));
+        const float l1 = fadd(mid, sq), l2 = fsub(mid, sq);
+        const float radf = fminf(ceilf(fmul(3.0f, fsqrt(fmaxf(l1, l2)))), RADIUS_CAP);
+        const float ndcx = fmul(q.hx, q.pw), ndcy = fmul(q.hy, q.pw);
+        const float pxx = fmul(fsub(fmul(fadd(ndcx, 1.0f), (float)v.W), 1.0f), 0.5f);
+        const float pxy = fmul(fsub(fmul(fadd(ndcy, 1.0f), (float)v.H), 1.0f), 0.5f);
+        const int x0 = min(v.gx, max(0, f2i_sat(fdiv(fsub(pxx, radf), (float)TILE))));
+        const int y0 = min(v.gy, max(0, f2i_sat(fdiv(fsub(pxy, radf), (float)TILE))));
+        const int x1 = min(v.gx, max(0, f2i_sat(fdiv(fadd(fadd(pxx, radf), (float)(TILE - 1)), (float)TILE))));
+        const int y1 = min(v.gy, max(0, f2i_sat(fdiv(fadd(fadd(pxy, radf), (float)(TILE - 1)), (float)TILE))));
+        const int area = (x1 - x0) * (y1 - y0);
+        if (area > 0) {
+            radius = (int)radf;
+            tiles = (uint32_t)area;
+            rect = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+            depth = q.tz;
+            // screen-space extent of {alpha >= 1/255}: q(d) <= 2 ln(255 o); bbox half widths sqrt(tau*a), sqrt(tau*c).
+            // Slightly inflated so the per-warp cull in the render kernels is conservative.
+            float ex = -1.0e30f, ey = -1.0e30f;
+            const float tau = 2.0f * logf(255.0f * o);
+            if (tau > 0.0f) {
+                ex = sqrtf(tau * q.a) * 1.0005f + 0.01f;
+                ey = sqrtf(tau * q.c) * 1.0005f + 0.01f;
+            }
+            r0 = make_float4(pxx, pxy, ex, ey);
+            r1 = make_float4(cA, cB, cC, o);
+            for (int y = y0; y < y1; ++y)
+                for (int x = x0; x < x1; ++x) atomicAdd(&counts[y * v.gx + x], 1u);
+        }
+    }
+    radii[i] = radius;
+    g.tiles[i] = tiles;
+    g.rect[i] = rect;
+    g.rec0[i] = r0;
+    g.rec1[i] = r1;
+    g.rec2[i] = make_float4(0.f, 0.f, 0.f, depth);
+}
+
+// ---------------------------------------------------------------------------------------
+// scan_tiles: exclusive scan of the per-tile counts (one CTA; T is a few thousand),
+// zeroes the emit cursors, reports {N, max count}.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(int T, const uint32_t* __restrict__ counts,
+                                                          uint32_t* __restrict__ starts, uint32_t* __restrict__ cursor,
+                                                          uint32_t* __restrict__ header) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    __shared__ uint32_t max_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0, max_s = 0;
+    __syncthreads();
+    uint32_t local_max = 0;
+    for (int base = 0; base < T; base += 1024) {
+        const int t = base + tid;
+        const uint32_t c = (t < T) ? counts[t] : 0u;
+        local_max = max(local_max, c);
+        uint32_t x = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t s = warp_sums[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, s, d);
+                if (lane >= d) s += y;
+            }
+            warp_sums[lane] = s;  // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        const uint32_t warp_off = (warp == 0) ? 0u : warp_sums[warp - 1];
+        if (t < T) {
+            starts[t] = carry + warp_off + x - c;
+            cursor[t] = 0u;
+        }
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + warp_off + x;
+        __syncthreads();
+    }
+    atomicMax(&max_s, local_max);
+    __syncthreads();
+    if (tid == 0) {
+        starts[T] = carry_s;
+        header[0] = carry_s;
+        header[1] = max_s;
+        header[2] = 0u;
+        header[3] = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// colour: SH degree 0..4 -> RGB (+0.5, clamp at 0, remember clamp bits).  The CTA's SH
+// slab (COLOR_THREADS x K x 3 floats, contiguous in HBM) is staged through shared memory
+// with coalesced 16-byte loads; each thread then walks its own row (odd stride: no bank
+// conflicts for K = 1, 9, 25).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(COLOR_THREADS)
+color_kernel(View v, const float* __restrict__ means, const float* __restrict__ shs, const float* __restrict__ colors,
+             const int* __restrict__ radii, GeomPtrs g) {
+    extern __shared__ __align__(16) float slab[];
+    const int base = blockIdx.x * COLOR_THREADS;
+    const int cnt = min(COLOR_THREADS, v.P - base);
+    const int i = base + threadIdx.x;
+    const bool vis = (threadIdx.x < cnt) && radii[i] > 0;
+    const int row = v.K * 3;
+    if (shs != nullptr) {
+        if (!__syncthreads_or(vis)) {
+            if (threadIdx.x < cnt) g.flags[i] = 0;
+            return;
+        }
+        const float* src = shs + (size_t)base * row;
+        const int nfl = cnt * row;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(slab);
+            const int n4 = nfl >> 2;
+            for (int k = threadIdx.x; k < n4; k += COLOR_THREADS) d4[k] = __ldcs(s4 + k);
+            for (int k = (n4 << 2) + threadIdx.x; k < nfl; k += COLOR_THREADS) slab[k] = src[k];
+        } else {
+            for (int k = threadIdx.x; k < nfl; k += COLOR_THREADS) slab[k] = src[k];
+        }
+        __syncthreads();
+    }
+    if (!vis) {
+        if (threadIdx.x < cnt) g.flags[i] = 0;
+        return;
+    }
+    float rgb[3];
+    uint8_t flags = 0;
+    if (shs == nullptr) {
+        rgb[0] = colors[3 * i], rgb[1] = colors[3 * i + 1], rgb[2] = colors[3 * i + 2];
+    } else {
+        float dx = means[3 * i] - v.campos[0], dy = means[3 * i + 1] - v.campos[1], dz = means[3 * i + 2] - v.campos[2];
+        const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+        dx *= inv, dy *= inv, dz *= inv;
+        float b[25];
+        sh_basis(v.deg, dx, dy, dz, b);
+        const float* my = slab + threadIdx.x * row;
+        rgb[0] = rgb[1] = rgb[2] = 0.5f;
+        for (int k = 0; k < v.K; ++k) {
+            rgb[0] = fmaf(b[k], my[3 * k + 0], rgb[0]);
+            rgb[1] = fmaf(b[k], my[3 * k + 1], rgb[1]);
+            rgb[2] = fmaf(b[k], my[3 * k + 2], rgb[2]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (rgb[c] < 0.0f) flags |= (uint8_t)(1u << c);
+            rgb[c] = fmaxf(rgb[c], 0.0f);
+        }
+    }
+    const float depth = g.rec2[i].w;
+    g.rec2[i] = make_float4(rgb[0], rgb[1], rgb[2], depth);
+    g.flags[i] = flags;
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means, const float* __restrict__ V,
+                                    uint8_t* __restrict__ present) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float tz = fadd(dot3(V[2], means[3 * i], V[6], means[3 * i + 1], V[10], means[3 * i + 2]), V[14]);
+    present[i] = (uint8_t)(tz > NEAR_CULL);
+}
+
+void launch_geometry(const View& v, const float* means, const float* cov3d, const float* opac, int* radii, GeomPtrs g,
+                     ImagePtrs im, cudaStream_t s) {
+    if (v.P == 0) return;
+    geometry_kernel<<<(v.P + GEO_THREADS - 1) / GEO_THREADS, GEO_THREADS, 0, s>>>(v, means, cov3d, opac, radii, g,
+                                                                                   im.counts);
+}
+
+void launch_scan_tiles(const View& v, ImagePtrs im, cudaStream_t s) {
+    scan_tiles_kernel<<<1, 1024, 0, s>>>(v.gx * v.gy, im.counts, im.starts, im.cursor, im.header);
+}
+
+void launch_color(const View& v, const float* means, const float* shs, const float* colors, const int* radii,
+                  GeomPtrs g, cudaStream_t s) {
+    if (v.P == 0) return;
+    const size_t smem = shs ? (size_t)COLOR_THREADS * v.K * 3 * sizeof(float) : 0;
+    color_kernel<<<(v.P + COLOR_THREADS - 1) / COLOR_THREADS, COLOR_THREADS, smem, s>>>(v, means, shs, colors, radii, g);
+}
+
+void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t s) {
+    if (P == 0) return;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means, view, present);
+}
+
+}  // namespace ggrt

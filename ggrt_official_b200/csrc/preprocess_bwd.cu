@@ -1,0 +1,240 @@
+// Per-Gaussian backward (A.5): conic -> cov2D -> cov3D and mean (through J), NDC mean ->
+// mean3D (through the full projection), colour -> SH coefficients and mean3D (through the
+// view direction).  Replaces upstream computeCov2DCUDA + preprocessCUDA (bwd), SURVEY.md
+// 8a row a13, fused into one pass.  Every output element is written (zeros for culled
+// Gaussians) so the caller needs no memset of the 300 B/Gaussian SH gradient.
+#include "common.cuh"
+
+namespace ggrt {
+
+constexpr int PB_THREADS = 128;
+
+__global__ void __launch_bounds__(PB_THREADS)
+preprocess_backward_kernel(View v, const float* __restrict__ means, const float* __restrict__ cov3d,
+                           const float* __restrict__ shs, const int* __restrict__ radii,
+                           const uint8_t* __restrict__ flags, const float* __restrict__ scratch,
+                           float* __restrict__ dmeans2D, float* __restrict__ dopacity, float* __restrict__ dmeans3D,
+                           float* __restrict__ dcov3D, float* __restrict__ dsh, float* __restrict__ dcolors) {
+    extern __shared__ __align__(16) float slab[];
+    __shared__ float sV[16], sM[16];
+    if (threadIdx.x < 16) sV[threadIdx.x] = v.view[threadIdx.x];
+    else if (threadIdx.x < 32) sM[threadIdx.x - 16] = v.proj[threadIdx.x - 16];
+
+    const int base = blockIdx.x * PB_THREADS;
+    const int cnt = min(PB_THREADS, v.P - base);
+    const int i = base + threadIdx.x;
+    const bool valid = threadIdx.x < cnt;
+    const bool vis = valid && radii[i] > 0;
+    const int row = v.K * 3;
+    const int nfl = cnt * row;
+    const bool any_vis = __syncthreads_or(vis);  // also publishes sV / sM
+
+    // stage the CTA's SH slab (coalesced); it is overwritten in place with dL/dsh
+    if (shs != nullptr) {
+        if (any_vis) {
+            const float* src = shs + (size_t)base * row;
+            if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                const float4* s4 = reinterpret_cast<const float4*>(src);
+                float4* d4 = reinterpret_cast<float4*>(slab);
+                const int n4 = nfl >> 2;
+                for (int k = threadIdx.x; k < n4; k += PB_THREADS) d4[k] = __ldcs(s4 + k);
+                for (int k = (n4 << 2) + threadIdx.x; k < nfl; k += PB_THREADS) slab[k] = src[k];
+            } else {
+                for (int k = threadIdx.x; k < nfl; k += PB_THREADS) slab[k] = src[k];
+            }
+        } else {
+            for (int k = threadIdx.x; k < nfl; k += PB_THREADS) slab[k] = 0.f;
+        }
+        __syncthreads();
+    }
+
+    float dmean[3] = {0.f, 0.f, 0.f};
+    float dS[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float g2x = 0.f, g2y = 0.f, gop = 0.f, dR = 0.f, dG = 0.f, dB = 0.f;
+    float* my = slab + threadIdx.x * row;
+
+    bool live = false;
+    Geo q;
+    float cv[6];
+    if (vis) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cv[k] = cov3d[6 * (size_t)i + k];
+        live = geometry(v, sV, sM, means[3 * i], means[3 * i + 1], means[3 * i + 2], cv, q);
+    }
+    if (live) {
+        const float* gs = scratch + (size_t)i * GRAD_STRIDE;
+        const float4 ga = *reinterpret_cast<const float4*>(gs);
+        const float4 gb = *reinterpret_cast<const float4*>(gs + 4);
+        const float gc = gs[8];
+        g2x = ga.x, g2y = ga.y;
+        const float gA = ga.z, gBh = ga.w, gC = gb.x;
+        gop = gb.y;
+        dR = gb.z, dG = gb.w, dB = gc;
+
+        // conic -> cov2D
+        const float a = q.a, b = q.b, c = q.c, det = q.det;
+        const float k2 = 1.0f / (det * det + 0.0000001f);
+        const float dL_da = k2 * (-c * c * gA + 2.0f * b * c * gBh + (det - a * c) * gC);
+        const float dL_dc = k2 * (-a * a * gC + 2.0f * a * b * gBh + (det - a * c) * gA);
+        const float dL_db = k2 * 2.0f * (b * c * gA - (det + 2.0f * b * b) * gBh + a * b * gC);
+        const float(*Tm)[3] = q.Tm;
+        // cov2D -> cov3D (xx,xy,xz,yy,yz,zz)
+        dS[0] = Tm[0][0] * Tm[0][0] * dL_da + Tm[0][0] * Tm[1][0] * dL_db + Tm[1][0] * Tm[1][0] * dL_dc;
+        dS[3] = Tm[0][1] * Tm[0][1] * dL_da + Tm[0][1] * Tm[1][1] * dL_db + Tm[1][1] * Tm[1][1] * dL_dc;
+        dS[5] = Tm[0][2] * Tm[0][2] * dL_da + Tm[0][2] * Tm[1][2] * dL_db + Tm[1][2] * Tm[1][2] * dL_dc;
+        dS[1] = 2.0f * Tm[0][0] * Tm[0][1] * dL_da + (Tm[0][0] * Tm[1][1] + Tm[0][1] * Tm[1][0]) * dL_db +
+                2.0f * Tm[1][0] * Tm[1][1] * dL_dc;
+        dS[2] = 2.0f * Tm[0][0] * Tm[0][2] * dL_da + (Tm[0][0] * Tm[1][2] + Tm[0][2] * Tm[1][0]) * dL_db +
+                2.0f * Tm[1][0] * Tm[1][2] * dL_dc;
+        dS[4] = 2.0f * Tm[0][1] * Tm[0][2] * dL_da + (Tm[0][1] * Tm[1][2] + Tm[0][2] * Tm[1][1]) * dL_db +
+                2.0f * Tm[1][1] * Tm[1][2] * dL_dc;
+        // cov2D -> Tm -> J -> t
+        const float S[3][3] = {{cv[0], cv[1], cv[2]}, {cv[1], cv[3], cv[4]}, {cv[2], cv[4], cv[5]}};
+        float dTm[2][3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float ts0 = Tm[0][0] * S[0][k] + Tm[0][1] * S[1][k] + Tm[0][2] * S[2][k];
+            const float ts1 = Tm[1][0] * S[0][k] + Tm[1][1] * S[1][k] + Tm[1][2] * S[2][k];
+            dTm[0][k] = 2.0f * dL_da * ts0 + dL_db * ts1;
+            dTm[1][k] = dL_db * ts0 + 2.0f * dL_dc * ts1;
+        }
+        const float dJ00 = dTm[0][0] * sV[0] + dTm[0][1] * sV[4] + dTm[0][2] * sV[8];
+        const float dJ02 = dTm[0][0] * sV[2] + dTm[0][1] * sV[6] + dTm[0][2] * sV[10];
+        const float dJ11 = dTm[1][0] * sV[1] + dTm[1][1] * sV[5] + dTm[1][2] * sV[9];
+        const float dJ12 = dTm[1][0] * sV[2] + dTm[1][1] * sV[6] + dTm[1][2] * sV[10];
+        const float limx = 1.3f * v.tanfovx, limy = 1.3f * v.tanfovy;
+        const float xmul = (q.txtz < -limx || q.txtz > limx) ? 0.0f : 1.0f;
+        const float ymul = (q.tytz < -limy || q.tytz > limy) ? 0.0f : 1.0f;
+        const float z1 = 1.0f / q.tz, z2 = z1 * z1, z3 = z2 * z1;
+        const float dtx = xmul * -v.fx * z2 * dJ02;
+        const float dty = ymul * -v.fy * z2 * dJ12;
+        const float dtz = -v.fx * z2 * dJ00 - v.fy * z2 * dJ11 + (2.0f * v.fx * q.cx) * z3 * dJ02 +
+                          (2.0f * v.fy * q.cy) * z3 * dJ12;
+        // NDC mean -> mean3D through the full projection
+        const float mw = q.pw;
+        const float mul1 = q.hx * mw * mw, mul2 = q.hy * mw * mw;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            dmean[k] = sV[4 * k + 0] * dtx + sV[4 * k + 1] * dty + sV[4 * k + 2] * dtz +
+                       (sM[4 * k + 0] * mw - sM[4 * k + 3] * mul1) * g2x +
+                       (sM[4 * k + 1] * mw - sM[4 * k + 3] * mul2) * g2y;
+        }
+    }
+
+    if (shs != nullptr) {
+        if (live) {
+            const uint8_t fl = flags[i];
+            if (fl & 1) dR = 0.f;
+            if (fl & 2) dG = 0.f;
+            if (fl & 4) dB = 0.f;
+            const float vx = means[3 * i] - v.campos[0], vy = means[3 * i + 1] - v.campos[1],
+                        vz = means[3 * i + 2] - v.campos[2];
+            const float len2 = vx * vx + vy * vy + vz * vz;
+            const float inv = rsqrtf(len2);
+            const float x = vx * inv, y = vy * inv, z = vz * inv;
+            float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+            // one SH term: accumulate dL/ddir from the stored coefficients, then overwrite them with dL/dsh
+#define GGRT_TERM(k, B, BX, BY, BZ)                                                        \
+    {                                                                                      \
+        const float s_ = my[3 * (k)] * dR + my[3 * (k) + 1] * dG + my[3 * (k) + 2] * dB;   \
+        ddx = fmaf((BX), s_, ddx), ddy = fmaf((BY), s_, ddy), ddz = fmaf((BZ), s_, ddz);   \
+        const float b_ = (B);                                                              \
+        my[3 * (k)] = b_ * dR, my[3 * (k) + 1] = b_ * dG, my[3 * (k) + 2] = b_ * dB;       \
+    }
+            GGRT_TERM(0, GGRT_SH_C0, 0.f, 0.f, 0.f)
+            if (v.deg > 0) {
+                GGRT_TERM(1, -GGRT_SH_C1 * y, 0.f, -GGRT_SH_C1, 0.f)
+                GGRT_TERM(2, GGRT_SH_C1 * z, 0.f, 0.f, GGRT_SH_C1)
+                GGRT_TERM(3, -GGRT_SH_C1 * x, -GGRT_SH_C1, 0.f, 0.f)
+            }
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            if (v.deg > 1) {
+                GGRT_TERM(4, GGRT_SH_C2_0 * xy, GGRT_SH_C2_0 * y, GGRT_SH_C2_0 * x, 0.f)
+                GGRT_TERM(5, GGRT_SH_C2_1 * yz, 0.f, GGRT_SH_C2_1 * z, GGRT_SH_C2_1 * y)
+                GGRT_TERM(6, GGRT_SH_C2_2 * (2.0f * zz - xx - yy), GGRT_SH_C2_2 * -2.0f * x, GGRT_SH_C2_2 * -2.0f * y,
+                          GGRT_SH_C2_2 * 4.0f * z)
+                GGRT_TERM(7, GGRT_SH_C2_3 * xz, GGRT_SH_C2_3 * z, 0.f, GGRT_SH_C2_3 * x)
+                GGRT_TERM(8, GGRT_SH_C2_4 * (xx - yy), GGRT_SH_C2_4 * 2.0f * x, GGRT_SH_C2_4 * -2.0f * y, 0.f)
+            }
+            if (v.deg > 2) {
+                GGRT_TERM(9, GGRT_SH_C3_0 * y * (3.0f * xx - yy), GGRT_SH_C3_0 * 6.0f * xy,
+                          GGRT_SH_C3_0 * (3.0f * xx - 3.0f * yy), 0.f)
+                GGRT_TERM(10, GGRT_SH_C3_1 * xy * z, GGRT_SH_C3_1 * yz, GGRT_SH_C3_1 * xz, GGRT_SH_C3_1 * xy)
+                GGRT_TERM(11, GGRT_SH_C3_2 * y * (4.0f * zz - xx - yy), GGRT_SH_C3_2 * -2.0f * xy,
+                          GGRT_SH_C3_2 * (4.0f * zz - xx - 3.0f * yy), GGRT_SH_C3_2 * 8.0f * yz)
+                GGRT_TERM(12, GGRT_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy), GGRT_SH_C3_3 * -6.0f * xz,
+                          GGRT_SH_C3_3 * -6.0f * yz, GGRT_SH_C3_3 * (6.0f * zz - 3.0f * xx - 3.0f * yy))
+                GGRT_TERM(13, GGRT_SH_C3_4 * x * (4.0f * zz - xx - yy), GGRT_SH_C3_4 * (4.0f * zz - 3.0f * xx - yy),
+                          GGRT_SH_C3_4 * -2.0f * xy, GGRT_SH_C3_4 * 8.0f * xz)
+                GGRT_TERM(14, GGRT_SH_C3_5 * z * (xx - yy), GGRT_SH_C3_5 * 2.0f * xz, GGRT_SH_C3_5 * -2.0f * yz,
+                          GGRT_SH_C3_5 * (xx - yy))
+                GGRT_TERM(15, GGRT_SH_C3_6 * x * (xx - 3.0f * yy), GGRT_SH_C3_6 * (3.0f * xx - 3.0f * yy),
+                          GGRT_SH_C3_6 * -6.0f * xy, 0.f)
+            }
+            if (v.deg > 3) {
+                GGRT_TERM(16, GGRT_SH_C4_0 * xy * (xx - yy), GGRT_SH_C4_0 * y * (3.0f * xx - yy),
+                          GGRT_SH_C4_0 * x * (xx - 3.0f * yy), 0.f)
+                GGRT_TERM(17, GGRT_SH_C4_1 * yz * (3.0f * xx - yy), GGRT_SH_C4_1 * 6.0f * xy * z,
+                          GGRT_SH_C4_1 * z * (3.0f * xx - 3.0f * yy), GGRT_SH_C4_1 * y * (3.0f * xx - yy))
+                GGRT_TERM(18, GGRT_SH_C4_2 * xy * (7.0f * zz - 1.0f), GGRT_SH_C4_2 * y * (7.0f * zz - 1.0f),
+                          GGRT_SH_C4_2 * x * (7.0f * zz - 1.0f), GGRT_SH_C4_2 * 14.0f * xy * z)
+                GGRT_TERM(19, GGRT_SH_C4_3 * yz * (7.0f * zz - 3.0f), 0.f, GGRT_SH_C4_3 * z * (7.0f * zz - 3.0f),
+                          GGRT_SH_C4_3 * y * (21.0f * zz - 3.0f))
+                GGRT_TERM(20, GGRT_SH_C4_4 * (zz * (35.0f * zz - 30.0f) + 3.0f), 0.f, 0.f,
+                          GGRT_SH_C4_4 * (140.0f * zz * z - 60.0f * z))
+                GGRT_TERM(21, GGRT_SH_C4_5 * xz * (7.0f * zz - 3.0f), GGRT_SH_C4_5 * z * (7.0f * zz - 3.0f), 0.f,
+                          GGRT_SH_C4_5 * x * (21.0f * zz - 3.0f))
+                GGRT_TERM(22, GGRT_SH_C4_6 * (xx - yy) * (7.0f * zz - 1.0f), GGRT_SH_C4_6 * 2.0f * x * (7.0f * zz - 1.0f),
+                          GGRT_SH_C4_6 * -2.0f * y * (7.0f * zz - 1.0f), GGRT_SH_C4_6 * (xx - yy) * 14.0f * z)
+                GGRT_TERM(23, GGRT_SH_C4_7 * xz * (xx - 3.0f * yy), GGRT_SH_C4_7 * z * (3.0f * xx - 3.0f * yy),
+                          GGRT_SH_C4_7 * -6.0f * xy * z, GGRT_SH_C4_7 * x * (xx - 3.0f * yy))
+                GGRT_TERM(24, GGRT_SH_C4_8 * (xx * (xx - 3.0f * yy) - yy * (3.0f * xx - yy)),
+                          GGRT_SH_C4_8 * (4.0f * xx * x - 12.0f * x * yy), GGRT_SH_C4_8 * (-12.0f * xx * y + 4.0f * yy * y),
+                          0.f)
+            }
+#undef GGRT_TERM
+            // through normalize(): (I |v|^2 - v v^T) / |v|^3
+            const float inv3 = inv * inv * inv;
+            const float dot = vx * ddx + vy * ddy + vz * ddz;
+            dmean[0] += (len2 * ddx - vx * dot) * inv3;
+            dmean[1] += (len2 * ddy - vy * dot) * inv3;
+            dmean[2] += (len2 * ddz - vz * dot) * inv3;
+        } else if (valid && any_vis) {
+            for (int k = 0; k < row; ++k) my[k] = 0.f;
+        }
+        __syncthreads();
+        // coalesced write-out of the dL/dsh slab
+        float* dst = dsh + (size_t)base * row;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            const float4* s4 = reinterpret_cast<const float4*>(slab);
+            const int n4 = nfl >> 2;
+            for (int k = threadIdx.x; k < n4; k += PB_THREADS) __stcs(d4 + k, s4[k]);
+            for (int k = (n4 << 2) + threadIdx.x; k < nfl; k += PB_THREADS) dst[k] = slab[k];
+        } else {
+            for (int k = threadIdx.x; k < nfl; k += PB_THREADS) dst[k] = slab[k];
+        }
+    } else if (valid) {
+        dcolors[3 * i] = dR, dcolors[3 * i + 1] = dG, dcolors[3 * i + 2] = dB;
+    }
+
+    if (valid) {
+        dmeans2D[3 * i] = g2x, dmeans2D[3 * i + 1] = g2y, dmeans2D[3 * i + 2] = 0.f;
+        dopacity[i] = gop;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dmeans3D[3 * i + k] = dmean[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dcov3D[6 * (size_t)i + k] = dS[k];
+    }
+}
+
+void launch_preprocess_backward(const View& v, const float* means, const float* cov3d, const float* shs,
+                                const int* radii, GeomPtrs g, const float* scratch, float* dmeans2D, float* dopacity,
+                                float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, cudaStream_t s) {
+    if (v.P == 0) return;
+    const size_t smem = shs ? (size_t)PB_THREADS * v.K * 3 * sizeof(float) : 0;
+    preprocess_backward_kernel<<<(v.P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, smem, s>>>(
+        v, means, cov3d, shs, radii, g.flags, scratch, dmeans2D, dopacity, dmeans3D, dcov3D, dsh, dcolors);
+}
+
+}  // namespace ggrt

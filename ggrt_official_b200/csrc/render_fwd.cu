@@ -1,0 +1,103 @@
+// Per-tile front-to-back alpha compositing (A.3).  Replaces upstream renderCUDA (fwd),
+// SURVEY.md 8a row a11.
+//
+// One CTA per 16x16 tile; warp w owns the 8x4 pixel block (w&1, w>>1) so each warp's
+// output rows are 32-byte contiguous.  A batch of 256 Gaussian records is staged into
+// shared memory; each warp first culls the batch against its pixel block with one
+// bounding-box test per lane (the records carry the {alpha >= 1/255} extent) and then
+// walks only the surviving bits of the ballot masks, in list order.  GGRt's splats are a
+// few pixels wide, so most (warp, Gaussian) pairs of a tile are culled.
+#include "common.cuh"
+
+namespace ggrt {
+
+constexpr int RENDER_THREADS = 256;
+
+__global__ void __launch_bounds__(RENDER_THREADS)
+render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __restrict__ rec1,
+                      const float4* __restrict__ rec2, const uint32_t* __restrict__ starts,
+                      const uint32_t* __restrict__ points, float* __restrict__ out_color,
+                      float* __restrict__ out_depth, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
+    __shared__ float4 s0[RENDER_THREADS], s1[RENDER_THREADS], s2[RENDER_THREADS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.y * v.gx + blockIdx.x;
+    const int bx0 = blockIdx.x * TILE + (warp & 1) * 8, by0 = blockIdx.y * TILE + (warp >> 1) * 4;
+    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+    const bool inside = px < v.W && py < v.H;
+    const float pxf = (float)px, pyf = (float)py;
+    const float wcx = (float)bx0 + 3.5f, wcy = (float)by0 + 1.5f;
+    const uint32_t start = starts[tile], end = starts[tile + 1];
+
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
+    uint32_t last = 0;
+    bool done = !inside;
+
+    for (uint32_t base = start; base < end; base += RENDER_THREADS) {
+        if (__syncthreads_and(done)) break;  // also orders the previous batch's reads before the refill
+        const uint32_t cnt = min((uint32_t)RENDER_THREADS, end - base);
+        if (tid < cnt) {
+            const uint32_t id = points[base + tid];
+            s0[tid] = rec0[id];
+            s1[tid] = rec1[id];
+            s2[tid] = rec2[id];
+        }
+        __syncthreads();
+        if (__all_sync(0xffffffffu, done)) continue;
+        for (uint32_t r = 0; r < cnt; r += 32) {
+            const uint32_t j = r + lane;
+            bool hit = false;
+            if (j < cnt) {
+                const float4 a = s0[j];
+                hit = (fabsf(a.x - wcx) <= a.z + 3.5f) && (fabsf(a.y - wcy) <= a.w + 1.5f);
+            }
+            uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const uint32_t jj = r + b;
+                if (!done) {
+                    const float4 a = s0[jj], c = s1[jj];
+                    const float dx = a.x - pxf, dy = a.y - pyf;
+                    const float power = -0.5f * (c.x * dx * dx + c.z * dy * dy) - c.y * dx * dy;
+                    if (power <= 0.0f) {
+                        const float alpha = fminf(ALPHA_MAX, c.w * __expf(power));
+                        if (alpha >= ALPHA_MIN) {
+                            const float Tn = T * (1.0f - alpha);
+                            if (Tn < T_EPS) {
+                                done = true;
+                            } else {
+                                const float4 col = s2[jj];
+                                const float w = alpha * T;
+                                C0 = fmaf(col.x, w, C0);
+                                C1 = fmaf(col.y, w, C1);
+                                C2 = fmaf(col.z, w, C2);
+                                D = fmaf(col.w, w, D);
+                                T = Tn;
+                                last = (base - start) + jj + 1;
+                            }
+                        }
+                    }
+                }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+    }
+    if (inside) {
+        const size_t pix = (size_t)py * v.W + px, hw = (size_t)v.H * v.W;
+        out_color[pix] = fmaf(T, v.bg[0], C0);
+        out_color[hw + pix] = fmaf(T, v.bg[1], C1);
+        out_color[2 * hw + pix] = fmaf(T, v.bg[2], C2);
+        out_depth[pix] = D;
+        final_T[pix] = T;
+        n_contrib[pix] = last;
+    }
+}
+
+void launch_render_forward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, float* out_color, float* out_depth,
+                           cudaStream_t s) {
+    dim3 grid(v.gx, v.gy);
+    render_forward_kernel<<<grid, RENDER_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points, out_color,
+                                                          out_depth, im.final_T, im.n_contrib);
+}
+
+}  // namespace ggrt

@@ -1,0 +1,59 @@
+"""Mirror of the pixelSplat decoder that drives the rasterizer in GGRt
+(/root/reference/ggrt/model/pixelsplat/decoder/decoder_splatting_cuda.py:29-85,
+decoder.py:20-23, ../types.py:7-12): flattens (batch, view), renders colour and, when a
+depth mode is given, a second degree-0 pass for depth."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+
+from .render import DepthRenderingMode, render_cuda, render_depth_cuda
+
+
+@dataclass
+class Gaussians:
+    means: Tensor  # [b,g,3]
+    covariances: Tensor  # [b,g,3,3]
+    harmonics: Tensor  # [b,g,3,d_sh]
+    opacities: Tensor  # [b,g]
+
+
+@dataclass
+class DecoderOutput:
+    color: Tensor  # [b,v,3,h,w]
+    depth: Optional[Tensor]  # [b,v,h,w]
+
+
+def _per_view(t: Tensor, v: int) -> Tensor:
+    """[b, ...] -> [(b v), ...] without copying until the rasterizer needs contiguity."""
+    return t[:, None].expand(t.shape[0], v, *t.shape[1:]).reshape(t.shape[0] * v, *t.shape[1:])
+
+
+class DecoderSplattingCUDA(nn.Module):
+    def __init__(self, background_color=(0.0, 0.0, 0.0)) -> None:
+        super().__init__()
+        self.background_color = torch.tensor(background_color, dtype=torch.float32)
+
+    def forward(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
+                image_shape: tuple, depth_mode: Optional[DepthRenderingMode] = None) -> DecoderOutput:
+        b, v = extrinsics.shape[:2]
+        bg = self.background_color.to(far.device)[None].expand(b * v, 3)
+        color = render_cuda(extrinsics.flatten(0, 1), intrinsics.flatten(0, 1), near.flatten(), far.flatten(),
+                            image_shape, bg, _per_view(gaussians.means, v), _per_view(gaussians.covariances, v),
+                            _per_view(gaussians.harmonics, v), _per_view(gaussians.opacities, v))
+        color = color.unflatten(0, (b, v))
+        depth = None
+        if depth_mode is not None:
+            depth = self.render_depth(gaussians, extrinsics, intrinsics, near, far, image_shape, depth_mode)
+        return DecoderOutput(color, depth)
+
+    def render_depth(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
+                     image_shape: tuple, mode: DepthRenderingMode = "depth") -> Tensor:
+        b, v = extrinsics.shape[:2]
+        result = render_depth_cuda(extrinsics.flatten(0, 1), intrinsics.flatten(0, 1), near.flatten(), far.flatten(),
+                                   image_shape, _per_view(gaussians.means, v), _per_view(gaussians.covariances, v),
+                                   _per_view(gaussians.opacities, v), mode=mode)
+        return result.unflatten(0, (b, v))

@@ -1,0 +1,258 @@
+"""Python front of the B200 rasterizer: the `diff_gaussian_rasterization` API surface.
+
+Drop-in for the external package GGRt imports at
+/root/reference/ggrt/model/pixelsplat/decoder/cuda_splatting.py:6-9 and calls at :101-125:
+same `GaussianRasterizationSettings` fields (with `debug` optional, because `render_cuda`
+omits it, :101-113), same `GaussianRasterizer(settings)(means3D=..., means2D=..., ...)`
+keywords, same argument validation, and a 3-tuple result `(color, radii, depth)` (the live
+call site unpacks three values, :118).
+
+Host code is PyTorch (allocation, streams, autograd); all compute is in libggrt_raster.so
+behind the C ABI of include/ggrt_raster.h.  There is no CPU or eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import NamedTuple, Optional
+
+import torch
+from torch import nn
+
+from . import _cabi
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool = False
+
+
+_tls = threading.local()
+
+
+def _pinned_counts() -> torch.Tensor:
+    buf = getattr(_tls, "counts", None)
+    if buf is None:
+        buf = torch.zeros(2, dtype=torch.int64).pin_memory()  # 2 x uint32 live in the first 8 bytes
+        _tls.counts = buf
+    return buf
+
+
+def _f32c(t: Optional[torch.Tensor], name: str, device) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the rasterizer has no CPU path")
+    if t.device != device:
+        raise RuntimeError(f"{name} is on {t.device}, expected {device}")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class _Call:
+    """Validated, contiguous inputs + the C settings struct for one rasterization."""
+
+    def __init__(self, means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: GaussianRasterizationSettings):
+        if not means3D.is_cuda:
+            raise RuntimeError("means3D must be a CUDA tensor: the rasterizer has no CPU path")
+        dev = means3D.device
+        self.device = dev
+        self.means3D = _f32c(means3D, "means3D", dev)
+        self.P = int(self.means3D.shape[0])
+        self.sh = _f32c(sh, "shs", dev)
+        self.colors = _f32c(colors_precomp, "colors_precomp", dev)
+        self.opacities = _f32c(opacities, "opacities", dev).reshape(-1)
+        self.cov3D = _f32c(cov3D_precomp, "cov3D_precomp", dev)
+        self.H, self.W = int(rs.image_height), int(rs.image_width)
+        self.deg = int(rs.sh_degree)
+        K = (self.deg + 1) ** 2
+        if self.means3D.dim() != 2 or self.means3D.shape[1] != 3:
+            raise ValueError(f"means3D must be [P,3], got {tuple(self.means3D.shape)}")
+        if self.cov3D.shape != (self.P, 6):
+            raise ValueError(f"cov3D_precomp must be [P,6], got {tuple(self.cov3D.shape)}")
+        if self.opacities.numel() != self.P:
+            raise ValueError(f"opacities must have P={self.P} elements, got {self.opacities.numel()}")
+        if self.sh is not None:
+            if self.sh.dim() != 3 or self.sh.shape[0] != self.P or self.sh.shape[2] != 3 or self.sh.shape[1] < K:
+                raise ValueError(f"shs must be [P,>={K},3] for sh_degree {self.deg}, got {tuple(self.sh.shape)}")
+            if self.sh.shape[1] != K:  # upstream reads the first (deg+1)^2 coefficients of a wider table
+                self.sh = self.sh[:, :K, :].contiguous()
+        if self.colors is not None and self.colors.shape != (self.P, 3):
+            raise ValueError(f"colors_precomp must be [P,3], got {tuple(self.colors.shape)}")
+        # settings tensors: always made contiguous (campos arrives as a stride-4 column slice, :111)
+        self.view = _f32c(rs.viewmatrix, "viewmatrix", dev).reshape(16)
+        self.proj = _f32c(rs.projmatrix, "projmatrix", dev).reshape(16)
+        self.campos = _f32c(rs.campos, "campos", dev).reshape(3)
+        self.bg = _f32c(rs.bg, "bg", dev).reshape(3)
+        s = _cabi.Settings()
+        s.image_height, s.image_width = self.H, self.W
+        s.tanfovx, s.tanfovy = float(rs.tanfovx), float(rs.tanfovy)
+        s.scale_modifier = float(rs.scale_modifier)
+        s.sh_degree = self.deg
+        s.prefiltered = int(bool(rs.prefiltered))
+        s.debug = int(bool(rs.debug))
+        s.viewmatrix, s.projmatrix = self.view.data_ptr(), self.proj.data_ptr()
+        s.campos, s.bg = self.campos.data_ptr(), self.bg.data_ptr()
+        self.settings = s
+
+
+def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: GaussianRasterizationSettings) -> dict:
+    """Runs the forward through the C ABI and returns outputs plus the opaque state buffers."""
+    L = _cabi.lib()
+    c = _Call(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs)
+    dev = c.device
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        sp = C.c_void_p(stream.cuda_stream)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        radii = torch.empty(c.P, dtype=torch.int32, device=dev)
+        geom = torch.empty(L.ggrt_raster_geom_bytes(c.P), **u8)
+        img = torch.empty(L.ggrt_raster_image_bytes(c.H, c.W), **u8)
+        color = torch.empty((3, c.H, c.W), dtype=torch.float32, device=dev)
+        depth = torch.empty((c.H, c.W), dtype=torch.float32, device=dev)
+        counts = _pinned_counts()
+        _cabi.check(L.ggrt_raster_forward_prepare(C.byref(c.settings), c.P, _ptr(c.means3D), _ptr(c.cov3D),
+                                                  _ptr(c.opacities), _ptr(c.sh), _ptr(c.colors), _ptr(radii),
+                                                  _ptr(geom), _ptr(img), C.c_void_p(counts.data_ptr()), sp),
+                    "forward_prepare")
+        # N sizes the caller-owned pair buffer; the colour kernel keeps the GPU busy while we wait
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        ev.synchronize()
+        packed = int(counts[0].item())
+        N, max_pairs = packed & 0xFFFFFFFF, (packed >> 32) & 0xFFFFFFFF
+        binning = torch.empty(L.ggrt_raster_binning_bytes(N), **u8)
+        _cabi.check(L.ggrt_raster_forward_render(C.byref(c.settings), c.P, N, max_pairs, _ptr(geom), _ptr(binning),
+                                                 _ptr(img), _ptr(color), _ptr(depth), sp), "forward_render")
+    return dict(call=c, color=color, depth=depth, radii=radii, geom=geom, img=img, binning=binning, N=N,
+                max_tile_pairs=max_pairs)
+
+
+def backward_raw(state: dict, grad_color: torch.Tensor) -> dict:
+    L = _cabi.lib()
+    c: _Call = state["call"]
+    dev = c.device
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        sp = C.c_void_p(stream.cuda_stream)
+        g = _f32c(grad_color, "grad_color", dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        scratch = torch.empty((c.P, 12), **f32)
+        out = dict(
+            dmeans2D=torch.empty((c.P, 3), **f32),
+            dopacity=torch.empty((c.P, 1), **f32),
+            dmeans3D=torch.empty((c.P, 3), **f32),
+            dcov3D=torch.empty((c.P, 6), **f32),
+            dsh=torch.empty_like(c.sh) if c.sh is not None else None,
+            dcolors=torch.empty((c.P, 3), **f32) if c.sh is None else None,
+        )
+        _cabi.check(L.ggrt_raster_backward(C.byref(c.settings), c.P, state["N"], _ptr(c.means3D), _ptr(c.cov3D),
+                                           _ptr(c.sh), _ptr(state["radii"]), _ptr(state["geom"]),
+                                           _ptr(state["binning"]), _ptr(state["img"]), _ptr(g), _ptr(scratch),
+                                           _ptr(out["dmeans2D"]), _ptr(out["dopacity"]), _ptr(out["dmeans3D"]),
+                                           _ptr(out["dcov3D"]), _ptr(out["dsh"]), _ptr(out["dcolors"]), sp),
+                    "backward")
+    return out
+
+
+def _dump(path: str, payload) -> None:
+    try:
+        torch.save(payload, path)
+        print(f"\nAn error occurred in the rasterizer. Inputs were written to {path} for debugging.")
+    except Exception:  # pragma: no cover - best effort
+        pass
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        try:
+            st = forward_raw(means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings)
+        except Exception:
+            if raster_settings.debug:
+                _dump("snapshot_fw.dump", (means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings))
+            raise
+        ctx.state = st
+        ctx.raster_settings = raster_settings
+        ctx.sh_shape = None if sh is None else tuple(sh.shape)
+        ctx.opacity_shape = tuple(opacities.shape)
+        ctx.mark_non_differentiable(st["radii"], st["depth"])
+        ctx.set_materialize_grads(False)
+        return st["color"], st["radii"], st["depth"]
+
+    @staticmethod
+    def backward(ctx, grad_color, _grad_radii=None, _grad_depth=None):
+        st = ctx.state
+        c: _Call = st["call"]
+        if grad_color is None:
+            return (None,) * 9
+        try:
+            g = backward_raw(st, grad_color)
+        except Exception:
+            if ctx.raster_settings.debug:
+                _dump("snapshot_bw.dump", (c.means3D, c.sh, c.colors, c.opacities, c.cov3D, grad_color))
+            raise
+        dsh = g["dsh"]
+        if dsh is not None and ctx.sh_shape != tuple(dsh.shape):  # wider SH table than (deg+1)^2: pad with zeros
+            full = torch.zeros(ctx.sh_shape, dtype=dsh.dtype, device=dsh.device)
+            full[:, : dsh.shape[1]] = dsh
+            dsh = full
+        return (g["dmeans3D"], g["dmeans2D"], dsh, g["dcolors"], g["dopacity"].reshape(ctx.opacity_shape), None, None,
+                g["dcov3D"], None)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions: torch.Tensor) -> torch.Tensor:
+        """Frustum test of upstream `markVisible` (unused by GGRt; kept for API completeness)."""
+        L = _cabi.lib()
+        rs = self.raster_settings
+        with torch.no_grad():
+            if not positions.is_cuda:
+                raise RuntimeError("positions must be a CUDA tensor: the rasterizer has no CPU path")
+            pos = _f32c(positions, "positions", positions.device)
+            view = _f32c(rs.viewmatrix, "viewmatrix", positions.device)
+            out = torch.empty(pos.shape[0], dtype=torch.uint8, device=pos.device)
+            with torch.cuda.device(pos.device):
+                sp = C.c_void_p(torch.cuda.current_stream(pos.device).cuda_stream)
+                _cabi.check(L.ggrt_raster_mark_visible(pos.shape[0], _ptr(pos), _ptr(view), _ptr(out), sp),
+                            "mark_visible")
+        return out.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or (
+                (scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        if cov3D_precomp is None:
+            raise NotImplementedError(
+                "scales/rotations are not supported: GGRt always passes cov3D_precomp (cuda_splatting.py:124)")
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                   self.raster_settings)

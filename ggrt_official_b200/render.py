@@ -1,0 +1,129 @@
+"""Host-side mirror of GGRt's render glue, for callers that do not have the reference tree.
+
+Same names, arguments and maths as
+/root/reference/ggrt/model/pixelsplat/decoder/cuda_splatting.py (get_projection_matrix
+:18-46, render_cuda :49-128, render_depth_cuda :227-269) and get_fov
+(ggrt/geometry/projection.py:233-247), written against this package's rasterizer.  The
+reference file itself also runs unmodified on top of the `diff_gaussian_rasterization`
+shim; tests/test_reference_caller.py checks both produce identical rasterizer calls.
+"""
+from __future__ import annotations
+
+from math import isqrt
+from typing import Literal, Optional
+
+import torch
+from torch import Tensor
+
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+
+DepthRenderingMode = Literal["depth", "disparity", "relative_disparity", "log"]
+
+
+def get_fov(intrinsics: Tensor) -> Tensor:
+    """[b,3,3] normalised intrinsics -> [b,2] (fov_x, fov_y): angle between the un-projected
+    mid-points of opposite image edges."""
+    inv = intrinsics.inverse()
+
+    def ray(p):
+        vec = torch.tensor(p, dtype=torch.float32, device=intrinsics.device)
+        vec = torch.einsum("bij,j->bi", inv, vec)
+        return vec / vec.norm(dim=-1, keepdim=True)
+
+    fov_x = (ray([0, 0.5, 1]) * ray([1, 0.5, 1])).sum(dim=-1).acos()
+    fov_y = (ray([0.5, 0, 1]) * ray([0.5, 1, 1])).sum(dim=-1).acos()
+    return torch.stack((fov_x, fov_y), dim=-1)
+
+
+def get_projection_matrix(near: Tensor, far: Tensor, fov_x: Tensor, fov_y: Tensor, intrinsics: Tensor) -> Tensor:
+    """Off-centre perspective matrix from the normalised intrinsics of batch element 0
+    (the reference indexes intrinsics[0], cuda_splatting.py:39-42); x,y -> (-1,1), z -> (0,1)."""
+    (b,) = near.shape
+    out = torch.zeros((b, 4, 4), dtype=torch.float32, device=near.device)
+    out[:, 0, 0] = 2 * near * intrinsics[0, 0, 0]
+    out[:, 1, 1] = 2 * near * intrinsics[0, 1, 1]
+    out[:, 0, 2] = 2 * intrinsics[0, 0, 2] - 1
+    out[:, 1, 2] = 2 * intrinsics[0, 1, 2] - 1
+    out[:, 3, 2] = 1
+    out[:, 2, 2] = far / (far - near)
+    out[:, 2, 3] = -(far * near) / (far - near)
+    return out
+
+
+def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple,
+                background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
+                gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor, scale_invariant: bool = True,
+                use_sh: bool = True, return_aux: bool = False):
+    """[b] views of [b,g] Gaussians -> [b,3,h,w].  With return_aux also the per-view radii and depth maps."""
+    assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    if scale_invariant:  # everything rescaled so that near == 1 (cuda_splatting.py:66-73)
+        scale = 1 / near
+        extrinsics = extrinsics.clone()
+        extrinsics[..., :3, 3] = extrinsics[..., :3, 3] * scale[:, None]
+        gaussian_covariances = gaussian_covariances * (scale[:, None, None, None] ** 2)
+        gaussian_means = gaussian_means * scale[:, None, None]
+        near = near * scale
+        far = far * scale
+
+    n = gaussian_sh_coefficients.shape[-1]
+    degree = isqrt(n) - 1
+    shs = gaussian_sh_coefficients.permute(0, 1, 3, 2).contiguous()  # b g xyz n -> b g n xyz
+
+    b = extrinsics.shape[0]
+    h, w = image_shape
+    fov_x, fov_y = get_fov(intrinsics).unbind(dim=-1)
+    tan_fov_x = (0.5 * fov_x).tan().tolist()  # one host sync for all views
+    tan_fov_y = (0.5 * fov_y).tan().tolist()
+    projection = get_projection_matrix(near, far, fov_x, fov_y, intrinsics).transpose(1, 2)
+    view = extrinsics.inverse().transpose(1, 2)
+    full = view @ projection
+    row, col = torch.triu_indices(3, 3)
+
+    images, radii_all, depths = [], [], []
+    for i in range(b):
+        mean_gradients = torch.zeros_like(gaussian_means[i], requires_grad=True)
+        settings = GaussianRasterizationSettings(
+            image_height=h, image_width=w, tanfovx=tan_fov_x[i], tanfovy=tan_fov_y[i], bg=background_color[i],
+            scale_modifier=1.0, viewmatrix=view[i], projmatrix=full[i], sh_degree=degree,
+            campos=extrinsics[i, :3, 3], prefiltered=False)
+        image, radii, depth = GaussianRasterizer(settings)(
+            means3D=gaussian_means[i], means2D=mean_gradients, shs=shs[i] if use_sh else None,
+            colors_precomp=None if use_sh else shs[i, :, 0, :], opacities=gaussian_opacities[i, ..., None],
+            cov3D_precomp=gaussian_covariances[i, :, row, col])
+        images.append(image)
+        radii_all.append(radii)
+        depths.append(depth)
+    out = torch.stack(images)
+    if return_aux:
+        return out, torch.stack(radii_all), torch.stack(depths)
+    return out
+
+
+def depth_to_relative_disparity(depth: Tensor, near: Tensor, far: Tensor, eps: float = 1e-10) -> Tensor:
+    """ggrt/model/pixelsplat/encoder/epipolar/conversions.py: 1 - (1/d - 1/far) / (1/near - 1/far)."""
+    disp_near = 1 / (near + eps)
+    disp_far = 1 / (far + eps)
+    disp = 1 / (depth + eps)
+    return 1 - (disp - disp_far) / (disp_near - disp_far + eps)
+
+
+def render_depth_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple,
+                      gaussian_means: Tensor, gaussian_covariances: Tensor, gaussian_opacities: Tensor,
+                      scale_invariant: bool = True, mode: DepthRenderingMode = "depth") -> Tensor:
+    """Depth as a 3-channel degree-0 'colour' through render_cuda, then the channel mean
+    (cuda_splatting.py:227-269); camera-space z is taken BEFORE the scale-invariant rescale."""
+    hom = torch.cat([gaussian_means, torch.ones_like(gaussian_means[..., :1])], dim=-1)
+    cam = torch.einsum("bij,bgj->bgi", extrinsics.inverse(), hom)
+    fake = cam[..., 2]
+    if mode == "disparity":
+        fake = 1 / fake
+    elif mode == "relative_disparity":
+        fake = depth_to_relative_disparity(fake, near[:, None], far[:, None])
+    elif mode == "log":
+        fake = fake.minimum(near[:, None]).maximum(far[:, None]).log()
+    b = fake.shape[0]
+    result = render_cuda(extrinsics, intrinsics, near, far, image_shape,
+                         torch.zeros((b, 3), dtype=fake.dtype, device=fake.device), gaussian_means,
+                         gaussian_covariances, fake[..., None, None].expand(-1, -1, 3, 1), gaussian_opacities,
+                         scale_invariant=scale_invariant)
+    return result.mean(dim=1)

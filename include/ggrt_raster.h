@@ -1,0 +1,140 @@
+/*
+ * ggrt_raster.h -- C ABI of libggrt_raster.so, the B200 (sm_100a) differentiable
+ * 3D-Gaussian tile rasterizer that replaces the external `diff_gaussian_rasterization`
+ * CUDA package on GGRt's render path.
+ *
+ * Reference interface replaced (the reference vendors no native code; these are the
+ * extension entry points its Python front binds, reached from
+ * /root/reference/ggrt/model/pixelsplat/decoder/cuda_splatting.py:6-9 (import) and
+ * :101-125 (the live call)):
+ *
+ *   _C.rasterize_gaussians(...)           -> ggrt_raster_forward_prepare + ggrt_raster_forward_render
+ *   _C.rasterize_gaussians_backward(...)  -> ggrt_raster_backward
+ *   _C.mark_visible(...)                  -> ggrt_raster_mark_visible
+ *
+ * Plain C: raw device pointers, sizes and a CUDA stream handle.  No torch / pybind
+ * types cross this boundary.  The library never allocates or frees device memory and
+ * keeps no state between calls; the caller owns every buffer (sizes from the
+ * ggrt_raster_*_bytes functions).  All float data is float32, all pointers are device
+ * pointers unless the name ends in `_host`.  Every function returns 0 on success or a
+ * negative GGRT_ERR_* code; ggrt_raster_last_error() returns a thread-local message.
+ *
+ * The forward is split in two because the number of tile-Gaussian pairs N is data
+ * dependent and the caller owns the N-sized buffer: `prepare` culls/projects every
+ * Gaussian, evaluates SH colours, counts pairs per tile and asynchronously copies
+ * {N, max pairs in one tile} to pinned host memory; the caller waits for that copy
+ * (colour evaluation keeps the GPU busy meanwhile), allocates
+ * ggrt_raster_binning_bytes(N) and calls `render`.
+ */
+#ifndef GGRT_RASTER_H
+#define GGRT_RASTER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGRT_RASTER_ABI_VERSION 1
+#define GGRT_RASTER_TILE 16 /* tile edge in pixels (tile ids are part of the contract) */
+
+#define GGRT_OK 0
+#define GGRT_ERR_INVALID_ARGUMENT (-1)
+#define GGRT_ERR_CUDA (-2)
+#define GGRT_ERR_UNSUPPORTED (-3)
+
+typedef void* ggrt_stream_t; /* a cudaStream_t */
+
+/* Mirrors GaussianRasterizationSettings as built at cuda_splatting.py:101-113. */
+typedef struct GgrtRasterSettings {
+    int32_t image_height;
+    int32_t image_width;
+    float tanfovx;
+    float tanfovy;
+    float scale_modifier; /* only meaningful with scales/rotations (unsupported: GGRt passes cov3D_precomp) */
+    int32_t sh_degree;    /* 0..4 */
+    int32_t prefiltered;  /* accepted, ignored (as upstream when cov3D is precomputed) */
+    int32_t debug;        /* non-zero: synchronise and check for errors after every kernel */
+    const float* viewmatrix; /* [4,4] device, row-major as passed: transposed world->camera */
+    const float* projmatrix; /* [4,4] device: viewmatrix @ projection^T */
+    const float* campos;     /* [3]   device */
+    const float* bg;         /* [3]   device */
+} GgrtRasterSettings;
+
+/* Byte offsets of the sub-arrays inside the caller-owned buffers (for tests / tools). */
+typedef struct GgrtRasterLayout {
+    /* geometry buffer, per Gaussian */
+    size_t geom_rec0;   /* float4[P]  {pix_x, pix_y, extent_x, extent_y} */
+    size_t geom_rec1;   /* float4[P]  {conic_A, conic_B, conic_C, opacity} */
+    size_t geom_rec2;   /* float4[P]  {r, g, b, view_depth} */
+    size_t geom_rect;   /* uint16x4[P] {tile_x0, tile_y0, tile_x1, tile_y1} */
+    size_t geom_tiles;  /* uint32[P]  tiles touched */
+    size_t geom_flags;  /* uint8[P]   bit c: colour channel c was clamped at 0 */
+    size_t geom_bytes;
+    /* image buffer, per tile / per pixel */
+    size_t img_counts;  /* uint32[T]   pairs per tile */
+    size_t img_starts;  /* uint32[T+1] exclusive scan of counts; [T] == N */
+    size_t img_cursor;  /* uint32[T]   scratch */
+    size_t img_header;  /* uint32[4]   {N, max pairs in a tile, 0, 0} */
+    size_t img_final_T; /* float[H*W]  */
+    size_t img_ncontrib;/* uint32[H*W] */
+    size_t img_bytes;
+    /* binning buffer, per pair */
+    size_t bin_keys;    /* uint64[N]  (depth_bits << 32 | gaussian_idx), sorted ascending inside each tile segment */
+    size_t bin_points;  /* uint32[N]  gaussian idx, tile-major then depth then idx */
+    size_t bin_bytes;
+} GgrtRasterLayout;
+
+int ggrt_raster_abi_version(void);
+const char* ggrt_raster_last_error(void);
+
+/* Buffer sizes / layout.  num_rendered may be 0. */
+int ggrt_raster_layout(int32_t P, int32_t image_height, int32_t image_width, int64_t num_rendered,
+                       GgrtRasterLayout* out);
+size_t ggrt_raster_geom_bytes(int32_t P);
+size_t ggrt_raster_image_bytes(int32_t image_height, int32_t image_width);
+size_t ggrt_raster_binning_bytes(int64_t num_rendered);
+
+/*
+ * Forward, phase 1.  Exactly one of shs [P,K,3] / colors_precomp [P,3] is non-NULL
+ * (K = (sh_degree+1)^2).  cov3D_precomp is [P,6] = (xx,xy,xz,yy,yz,zz).  opacities [P].
+ * Writes radii [P] (int32; 0 = culled), fills geom_buffer and the tile tables of
+ * image_buffer, then enqueues a copy of {N, max pairs per tile} to counts_host
+ * (2 x uint32 of pinned host memory; may be NULL if the caller reads img_header itself).
+ */
+int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, int32_t P, const float* means3D,
+                                const float* cov3D_precomp, const float* opacities, const float* shs,
+                                const float* colors_precomp, int32_t* radii, void* geom_buffer, void* image_buffer,
+                                uint32_t* counts_host, ggrt_stream_t stream);
+
+/*
+ * Forward, phase 2.  num_rendered / max_tile_pairs are the two values `prepare`
+ * reported; binning_buffer holds ggrt_raster_binning_bytes(num_rendered) bytes.
+ * Writes out_color [3,H,W], out_depth [H,W] (sum of view depth * alpha * T, no
+ * background, no normalisation) and the per-pixel state needed by backward.
+ */
+int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, int64_t num_rendered,
+                               uint32_t max_tile_pairs, const void* geom_buffer, void* binning_buffer,
+                               void* image_buffer, float* out_color, float* out_depth, ggrt_stream_t stream);
+
+/*
+ * Backward.  dL_dout_color [3,H,W].  grad_scratch is [P,12] float32 scratch (zeroed
+ * by the callee).  Outputs, all overwritten: dL_dmeans2D [P,3] (gradient w.r.t. NDC
+ * xy, z = 0), dL_dopacity [P], dL_dmeans3D [P,3], dL_dcov3D [P,6], and either
+ * dL_dsh [P,K,3] (when shs was given) or dL_dcolors [P,3]; the unused one is NULL.
+ */
+int ggrt_raster_backward(const GgrtRasterSettings* settings, int32_t P, int64_t num_rendered, const float* means3D,
+                         const float* cov3D_precomp, const float* shs, const int32_t* radii, const void* geom_buffer,
+                         const void* binning_buffer, const void* image_buffer, const float* dL_dout_color,
+                         float* grad_scratch, float* dL_dmeans2D, float* dL_dopacity, float* dL_dmeans3D,
+                         float* dL_dcov3D, float* dL_dsh, float* dL_dcolors, ggrt_stream_t stream);
+
+/* Frustum test only (upstream markVisible): present[i] = view-space z > 0.2. */
+int ggrt_raster_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present,
+                             ggrt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGRT_RASTER_H */

@@ -1,0 +1,123 @@
+"""Runs the CUDA path through the C ABI (via the Python front) and compares with the oracle."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ggrt_official_b200 import GaussianRasterizationSettings, _cabi
+from ggrt_official_b200 import rasterizer as R
+from oracle import c_oracle as co
+from tests.helpers import oracle_camera
+
+
+def settings_from(ri, dev, debug=False):
+    t = lambda a: torch.tensor(np.asarray(a), device=dev)
+    return GaussianRasterizationSettings(
+        image_height=ri.image_height, image_width=ri.image_width, tanfovx=ri.tanfovx, tanfovy=ri.tanfovy, bg=t(ri.bg),
+        scale_modifier=1.0, viewmatrix=t(ri.viewmatrix), projmatrix=t(ri.projmatrix), sh_degree=ri.sh_degree,
+        campos=t(ri.campos), prefiltered=False, debug=debug)
+
+
+def _view(buf, off, dtype, count):
+    n = count * torch.tensor([], dtype=dtype).element_size()
+    return buf[off: off + n].view(dtype)
+
+
+def run_cuda_forward(ri, dev="cuda:0", colors=None, debug=False):
+    t = lambda a: torch.tensor(np.asarray(a), device=dev)
+    rs = settings_from(ri, dev, debug=debug)
+    sh = None if colors is not None else t(ri.shs)
+    col = t(colors) if colors is not None else None
+    st = R.forward_raw(t(ri.means3D), sh, col, t(ri.opacities), t(ri.cov3D), rs)
+    torch.cuda.synchronize()
+    return st
+
+
+def unpack_state(st):
+    """Views of the opaque buffers as numpy arrays (layout from ggrt_raster_layout)."""
+    c = st["call"]
+    P, H, W, N = c.P, c.H, c.W, st["N"]
+    L = _cabi.layout(P, H, W, N)
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    g, im, b = st["geom"], st["img"], st["binning"]
+    out = dict(
+        rec0=_view(g, L.geom_rec0, torch.float32, 4 * P).reshape(P, 4),
+        rec1=_view(g, L.geom_rec1, torch.float32, 4 * P).reshape(P, 4),
+        rec2=_view(g, L.geom_rec2, torch.float32, 4 * P).reshape(P, 4),
+        rect=_view(g, L.geom_rect, torch.int16, 4 * P).reshape(P, 4),
+        tiles=_view(g, L.geom_tiles, torch.int32, P),
+        flags=_view(g, L.geom_flags, torch.uint8, P),
+        counts=_view(im, L.img_counts, torch.int32, T),
+        starts=_view(im, L.img_starts, torch.int32, T + 1),
+        header=_view(im, L.img_header, torch.int32, 4),
+        final_T=_view(im, L.img_final_T, torch.float32, H * W).reshape(H, W),
+        n_contrib=_view(im, L.img_ncontrib, torch.int32, H * W).reshape(H, W),
+        keys=_view(b, L.bin_keys, torch.int64, N),
+        points=_view(b, L.bin_points, torch.int32, N),
+    )
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def oracle_forward(ri, colors=None):
+    cam = oracle_camera(ri)
+    return cam, co.forward(cam, ri.means3D, ri.cov3D, ri.opacities, sh=None if colors is not None else ri.shs,
+                           colors=colors)
+
+
+def compare_forward(st, f, depth_scale=None):
+    """Returns a dict of mismatch counts / max errors between the CUDA state and the oracle forward."""
+    u = unpack_state(st)
+    pre, b, img = f["pre"], f["bin"], f["img"]
+    vis = pre["radii"] > 0
+    res = {}
+    res["N"] = (st["N"], b["N"])
+    res["radii_mismatch"] = int((st["radii"].cpu().numpy() != pre["radii"]).sum())
+    res["rect_mismatch"] = int((u["rect"].astype(np.int32) != pre["rect"]).any(axis=1).sum())
+    res["tiles_mismatch"] = int((u["tiles"].astype(np.uint32) != pre["tiles_touched"]).sum())
+    res["xy_bits_mismatch"] = int((u["rec0"][vis, :2].view(np.uint32) != pre["xy"][vis].view(np.uint32)).sum())
+    res["conic_bits_mismatch"] = int((u["rec1"][vis].view(np.uint32) != pre["conic_opacity"][vis].view(np.uint32)).sum())
+    res["depth_bits_mismatch"] = int((u["rec2"][vis, 3].view(np.uint32) != pre["depth"][vis].view(np.uint32)).sum())
+    res["rgb_max_err"] = float(np.abs(u["rec2"][vis, :3] - pre["rgb"][vis]).max()) if vis.any() else 0.0
+    oflags = pre["clamped"][:, 0] | (pre["clamped"][:, 1] << 1) | (pre["clamped"][:, 2] << 2)
+    res["flags_mismatch"] = int((u["flags"][vis] != oflags[vis]).sum())  # colours within rounding of 0 may differ
+    # ranges: only non-empty tiles carry meaningful (start,end) in the reference
+    ne = (b["ranges"][:, 1] - b["ranges"][:, 0]) > 0
+    s32 = u["starts"].astype(np.uint32)
+    res["starts_mismatch"] = int((s32[:-1][ne] != b["ranges"][ne, 0]).sum() + (s32[1:][ne] != b["ranges"][ne, 1]).sum()
+                                 + ((s32[1:] - s32[:-1])[~ne] != 0).sum())
+    if b["N"] == st["N"] and b["N"] > 0:
+        k = u["keys"].astype(np.uint64)
+        res["point_list_mismatch"] = int((u["points"].astype(np.uint32) != b["point_list"]).sum())
+        res["key_depth_mismatch"] = int(((k >> np.uint64(32)).astype(np.uint32) != (b["keys"] & np.uint64(0xFFFFFFFF)).astype(np.uint32)).sum())
+        res["key_idx_mismatch"] = int(((k & np.uint64(0xFFFFFFFF)).astype(np.uint32) != b["point_list"]).sum())
+    ok = img["fragile"] == 0
+    res["fragile_pixels"] = int((~ok).sum())
+    col = st["color"].cpu().numpy()
+    dep = st["depth"].cpu().numpy()
+    res["color_max_err"] = float(np.abs(col - f["color"])[:, ok].max())
+    res["color_max_err_fragile"] = float(np.abs(col - f["color"])[:, ~ok].max()) if (~ok).any() else 0.0
+    ds = depth_scale if depth_scale is not None else max(1.0, float(np.abs(f["depth"]).max()))
+    res["depth_max_relerr"] = float(np.abs(dep - f["depth"])[ok].max() / ds)
+    res["final_T_max_err"] = float(np.abs(u["final_T"] - img["final_T"])[ok].max())
+    res["n_contrib_mismatch"] = int((u["n_contrib"].astype(np.uint32) != img["n_contrib"])[ok].sum())
+    return res
+
+
+def grad_errors(got: dict, ref: dict, use_sh=True):
+    """max |got-ref| / max |ref| per gradient tensor, and the fraction of elements outside 1e-3 rel + floor."""
+    pairs = dict(dmeans3D=(got["dmeans3D"], ref["dmeans3D"]), dcov3D=(got["dcov3D"], ref["dcov3D"]),
+                 dopacity=(got["dopacity"].reshape(-1), ref["dopacity"]),
+                 dmeans2D=(got["dmeans2D"][:, :2], ref["dmean2D"]))
+    if use_sh:
+        pairs["dsh"] = (got["dsh"], ref["dsh"])
+    else:
+        pairs["dcolors"] = (got["dcolors"], ref["dcolor"])
+    out = {}
+    for k, (a, b) in pairs.items():
+        a = a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+        a64, b64 = a.astype(np.float64), np.asarray(b, np.float64)
+        scale = max(np.abs(b64).max(), 1e-30)
+        bad = np.abs(a64 - b64) > 1e-3 * np.abs(b64) + 1e-5 * scale
+        out[k] = dict(max_rel=float(np.abs(a64 - b64).max() / scale), frac_bad=float(bad.mean()),
+                      nonfinite=int((~np.isfinite(a64)).sum()))
+    return out
