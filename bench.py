@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the rasterizer hot path: forward+backward frames/s on BASELINE.json's configs.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4] [--impl ours|reference]
+
+N>1 is launched by the driver under torch.distributed.run (one rank per GPU, NCCL):
+every rank renders a different target view of the same Gaussians (weak scaling: one frame
+per GPU per step) and the Gaussian gradients are all-reduced inside the timed step.
+
+One JSON line on stdout (rank 0).  `value` = frames/s with inputs resident in HBM, timed
+through the C ABI; `e2e` = the same metric through GaussianRasterizer (autograd) with the
+inputs copied from pinned host memory and the image read back every step; `roofline` =
+algorithmic bytes of the dominant kernel / its CUDA-event duration; `cpu_baseline` = the
+CPU oracle (a port: the reference has no CPU path) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (P, H, W, description) -- SURVEY.md 8d
+    "c1": (10_000, 256, 256, "C1: 10K Gaussians, 256x256 (correctness config)"),
+    "c2": (300_000, 756, 1008, "C2: LLFF fern shape, 4 source views -> 300K Gaussians, 1008x756, SH degree 4, fwd+bwd"),
+    "c3": (921_600, 1280, 1920, "C3: Waymo scene-019 shape, 921.6K Gaussians, 1920x1280, SH degree 4, fwd+bwd"),
+    "c4": (600_000, 756, 1008, "C4: 8 source views -> 600K Gaussians, 1008x756, SH degree 4, fwd+bwd"),
+}
+METRIC = "rasterizer fwd+bwd frames/sec @1008x756, 300K Gaussians"
+SH_DEGREE = 4
+
+
+def alg_bytes(P, N, H, W, K=25):
+    """Algorithmic HBM bytes per launch of each kernel group (restated in DESIGN.md)."""
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    HW = H * W
+    return {
+        "geometry+color": P * (40 + 12 * K) + 52 * P,
+        "binning": 12 * N + 24 * N + 8 * T,  # emit + one read/one write of the pairs + ranges
+        "render_forward": 4 * N + 36 * P + 8 * T + 20 * HW,
+        "render_backward": 4 * N + 36 * P + 20 * HW + 44 * P,
+        "preprocess_backward": P * (44 + 40 + 12 * K + 4) + P * (36 + 12 * K),
+    }
+
+
+STAGE_GROUP = {
+    "geometry": "geometry+color", "scan_tiles": "binning", "color": "geometry+color", "emit": "binning",
+    "sort_tiles": "binning", "render_forward": "render_forward", "render_backward": "render_backward",
+    "preprocess_backward": "preprocess_backward",
+}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(workload: str, rank: int):
+    from ggrt_official_b200.synthetic import SEED, image_gradient, make_scene, small_se3, to_raster_inputs
+
+    P, H, W, _ = WORKLOADS[workload]
+    scene = make_scene(P, H, W, sh_degree=SH_DEGREE, seed=SEED)
+    if rank > 0:  # another target view of the same Gaussians (independent unit: cuda_splatting.py:93-127)
+        rng = np.random.default_rng(SEED + 1000 + rank)
+        scene.extrinsics = (scene.extrinsics.astype(np.float64) @ small_se3(rng).astype(np.float64)).astype(np.float32)
+    return to_raster_inputs(scene), image_gradient(H, W, seed=SEED + rank)
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port (the reference's rasterizer is CUDA-only and not vendored), all host threads."""
+    if rank != 0:
+        return
+    from oracle import c_oracle as co
+
+    ri, g = make_inputs(args.workload, 0)
+    cam = co.Camera(W=ri.image_width, H=ri.image_height, tanfovx=ri.tanfovx, tanfovy=ri.tanfovy, view=ri.viewmatrix,
+                    proj=ri.projmatrix, campos=ri.campos, bg=ri.bg, deg=ri.sh_degree)
+
+    def step():
+        f = co.forward(cam, ri.means3D, ri.cov3D, ri.opacities, sh=ri.shs)
+        co.backward(cam, ri.means3D, ri.cov3D, ri.opacities, f, g, sh=ri.shs)
+        return f["bin"]["N"]
+
+    for _ in range(args.warmup):
+        N = step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        N = step()
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    P, H, W, desc = WORKLOADS[args.workload]
+    sample = f"{args.steps} full frames (fwd+bwd) of the same workload, one frame per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "P": P, "H": H, "W": W, "N_pairs": int(N), "sh_degree": SH_DEGREE,
+                   "note": "CPU oracle port (oracle/raster_oracle.c, OpenMP): the reference rasterizer is an "
+                           "un-vendored CUDA-only package, no reference binary exists on this box"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": co.num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from ggrt_official_b200 import GaussianRasterizationSettings, GaussianRasterizer, _cabi
+    from ggrt_official_b200 import rasterizer as R
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the rasterizer has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    P, H, W, desc = WORKLOADS[args.workload]
+    ri, g_np = make_inputs(args.workload, rank)
+    K = (SH_DEGREE + 1) ** 2
+
+    t = lambda a: torch.tensor(np.asarray(a), device=dev)
+    means, cov, opac, shs = t(ri.means3D), t(ri.cov3D), t(ri.opacities), t(ri.shs)
+    grad_img = t(g_np)
+    rs = GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=ri.tanfovx, tanfovy=ri.tanfovy, bg=t(ri.bg), scale_modifier=1.0,
+        viewmatrix=t(ri.viewmatrix), projmatrix=t(ri.projmatrix), sh_degree=ri.sh_degree, campos=t(ri.campos),
+        prefiltered=False)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    state = {}
+
+    def step():
+        st = R.forward_raw(means, shs, None, opac, cov, rs)
+        grads = R.backward_raw(st, grad_img)
+        if world > 1:  # Gaussian gradients of the per-GPU views are summed
+            for k in ("dmeans3D", "dcov3D", "dopacity", "dsh"):
+                dist.all_reduce(grads[k])
+        state["N"], state["max_tile_pairs"] = st["N"], st["max_tile_pairs"]
+        return grads
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+
+    # ---- timed region: K steps, L2 flushed before each, CUDA events on the launching stream -------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    for a, b in evs:
+        flush_buf.zero_()
+        a.record()
+        step()
+        b.record()
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt.item())
+    fps = world * args.steps / (total_ms * 1e-3)
+
+    # ---- per-kernel durations (same process, same inputs, CUDA events inside the library) ---------
+    stage_ms = {}
+    _cabi.profile_enable(True)
+    nprof = min(args.steps, 20)
+    for _ in range(nprof):
+        flush_buf.zero_()
+        st = R.forward_raw(means, shs, None, opac, cov, rs)
+        fw = _cabi.profile_read()
+        R.backward_raw(st, grad_img)
+        bw = _cabi.profile_read()
+        for k in fw:
+            v = fw[k] if k not in ("render_backward", "preprocess_backward") else bw[k]
+            stage_ms[k] = stage_ms.get(k, 0.0) + v / nprof
+    _cabi.profile_enable(False)
+    N = state["N"]
+    ab = alg_bytes(P, N, H, W, K)
+    group_ms = {}
+    for k, v in stage_ms.items():
+        group_ms[STAGE_GROUP[k]] = group_ms.get(STAGE_GROUP[k], 0.0) + v
+    top = max(group_ms, key=group_ms.get)
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    achieved = ab[top] / (group_ms[top] * 1e-3) / 1e9
+    path_bytes = sum(ab.values())
+    kernel_sum_ms = sum(stage_ms.values())
+    roofline = {
+        "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None, "peak_source": peak_src, "kernel_ms": group_ms[top], "algorithmic_bytes": ab[top],
+        "kernel_share_of_step": group_ms[top] / kernel_sum_ms if kernel_sum_ms else None,
+        "stage_ms": {k: round(v, 5) for k, v in stage_ms.items()},
+        "whole_path": {"algorithmic_bytes": path_bytes, "achieved": path_bytes / (total_ms / args.steps * 1e-3) / 1e9,
+                       "frac": path_bytes / (total_ms / args.steps * 1e-3) / 1e9 / peak},
+    }
+
+    # ---- end to end: host buffers -> GaussianRasterizer (autograd) -> image back on the host -------
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_means, h_cov, h_opac, h_shs = pin(ri.means3D), pin(ri.cov3D), pin(ri.opacities), pin(ri.shs)
+    h_img = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
+    h_loss = torch.empty((), dtype=torch.float32).pin_memory()
+    h2d = sum(x.numel() * 4 for x in (h_means, h_cov, h_opac, h_shs))
+    d2h = h_img.numel() * 4 + 4
+    rasterizer = GaussianRasterizer(rs)
+
+    def e2e_step():
+        m = h_means.to(dev, non_blocking=True).requires_grad_()
+        c = h_cov.to(dev, non_blocking=True).requires_grad_()
+        o = h_opac.to(dev, non_blocking=True).requires_grad_()
+        s = h_shs.to(dev, non_blocking=True).requires_grad_()
+        m2 = torch.zeros_like(m, requires_grad=True)
+        image, radii, _ = rasterizer(means3D=m, means2D=m2, shs=s, colors_precomp=None, opacities=o, cov3D_precomp=c)
+        loss = (image * grad_img).sum()
+        loss.backward()
+        if world > 1:
+            for p_ in (m, c, o, s):
+                dist.all_reduce(p_.grad)
+        h_img.copy_(image.detach(), non_blocking=True)
+        h_loss.copy_(loss.detach(), non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    n_e2e = min(args.steps, 20)
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_e2e)]
+    for a, b in ev2:
+        a.record()
+        e2e_step()
+        b.record()
+    sync_all()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    t2 = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_fps = world * n_e2e / (float(t2.item()) * 1e-3)
+
+    # ---- CPU baseline: the oracle port on a bounded sample (rank 0, N=1 only) ----------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import c_oracle as co
+
+        cam = co.Camera(W=W, H=H, tanfovx=ri.tanfovx, tanfovy=ri.tanfovy, view=ri.viewmatrix, proj=ri.projmatrix,
+                        campos=ri.campos, bg=ri.bg, deg=ri.sh_degree)
+
+        def cpu_frame():
+            f = co.forward(cam, ri.means3D, ri.cov3D, ri.opacities, sh=ri.shs)
+            co.backward(cam, ri.means3D, ri.cov3D, ri.opacities, f, g_np, sh=ri.shs)
+
+        t0 = time.perf_counter()
+        cpu_frame()
+        one = time.perf_counter() - t0
+        n = int(min(50, max(2, round(12.0 / max(one, 1e-3)))))
+        t0 = time.perf_counter()
+        for _ in range(n):
+            cpu_frame()
+        dt = time.perf_counter() - t0
+        cpu = {"value": n / dt, "unit": "frames/s", "cores": co.num_threads(), "kind": "port",
+               "sample": f"{n} full frames (fwd+bwd) of the same workload after one warm-up frame"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "P": P, "H": H, "W": W, "N_pairs": int(N),
+                       "max_pairs_per_tile": int(state["max_tile_pairs"]), "sh_degree": SH_DEGREE,
+                       "views_per_step": world, "l2": "flushed before every timed step (256 MiB write)",
+                       "parallelism": f"one target view per GPU x{world}" + (", NCCL all-reduce of Gaussian gradients"
+                                                                            if world > 1 else "")},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": n_e2e},
+            "gpu_launches": 8 * args.steps,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -53,7 +53,11 @@ EXPORTS = (
     "ggrt_raster_forward_render",
     "ggrt_raster_backward",
     "ggrt_raster_mark_visible",
+    "ggrt_raster_profile_enable",
+    "ggrt_raster_profile_read",
+    "ggrt_raster_stage_name",
 )
+STAGE_COUNT = 8
 
 
 def library_path() -> Path:
@@ -81,6 +85,10 @@ def lib():
     L.ggrt_raster_forward_render.argtypes = [C.POINTER(Settings), i32, i64, u32, vp, vp, vp, vp, vp, vp]
     L.ggrt_raster_backward.argtypes = [C.POINTER(Settings), i32, i64] + [vp] * 16
     L.ggrt_raster_mark_visible.argtypes = [i32, vp, vp, vp, vp]
+    L.ggrt_raster_profile_enable.argtypes = [i32]
+    L.ggrt_raster_profile_read.argtypes = [C.POINTER(C.c_float)]
+    L.ggrt_raster_stage_name.argtypes = [i32]
+    L.ggrt_raster_stage_name.restype = C.c_char_p
     if L.ggrt_raster_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libggrt_raster ABI {L.ggrt_raster_abi_version()} != expected {ABI_VERSION}")
     _lib = L
@@ -97,3 +105,14 @@ def layout(P: int, H: int, W: int, N: int) -> Layout:
     out = Layout()
     check(lib().ggrt_raster_layout(P, H, W, N, C.byref(out)), "layout")
     return out
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().ggrt_raster_profile_enable(int(bool(on))), "profile_enable")
+
+
+def profile_read() -> dict:
+    """Per-kernel milliseconds of the most recent forward/backward on this thread."""
+    buf = (C.c_float * STAGE_COUNT)()
+    check(lib().ggrt_raster_profile_read(buf), "profile_read")
+    return {lib().ggrt_raster_stage_name(i).decode(): float(buf[i]) for i in range(STAGE_COUNT)}

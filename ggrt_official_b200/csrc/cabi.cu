@@ -26,6 +26,33 @@ int check_launch(const char* what, int debug, cudaStream_t s) {
     return GGRT_OK;
 }
 
+// ---- optional per-kernel timing -------------------------------------------------------
+struct Profiler {
+    bool on = false;
+    bool made = false;
+    bool used[GGRT_STAGE_COUNT] = {};
+    cudaEvent_t a[GGRT_STAGE_COUNT], b[GGRT_STAGE_COUNT];
+};
+static thread_local Profiler g_prof;
+
+struct StageTimer {  // RAII: records start/stop events around one launch when profiling is on
+    int stage;
+    cudaStream_t s;
+    StageTimer(int stage_, cudaStream_t s_) : stage(stage_), s(s_) {
+        if (!g_prof.on) return;
+        if (!g_prof.made) {
+            for (int i = 0; i < GGRT_STAGE_COUNT; ++i) cudaEventCreate(&g_prof.a[i]), cudaEventCreate(&g_prof.b[i]);
+            g_prof.made = true;
+        }
+        cudaEventRecord(g_prof.a[stage], s);
+    }
+    ~StageTimer() {
+        if (!g_prof.on) return;
+        cudaEventRecord(g_prof.b[stage], s);
+        g_prof.used[stage] = true;
+    }
+};
+
 void compute_layout(int P, int H, int W, long long N, GgrtRasterLayout* L) {
     memset(L, 0, sizeof(*L));
     const size_t p = (size_t)(P > 0 ? P : 0);
@@ -200,16 +227,17 @@ int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, int32_t P, c
     ImagePtrs im = image_ptrs(image_buffer, v.H, v.W);
     if (cudaMemsetAsync(im.counts, 0, (size_t)v.gx * v.gy * sizeof(uint32_t), s) != cudaSuccess)
         return check_launch("memset tile counts", 0, s);
-    launch_geometry(v, means3D, cov3D_precomp, opacities, radii, g, im, s);
+    for (int i = 0; i < GGRT_STAGE_COUNT; ++i) g_prof.used[i] = false;
+    { StageTimer t_(GGRT_STAGE_GEOMETRY, s); launch_geometry(v, means3D, cov3D_precomp, opacities, radii, g, im, s); }
     GGRT_TRY(check_launch("geometry", dbg, s));
-    launch_scan_tiles(v, im, s);
+    { StageTimer t_(GGRT_STAGE_SCAN_TILES, s); launch_scan_tiles(v, im, s); }
     GGRT_TRY(check_launch("scan_tiles", dbg, s));
     if (counts_host) {
         if (cudaMemcpyAsync(counts_host, im.header, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess)
             return check_launch("copy pair counts", 0, s);
     }
     // colour evaluation does not depend on N: it runs while the host waits for the counts
-    launch_color(v, means3D, shs, colors_precomp, radii, g, s);
+    { StageTimer t_(GGRT_STAGE_COLOR, s); launch_color(v, means3D, shs, colors_precomp, radii, g, s); }
     GGRT_TRY(check_launch("color", dbg, s));
     return GGRT_OK;
 }
@@ -234,12 +262,12 @@ int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, in
     ImagePtrs im = image_ptrs(image_buffer, v.H, v.W);
     BinPtrs b = bin_ptrs(binning_buffer, num_rendered);
     if (num_rendered > 0) {
-        launch_emit(v, nullptr, g, im, b, s);
+        { StageTimer t_(GGRT_STAGE_EMIT, s); launch_emit(v, nullptr, g, im, b, s); }
         GGRT_TRY(check_launch("emit", dbg, s));
-        launch_sort_tiles(v, im, b, max_tile_pairs, s);
+        { StageTimer t_(GGRT_STAGE_SORT_TILES, s); launch_sort_tiles(v, im, b, max_tile_pairs, s); }
         GGRT_TRY(check_launch("sort_tiles", dbg, s));
     }
-    launch_render_forward(v, g, im, b, out_color, out_depth, s);
+    { StageTimer t_(GGRT_STAGE_RENDER_FORWARD, s); launch_render_forward(v, g, im, b, out_color, out_depth, s); }
     GGRT_TRY(check_launch("render_forward", dbg, s));
     return GGRT_OK;
 }
@@ -269,11 +297,14 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, int32_t P, int64_t 
     if (cudaMemsetAsync(grad_scratch, 0, (size_t)P * GRAD_STRIDE * sizeof(float), s) != cudaSuccess)
         return check_launch("memset grad scratch", 0, s);
     if (num_rendered > 0) {
-        launch_render_backward(v, g, im, b, dL_dout_color, grad_scratch, s);
+        { StageTimer t_(GGRT_STAGE_RENDER_BACKWARD, s); launch_render_backward(v, g, im, b, dL_dout_color, grad_scratch, s); }
         GGRT_TRY(check_launch("render_backward", dbg, s));
     }
-    launch_preprocess_backward(v, means3D, cov3D_precomp, shs, radii, g, grad_scratch, dL_dmeans2D, dL_dopacity,
-                               dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dcolors, s);
+    {
+        StageTimer t_(GGRT_STAGE_PREPROCESS_BACKWARD, s);
+        launch_preprocess_backward(v, means3D, cov3D_precomp, shs, radii, g, grad_scratch, dL_dmeans2D, dL_dopacity,
+                                   dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dcolors, s);
+    }
     GGRT_TRY(check_launch("preprocess_backward", dbg, s));
     return GGRT_OK;
 }
@@ -287,6 +318,36 @@ int ggrt_raster_mark_visible(int32_t P, const float* means3D, const float* viewm
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     launch_mark_visible(P, means3D, viewmatrix, present, s);
     return check_launch("mark_visible", 0, s);
+}
+
+int ggrt_raster_profile_enable(int32_t on) {
+    g_prof.on = on != 0;
+    for (int i = 0; i < GGRT_STAGE_COUNT; ++i) g_prof.used[i] = false;
+    return GGRT_OK;
+}
+
+int ggrt_raster_profile_read(float* ms_out) {
+    if (!ms_out) {
+        set_error("profile_read: NULL output");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    for (int i = 0; i < GGRT_STAGE_COUNT; ++i) {
+        ms_out[i] = 0.f;
+        if (!g_prof.made || !g_prof.used[i]) continue;
+        if (cudaEventSynchronize(g_prof.b[i]) != cudaSuccess ||
+            cudaEventElapsedTime(&ms_out[i], g_prof.a[i], g_prof.b[i]) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("profile_read: event query failed for stage %d", i);
+            return GGRT_ERR_CUDA;
+        }
+    }
+    return GGRT_OK;
+}
+
+const char* ggrt_raster_stage_name(int32_t stage) {
+    static const char* names[GGRT_STAGE_COUNT] = {"geometry", "scan_tiles", "color", "emit", "sort_tiles",
+                                                  "render_forward", "render_backward", "preprocess_backward"};
+    return (stage >= 0 && stage < GGRT_STAGE_COUNT) ? names[stage] : "?";
 }
 
 }  // extern "C"

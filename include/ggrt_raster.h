@@ -134,6 +134,26 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, int32_t P, int64_t 
 int ggrt_raster_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present,
                              ggrt_stream_t stream);
 
+/*
+ * Per-kernel timing (diagnostics; off by default).  When enabled for the calling thread,
+ * every kernel launch of the calls above is bracketed by CUDA events on the caller's
+ * stream.  ggrt_raster_profile_read waits for the events of the most recent
+ * forward_prepare / forward_render / backward calls and writes their durations in
+ * milliseconds, indexed by GGRT_STAGE_* (a stage that did not run reports 0).
+ */
+#define GGRT_STAGE_GEOMETRY 0
+#define GGRT_STAGE_SCAN_TILES 1
+#define GGRT_STAGE_COLOR 2
+#define GGRT_STAGE_EMIT 3
+#define GGRT_STAGE_SORT_TILES 4
+#define GGRT_STAGE_RENDER_FORWARD 5
+#define GGRT_STAGE_RENDER_BACKWARD 6
+#define GGRT_STAGE_PREPROCESS_BACKWARD 7
+#define GGRT_STAGE_COUNT 8
+int ggrt_raster_profile_enable(int32_t on);
+int ggrt_raster_profile_read(float* ms_out /* [GGRT_STAGE_COUNT], host */);
+const char* ggrt_raster_stage_name(int32_t stage);
+
 #ifdef __cplusplus
 }
 #endif
