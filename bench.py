@@ -277,11 +277,15 @@ def run_ours(args, rank, world, local_rank):
     d2h = h_img.numel() * 4 + 4
     rasterizer = GaussianRasterizer(rs)
 
+    # device staging tensors are allocated once (as a training loop would) and refilled every step
+    d_in = [torch.empty_like(x, device=dev).requires_grad_() for x in (h_means, h_cov, h_opac, h_shs)]
+
     def e2e_step():
-        m = h_means.to(dev, non_blocking=True).requires_grad_()
-        c = h_cov.to(dev, non_blocking=True).requires_grad_()
-        o = h_opac.to(dev, non_blocking=True).requires_grad_()
-        s = h_shs.to(dev, non_blocking=True).requires_grad_()
+        with torch.no_grad():
+            for d_, h_ in zip(d_in, (h_means, h_cov, h_opac, h_shs)):
+                d_.copy_(h_, non_blocking=True)
+                d_.grad = None
+        m, c, o, s = d_in
         m2 = torch.zeros_like(m, requires_grad=True)
         image, radii, _ = rasterizer(means3D=m, means2D=m2, shs=s, colors_precomp=None, opacities=o, cov3D_precomp=c)
         loss = (image * grad_img).sum()
@@ -292,7 +296,7 @@ def run_ours(args, rank, world, local_rank):
         h_img.copy_(image.detach(), non_blocking=True)
         h_loss.copy_(loss.detach(), non_blocking=True)
 
-    for _ in range(3):
+    for _ in range(5):
         e2e_step()
     sync_all()
     n_e2e = min(args.steps, 20)

@@ -29,12 +29,25 @@ def sources():
     return sorted(CSRC.glob("*.cu"))
 
 
+STAMP = LIB_DIR / "libggrt_raster.sha256"
+
+
+def source_hash() -> str:
+    """Content hash of every file the library is built from (mtimes do not survive the copy to the GPU box)."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    deps = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "ggrt_raster.h"]
+    for d in deps:
+        h.update(d.name.encode())
+        h.update(d.read_bytes())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    if not LIB.exists():
+    if not LIB.exists() or not STAMP.exists():
         return True
-    t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "ggrt_raster.h"]
-    return any(d.stat().st_mtime > t for d in deps)
+    return STAMP.read_text().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
@@ -51,6 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         print(res.stdout, res.stderr)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+    STAMP.write_text(source_hash())
     return LIB
 
 

@@ -16,18 +16,29 @@ constexpr int EMIT_THREADS = 256;
 constexpr int SORT_THREADS = 256;
 
 __global__ void __launch_bounds__(EMIT_THREADS)
-emit_kernel(View v, GeomPtrs g, const uint32_t* __restrict__ starts, uint32_t* __restrict__ cursor,
-            unsigned long long* __restrict__ keys) {
+emit_kernel(View v, GeomPtrs g, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ counts,
+            uint32_t* __restrict__ cursor, unsigned long long* __restrict__ keys) {
     const int i = blockIdx.x * EMIT_THREADS + threadIdx.x;
     if (i >= v.P) return;
     if (g.tiles[i] == 0) return;
     const ushort4 r = g.rect[i];
     const unsigned long long key = ((unsigned long long)__float_as_uint(g.rec2[i].w) << 32) | (uint32_t)i;
+    const int sub = i & (SUBS - 1);
     for (int y = r.y; y < r.w; ++y)
         for (int x = r.x; x < r.z; ++x) {
-            const int t = y * v.gx + x;
-            const uint32_t slot = starts[t] + atomicAdd(&cursor[t], 1u);
-            keys[slot] = key;
+            const int tile = y * v.gx + x;
+            const int t = (tile << SUBS_LOG2) + sub;
+            const uint32_t local = atomicAdd(&cursor[t], 1u);
+            // sub-segment offset inside the tile segment: counts of the lower sub-counters (one 64 B line)
+            const uint4* c4 = reinterpret_cast<const uint4*>(counts) + (size_t)tile * (SUBS / 4);
+            uint32_t base = starts[tile];
+#pragma unroll
+            for (int q = 0; q < SUBS / 4; ++q) {
+                const uint4 c = c4[q];
+                base += (4 * q + 0 < sub ? c.x : 0u) + (4 * q + 1 < sub ? c.y : 0u) + (4 * q + 2 < sub ? c.z : 0u) +
+                        (4 * q + 3 < sub ? c.w : 0u);
+            }
+            keys[base + local] = key;
         }
 }
 
@@ -45,17 +56,18 @@ __device__ __forceinline__ void bitonic_sort(unsigned long long* a, uint32_t n) 
     uint32_t n2 = 1;
     while (n2 < n) n2 <<= 1;
     const uint32_t half = n2 >> 1;
-    for (uint32_t k = 2; k <= n2; k <<= 1) {
-        const uint32_t hk = k >> 1;
+    for (uint32_t lk = 1; (1u << lk) <= n2; ++lk) {  // k = 2^lk: block size of this merge
+        const uint32_t k = 1u << lk, hk = k >> 1;
         for (uint32_t t = threadIdx.x; t < half; t += SORT_THREADS) {
-            const uint32_t blk = t / hk, off = t - blk * hk;
-            const uint32_t i = blk * k + off, l = blk * k + (k - 1 - off);
+            const uint32_t blk = t >> (lk - 1), off = t & (hk - 1);
+            const uint32_t i = (blk << lk) + off, l = (blk << lk) + (k - 1 - off);
             if (l < n) cmpxchg(a, i, l);
         }
         __syncthreads();
-        for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+        for (int lj = (int)lk - 2; lj >= 0; --lj) {  // j = 2^lj: half-cleaner distance
+            const uint32_t j = 1u << lj;
             for (uint32_t t = threadIdx.x; t < half; t += SORT_THREADS) {
-                const uint32_t i = 2 * j * (t / j) + (t % j), l = i + j;
+                const uint32_t i = ((t >> lj) << (lj + 1)) + (t & (j - 1)), l = i + j;
                 if (l < n) cmpxchg(a, i, l);
             }
             __syncthreads();
@@ -90,7 +102,8 @@ sort_tiles_kernel(int T, const uint32_t* __restrict__ starts, unsigned long long
 
 void launch_emit(const View& v, const int*, GeomPtrs g, ImagePtrs im, BinPtrs b, cudaStream_t s) {
     if (v.P == 0) return;
-    emit_kernel<<<(v.P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, s>>>(v, g, im.starts, im.cursor, b.keys);
+    emit_kernel<<<(v.P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, s>>>(v, g, im.starts, im.counts, im.cursor,
+                                                                                 b.keys);
 }
 
 void launch_sort_tiles(const View& v, ImagePtrs im, BinPtrs b, uint32_t max_tile_pairs, cudaStream_t s) {

@@ -68,9 +68,9 @@ void compute_layout(int P, int H, int W, long long N, GgrtRasterLayout* L) {
     const size_t gx = (size_t)(W + TILE - 1) / TILE, gy = (size_t)(H + TILE - 1) / TILE, T = gx * gy;
     const size_t px = (size_t)H * W;
     off = 0;
-    L->img_counts = off; off = align_up(off + T * sizeof(uint32_t));
+    L->img_counts = off; off = off + T * SUBS * sizeof(uint32_t);  // counts and cursor are zeroed by one memset
+    L->img_cursor = off; off = align_up(off + T * SUBS * sizeof(uint32_t));
     L->img_starts = off; off = align_up(off + (T + 1) * sizeof(uint32_t));
-    L->img_cursor = off; off = align_up(off + T * sizeof(uint32_t));
     L->img_header = off; off = align_up(off + 4 * sizeof(uint32_t));
     L->img_final_T = off; off = align_up(off + px * sizeof(float));
     L->img_ncontrib = off; off = align_up(off + px * sizeof(uint32_t));
@@ -213,7 +213,7 @@ int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, int32_t P, c
                                 uint32_t* counts_host, ggrt_stream_t stream) {
     View v;
     GGRT_TRY(make_view(settings, P, &v));
-    if ((shs == nullptr) == (colors_precomp == nullptr)) {
+    if (P > 0 && (shs == nullptr) == (colors_precomp == nullptr)) {
         set_error("exactly one of shs / colors_precomp must be given");
         return GGRT_ERR_INVALID_ARGUMENT;
     }
@@ -225,7 +225,7 @@ int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, int32_t P, c
     const int dbg = settings->debug;
     GeomPtrs g = geom_ptrs(geom_buffer, P);
     ImagePtrs im = image_ptrs(image_buffer, v.H, v.W);
-    if (cudaMemsetAsync(im.counts, 0, (size_t)v.gx * v.gy * sizeof(uint32_t), s) != cudaSuccess)
+    if (cudaMemsetAsync(im.counts, 0, 2 * (size_t)v.gx * v.gy * SUBS * sizeof(uint32_t), s) != cudaSuccess)
         return check_launch("memset tile counts", 0, s);
     for (int i = 0; i < GGRT_STAGE_COUNT; ++i) g_prof.used[i] = false;
     { StageTimer t_(GGRT_STAGE_GEOMETRY, s); launch_geometry(v, means3D, cov3D_precomp, opacities, radii, g, im, s); }

@@ -17,6 +17,11 @@ constexpr float ALPHA_MAX = 0.99f;
 constexpr float T_EPS = 0.0001f;
 constexpr float RADIUS_CAP = 1.0e6f;
 constexpr int GRAD_STRIDE = 12;     // floats per Gaussian in the backward scratch
+// Each tile owns SUBS pair counters (sub-counter = Gaussian index mod SUBS): same-address
+// atomics serialise in L2, so spreading a tile's ~300 increments over 16 addresses cuts the
+// binning kernels' critical path ~16x.  Sub-segments are contiguous inside the tile segment.
+constexpr int SUBS = 16;
+constexpr int SUBS_LOG2 = 4;
 
 // grad_scratch slot meaning (A.4): NDC-mean x,y | conic A, B(half convention), C | opacity | colour r,g,b
 enum GradSlot { G_MX = 0, G_MY = 1, G_CA = 2, G_CB = 3, G_CC = 4, G_OP = 5, G_R = 6, G_G = 7, G_B = 8 };

@@ -75,8 +75,9 @@ geometry_kernel(View v, const float* __restrict__ means, const float* __restrict
             }
             r0 = make_float4(pxx, pxy, ex, ey);
             r1 = make_float4(cA, cB, cC, o);
+            const int sub = i & (SUBS - 1);
             for (int y = y0; y < y1; ++y)
-                for (int x = x0; x < x1; ++x) atomicAdd(&counts[y * v.gx + x], 1u);
+                for (int x = x0; x < x1; ++x) atomicAdd(&counts[((y * v.gx + x) << SUBS_LOG2) + sub], 1u);
         }
     }
     radii[i] = radius;
@@ -88,56 +89,94 @@ geometry_kernel(View v, const float* __restrict__ means, const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------
-// scan_tiles: exclusive scan of the per-tile counts (one CTA; T is a few thousand),
-// zeroes the emit cursors, reports {N, max count}.
+// scan_tiles: per-tile totals of the SUBS pair counters and their exclusive scan (one CTA;
+// T is a few thousand, the counters are L2 resident).  Reports {N, max pairs in one tile}.
+// Each thread owns a run of whole tiles and issues all its loads before the block scan.
 // ---------------------------------------------------------------------------------------
+constexpr int SCAN_MAX_PER = 8;  // tiles per thread held in registers (T <= 8192); larger images loop
+
 __global__ void __launch_bounds__(1024) scan_tiles_kernel(int T, const uint32_t* __restrict__ counts,
-                                                          uint32_t* __restrict__ starts, uint32_t* __restrict__ cursor,
+                                                          uint32_t* __restrict__ starts,
                                                           uint32_t* __restrict__ header) {
     __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
     __shared__ uint32_t max_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry_s = 0, max_s = 0;
+    if (tid == 0) max_s = 0;
+    const int per = (T + 1023) / 1024;  // tiles per thread
+    const int t0 = min(T, tid * per), t1 = min(T, t0 + per);
+    const uint4* c4 = reinterpret_cast<const uint4*>(counts);
+    uint32_t tot[SCAN_MAX_PER];
+    uint32_t sum = 0, local_max = 0;
+    if (per <= SCAN_MAX_PER) {
+        uint4 c[SCAN_MAX_PER][SUBS / 4];
+#pragma unroll
+        for (int u = 0; u < SCAN_MAX_PER; ++u)
+#pragma unroll
+            for (int q = 0; q < SUBS / 4; ++q)
+                c[u][q] = (t0 + u < t1) ? c4[(size_t)(t0 + u) * (SUBS / 4) + q] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < SCAN_MAX_PER; ++u) {
+            uint32_t ts = 0;
+#pragma unroll
+            for (int q = 0; q < SUBS / 4; ++q) ts += c[u][q].x + c[u][q].y + c[u][q].z + c[u][q].w;
+            tot[u] = ts;
+            local_max = max(local_max, ts);
+            sum += ts;
+        }
+    } else {
+        for (int t = t0; t < t1; ++t) {
+            uint32_t ts = 0;
+            for (int q = 0; q < SUBS / 4; ++q) {
+                const uint4 c = c4[(size_t)t * (SUBS / 4) + q];
+                ts += c.x + c.y + c.z + c.w;
+            }
+            local_max = max(local_max, ts);
+            sum += ts;
+        }
+    }
+    uint32_t x = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
     __syncthreads();
-    uint32_t local_max = 0;
-    for (int base = 0; base < T; base += 1024) {
-        const int t = base + tid;
-        const uint32_t c = (t < T) ? counts[t] : 0u;
-        local_max = max(local_max, c);
-        uint32_t x = c;
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-            if (lane >= d) x += y;
+            const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += y;
         }
-        if (lane == 31) warp_sums[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t s = warp_sums[lane];
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    uint32_t run = (warp == 0 ? 0u : warp_sums[warp - 1]) + x - sum;  // exclusive prefix of this thread's run
+    if (per <= SCAN_MAX_PER) {
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, s, d);
-                if (lane >= d) s += y;
+        for (int u = 0; u < SCAN_MAX_PER; ++u)
+            if (t0 + u < t1) {
+                starts[t0 + u] = run;
+                run += tot[u];
             }
-            warp_sums[lane] = s;  // inclusive over warps
+    } else {
+        for (int t = t0; t < t1; ++t) {
+            uint32_t ts = 0;
+            for (int q = 0; q < SUBS / 4; ++q) {
+                const uint4 c = c4[(size_t)t * (SUBS / 4) + q];
+                ts += c.x + c.y + c.z + c.w;
+            }
+            starts[t] = run;
+            run += ts;
         }
-        __syncthreads();
-        const uint32_t carry = carry_s;
-        const uint32_t warp_off = (warp == 0) ? 0u : warp_sums[warp - 1];
-        if (t < T) {
-            starts[t] = carry + warp_off + x - c;
-            cursor[t] = 0u;
-        }
-        __syncthreads();
-        if (tid == 1023) carry_s = carry + warp_off + x;
-        __syncthreads();
     }
     atomicMax(&max_s, local_max);
     __syncthreads();
-    if (tid == 0) {
-        starts[T] = carry_s;
-        header[0] = carry_s;
+    if (tid == 1023) {
+        const uint32_t total = warp_sums[31];
+        starts[T] = total;
+        header[0] = total;
         header[1] = max_s;
         header[2] = 0u;
         header[3] = 0u;
@@ -225,7 +264,7 @@ void launch_geometry(const View& v, const float* means, const float* cov3d, cons
 }
 
 void launch_scan_tiles(const View& v, ImagePtrs im, cudaStream_t s) {
-    scan_tiles_kernel<<<1, 1024, 0, s>>>(v.gx * v.gy, im.counts, im.starts, im.cursor, im.header);
+    scan_tiles_kernel<<<1, 1024, 0, s>>>(v.gx * v.gy, im.counts, im.starts, im.header);
 }
 
 void launch_color(const View& v, const float* means, const float* shs, const float* colors, const int* radii,

@@ -4,8 +4,9 @@
 //
 // Same tile / warp / batch structure and the same per-warp bounding-box cull as the
 // forward.  Per (warp, Gaussian) the 9 partial gradients are reduced over the 32 pixels
-// with shuffles, lane 0 adds them into a per-batch shared-memory accumulator, and the
-// CTA flushes one set of global reductions per (tile, Gaussian).
+// with a transposed shuffle butterfly (14 shuffles for 9 values), added into a per-batch
+// shared-memory accumulator, and the CTA flushes one set of global reductions per
+// (tile, Gaussian).
 #include "common.cuh"
 
 namespace ggrt {
@@ -17,6 +18,29 @@ __device__ __forceinline__ float warp_sum(float x) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
     return x;
+}
+
+// Transposed butterfly: reduces g[0..7] over the warp with 4+2+1+1+1 = 9 shuffles instead of
+// 8*5 = 40 (each step halves the number of live values per lane).  On return every lane l
+// holds the warp total of value (l >> 2).
+__device__ __forceinline__ float reduce8_transposed(const float (&g)[NV], int lane) {
+    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
+    float r4[4], r2[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = u16 ? g[i] : g[i + 4], keep = u16 ? g[i + 4] : g[i];
+        r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = u8 ? r4[i] : r4[i + 2], keep = u8 ? r4[i + 2] : r4[i];
+        r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float send = u4 ? r2[0] : r2[1], keep = u4 ? r2[1] : r2[0];
+    float r = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
 }
 
 __global__ void __launch_bounds__(RENDER_THREADS)
@@ -137,12 +161,10 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
                         }
                     }
                     if (__any_sync(0xffffffffu, act)) {
-#pragma unroll
-                        for (int k = 0; k < NV; ++k) g[k] = warp_sum(g[k]);
-                        if (lane == 0) {
-#pragma unroll
-                            for (int k = 0; k < NV; ++k) atomicAdd(&sg[jj * NV + k], g[k]);
-                        }
+                        const float r = reduce8_transposed(g, lane);  // lane l: total of value l >> 2
+                        const float r8 = warp_sum(g[8]);
+                        if ((lane & 3) == 0) atomicAdd(&sg[jj * NV + (lane >> 2)], r);
+                        if (lane == 1) atomicAdd(&sg[jj * NV + 8], r8);
                     }
                 }
             }

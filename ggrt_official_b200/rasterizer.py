@@ -188,7 +188,9 @@ class _RasterizeGaussians(torch.autograd.Function):
             if raster_settings.debug:
                 _dump("snapshot_fw.dump", (means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings))
             raise
-        ctx.state = st
+        # keep only what backward needs; the outputs must not be referenced from ctx (that would be a
+        # grad_fn <-> output reference cycle and the buffers would wait for the garbage collector)
+        ctx.state = {k: st[k] for k in ("call", "radii", "geom", "img", "binning", "N")}
         ctx.raster_settings = raster_settings
         ctx.sh_shape = None if sh is None else tuple(sh.shape)
         ctx.opacity_shape = tuple(opacities.shape)

@@ -38,6 +38,7 @@ extern "C" {
 
 #define GGRT_RASTER_ABI_VERSION 1
 #define GGRT_RASTER_TILE 16 /* tile edge in pixels (tile ids are part of the contract) */
+#define GGRT_RASTER_SUBS 16 /* pair counters per tile (contention spreading) */
 
 #define GGRT_OK 0
 #define GGRT_ERR_INVALID_ARGUMENT (-1)
@@ -73,9 +74,9 @@ typedef struct GgrtRasterLayout {
     size_t geom_flags;  /* uint8[P]   bit c: colour channel c was clamped at 0 */
     size_t geom_bytes;
     /* image buffer, per tile / per pixel */
-    size_t img_counts;  /* uint32[T]   pairs per tile */
-    size_t img_starts;  /* uint32[T+1] exclusive scan of counts; [T] == N */
-    size_t img_cursor;  /* uint32[T]   scratch */
+    size_t img_counts;  /* uint32[T*16] pairs per (tile, sub-counter); sub-counter = gaussian idx % 16 */
+    size_t img_cursor;  /* uint32[T*16] scratch (directly after img_counts) */
+    size_t img_starts;  /* uint32[T+1]  exclusive scan of the per-tile totals; tile t owns [starts[t], starts[t+1]); [T] == N */
     size_t img_header;  /* uint32[4]   {N, max pairs in a tile, 0, 0} */
     size_t img_final_T; /* float[H*W]  */
     size_t img_ncontrib;/* uint32[H*W] */

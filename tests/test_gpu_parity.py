@@ -125,12 +125,11 @@ def test_autograd_module_end_to_end():
 
 def test_empty_and_culled_inputs():
     dev = "cuda:0"
-    _, ri = small_case(64, 32, 32, 0, seed=1)
+    _, ri = small_case(64, 32, 32, 0, seed=1, behind_fraction=0.0)
     rs = G.settings_from(ri, dev)
-    # every Gaussian behind the camera: image is the background, radii all zero, gradients zero
-    means = torch.tensor(ri.means3D, device=dev)
-    means = (means - 2 * (means @ torch.tensor(ri.viewmatrix[:3, 2], device=dev))[:, None]
-             * torch.tensor(ri.viewmatrix[:3, 2], device=dev)[None] * 3).requires_grad_()
+    # every Gaussian behind the camera (point reflection through the camera centre): image is the
+    # background, radii all zero, gradients zero
+    means = (2 * torch.tensor(ri.campos, device=dev)[None] - torch.tensor(ri.means3D, device=dev)).requires_grad_()
     rs = rs._replace(bg=torch.tensor([0.25, 0.5, 0.75], device=dev))
     img, radii, depth = GaussianRasterizer(rs)(means3D=means, means2D=torch.zeros_like(means, requires_grad=True),
                                                 shs=torch.tensor(ri.shs, device=dev), opacities=torch.tensor(ri.opacities, device=dev),
