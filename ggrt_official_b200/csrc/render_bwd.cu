@@ -4,15 +4,19 @@
 //
 // Same tile / warp / batch structure and the same per-warp bounding-box cull as the
 // forward.  Per (warp, Gaussian) the 9 partial gradients are reduced over the 32 pixels
-// with a transposed shuffle butterfly (14 shuffles for 9 values), added into a per-batch
-// shared-memory accumulator, and the CTA flushes one set of global reductions per
-// (tile, Gaussian).
-#include "common.cuh"
+// with a transposed shuffle butterfly (14 shuffles for 9 values, leaving value k in lane
+// 4k) and committed with two warp-level global reductions (RED.ADD.F32: 8 lanes hit one
+// 48-byte scratch row, then the 9th value).  No shared-memory float atomics: those
+// compile to compare-and-swap loops on this architecture.
+#include "render_common.cuh"
 
 namespace ggrt {
 
-constexpr int RENDER_THREADS = 256;
 constexpr int NV = 9;  // gradient values per Gaussian (GradSlot)
+
+__device__ __forceinline__ void red_add(float* addr, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
 
 __device__ __forceinline__ float warp_sum(float x) {
 #pragma unroll
@@ -43,15 +47,15 @@ __device__ __forceinline__ float reduce8_transposed(const float (&g)[NV], int la
     return r;
 }
 
-__global__ void __launch_bounds__(RENDER_THREADS)
+__global__ void __launch_bounds__(RENDER_THREADS, 3)
 render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __restrict__ rec1,
                        const float4* __restrict__ rec2, const uint32_t* __restrict__ starts,
                        const uint32_t* __restrict__ points, const float* __restrict__ final_T,
                        const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dout,
                        float* __restrict__ scratch) {
-    __shared__ float4 s0[RENDER_THREADS], s1[RENDER_THREADS], s2[RENDER_THREADS];
+    __shared__ __align__(16) unsigned char srec[RENDER_THREADS * REC_BYTES];
     __shared__ uint32_t sid[RENDER_THREADS];
-    __shared__ float sg[RENDER_THREADS * NV];
+    const uint32_t sbase = smem_addr(srec);
     __shared__ uint32_t block_last_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -84,98 +88,93 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
     if (block_last == 0) return;
 
     const float bg_dot = v.bg[0] * d0 + v.bg[1] * d1 + v.bg[2] * d2;
-    const float half_w = 0.5f * (float)v.W, half_h = 0.5f * (float)v.H;
+    const float neg_half_w = -0.5f * (float)v.W, neg_half_h = -0.5f * (float)v.H;
+    const float tb = -Tfin * bg_dot;
     float T = Tfin;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
+    // destination of this lane after the butterfly: lane 4k owns slot k (k < 8), lane 1 owns slot 8
+    const int my_slot = (lane == 1) ? 8 : (lane >> 2);
+    const bool commits = ((lane & 3) == 0) || lane == 1;
 
     const int nb = (int)((block_last + RENDER_THREADS - 1) / RENDER_THREADS);
     for (int bi = nb - 1; bi >= 0; --bi) {
         const uint32_t boff = (uint32_t)bi * RENDER_THREADS;
         const uint32_t cnt = min((uint32_t)RENDER_THREADS, block_last - boff);
-        __syncthreads();  // previous batch fully flushed before the refill
+        __syncthreads();  // every warp is done with the previous batch before the refill
         if (tid < cnt) {
             const uint32_t id = points[start + boff + tid];
             sid[tid] = id;
-            s0[tid] = rec0[id];
-            s1[tid] = rec1[id];
-            s2[tid] = rec2[id];
+            const uint32_t dst = sbase + tid * REC_BYTES;
+            sts128(dst, rec0[id]);
+            sts128(dst + 16, rec1[id]);
+            sts128(dst + 32, rec2[id]);
         }
-#pragma unroll
-        for (int k = 0; k < NV; ++k) sg[tid * NV + k] = 0.f;
         __syncthreads();
+        if (warp_last <= boff) continue;
 
-        if (warp_last > boff) {
-            for (int r = (int)((cnt - 1) & ~31u); r >= 0; r -= 32) {
-                const uint32_t j = (uint32_t)r + lane;
-                bool hit = false;
-                if (j < cnt) {
-                    const float4 a = s0[j];
-                    hit = (fabsf(a.x - wcx) <= a.z + 3.5f) && (fabsf(a.y - wcy) <= a.w + 1.5f);
-                }
-                uint32_t mask = __ballot_sync(0xffffffffu, hit);
-                while (mask) {
-                    const int b = 31 - __clz(mask);
-                    mask &= ~(1u << b);
-                    const uint32_t jj = (uint32_t)r + b;
-                    const uint32_t pos = boff + jj;  // 0-based list position; contributor id is pos+1
-                    float g[NV];
+        for (int r = (int)((cnt - 1) & ~31u); r >= 0; r -= 32) {
+            const uint32_t j = (uint32_t)r + lane;
+            bool hit = false;
+            if (j < cnt) {
+                const float4 a = lds128(sbase + j * REC_BYTES);
+                hit = (fabsf(a.x - wcx) <= a.z + 3.5f) && (fabsf(a.y - wcy) <= a.w + 1.5f);
+            }
+            uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            while (mask) {
+                const int b = 31 - __clz(mask);
+                mask &= ~(1u << b);
+                const uint32_t jj = (uint32_t)r + b;
+                const uint32_t pos = boff + jj;  // 0-based list position; contributor id is pos+1
+                float g[NV];
 #pragma unroll
-                    for (int k = 0; k < NV; ++k) g[k] = 0.f;
-                    bool act = false;
-                    if (pos < last) {
-                        const float4 a = s0[jj], c = s1[jj];
-                        const float dx = a.x - pxf, dy = a.y - pyf;
-                        const float power = -0.5f * (c.x * dx * dx + c.z * dy * dy) - c.y * dx * dy;
-                        if (power <= 0.0f) {
-                            const float G = __expf(power);
-                            const float alpha = fminf(ALPHA_MAX, c.w * G);
-                            if (alpha >= ALPHA_MIN) {
-                                act = true;
-                                const float4 col = s2[jj];
-                                const float om = 1.0f - alpha;
-                                const float inv_om = __fdividef(1.0f, om);
-                                T = T * inv_om;
-                                const float w = alpha * T;
-                                acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0;
-                                acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1;
-                                acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2;
-                                lc0 = col.x, lc1 = col.y, lc2 = col.z;
-                                float dL_dalpha = (col.x - acc0) * d0 + (col.y - acc1) * d1 + (col.z - acc2) * d2;
-                                dL_dalpha *= T;
-                                last_alpha = alpha;
-                                dL_dalpha += (-Tfin * inv_om) * bg_dot;
-                                const float dL_dG = c.w * dL_dalpha;
-                                const float gdx = G * dx, gdy = G * dy;
-                                const float dG_ddelx = -gdx * c.x - gdy * c.y;
-                                const float dG_ddely = -gdy * c.z - gdx * c.y;
-                                g[G_MX] = dL_dG * dG_ddelx * half_w;
-                                g[G_MY] = dL_dG * dG_ddely * half_h;
-                                g[G_CA] = -0.5f * gdx * dx * dL_dG;
-                                g[G_CB] = -0.5f * gdx * dy * dL_dG;
-                                g[G_CC] = -0.5f * gdy * dy * dL_dG;
-                                g[G_OP] = G * dL_dalpha;
-                                g[G_R] = w * d0;
-                                g[G_G] = w * d1;
-                                g[G_B] = w * d2;
-                            }
+                for (int k = 0; k < NV; ++k) g[k] = 0.f;
+                bool act = false;
+                if (pos < last) {
+                    const uint32_t src = sbase + jj * REC_BYTES;
+                    const float2 xy = lds64(src);
+                    const float4 c = lds128(src + 16);
+                    const float dx = xy.x - pxf, dy = xy.y - pyf;
+                    const float dxx = dx * dx, dyy = dy * dy, dxy = dx * dy;
+                    const float power = -0.5f * (c.x * dxx + c.z * dyy) - c.y * dxy;
+                    if (power <= 0.0f) {
+                        const float G = ex2_approx(power * LOG2E);
+                        const float alpha = fminf(ALPHA_MAX, c.w * G);
+                        if (alpha >= ALPHA_MIN) {
+                            act = true;
+                            const float4 col = lds128(src + 32);
+                            const float inv_om = rcp_approx(1.0f - alpha);
+                            T *= inv_om;
+                            const float w = alpha * T;
+                            const float keep = 1.0f - last_alpha;
+                            acc0 = fmaf(last_alpha, lc0, keep * acc0);
+                            acc1 = fmaf(last_alpha, lc1, keep * acc1);
+                            acc2 = fmaf(last_alpha, lc2, keep * acc2);
+                            lc0 = col.x, lc1 = col.y, lc2 = col.z;
+                            last_alpha = alpha;
+                            float dL_dalpha = (col.x - acc0) * d0;
+                            dL_dalpha = fmaf(col.y - acc1, d1, dL_dalpha);
+                            dL_dalpha = fmaf(col.z - acc2, d2, dL_dalpha);
+                            dL_dalpha = fmaf(dL_dalpha, T, tb * inv_om);  // + (-T_final / (1 - alpha)) * bg . dL/dpix
+                            const float q = G * dL_dalpha;   // dL/dopacity contribution
+                            const float t = c.w * q;          // dL/dG * G
+                            const float h = -0.5f * t;
+                            g[G_MX] = (t * neg_half_w) * fmaf(c.x, dx, c.y * dy);
+                            g[G_MY] = (t * neg_half_h) * fmaf(c.z, dy, c.y * dx);
+                            g[G_CA] = h * dxx;
+                            g[G_CB] = h * dxy;
+                            g[G_CC] = h * dyy;
+                            g[G_OP] = q;
+                            g[G_R] = w * d0;
+                            g[G_G] = w * d1;
+                            g[G_B] = w * d2;
                         }
                     }
-                    if (__any_sync(0xffffffffu, act)) {
-                        const float r = reduce8_transposed(g, lane);  // lane l: total of value l >> 2
-                        const float r8 = warp_sum(g[8]);
-                        if ((lane & 3) == 0) atomicAdd(&sg[jj * NV + (lane >> 2)], r);
-                        if (lane == 1) atomicAdd(&sg[jj * NV + 8], r8);
-                    }
                 }
-            }
-        }
-        __syncthreads();
-        if (tid < cnt) {
-            float* dst = scratch + (size_t)sid[tid] * GRAD_STRIDE;
-#pragma unroll
-            for (int k = 0; k < NV; ++k) {
-                const float x = sg[tid * NV + k];
-                if (x != 0.f) atomicAdd(dst + k, x);
+                if (__any_sync(0xffffffffu, act)) {
+                    const float r8 = reduce8_transposed(g, lane);  // lane l: total of value l >> 2
+                    const float r9 = warp_sum(g[8]);
+                    if (commits) red_add(scratch + (size_t)sid[jj] * GRAD_STRIDE + my_slot, lane == 1 ? r9 : r8);
+                }
             }
         }
     }

@@ -2,23 +2,22 @@
 // SURVEY.md 8a row a11.
 //
 // One CTA per 16x16 tile; warp w owns the 8x4 pixel block (w&1, w>>1) so each warp's
-// output rows are 32-byte contiguous.  A batch of 256 Gaussian records is staged into
-// shared memory; each warp first culls the batch against its pixel block with one
-// bounding-box test per lane (the records carry the {alpha >= 1/255} extent) and then
+// output rows are 32-byte contiguous.  A batch of 256 Gaussian records (48 B each) is
+// staged into shared memory; each warp first culls the batch against its pixel block with
+// one bounding-box test per lane (the records carry the {alpha >= 1/255} extent) and then
 // walks only the surviving bits of the ballot masks, in list order.  GGRt's splats are a
 // few pixels wide, so most (warp, Gaussian) pairs of a tile are culled.
-#include "common.cuh"
+#include "render_common.cuh"
 
 namespace ggrt {
 
-constexpr int RENDER_THREADS = 256;
-
-__global__ void __launch_bounds__(RENDER_THREADS)
+__global__ void __launch_bounds__(RENDER_THREADS, 4)
 render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __restrict__ rec1,
                       const float4* __restrict__ rec2, const uint32_t* __restrict__ starts,
                       const uint32_t* __restrict__ points, float* __restrict__ out_color,
                       float* __restrict__ out_depth, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
-    __shared__ float4 s0[RENDER_THREADS], s1[RENDER_THREADS], s2[RENDER_THREADS];
+    __shared__ __align__(16) unsigned char srec[RENDER_THREADS * REC_BYTES];
+    const uint32_t sbase = smem_addr(srec);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.y * v.gx + blockIdx.x;
     const int bx0 = blockIdx.x * TILE + (warp & 1) * 8, by0 = blockIdx.y * TILE + (warp >> 1) * 4;
@@ -37,36 +36,40 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
         const uint32_t cnt = min((uint32_t)RENDER_THREADS, end - base);
         if (tid < cnt) {
             const uint32_t id = points[base + tid];
-            s0[tid] = rec0[id];
-            s1[tid] = rec1[id];
-            s2[tid] = rec2[id];
+            const uint32_t dst = sbase + tid * REC_BYTES;
+            sts128(dst, rec0[id]);
+            sts128(dst + 16, rec1[id]);
+            sts128(dst + 32, rec2[id]);
         }
         __syncthreads();
         if (__all_sync(0xffffffffu, done)) continue;
         for (uint32_t r = 0; r < cnt; r += 32) {
-            const uint32_t j = r + lane;
+            // lane l tests list entry r + 31 - l, so the highest set bit of the ballot is the first entry
+            const uint32_t j = r + 31 - lane;
             bool hit = false;
             if (j < cnt) {
-                const float4 a = s0[j];
+                const float4 a = lds128(sbase + j * REC_BYTES);
                 hit = (fabsf(a.x - wcx) <= a.z + 3.5f) && (fabsf(a.y - wcy) <= a.w + 1.5f);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
             while (mask) {
-                const int b = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const uint32_t jj = r + b;
+                const int lz = __clz(mask);
+                mask &= ~(0x80000000u >> lz);
+                const uint32_t jj = r + lz;
+                const uint32_t src = sbase + jj * REC_BYTES;
                 if (!done) {
-                    const float4 a = s0[jj], c = s1[jj];
-                    const float dx = a.x - pxf, dy = a.y - pyf;
+                    const float2 xy = lds64(src);
+                    const float4 c = lds128(src + 16);
+                    const float dx = xy.x - pxf, dy = xy.y - pyf;
                     const float power = -0.5f * (c.x * dx * dx + c.z * dy * dy) - c.y * dx * dy;
                     if (power <= 0.0f) {
-                        const float alpha = fminf(ALPHA_MAX, c.w * __expf(power));
+                        const float alpha = fminf(ALPHA_MAX, c.w * ex2_approx(power * LOG2E));
                         if (alpha >= ALPHA_MIN) {
                             const float Tn = T * (1.0f - alpha);
                             if (Tn < T_EPS) {
                                 done = true;
                             } else {
-                                const float4 col = s2[jj];
+                                const float4 col = lds128(src + 32);
                                 const float w = alpha * T;
                                 C0 = fmaf(col.x, w, C0);
                                 C1 = fmaf(col.y, w, C1);
