@@ -2,49 +2,31 @@
 // SURVEY.md 8a row a12 -- the dominant cost of fwd+bwd upstream because every pixel
 // issues ~10 global float atomics per contributing Gaussian.
 //
-// Same tile / warp / batch structure and the same per-warp bounding-box cull as the
-// forward.  Per (warp, Gaussian) the 9 partial gradients are reduced over the 32 pixels
-// with a transposed shuffle butterfly (14 shuffles for 9 values, leaving value k in lane
-// 4k) and committed with two warp-level global reductions (RED.ADD.F32: 8 lanes hit one
-// 48-byte scratch row, then the 9th value).  No shared-memory float atomics: those
-// compile to compare-and-swap loops on this architecture.
+// Work decomposition ("Gaussian-parallel"): one CTA per 16x16 tile, warp w owns the 8x4
+// pixel block (w&1, w>>1) as in the forward.  A batch of up to 512 Gaussian records is
+// staged into shared memory; each warp culls it against its pixel block (bounding box of
+// {alpha >= 1/255}) into a back-to-front queue and then processes the queue 32 Gaussians
+// at a time with LANES = GAUSSIANS: for every pixel of the block the 32 lanes evaluate
+// their Gaussian's alpha, a warp prefix product of (1-alpha) recovers each Gaussian's
+// transmittance T_i from the transmittance behind the chunk, and a warp prefix sum gives
+// the colour accumulated behind it.  Every lane accumulates the 9 partial gradients of ITS
+// Gaussian over the block's pixels in registers, so there is no per-Gaussian cross-lane
+// reduction (the upstream bottleneck) -- one set of global RED.ADD.F32 per lane per chunk.
+//   dL/dalpha_i = T_i (c_i . g) - [ sum_{j behind i} w_j (c_j . g) + T_final (bg . g) ] / (1 - alpha_i)
+// Per-pixel running state {T behind, sum behind} lives in shared memory between chunks.
 #include "render_common.cuh"
 
 namespace ggrt {
 
-constexpr int NV = 9;  // gradient values per Gaussian (GradSlot)
+constexpr int BWD_BATCH = 512;
+constexpr int NWARPS = RENDER_THREADS / 32;
+#ifndef GGRT_BWD_PIX_UNROLL
+#define GGRT_BWD_PIX_UNROLL 2
+#endif
+constexpr int PIX_UNROLL = GGRT_BWD_PIX_UNROLL;
 
 __device__ __forceinline__ void red_add(float* addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
-}
-
-__device__ __forceinline__ float warp_sum(float x) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-    return x;
-}
-
-// Transposed butterfly: reduces g[0..7] over the warp with 4+2+1+1+1 = 9 shuffles instead of
-// 8*5 = 40 (each step halves the number of live values per lane).  On return every lane l
-// holds the warp total of value (l >> 2).
-__device__ __forceinline__ float reduce8_transposed(const float (&g)[NV], int lane) {
-    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
-    float r4[4], r2[2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = u16 ? g[i] : g[i + 4], keep = u16 ? g[i + 4] : g[i];
-        r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = u8 ? r4[i] : r4[i + 2], keep = u8 ? r4[i + 2] : r4[i];
-        r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    const float send = u4 ? r2[0] : r2[1], keep = u4 ? r2[1] : r2[0];
-    float r = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    r += __shfl_xor_sync(0xffffffffu, r, 2);
-    r += __shfl_xor_sync(0xffffffffu, r, 1);
-    return r;
 }
 
 __global__ void __launch_bounds__(RENDER_THREADS, 3)
@@ -53,32 +35,39 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
                        const uint32_t* __restrict__ points, const float* __restrict__ final_T,
                        const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dout,
                        float* __restrict__ scratch) {
-    __shared__ __align__(16) unsigned char srec[RENDER_THREADS * REC_BYTES];
-    __shared__ uint32_t sid[RENDER_THREADS];
-    const uint32_t sbase = smem_addr(srec);
+    __shared__ __align__(16) unsigned char srec[BWD_BATCH * REC_BYTES];
+    __shared__ uint32_t sid[BWD_BATCH];
+    __shared__ unsigned short squeue[NWARPS][BWD_BATCH];
+    __shared__ float4 spix_g[NWARPS][32];   // per pixel {g_r, g_g, g_b, bits(last)}
+    __shared__ float4 spix_s[NWARPS][32];   // per pixel {x, y, T behind, sum behind}
     __shared__ uint32_t block_last_s;
 
+    const uint32_t sbase = smem_addr(srec);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.y * v.gx + blockIdx.x;
     const int bx0 = blockIdx.x * TILE + (warp & 1) * 8, by0 = blockIdx.y * TILE + (warp >> 1) * 4;
-    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
-    const bool inside = px < v.W && py < v.H;
-    const float pxf = (float)px, pyf = (float)py;
     const float wcx = (float)bx0 + 3.5f, wcy = (float)by0 + 1.5f;
     const uint32_t start = starts[tile];
 
-    float Tfin = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    // ---- per-pixel constants / initial state (lane = pixel here) -------------------------------
     uint32_t last = 0;
-    if (inside) {
-        const size_t pix = (size_t)py * v.W + px, hw = (size_t)v.H * v.W;
-        Tfin = final_T[pix];
-        last = n_contrib[pix];
-        d0 = dL_dout[pix];
-        d1 = dL_dout[hw + pix];
-        d2 = dL_dout[2 * hw + pix];
+    {
+        const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+        float Tfin = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+        if (px < v.W && py < v.H) {
+            const size_t pix = (size_t)py * v.W + px, hw = (size_t)v.H * v.W;
+            Tfin = final_T[pix];
+            last = n_contrib[pix];
+            d0 = dL_dout[pix];
+            d1 = dL_dout[hw + pix];
+            d2 = dL_dout[2 * hw + pix];
+        }
+        // pixels with a zero upstream gradient contribute nothing (crop training leaves most tiles empty)
+        if (d0 == 0.f && d1 == 0.f && d2 == 0.f) last = 0;
+        const float bg_dot = v.bg[0] * d0 + v.bg[1] * d1 + v.bg[2] * d2;
+        spix_g[warp][lane] = make_float4(d0, d1, d2, __uint_as_float(last));
+        spix_s[warp][lane] = make_float4((float)px, (float)py, Tfin, Tfin * bg_dot);
     }
-    // pixels with a zero upstream gradient contribute nothing (crop training leaves most tiles empty)
-    if (d0 == 0.f && d1 == 0.f && d2 == 0.f) last = 0;
     if (tid == 0) block_last_s = 0;
     __syncthreads();
     const uint32_t warp_last = __reduce_max_sync(0xffffffffu, last);
@@ -86,25 +75,20 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
     __syncthreads();
     const uint32_t block_last = block_last_s;
     if (block_last == 0) return;
+    const uint32_t pmask = __ballot_sync(0xffffffffu, last > 0);  // pixels of this warp that matter
 
-    const float bg_dot = v.bg[0] * d0 + v.bg[1] * d1 + v.bg[2] * d2;
     const float neg_half_w = -0.5f * (float)v.W, neg_half_h = -0.5f * (float)v.H;
-    const float tb = -Tfin * bg_dot;
-    float T = Tfin;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
-    // destination of this lane after the butterfly: lane 4k owns slot k (k < 8), lane 1 owns slot 8
-    const int my_slot = (lane == 1) ? 8 : (lane >> 2);
-    const bool commits = ((lane & 3) == 0) || lane == 1;
+    const uint32_t gaddr = smem_addr(&spix_g[warp][0]), saddr = smem_addr(&spix_s[warp][0]);
 
-    const int nb = (int)((block_last + RENDER_THREADS - 1) / RENDER_THREADS);
+    const int nb = (int)((block_last + BWD_BATCH - 1) / BWD_BATCH);
     for (int bi = nb - 1; bi >= 0; --bi) {
-        const uint32_t boff = (uint32_t)bi * RENDER_THREADS;
-        const uint32_t cnt = min((uint32_t)RENDER_THREADS, block_last - boff);
+        const uint32_t boff = (uint32_t)bi * BWD_BATCH;
+        const uint32_t cnt = min((uint32_t)BWD_BATCH, block_last - boff);
         __syncthreads();  // every warp is done with the previous batch before the refill
-        if (tid < cnt) {
-            const uint32_t id = points[start + boff + tid];
-            sid[tid] = id;
-            const uint32_t dst = sbase + tid * REC_BYTES;
+        for (uint32_t k = tid; k < cnt; k += RENDER_THREADS) {
+            const uint32_t id = points[start + boff + k];
+            sid[k] = id;
+            const uint32_t dst = sbase + k * REC_BYTES;
             sts128(dst, rec0[id]);
             sts128(dst + 16, rec1[id]);
             sts128(dst + 32, rec2[id]);
@@ -112,69 +96,119 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
         __syncthreads();
         if (warp_last <= boff) continue;
 
-        for (int r = (int)((cnt - 1) & ~31u); r >= 0; r -= 32) {
-            const uint32_t j = (uint32_t)r + lane;
+        // ---- cull the batch against this warp's pixel block into a back-to-front queue -----------
+        uint32_t qn = 0;
+        const uint32_t lim = min(cnt, warp_last - boff);  // entries at or beyond warp_last never contribute here
+        for (int r = (int)((lim - 1) & ~31u); r >= 0; r -= 32) {
+            const uint32_t j = (uint32_t)r + 31 - lane;  // lane 0 tests the backmost entry of the round
             bool hit = false;
-            if (j < cnt) {
+            if (j < lim) {
                 const float4 a = lds128(sbase + j * REC_BYTES);
                 hit = (fabsf(a.x - wcx) <= a.z + 3.5f) && (fabsf(a.y - wcy) <= a.w + 1.5f);
             }
-            uint32_t mask = __ballot_sync(0xffffffffu, hit);
-            while (mask) {
-                const int b = 31 - __clz(mask);
-                mask &= ~(1u << b);
-                const uint32_t jj = (uint32_t)r + b;
-                const uint32_t pos = boff + jj;  // 0-based list position; contributor id is pos+1
-                float g[NV];
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (hit) squeue[warp][qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
+            qn += __popc(m);
+        }
+        __syncwarp();
+
+        // ---- 32 queued Gaussians at a time: lane = Gaussian ----------------------------------------
+        for (uint32_t c0 = 0; c0 < qn; c0 += 32) {
+            const bool valid = c0 + lane < qn;
+            const uint32_t jj = valid ? squeue[warp][c0 + lane] : 0u;
+            const uint32_t src = sbase + jj * REC_BYTES;
+            const float2 gxy = lds64(src);
+            float4 con = lds128(src + 16);
+            const float4 col = lds128(src + 32);
+            if (!valid) con.w = 0.f;  // zero opacity: never active
+            const uint32_t pos = valid ? boff + jj : 0xffffffffu;  // 0-based list position
+            float a_op = 0.f, a_mx = 0.f, a_my = 0.f, a_A = 0.f, a_B = 0.f, a_C = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f;
+
+            // PIX_UNROLL pixels are processed per iteration: their scans are independent dependency chains
+            // that the scheduler interleaves (the kernel is shuffle-latency bound otherwise).
+            uint32_t pm = pmask;
+            while (pm) {
+                int p[PIX_UNROLL];
+                bool pv[PIX_UNROLL];
 #pragma unroll
-                for (int k = 0; k < NV; ++k) g[k] = 0.f;
-                bool act = false;
-                if (pos < last) {
-                    const uint32_t src = sbase + jj * REC_BYTES;
-                    const float2 xy = lds64(src);
-                    const float4 c = lds128(src + 16);
-                    const float dx = xy.x - pxf, dy = xy.y - pyf;
-                    const float dxx = dx * dx, dyy = dy * dy, dxy = dx * dy;
-                    const float power = -0.5f * (c.x * dxx + c.z * dyy) - c.y * dxy;
-                    if (power <= 0.0f) {
-                        const float G = ex2_approx(power * LOG2E);
-                        const float alpha = fminf(ALPHA_MAX, c.w * G);
-                        if (alpha >= ALPHA_MIN) {
-                            act = true;
-                            const float4 col = lds128(src + 32);
-                            const float inv_om = rcp_approx(1.0f - alpha);
-                            T *= inv_om;
-                            const float w = alpha * T;
-                            const float keep = 1.0f - last_alpha;
-                            acc0 = fmaf(last_alpha, lc0, keep * acc0);
-                            acc1 = fmaf(last_alpha, lc1, keep * acc1);
-                            acc2 = fmaf(last_alpha, lc2, keep * acc2);
-                            lc0 = col.x, lc1 = col.y, lc2 = col.z;
-                            last_alpha = alpha;
-                            float dL_dalpha = (col.x - acc0) * d0;
-                            dL_dalpha = fmaf(col.y - acc1, d1, dL_dalpha);
-                            dL_dalpha = fmaf(col.z - acc2, d2, dL_dalpha);
-                            dL_dalpha = fmaf(dL_dalpha, T, tb * inv_om);  // + (-T_final / (1 - alpha)) * bg . dL/dpix
-                            const float q = G * dL_dalpha;   // dL/dopacity contribution
-                            const float t = c.w * q;          // dL/dG * G
-                            const float h = -0.5f * t;
-                            g[G_MX] = (t * neg_half_w) * fmaf(c.x, dx, c.y * dy);
-                            g[G_MY] = (t * neg_half_h) * fmaf(c.z, dy, c.y * dx);
-                            g[G_CA] = h * dxx;
-                            g[G_CB] = h * dxy;
-                            g[G_CC] = h * dyy;
-                            g[G_OP] = q;
-                            g[G_R] = w * d0;
-                            g[G_G] = w * d1;
-                            g[G_B] = w * d2;
+                for (int u = 0; u < PIX_UNROLL; ++u) {
+                    pv[u] = pm != 0;
+                    p[u] = pv[u] ? __ffs(pm) - 1 : p[0];
+                    pm &= pm - 1;
+                }
+                float4 pg[PIX_UNROLL], ps[PIX_UNROLL];
+                float dx[PIX_UNROLL], dy[PIX_UNROLL], dxx[PIX_UNROLL], dyy[PIX_UNROLL], dxy[PIX_UNROLL];
+                float G[PIX_UNROLL], alpha[PIX_UNROLL], inv_om[PIX_UNROLL], s[PIX_UNROLL], A[PIX_UNROLL], B[PIX_UNROLL];
+                bool act[PIX_UNROLL];
+#pragma unroll
+                for (int u = 0; u < PIX_UNROLL; ++u) {
+                    pg[u] = lds128(gaddr + p[u] * 16);   // {g_r, g_g, g_b, last}
+                    ps[u] = lds128(saddr + p[u] * 16);   // {x, y, T behind, sum behind}
+                }
+#pragma unroll
+                for (int u = 0; u < PIX_UNROLL; ++u) {
+                    dx[u] = gxy.x - ps[u].x, dy[u] = gxy.y - ps[u].y;
+                    dxx[u] = dx[u] * dx[u], dyy[u] = dy[u] * dy[u], dxy[u] = dx[u] * dy[u];
+                    const float power = -0.5f * (con.x * dxx[u] + con.z * dyy[u]) - con.y * dxy[u];
+                    G[u] = ex2_approx(power * LOG2E);
+                    const float alpha_raw = fminf(ALPHA_MAX, con.w * G[u]);
+                    act[u] = pv[u] && (pos < __float_as_uint(pg[u].w)) && (power <= 0.0f) && (alpha_raw >= ALPHA_MIN);
+                    alpha[u] = act[u] ? alpha_raw : 0.f;
+                    inv_om[u] = rcp_approx(1.0f - alpha[u]);
+                    s[u] = fmaf(col.z, pg[u].z, fmaf(col.y, pg[u].y, col.x * pg[u].x));
+                    // Going back to front each Gaussian maps the running pair (T, R) to (a T, R + b T) with
+                    // a = 1/(1-alpha), b = alpha (c.g)/(1-alpha).  These maps compose associatively, so ONE
+                    // warp scan (lane 0 = backmost) yields every lane's transmittance and the sum behind it.
+                    A[u] = inv_om[u];
+                    B[u] = alpha[u] * s[u] * inv_om[u];
+                }
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+                    for (int u = 0; u < PIX_UNROLL; ++u) {
+                        const float Ap = __shfl_up_sync(0xffffffffu, A[u], d);
+                        const float Bp = __shfl_up_sync(0xffffffffu, B[u], d);
+                        if (lane >= d) {
+                            B[u] = fmaf(B[u], Ap, Bp);
+                            A[u] *= Ap;
                         }
                     }
                 }
-                if (__any_sync(0xffffffffu, act)) {
-                    const float r8 = reduce8_transposed(g, lane);  // lane l: total of value l >> 2
-                    const float r9 = warp_sum(g[8]);
-                    if (commits) red_add(scratch + (size_t)sid[jj] * GRAD_STRIDE + my_slot, lane == 1 ? r9 : r8);
+#pragma unroll
+                for (int u = 0; u < PIX_UNROLL; ++u) {
+                    const float Ti = ps[u].z * A[u];                    // transmittance in front of this Gaussian
+                    const float w = alpha[u] * Ti;
+                    const float Rtot = fmaf(ps[u].z, B[u], ps[u].w);   // sum behind, this Gaussian included
+                    const float dL_dalpha = fmaf(Ti, s[u], -(Rtot - w * s[u]) * inv_om[u]);
+                    const float q = act[u] ? G[u] * dL_dalpha : 0.f;
+                    const float t = con.w * q;
+                    a_op += q;
+                    a_mx = fmaf(t, fmaf(con.x, dx[u], con.y * dy[u]), a_mx);
+                    a_my = fmaf(t, fmaf(con.z, dy[u], con.y * dx[u]), a_my);
+                    a_A = fmaf(t, dxx[u], a_A);
+                    a_B = fmaf(t, dxy[u], a_B);
+                    a_C = fmaf(t, dyy[u], a_C);
+                    a_r = fmaf(w, pg[u].x, a_r);
+                    a_g = fmaf(w, pg[u].y, a_g);
+                    a_b = fmaf(w, pg[u].z, a_b);
+                    if (lane == 31 && pv[u]) {  // frontmost lane holds the chunk totals: state behind the next chunk
+                        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr + p[u] * 16 + 8), "f"(Ti), "f"(Rtot)
+                                     : "memory");
+                    }
                 }
+            }
+            __syncwarp();
+            if (valid) {
+                float* dst = scratch + (size_t)sid[jj] * GRAD_STRIDE;
+                red_add(dst + G_MX, a_mx * neg_half_w);
+                red_add(dst + G_MY, a_my * neg_half_h);
+                red_add(dst + G_CA, -0.5f * a_A);
+                red_add(dst + G_CB, -0.5f * a_B);
+                red_add(dst + G_CC, -0.5f * a_C);
+                red_add(dst + G_OP, a_op);
+                red_add(dst + G_R, a_r);
+                red_add(dst + G_G, a_g);
+                red_add(dst + G_B, a_b);
             }
         }
     }
