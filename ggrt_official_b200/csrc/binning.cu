@@ -111,7 +111,7 @@ void launch_sort_tiles(const View& v, ImagePtrs im, BinPtrs b, uint32_t max_tile
     uint32_t cap = 1024;
     while (cap < max_tile_pairs && cap < 16384) cap <<= 1;
     const size_t smem = (size_t)cap * sizeof(unsigned long long);
-    if (smem > 48 * 1024)  // per-device attribute; cheap host-side call
+    if (smem > 32 * 1024)  // per-device attribute; cheap host-side call
         cudaFuncSetAttribute(sort_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
     sort_tiles_kernel<<<v.gx * v.gy, SORT_THREADS, smem, s>>>(v.gx * v.gy, im.starts, b.keys, b.points, cap);
 }

@@ -2,6 +2,7 @@
 // rect + per-tile pair counting), tile scan, SH colour evaluation, mark_visible.
 // Replaces upstream preprocessCUDA + the scan of tiles_touched.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ggrt {
 
@@ -184,68 +185,127 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(int T, const uint32_t*
 }
 
 // ---------------------------------------------------------------------------------------
-// colour: SH degree 0..4 -> RGB (+0.5, clamp at 0, remember clamp bits).  The CTA's SH
-// slab (COLOR_THREADS x K x 3 floats, contiguous in HBM) is staged through shared memory
-// with coalesced 16-byte loads; each thread then walks its own row (odd stride: no bank
-// conflicts for K = 1, 9, 25).
+// colour: SH degree 0..4 -> RGB (+0.5, clamp at 0, remember clamp bits).  HBM-bound: 12 K
+// bytes per Gaussian (300 B at degree 4) are read exactly once.
+//
+// Persistent CTAs (2 per SM); each walks slabs of COLOR_THREADS Gaussians.  A slab's SH block
+// is contiguous in HBM (COLOR_THREADS x K x 3 floats) and is pulled into a 2-stage shared
+// memory ring by the TMA engine (cp.async.bulk + mbarrier): one elected thread issues the
+// copy of slab i+2 while all threads evaluate slab i.  Each thread then walks its own row
+// (odd stride: no bank conflicts for K = 1, 9, 25).  Ragged / unaligned slabs fall back to
+// cooperative 16-byte (or scalar) loads into the same buffer.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(COLOR_THREADS)
+constexpr int COLOR_STAGES = 2;
+
+__device__ __forceinline__ void fill_slab_generic(float* slab, const float* src, int nfl, int nthreads) {
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(slab);
+        const int n4 = nfl >> 2;
+        for (int k = threadIdx.x; k < n4; k += nthreads) d4[k] = __ldcs(s4 + k);
+        for (int k = (n4 << 2) + threadIdx.x; k < nfl; k += nthreads) slab[k] = src[k];
+    } else {
+        for (int k = threadIdx.x; k < nfl; k += nthreads) slab[k] = src[k];
+    }
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(COLOR_THREADS, 3)
 color_kernel(View v, const float* __restrict__ means, const float* __restrict__ shs, const float* __restrict__ colors,
-             const int* __restrict__ radii, GeomPtrs g) {
-    extern __shared__ __align__(16) float slab[];
-    const int base = blockIdx.x * COLOR_THREADS;
-    const int cnt = min(COLOR_THREADS, v.P - base);
-    const int i = base + threadIdx.x;
-    const bool vis = (threadIdx.x < cnt) && radii[i] > 0;
-    const int row = v.K * 3;
+             const int* __restrict__ radii, GeomPtrs g, int num_slabs) {
+    extern __shared__ __align__(128) float slab_ring[];
+    __shared__ __align__(8) unsigned long long full_bar[COLOR_STAGES];
+    constexpr int KK = (DEG + 1) * (DEG + 1);
+    constexpr int row = KK * 3;
+    const int slab_floats = COLOR_THREADS * row;
+    const bool tma_ok = shs != nullptr && (reinterpret_cast<uintptr_t>(shs) & 15) == 0;  // slab bases are 16 B multiples
+
     if (shs != nullptr) {
-        if (!__syncthreads_or(vis)) {
-            if (threadIdx.x < cnt) g.flags[i] = 0;
-            return;
-        }
-        const float* src = shs + (size_t)base * row;
-        const int nfl = cnt * row;
-        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-            const float4* s4 = reinterpret_cast<const float4*>(src);
-            float4* d4 = reinterpret_cast<float4*>(slab);
-            const int n4 = nfl >> 2;
-            for (int k = threadIdx.x; k < n4; k += COLOR_THREADS) d4[k] = __ldcs(s4 + k);
-            for (int k = (n4 << 2) + threadIdx.x; k < nfl; k += COLOR_THREADS) slab[k] = src[k];
-        } else {
-            for (int k = threadIdx.x; k < nfl; k += COLOR_THREADS) slab[k] = src[k];
+        if (threadIdx.x == 0) {
+            for (int st = 0; st < COLOR_STAGES; ++st) mbar_init(smem_u32(&full_bar[st]), 1);
+            fence_mbar_init();
         }
         __syncthreads();
-    }
-    if (!vis) {
-        if (threadIdx.x < cnt) g.flags[i] = 0;
-        return;
-    }
-    float rgb[3];
-    uint8_t flags = 0;
-    if (shs == nullptr) {
-        rgb[0] = colors[3 * i], rgb[1] = colors[3 * i + 1], rgb[2] = colors[3 * i + 2];
-    } else {
-        float dx = means[3 * i] - v.campos[0], dy = means[3 * i + 1] - v.campos[1], dz = means[3 * i + 2] - v.campos[2];
-        const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-        dx *= inv, dy *= inv, dz *= inv;
-        float b[25];
-        sh_basis(v.deg, dx, dy, dz, b);
-        const float* my = slab + threadIdx.x * row;
-        rgb[0] = rgb[1] = rgb[2] = 0.5f;
-        for (int k = 0; k < v.K; ++k) {
-            rgb[0] = fmaf(b[k], my[3 * k + 0], rgb[0]);
-            rgb[1] = fmaf(b[k], my[3 * k + 1], rgb[1]);
-            rgb[2] = fmaf(b[k], my[3 * k + 2], rgb[2]);
+        if (threadIdx.x == 0 && tma_ok) {  // prologue: fill the ring
+            for (int st = 0; st < COLOR_STAGES; ++st) {
+                const int sl = blockIdx.x + st * gridDim.x;
+                if (sl >= num_slabs) break;
+                const int cnt = min(COLOR_THREADS, v.P - sl * COLOR_THREADS);
+                const uint32_t bytes = (uint32_t)cnt * row * 4u;
+                if ((bytes & 15u) == 0) {
+                    mbar_expect_tx(smem_u32(&full_bar[st]), bytes);
+                    bulk_g2s(smem_u32(slab_ring + st * slab_floats), shs + (size_t)sl * slab_floats, bytes,
+                             smem_u32(&full_bar[st]));
+                }
+            }
         }
+    }
+
+    int it = 0;
+    for (int sl = blockIdx.x; sl < num_slabs; sl += gridDim.x, ++it) {
+        const int st = it % COLOR_STAGES;
+        const uint32_t parity = (uint32_t)(it / COLOR_STAGES) & 1u;
+        const int base = sl * COLOR_THREADS;
+        const int cnt = min(COLOR_THREADS, v.P - base);
+        const int i = base + threadIdx.x;
+        const bool valid = threadIdx.x < cnt;
+        const bool vis = valid && radii[i] > 0;
+        float* slab = slab_ring + st * slab_floats;
+        if (shs != nullptr) {
+            const uint32_t bytes = (uint32_t)cnt * row * 4u;
+            if (tma_ok && (bytes & 15u) == 0) {
+                mbar_wait(smem_u32(&full_bar[st]), parity);
+            } else {
+                fill_slab_generic(slab, shs + (size_t)base * row, cnt * row, COLOR_THREADS);
+                __syncthreads();
+            }
+        }
+        if (valid) {
+            float rgb[3] = {0.f, 0.f, 0.f};
+            uint8_t flags = 0;
+            if (vis) {
+                if (shs == nullptr) {
+                    rgb[0] = colors[3 * i], rgb[1] = colors[3 * i + 1], rgb[2] = colors[3 * i + 2];
+                } else {
+                    float dx = means[3 * i] - v.campos[0], dy = means[3 * i + 1] - v.campos[1],
+                          dz = means[3 * i + 2] - v.campos[2];
+                    const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+                    dx *= inv, dy *= inv, dz *= inv;
+                    float b[25];
+                    sh_basis(DEG, dx, dy, dz, b);
+                    const float* my = slab + threadIdx.x * row;
+                    rgb[0] = rgb[1] = rgb[2] = 0.5f;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            if (rgb[c] < 0.0f) flags |= (uint8_t)(1u << c);
-            rgb[c] = fmaxf(rgb[c], 0.0f);
+                    for (int k = 0; k < KK; ++k) {
+                        rgb[0] = fmaf(b[k], my[3 * k + 0], rgb[0]);
+                        rgb[1] = fmaf(b[k], my[3 * k + 1], rgb[1]);
+                        rgb[2] = fmaf(b[k], my[3 * k + 2], rgb[2]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        if (rgb[c] < 0.0f) flags |= (uint8_t)(1u << c);
+                        rgb[c] = fmaxf(rgb[c], 0.0f);
+                    }
+                }
+                const float depth = g.rec2[i].w;
+                g.rec2[i] = make_float4(rgb[0], rgb[1], rgb[2], depth);
+            }
+            g.flags[i] = flags;
+        }
+        if (shs != nullptr) {
+            __syncthreads();  // every thread is done reading this stage
+            const int nsl = sl + COLOR_STAGES * gridDim.x;
+            if (threadIdx.x == 0 && tma_ok && nsl < num_slabs) {
+                const int ncnt = min(COLOR_THREADS, v.P - nsl * COLOR_THREADS);
+                const uint32_t nbytes = (uint32_t)ncnt * row * 4u;
+                if ((nbytes & 15u) == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(smem_u32(&full_bar[st]), nbytes);
+                    bulk_g2s(smem_u32(slab), shs + (size_t)nsl * slab_floats, nbytes, smem_u32(&full_bar[st]));
+                }
+            }
         }
     }
-    const float depth = g.rec2[i].w;
-    g.rec2[i] = make_float4(rgb[0], rgb[1], rgb[2], depth);
-    g.flags[i] = flags;
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means, const float* __restrict__ V,
@@ -270,8 +330,26 @@ void launch_scan_tiles(const View& v, ImagePtrs im, cudaStream_t s) {
 void launch_color(const View& v, const float* means, const float* shs, const float* colors, const int* radii,
                   GeomPtrs g, cudaStream_t s) {
     if (v.P == 0) return;
-    const size_t smem = shs ? (size_t)COLOR_THREADS * v.K * 3 * sizeof(float) : 0;
-    color_kernel<<<(v.P + COLOR_THREADS - 1) / COLOR_THREADS, COLOR_THREADS, smem, s>>>(v, means, shs, colors, radii, g);
+    const size_t smem = shs ? (size_t)COLOR_STAGES * COLOR_THREADS * v.K * 3 * sizeof(float) : 0;
+    const int num_slabs = (v.P + COLOR_THREADS - 1) / COLOR_THREADS;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = min(num_slabs, 2 * sms);  // persistent: 2 CTAs per SM, each streams slabs through its ring
+#define GGRT_LAUNCH_COLOR(D)                                                                                        \
+    case D:                                                                                                         \
+        if (smem > 32 * 1024)                                                                                       \
+            cudaFuncSetAttribute(color_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+        color_kernel<D><<<grid, COLOR_THREADS, smem, s>>>(v, means, shs, colors, radii, g, num_slabs);              \
+        break;
+    switch (v.deg) {
+        GGRT_LAUNCH_COLOR(0)
+        GGRT_LAUNCH_COLOR(1)
+        GGRT_LAUNCH_COLOR(2)
+        GGRT_LAUNCH_COLOR(3)
+        GGRT_LAUNCH_COLOR(4)
+    }
+#undef GGRT_LAUNCH_COLOR
 }
 
 void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t s) {

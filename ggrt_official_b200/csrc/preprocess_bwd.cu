@@ -3,35 +3,74 @@
 // view direction).  Replaces upstream computeCov2DCUDA + preprocessCUDA (bwd), SURVEY.md
 // 8a row a13, fused into one pass.  Every output element is written (zeros for culled
 // Gaussians) so the caller needs no memset of the 300 B/Gaussian SH gradient.
+//
+// HBM-bound (about 700 B per Gaussian at SH degree 4).  Persistent CTAs, 2 per SM; the SH
+// slab of PB_THREADS Gaussians (contiguous in HBM) is pulled into a 2-stage shared-memory
+// ring by the TMA engine (cp.async.bulk + mbarrier), overwritten in place with dL/dsh by the
+// threads (one row each, odd stride), and written back with a TMA bulk store
+// (cp.async.bulk.global.shared) while the next slab is processed.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ggrt {
 
 constexpr int PB_THREADS = 128;
 
-__global__ void __launch_bounds__(PB_THREADS)
+constexpr int PB_STAGES = 2;
+
+__global__ void __launch_bounds__(PB_THREADS, 3)
 preprocess_backward_kernel(View v, const float* __restrict__ means, const float* __restrict__ cov3d,
                            const float* __restrict__ shs, const int* __restrict__ radii,
                            const uint8_t* __restrict__ flags, const float* __restrict__ scratch,
                            float* __restrict__ dmeans2D, float* __restrict__ dopacity, float* __restrict__ dmeans3D,
-                           float* __restrict__ dcov3D, float* __restrict__ dsh, float* __restrict__ dcolors) {
-    extern __shared__ __align__(16) float slab[];
+                           float* __restrict__ dcov3D, float* __restrict__ dsh, float* __restrict__ dcolors,
+                           int num_slabs) {
+    extern __shared__ __align__(128) float slab_ring[];
+    __shared__ __align__(8) unsigned long long full_bar[PB_STAGES];
     __shared__ float sV[16], sM[16];
     if (threadIdx.x < 16) sV[threadIdx.x] = v.view[threadIdx.x];
     else if (threadIdx.x < 32) sM[threadIdx.x - 16] = v.proj[threadIdx.x - 16];
 
-    const int base = blockIdx.x * PB_THREADS;
+    const int row = v.K * 3;
+    const int slab_floats = PB_THREADS * row;
+    const bool tma_ok = shs != nullptr && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(dsh) & 15) == 0;
+    if (shs != nullptr && threadIdx.x == 0) {
+        for (int st = 0; st < PB_STAGES; ++st) mbar_init(smem_u32(&full_bar[st]), 1);
+        fence_mbar_init();
+    }
+    __syncthreads();  // publishes sV / sM and the barriers
+    if (threadIdx.x == 0 && tma_ok) {  // prologue: fill the ring
+        for (int st = 0; st < PB_STAGES; ++st) {
+            const int sl = blockIdx.x + st * gridDim.x;
+            if (sl >= num_slabs) break;
+            const uint32_t bytes = (uint32_t)min(PB_THREADS, v.P - sl * PB_THREADS) * row * 4u;
+            if ((bytes & 15u) == 0) {
+                mbar_expect_tx(smem_u32(&full_bar[st]), bytes);
+                bulk_g2s(smem_u32(slab_ring + st * slab_floats), shs + (size_t)sl * slab_floats, bytes,
+                         smem_u32(&full_bar[st]));
+            }
+        }
+    }
+
+    int it = 0;
+    for (int sl = blockIdx.x; sl < num_slabs; sl += gridDim.x, ++it) {
+    const int st = it % PB_STAGES;
+    const uint32_t parity = (uint32_t)(it / PB_STAGES) & 1u;
+    float* slab = slab_ring + st * slab_floats;
+    const int base = sl * PB_THREADS;
     const int cnt = min(PB_THREADS, v.P - base);
     const int i = base + threadIdx.x;
     const bool valid = threadIdx.x < cnt;
     const bool vis = valid && radii[i] > 0;
-    const int row = v.K * 3;
     const int nfl = cnt * row;
-    const bool any_vis = __syncthreads_or(vis);  // also publishes sV / sM
+    const bool slab_tma = tma_ok && ((nfl * 4) & 15) == 0;
 
-    // stage the CTA's SH slab (coalesced); it is overwritten in place with dL/dsh
+    // the CTA's SH slab (staged by TMA, or cooperatively when ragged); it is overwritten in place with dL/dsh
     if (shs != nullptr) {
-        if (any_vis) {
+        if (slab_tma) {
+            mbar_wait(smem_u32(&full_bar[st]), parity);
+        } else {
             const float* src = shs + (size_t)base * row;
             if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
                 const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -42,10 +81,8 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             } else {
                 for (int k = threadIdx.x; k < nfl; k += PB_THREADS) slab[k] = src[k];
             }
-        } else {
-            for (int k = threadIdx.x; k < nfl; k += PB_THREADS) slab[k] = 0.f;
+            __syncthreads();
         }
-        __syncthreads();
     }
 
     float dmean[3] = {0.f, 0.f, 0.f};
@@ -199,20 +236,39 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             dmean[0] += (len2 * ddx - vx * dot) * inv3;
             dmean[1] += (len2 * ddy - vy * dot) * inv3;
             dmean[2] += (len2 * ddz - vz * dot) * inv3;
-        } else if (valid && any_vis) {
+        } else if (valid) {
             for (int k = 0; k < row; ++k) my[k] = 0.f;
         }
-        __syncthreads();
-        // coalesced write-out of the dL/dsh slab
+        // write-out of the dL/dsh slab: TMA bulk store, or coalesced stores when ragged / unaligned
         float* dst = dsh + (size_t)base * row;
-        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-            float4* d4 = reinterpret_cast<float4*>(dst);
-            const float4* s4 = reinterpret_cast<const float4*>(slab);
-            const int n4 = nfl >> 2;
-            for (int k = threadIdx.x; k < n4; k += PB_THREADS) __stcs(d4 + k, s4[k]);
-            for (int k = (n4 << 2) + threadIdx.x; k < nfl; k += PB_THREADS) dst[k] = slab[k];
+        if (slab_tma) {
+            fence_proxy_async();  // this thread's generic writes -> visible to the async proxy
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                bulk_s2g(dst, smem_u32(slab), (uint32_t)nfl * 4u);
+                bulk_commit();
+                const int nsl = sl + PB_STAGES * gridDim.x;
+                if (nsl < num_slabs) {
+                    const uint32_t nbytes = (uint32_t)min(PB_THREADS, v.P - nsl * PB_THREADS) * row * 4u;
+                    if ((nbytes & 15u) == 0) {
+                        bulk_wait_read0();  // the store has drained this stage before it is refilled
+                        mbar_expect_tx(smem_u32(&full_bar[st]), nbytes);
+                        bulk_g2s(smem_u32(slab), shs + (size_t)nsl * slab_floats, nbytes, smem_u32(&full_bar[st]));
+                    }
+                }
+            }
         } else {
-            for (int k = threadIdx.x; k < nfl; k += PB_THREADS) dst[k] = slab[k];
+            __syncthreads();
+            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                float4* d4 = reinterpret_cast<float4*>(dst);
+                const float4* s4 = reinterpret_cast<const float4*>(slab);
+                const int n4 = nfl >> 2;
+                for (int k = threadIdx.x; k < n4; k += PB_THREADS) __stcs(d4 + k, s4[k]);
+                for (int k = (n4 << 2) + threadIdx.x; k < nfl; k += PB_THREADS) dst[k] = slab[k];
+            } else {
+                for (int k = threadIdx.x; k < nfl; k += PB_THREADS) dst[k] = slab[k];
+            }
+            __syncthreads();  // stage free again
         }
     } else if (valid) {
         dcolors[3 * i] = dR, dcolors[3 * i + 1] = dG, dcolors[3 * i + 2] = dB;
@@ -226,15 +282,24 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
 #pragma unroll
         for (int k = 0; k < 6; ++k) dcov3D[6 * (size_t)i + k] = dS[k];
     }
+    }  // slab loop
+    if (threadIdx.x == 0) bulk_wait0();  // all bulk stores of this CTA have completed
 }
 
 void launch_preprocess_backward(const View& v, const float* means, const float* cov3d, const float* shs,
                                 const int* radii, GeomPtrs g, const float* scratch, float* dmeans2D, float* dopacity,
                                 float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, cudaStream_t s) {
     if (v.P == 0) return;
-    const size_t smem = shs ? (size_t)PB_THREADS * v.K * 3 * sizeof(float) : 0;
-    preprocess_backward_kernel<<<(v.P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, smem, s>>>(
-        v, means, cov3d, shs, radii, g.flags, scratch, dmeans2D, dopacity, dmeans3D, dcov3D, dsh, dcolors);
+    const size_t smem = shs ? (size_t)PB_STAGES * PB_THREADS * v.K * 3 * sizeof(float) : 0;
+    const int num_slabs = (v.P + PB_THREADS - 1) / PB_THREADS;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (smem > 32 * 1024)
+        cudaFuncSetAttribute(preprocess_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = min(num_slabs, 2 * sms);  // persistent: 2 CTAs per SM
+    preprocess_backward_kernel<<<grid, PB_THREADS, smem, s>>>(v, means, cov3d, shs, radii, g.flags, scratch, dmeans2D,
+                                                              dopacity, dmeans3D, dcov3D, dsh, dcolors, num_slabs);
 }
 
 }  // namespace ggrt
