@@ -188,6 +188,15 @@ def run_ours(args, rank, world, local_rank):
         viewmatrix=t(ri.viewmatrix), projmatrix=t(ri.projmatrix), sh_degree=ri.sh_degree, campos=t(ri.campos),
         prefiltered=False)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    flush_src = torch.zeros(64 << 20, dtype=torch.float32, device=dev)  # 256 MiB, read-only
+    flush_sink = torch.zeros((), dtype=torch.float32, device=dev)
+
+    def flush_l2():
+        """Evict the working set: write 256 MiB, then read 256 MiB so the dirty lines of the write are
+        themselves written back before the timed step (otherwise the step pays for the flush's write-back)."""
+        flush_buf.zero_()
+        flush_sink.copy_(flush_src.sum())
+
     state = {}
 
     def step():
@@ -216,7 +225,7 @@ def run_ours(args, rank, world, local_rank):
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync_all()
     for a, b in evs:
-        flush_buf.zero_()
+        flush_l2()
         a.record()
         step()
         b.record()
@@ -234,7 +243,7 @@ def run_ours(args, rank, world, local_rank):
     _cabi.profile_enable(True)
     nprof = min(args.steps, 20)
     for _ in range(nprof):
-        flush_buf.zero_()
+        flush_l2()
         st = R.forward_raw(means, shs, None, opac, cov, rs)
         fw = _cabi.profile_read()
         R.backward_raw(st, grad_img)
@@ -342,7 +351,7 @@ def run_ours(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "P": P, "H": H, "W": W, "N_pairs": int(N),
                        "max_pairs_per_tile": int(state["max_tile_pairs"]), "sh_degree": SH_DEGREE,
-                       "views_per_step": world, "l2": "flushed before every timed step (256 MiB write)",
+                       "views_per_step": world, "l2": "flushed before every timed step (256 MiB write, then 256 MiB read so the step does not pay the flush's write-back)",
                        "parallelism": f"one target view per GPU x{world}" + (", NCCL all-reduce of Gaussian gradients"
                                                                             if world > 1 else "")},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

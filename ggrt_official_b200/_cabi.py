@@ -69,7 +69,10 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    import os
+
+    override = os.environ.get("GGRT_RASTER_LIB")  # tuning experiments: a library built with other -D knobs
+    path = Path(override) if override else _build.build()
     L = C.CDLL(str(path))
     vp, i32, i64, u32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_size_t
     L.ggrt_raster_abi_version.restype = C.c_int

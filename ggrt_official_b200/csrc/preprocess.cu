@@ -7,7 +7,13 @@
 namespace ggrt {
 
 constexpr int GEO_THREADS = 256;
-constexpr int COLOR_THREADS = 128;
+#ifndef GGRT_COLOR_THREADS
+#define GGRT_COLOR_THREADS 128
+#endif
+#ifndef GGRT_COLOR_STAGES
+#define GGRT_COLOR_STAGES 2
+#endif
+constexpr int COLOR_THREADS = GGRT_COLOR_THREADS;
 
 // ---------------------------------------------------------------------------------------
 // geometry: one thread per Gaussian.  Reads 40 B, writes 2 records + rect + radius.
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(int T, const uint32_t*
 // (odd stride: no bank conflicts for K = 1, 9, 25).  Ragged / unaligned slabs fall back to
 // cooperative 16-byte (or scalar) loads into the same buffer.
 // ---------------------------------------------------------------------------------------
-constexpr int COLOR_STAGES = 2;
+constexpr int COLOR_STAGES = GGRT_COLOR_STAGES;
 
 __device__ __forceinline__ void fill_slab_generic(float* slab, const float* src, int nfl, int nthreads) {
     if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
@@ -241,6 +247,22 @@ color_kernel(View v, const float* __restrict__ means, const float* __restrict__ 
         }
     }
 
+    // per-Gaussian scalars of the NEXT slab are prefetched into registers while the current one is evaluated,
+    // so their DRAM latency is not serialised with the slab wait
+    int n_radius = 0;
+    float n_mx = 0.f, n_my = 0.f, n_mz = 0.f, n_depth = 0.f;
+    auto prefetch = [&](int sl) {
+        const int i = sl * COLOR_THREADS + threadIdx.x;
+        n_radius = 0;
+        if (sl < num_slabs && i < v.P) {
+            n_radius = radii[i];
+            n_mx = means[3 * i], n_my = means[3 * i + 1], n_mz = means[3 * i + 2];
+            n_depth = g.rec2[i].w;
+        }
+    };
+    prefetch(blockIdx.x);
+    const float cpx = v.campos[0], cpy = v.campos[1], cpz = v.campos[2];
+
     int it = 0;
     for (int sl = blockIdx.x; sl < num_slabs; sl += gridDim.x, ++it) {
         const int st = it % COLOR_STAGES;
@@ -249,7 +271,9 @@ color_kernel(View v, const float* __restrict__ means, const float* __restrict__ 
         const int cnt = min(COLOR_THREADS, v.P - base);
         const int i = base + threadIdx.x;
         const bool valid = threadIdx.x < cnt;
-        const bool vis = valid && radii[i] > 0;
+        const bool vis = valid && n_radius > 0;
+        const float mx = n_mx, my_ = n_my, mz = n_mz, depth = n_depth;
+        prefetch(sl + gridDim.x);
         float* slab = slab_ring + st * slab_floats;
         if (shs != nullptr) {
             const uint32_t bytes = (uint32_t)cnt * row * 4u;
@@ -267,8 +291,7 @@ color_kernel(View v, const float* __restrict__ means, const float* __restrict__ 
                 if (shs == nullptr) {
                     rgb[0] = colors[3 * i], rgb[1] = colors[3 * i + 1], rgb[2] = colors[3 * i + 2];
                 } else {
-                    float dx = means[3 * i] - v.campos[0], dy = means[3 * i + 1] - v.campos[1],
-                          dz = means[3 * i + 2] - v.campos[2];
+                    float dx = mx - cpx, dy = my_ - cpy, dz = mz - cpz;
                     const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
                     dx *= inv, dy *= inv, dz *= inv;
                     float b[25];
@@ -287,7 +310,6 @@ color_kernel(View v, const float* __restrict__ means, const float* __restrict__ 
                         rgb[c] = fmaxf(rgb[c], 0.0f);
                     }
                 }
-                const float depth = g.rec2[i].w;
                 g.rec2[i] = make_float4(rgb[0], rgb[1], rgb[2], depth);
             }
             g.flags[i] = flags;
@@ -335,7 +357,8 @@ void launch_color(const View& v, const float* means, const float* shs, const flo
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = min(num_slabs, 2 * sms);  // persistent: 2 CTAs per SM, each streams slabs through its ring
+    const int per_sm = smem ? max(1, min(8, (int)((220 * 1024) / (smem + 1024)))) : 8;
+    const int grid = min(num_slabs, per_sm * sms);  // persistent CTAs, each streams slabs through its ring
 #define GGRT_LAUNCH_COLOR(D)                                                                                        \
     case D:                                                                                                         \
         if (smem > 32 * 1024)                                                                                       \

@@ -14,9 +14,15 @@
 
 namespace ggrt {
 
-constexpr int PB_THREADS = 128;
+#ifndef GGRT_PB_THREADS
+#define GGRT_PB_THREADS 128
+#endif
+#ifndef GGRT_PB_STAGES
+#define GGRT_PB_STAGES 2
+#endif
+constexpr int PB_THREADS = GGRT_PB_THREADS;
 
-constexpr int PB_STAGES = 2;
+constexpr int PB_STAGES = GGRT_PB_STAGES;
 
 __global__ void __launch_bounds__(PB_THREADS, 3)
 preprocess_backward_kernel(View v, const float* __restrict__ means, const float* __restrict__ cov3d,
@@ -53,6 +59,32 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
         }
     }
 
+    // per-Gaussian inputs of the NEXT slab are prefetched into registers (one DRAM latency, overlapped with
+    // the evaluation of the current slab) instead of being loaded behind data-dependent branches
+    int n_radius = 0;
+    uint32_t n_flags = 0;
+    float n_mean[3] = {0.f, 0.f, 0.f}, n_cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float4 n_ga = make_float4(0.f, 0.f, 0.f, 0.f), n_gb = n_ga;
+    float n_gc = 0.f;
+    auto prefetch = [&](int sl) {
+        const int i = sl * PB_THREADS + threadIdx.x;
+        n_radius = 0;
+        if (sl < num_slabs && i < v.P) {
+            n_radius = radii[i];
+            n_flags = flags[i];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) n_mean[k] = means[3 * (size_t)i + k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) n_cv[k] = cov3d[6 * (size_t)i + k];
+            const float* gs = scratch + (size_t)i * GRAD_STRIDE;
+            n_ga = *reinterpret_cast<const float4*>(gs);
+            n_gb = *reinterpret_cast<const float4*>(gs + 4);
+            n_gc = gs[8];
+        }
+    };
+    prefetch(blockIdx.x);
+    const float cpx = v.campos[0], cpy = v.campos[1], cpz = v.campos[2];
+
     int it = 0;
     for (int sl = blockIdx.x; sl < num_slabs; sl += gridDim.x, ++it) {
     const int st = it % PB_STAGES;
@@ -62,9 +94,17 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     const int cnt = min(PB_THREADS, v.P - base);
     const int i = base + threadIdx.x;
     const bool valid = threadIdx.x < cnt;
-    const bool vis = valid && radii[i] > 0;
+    const bool vis = valid && n_radius > 0;
     const int nfl = cnt * row;
     const bool slab_tma = tma_ok && ((nfl * 4) & 15) == 0;
+    const uint32_t fl = n_flags;
+    const float mean_x = n_mean[0], mean_y = n_mean[1], mean_z = n_mean[2];
+    float cv[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cv[k] = n_cv[k];
+    const float4 ga = n_ga, gb = n_gb;
+    const float gc = n_gc;
+    prefetch(sl + gridDim.x);
 
     // the CTA's SH slab (staged by TMA, or cooperatively when ragged); it is overwritten in place with dL/dsh
     if (shs != nullptr) {
@@ -92,17 +132,8 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
 
     bool live = false;
     Geo q;
-    float cv[6];
-    if (vis) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) cv[k] = cov3d[6 * (size_t)i + k];
-        live = geometry(v, sV, sM, means[3 * i], means[3 * i + 1], means[3 * i + 2], cv, q);
-    }
+    if (vis) live = geometry(v, sV, sM, mean_x, mean_y, mean_z, cv, q);
     if (live) {
-        const float* gs = scratch + (size_t)i * GRAD_STRIDE;
-        const float4 ga = *reinterpret_cast<const float4*>(gs);
-        const float4 gb = *reinterpret_cast<const float4*>(gs + 4);
-        const float gc = gs[8];
         g2x = ga.x, g2y = ga.y;
         const float gA = ga.z, gBh = ga.w, gC = gb.x;
         gop = gb.y;
@@ -160,12 +191,10 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
 
     if (shs != nullptr) {
         if (live) {
-            const uint8_t fl = flags[i];
             if (fl & 1) dR = 0.f;
             if (fl & 2) dG = 0.f;
             if (fl & 4) dB = 0.f;
-            const float vx = means[3 * i] - v.campos[0], vy = means[3 * i + 1] - v.campos[1],
-                        vz = means[3 * i + 2] - v.campos[2];
+            const float vx = mean_x - cpx, vy = mean_y - cpy, vz = mean_z - cpz;
             const float len2 = vx * vx + vy * vy + vz * vz;
             const float inv = rsqrtf(len2);
             const float x = vx * inv, y = vy * inv, z = vz * inv;
@@ -297,7 +326,8 @@ void launch_preprocess_backward(const View& v, const float* means, const float* 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (smem > 32 * 1024)
         cudaFuncSetAttribute(preprocess_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int grid = min(num_slabs, 2 * sms);  // persistent: 2 CTAs per SM
+    const int per_sm = smem ? max(1, min(8, (int)((220 * 1024) / (smem + 1024)))) : 8;
+    const int grid = min(num_slabs, per_sm * sms);  // persistent CTAs
     preprocess_backward_kernel<<<grid, PB_THREADS, smem, s>>>(v, means, cov3d, shs, radii, g.flags, scratch, dmeans2D,
                                                               dopacity, dmeans3D, dcov3D, dsh, dcolors, num_slabs);
 }
