@@ -199,12 +199,17 @@ def run_ours(args, rank, world, local_rank):
 
     state = {}
 
+    from ggrt_official_b200.view_parallel import GradientArena
+
+    arena = GradientArena.allocate(P, K, dev) if world > 1 else None
+
     def step():
         st = R.forward_raw(means, shs, None, opac, cov, rs)
-        grads = R.backward_raw(st, grad_img)
-        if world > 1:  # Gaussian gradients of the per-GPU views are summed
-            for k in ("dmeans3D", "dcov3D", "dopacity", "dsh"):
-                dist.all_reduce(grads[k])
+        # the Gaussian gradients land in one contiguous arena that is summed over the per-GPU views with
+        # a single NCCL all-reduce
+        grads = R.backward_raw(st, grad_img, out=arena.views if arena else None)
+        if arena:
+            arena.all_reduce()
         state["N"], state["max_tile_pairs"] = st["N"], st["max_tile_pairs"]
         return grads
 

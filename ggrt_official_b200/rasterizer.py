@@ -143,7 +143,9 @@ def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: Gauss
                 max_tile_pairs=max_pairs)
 
 
-def backward_raw(state: dict, grad_color: torch.Tensor) -> dict:
+def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = None) -> dict:
+    """Runs the backward through the C ABI.  `out` may supply preallocated, contiguous float32 output
+    tensors (e.g. views into one gradient arena that is all-reduced across GPUs afterwards)."""
     L = _cabi.lib()
     c: _Call = state["call"]
     dev = c.device
@@ -153,13 +155,23 @@ def backward_raw(state: dict, grad_color: torch.Tensor) -> dict:
         g = _f32c(grad_color, "grad_color", dev)
         f32 = dict(dtype=torch.float32, device=dev)
         scratch = torch.empty((c.P, 12), **f32)
+        given = out or {}
+
+        def buf(name, shape):
+            t = given.get(name)
+            if t is None:
+                return torch.empty(shape, **f32)
+            if tuple(t.shape) != tuple(shape) or t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
+                raise ValueError(f"out[{name!r}] must be a contiguous float32 {tuple(shape)} tensor on {dev}")
+            return t
+
         out = dict(
-            dmeans2D=torch.empty((c.P, 3), **f32),
-            dopacity=torch.empty((c.P, 1), **f32),
-            dmeans3D=torch.empty((c.P, 3), **f32),
-            dcov3D=torch.empty((c.P, 6), **f32),
-            dsh=torch.empty_like(c.sh) if c.sh is not None else None,
-            dcolors=torch.empty((c.P, 3), **f32) if c.sh is None else None,
+            dmeans2D=buf("dmeans2D", (c.P, 3)),
+            dopacity=buf("dopacity", (c.P, 1)),
+            dmeans3D=buf("dmeans3D", (c.P, 3)),
+            dcov3D=buf("dcov3D", (c.P, 6)),
+            dsh=buf("dsh", tuple(c.sh.shape)) if c.sh is not None else None,
+            dcolors=buf("dcolors", (c.P, 3)) if c.sh is None else None,
         )
         _cabi.check(L.ggrt_raster_backward(C.byref(c.settings), c.P, state["N"], _ptr(c.means3D), _ptr(c.cov3D),
                                            _ptr(c.sh), _ptr(state["radii"]), _ptr(state["geom"]),

@@ -1,0 +1,81 @@
+"""Host-side API surface of the drop-in package (no GPU)."""
+import numpy as np
+import pytest
+import torch
+
+import diff_gaussian_rasterization as dgr
+from ggrt_official_b200 import GaussianRasterizationSettings, GaussianRasterizer
+from ggrt_official_b200.view_parallel import GradientArena, shard_views
+
+
+def _settings(**kw):
+    base = dict(image_height=32, image_width=32, tanfovx=1.0, tanfovy=1.0, bg=torch.zeros(3), scale_modifier=1.0,
+                viewmatrix=torch.eye(4), projmatrix=torch.eye(4), sh_degree=0, campos=torch.zeros(3),
+                prefiltered=False)
+    base.update(kw)
+    return GaussianRasterizationSettings(**base)
+
+
+def test_shim_exports_the_names_ggrt_imports():
+    # cuda_splatting.py:6-9
+    assert dgr.GaussianRasterizationSettings is GaussianRasterizationSettings
+    assert dgr.GaussianRasterizer is GaussianRasterizer
+
+
+def test_settings_debug_is_optional():
+    # render_cuda omits `debug` (cuda_splatting.py:101-113); render_cuda_orthographic passes it (:193-206)
+    assert _settings().debug is False
+    assert _settings(debug=True).debug is True
+    assert _settings()._fields[:11] == ("image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier",
+                                        "viewmatrix", "projmatrix", "sh_degree", "campos", "prefiltered")
+
+
+def test_exactly_one_of_checks():
+    r = GaussianRasterizer(_settings())
+    P = 4
+    m, o, c6 = torch.zeros(P, 3), torch.zeros(P, 1), torch.zeros(P, 6)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(means3D=m, means2D=m, opacities=o, cov3D_precomp=c6)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(means3D=m, means2D=m, opacities=o, shs=torch.zeros(P, 1, 3), colors_precomp=torch.zeros(P, 3),
+          cov3D_precomp=c6)
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=m, means2D=m, opacities=o, shs=torch.zeros(P, 1, 3))
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=m, means2D=m, opacities=o, shs=torch.zeros(P, 1, 3), scales=torch.zeros(P, 3),
+          rotations=torch.zeros(P, 4), cov3D_precomp=c6)
+    with pytest.raises(NotImplementedError):
+        r(means3D=m, means2D=m, opacities=o, shs=torch.zeros(P, 1, 3), scales=torch.zeros(P, 3),
+          rotations=torch.zeros(P, 4))
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are rejected loudly: there is no eager / oracle path inside the product."""
+    r = GaussianRasterizer(_settings())
+    P = 4
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        r(means3D=torch.zeros(P, 3), means2D=torch.zeros(P, 3), opacities=torch.zeros(P, 1),
+          shs=torch.zeros(P, 1, 3), cov3D_precomp=torch.zeros(P, 6))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        r.markVisible(torch.zeros(P, 3))
+
+
+def test_product_does_not_import_the_oracle():
+    import pathlib
+    import re
+
+    pkg = pathlib.Path(__file__).resolve().parent.parent / "ggrt_official_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", f.read_text(), re.M), f
+
+
+def test_shard_views_and_arena():
+    assert shard_views(8, 0, 8) == [0] and shard_views(8, 7, 8) == [7]
+    assert shard_views(5, 1, 2) == [1, 3] and shard_views(1, 1, 2) == []
+    assert sorted(sum((shard_views(7, r, 3) for r in range(3)), [])) == list(range(7))
+    a = GradientArena.allocate(10, 25, "cpu")
+    assert a.flat.numel() == 10 * (3 + 6 + 1 + 75)
+    a.flat.zero_()
+    a.views["dsh"].fill_(1.0)
+    assert float(a.flat.sum()) == 10 * 75 and a.views["dcov3D"].shape == (10, 6)
+    assert a.all_reduce() is None  # no process group: a no-op

@@ -1,0 +1,61 @@
+"""The C-ABI library loads, exports every symbol the header declares, and its host-side
+helpers behave (no compute call: this runs without a GPU)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+from ggrt_official_b200 import _cabi
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = (ROOT / "include" / "ggrt_raster.h").read_text()
+
+
+def declared_functions():
+    names = set(re.findall(r"\b(ggrt_raster_\w+)\s*\(", HEADER))
+    return sorted(names)
+
+
+def test_header_cites_the_reference_interface():
+    assert "cuda_splatting.py:6-9" in HEADER and ":101-125" in HEADER and "rasterize_gaussians" in HEADER
+
+
+def test_every_declared_symbol_is_exported():
+    lib = _cabi.lib()
+    names = declared_functions()
+    assert len(names) >= 12, names
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ggrt_raster.h but not exported"
+    assert set(_cabi.EXPORTS) == set(names)
+
+
+def test_abi_version_and_layout():
+    lib = _cabi.lib()
+    assert lib.ggrt_raster_abi_version() == _cabi.ABI_VERSION
+    P, H, W, N = 1000, 100, 75, 2500
+    L = _cabi.layout(P, H, W, N)
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    assert L.geom_bytes == lib.ggrt_raster_geom_bytes(P) >= P * (48 + 8 + 4 + 1)
+    assert L.img_bytes == lib.ggrt_raster_image_bytes(H, W) >= 8 * H * W + 4 * (T + 1) + 2 * 4 * 16 * T
+    assert L.bin_bytes == lib.ggrt_raster_binning_bytes(N) >= 12 * N
+    offs = [L.geom_rec0, L.geom_rec1, L.geom_rec2, L.geom_rect, L.geom_tiles, L.geom_flags]
+    assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
+    assert L.img_cursor == L.img_counts + 4 * 16 * T  # zeroed by one memset
+    assert lib.ggrt_raster_binning_bytes(0) > 0  # never a zero-sized allocation
+
+
+def test_argument_errors_are_reported_without_touching_cuda():
+    lib = _cabi.lib()
+    rc = lib.ggrt_raster_forward_prepare(None, 0, None, None, None, None, None, None, None, None, None, None)
+    assert rc == -1
+    assert b"settings" in lib.ggrt_raster_last_error()
+    s = _cabi.Settings()
+    s.image_height, s.image_width, s.tanfovx, s.tanfovy, s.sh_degree = 16, 16, 1.0, 1.0, 7
+    dummy = C.c_void_p(16)
+    s.viewmatrix = s.projmatrix = s.campos = s.bg = 16
+    rc = lib.ggrt_raster_forward_prepare(C.byref(s), 1, dummy, dummy, dummy, dummy, None, dummy, dummy, dummy, None, None)
+    assert rc == -3 and b"sh_degree" in lib.ggrt_raster_last_error()
+    with pytest.raises(RuntimeError, match="sh_degree"):
+        _cabi.check(rc, "forward_prepare")
+    assert lib.ggrt_raster_stage_name(6) == b"render_backward"
