@@ -270,12 +270,24 @@ def run_ours(args, rank, world, local_rank):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # measured DRAM traffic of the same kernel(s) from the committed ncu --set full capture (per launch)
+    traffic, traffic_src = None, None
+    try:
+        prof = json.loads((ROOT / "profiles" / "r1_ncu_kernels.json").read_text())
+        if prof.get("workload", "").startswith(WORKLOADS[args.workload][3][:2]):
+            members = [k for k, grp in STAGE_GROUP.items() if grp == top]
+            vals = [v["dram_traffic_bytes"] for name, v in prof["kernels"].items()
+                    if any(name.startswith(m + "_kernel") for m in members)]
+            if vals:
+                traffic, traffic_src = int(sum(vals)), "profiles/r1_ncu_kernels.json (dram__bytes_read.sum + dram__bytes_write.sum)"
+    except Exception:
+        pass
     achieved = ab[top] / (group_ms[top] * 1e-3) / 1e9
     path_bytes = sum(ab.values())
     kernel_sum_ms = sum(stage_ms.values())
     roofline = {
         "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src, "kernel_ms": group_ms[top], "algorithmic_bytes": ab[top],
+        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms": group_ms[top], "algorithmic_bytes": ab[top],
         "kernel_share_of_step": group_ms[top] / kernel_sum_ms if kernel_sum_ms else None,
         "stage_ms": {k: round(v, 5) for k, v in stage_ms.items()},
         "whole_path": {"algorithmic_bytes": path_bytes, "achieved": path_bytes / (total_ms / args.steps * 1e-3) / 1e9,
