@@ -47,7 +47,7 @@ geometry_kernel(View v, const float* __restrict__ means, const float* __restrict
     int radius = 0;
     uint32_t tiles = 0;
     ushort4 rect = make_ushort4(0, 0, 0, 0);
-    float4 r0 = make_float4(0.f, 0.f, -1.0e30f, -1.0e30f);
+    float4 r0 = make_float4(0.f, 0.f, -1.0f, 0.f);
     float4 r1 = make_float4(0.f, 0.f, 0.f, 0.f);
     float depth = 0.f;
 
@@ -72,15 +72,13 @@ geometry_kernel(View v, const float* __restrict__ means, const float* __restrict
             tiles = (uint32_t)area;
             rect = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
             depth = q.tz;
-            // screen-space extent of {alpha >= 1/255}: q(d) <= 2 ln(255 o); bbox half widths sqrt(tau*a), sqrt(tau*c).
-            // Slightly inflated so the per-warp cull in the render kernels is conservative.
-            float ex = -1.0e30f, ey = -1.0e30f;
+            // {alpha >= 1/255} <=> q(d) = A dx^2 + 2B dx dy + C dy^2 <= tau = 2 ln(255 o).  The render kernels cull
+            // (warp pixel block, Gaussian) pairs with an exact ellipse-vs-rectangle test against tau, slightly
+            // inflated so that float rounding of the per-pixel power can never contradict the cull.
+            float tau_c = -1.0f;  // opacity below 1/255: never visible
             const float tau = 2.0f * logf(255.0f * o);
-            if (tau > 0.0f) {
-                ex = sqrtf(tau * q.a) * 1.0005f + 0.01f;
-                ey = sqrtf(tau * q.c) * 1.0005f + 0.01f;
-            }
-            r0 = make_float4(pxx, pxy, ex, ey);
+            if (tau > 0.0f) tau_c = tau * 1.001f + 0.02f;
+            r0 = make_float4(pxx, pxy, tau_c, 0.0f);
             r1 = make_float4(cA, cB, cC, o);
             const int sub = i & (SUBS - 1);
             for (int y = y0; y < y1; ++y)

@@ -28,6 +28,10 @@ constexpr int PIX_UNROLL = GGRT_BWD_PIX_UNROLL;
 __device__ __forceinline__ void red_add(float* addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
+// 16-byte vector reduction (sm_90+): one L2 operation for four adjacent floats
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 __global__ void __launch_bounds__(RENDER_THREADS, 3)
 render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __restrict__ rec1,
@@ -46,7 +50,7 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.y * v.gx + blockIdx.x;
     const int bx0 = blockIdx.x * TILE + (warp & 1) * 8, by0 = blockIdx.y * TILE + (warp >> 1) * 4;
-    const float wcx = (float)bx0 + 3.5f, wcy = (float)by0 + 1.5f;
+    const float bx0f = (float)bx0, by0f = (float)by0;
     const uint32_t start = starts[tile];
 
     // ---- per-pixel constants / initial state (lane = pixel here) -------------------------------
@@ -104,7 +108,8 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
             bool hit = false;
             if (j < lim) {
                 const float4 a = lds128(sbase + j * REC_BYTES);
-                hit = (fabsf(a.x - wcx) <= a.z + 3.5f) && (fabsf(a.y - wcy) <= a.w + 1.5f);
+                const float4 c = lds128(sbase + j * REC_BYTES + 16);
+                hit = ellipse_hits_rect(a.x, a.y, a.z, c.x, c.y, c.z, bx0f, by0f, 7.0f, 3.0f);
             }
             const uint32_t m = __ballot_sync(0xffffffffu, hit);
             if (hit) squeue[warp][qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
@@ -200,14 +205,9 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
             __syncwarp();
             if (valid) {
                 float* dst = scratch + (size_t)sid[jj] * GRAD_STRIDE;
-                red_add(dst + G_MX, a_mx * neg_half_w);
-                red_add(dst + G_MY, a_my * neg_half_h);
-                red_add(dst + G_CA, -0.5f * a_A);
-                red_add(dst + G_CB, -0.5f * a_B);
-                red_add(dst + G_CC, -0.5f * a_C);
-                red_add(dst + G_OP, a_op);
-                red_add(dst + G_R, a_r);
-                red_add(dst + G_G, a_g);
+                // scratch rows are 48 B (16-B aligned): slots {mx,my,A,B} {C,op,r,g} {b}
+                red_add_v4(dst + G_MX, a_mx * neg_half_w, a_my * neg_half_h, -0.5f * a_A, -0.5f * a_B);
+                red_add_v4(dst + G_CC, -0.5f * a_C, a_op, a_r, a_g);
                 red_add(dst + G_B, a_b);
             }
         }

@@ -6,7 +6,7 @@
 namespace ggrt {
 
 constexpr int RENDER_THREADS = 256;
-constexpr int REC_BYTES = 48;  // {x, y, ext_x, ext_y | A, B, C, opacity | r, g, b, depth}
+constexpr int REC_BYTES = 48;  // {x, y, tau', - | A, B, C, opacity | r, g, b, depth}
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -32,6 +32,30 @@ __device__ __forceinline__ float2 lds64(uint32_t a) {
 }
 __device__ __forceinline__ void sts128(uint32_t a, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Exact (conservative) test: does the ellipse {q(p - g) <= tau'} reach the pixel rectangle
+// [x0, x0+w] x [y0, y0+h]?  q is convex with its minimum at g, so its minimum over the rectangle is 0 when g is
+// inside and otherwise lies on an edge facing g: minimise the 1-D quadratic along the (at most two) facing edges.
+// Run by one lane per candidate Gaussian in the cull phase, so its ~25 instructions are amortised over the whole
+// pixel block.
+__device__ __forceinline__ bool ellipse_hits_rect(float gx, float gy, float tau_c, float A, float B, float C,
+                                                  float x0, float y0, float w, float h) {
+    const float lox = x0 - gx, hix = lox + w, loy = y0 - gy, hiy = loy + h;  // rectangle relative to the centre
+    const float dxe = fminf(fmaxf(0.f, lox), hix), dye = fminf(fmaxf(0.f, loy), hiy);  // nearest point, per axis
+    float qmin = 0.f;
+    if (dxe != 0.f || dye != 0.f) {
+        qmin = 3.0e38f;
+        if (dye != 0.f) {  // horizontal edge y = dye: free dx in [lox, hix]
+            const float dx = fminf(fmaxf(-B * dye * rcp_approx(A), lox), hix);
+            qmin = A * dx * dx + 2.0f * B * dx * dye + C * dye * dye;
+        }
+        if (dxe != 0.f) {  // vertical edge x = dxe: free dy in [loy, hiy]
+            const float dy = fminf(fmaxf(-B * dxe * rcp_approx(C), loy), hiy);
+            qmin = fminf(qmin, A * dxe * dxe + 2.0f * B * dxe * dy + C * dy * dy);
+        }
+    }
+    return qmin <= tau_c;
 }
 
 }  // namespace ggrt

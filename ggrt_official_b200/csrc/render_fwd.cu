@@ -24,7 +24,7 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
     const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
     const bool inside = px < v.W && py < v.H;
     const float pxf = (float)px, pyf = (float)py;
-    const float wcx = (float)bx0 + 3.5f, wcy = (float)by0 + 1.5f;
+    const float bx0f = (float)bx0, by0f = (float)by0;
     const uint32_t start = starts[tile], end = starts[tile + 1];
 
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
@@ -49,7 +49,8 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
             bool hit = false;
             if (j < cnt) {
                 const float4 a = lds128(sbase + j * REC_BYTES);
-                hit = (fabsf(a.x - wcx) <= a.z + 3.5f) && (fabsf(a.y - wcy) <= a.w + 1.5f);
+                const float4 c = lds128(sbase + j * REC_BYTES + 16);
+                hit = ellipse_hits_rect(a.x, a.y, a.z, c.x, c.y, c.z, bx0f, by0f, 7.0f, 3.0f);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
             while (mask) {

@@ -66,7 +66,7 @@ typedef struct GgrtRasterSettings {
 /* Byte offsets of the sub-arrays inside the caller-owned buffers (for tests / tools). */
 typedef struct GgrtRasterLayout {
     /* geometry buffer, per Gaussian */
-    size_t geom_rec0;   /* float4[P]  {pix_x, pix_y, extent_x, extent_y} */
+    size_t geom_rec0;   /* float4[P]  {pix_x, pix_y, cull threshold tau, 0} */
     size_t geom_rec1;   /* float4[P]  {conic_A, conic_B, conic_C, opacity} */
     size_t geom_rec2;   /* float4[P]  {r, g, b, view_depth} */
     size_t geom_rect;   /* uint16x4[P] {tile_x0, tile_y0, tile_x1, tile_y1} */
