@@ -127,6 +127,8 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
             const float4 col = lds128(src + 32);
             if (!valid) con.w = 0.f;  // zero opacity: never active
             const uint32_t pos = valid ? boff + jj : 0xffffffffu;  // 0-based list position
+            // exponent of the Gaussian in base 2 with the -1/2 folded in: G = 2^(ea dx^2 + eb dx dy + ec dy^2)
+            const float ea = -0.5f * LOG2E * con.x, eb = -LOG2E * con.y, ec = -0.5f * LOG2E * con.z;
             float a_op = 0.f, a_mx = 0.f, a_my = 0.f, a_A = 0.f, a_B = 0.f, a_C = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f;
 
             // PIX_UNROLL pixels are processed per iteration: their scans are independent dependency chains
@@ -154,10 +156,10 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
                 for (int u = 0; u < PIX_UNROLL; ++u) {
                     dx[u] = gxy.x - ps[u].x, dy[u] = gxy.y - ps[u].y;
                     dxx[u] = dx[u] * dx[u], dyy[u] = dy[u] * dy[u], dxy[u] = dx[u] * dy[u];
-                    const float power = -0.5f * (con.x * dxx[u] + con.z * dyy[u]) - con.y * dxy[u];
-                    G[u] = ex2_approx(power * LOG2E);
+                    const float power2 = fmaf(ea, dxx[u], fmaf(ec, dyy[u], eb * dxy[u]));  // log2 of the Gaussian
+                    G[u] = ex2_approx(power2);
                     const float alpha_raw = fminf(ALPHA_MAX, con.w * G[u]);
-                    act[u] = pv[u] && (pos < __float_as_uint(pg[u].w)) && (power <= 0.0f) && (alpha_raw >= ALPHA_MIN);
+                    act[u] = pv[u] && (pos < __float_as_uint(pg[u].w)) && (power2 <= 0.0f) && (alpha_raw >= ALPHA_MIN);
                     alpha[u] = act[u] ? alpha_raw : 0.f;
                     inv_om[u] = rcp_approx(1.0f - alpha[u]);
                     s[u] = fmaf(col.z, pg[u].z, fmaf(col.y, pg[u].y, col.x * pg[u].x));
@@ -188,8 +190,8 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
                     const float q = act[u] ? G[u] * dL_dalpha : 0.f;
                     const float t = con.w * q;
                     a_op += q;
-                    a_mx = fmaf(t, fmaf(con.x, dx[u], con.y * dy[u]), a_mx);
-                    a_my = fmaf(t, fmaf(con.z, dy[u], con.y * dx[u]), a_my);
+                    a_mx = fmaf(t, dx[u], a_mx);  // first moments; the conic is applied once per chunk below
+                    a_my = fmaf(t, dy[u], a_my);
                     a_A = fmaf(t, dxx[u], a_A);
                     a_B = fmaf(t, dxy[u], a_B);
                     a_C = fmaf(t, dyy[u], a_C);
@@ -206,7 +208,8 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
             if (valid) {
                 float* dst = scratch + (size_t)sid[jj] * GRAD_STRIDE;
                 // scratch rows are 48 B (16-B aligned): slots {mx,my,A,B} {C,op,r,g} {b}
-                red_add_v4(dst + G_MX, a_mx * neg_half_w, a_my * neg_half_h, -0.5f * a_A, -0.5f * a_B);
+                const float gmx = fmaf(con.x, a_mx, con.y * a_my), gmy = fmaf(con.z, a_my, con.y * a_mx);
+                red_add_v4(dst + G_MX, gmx * neg_half_w, gmy * neg_half_h, -0.5f * a_A, -0.5f * a_B);
                 red_add_v4(dst + G_CC, -0.5f * a_C, a_op, a_r, a_g);
                 red_add(dst + G_B, a_b);
             }

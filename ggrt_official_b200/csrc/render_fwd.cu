@@ -37,8 +37,11 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
         if (tid < cnt) {
             const uint32_t id = points[base + tid];
             const uint32_t dst = sbase + tid * REC_BYTES;
+            // the conic is staged pre-scaled: G = 2^(ea dx^2 + eb dx dy + ec dy^2), ea = -A log2(e)/2, eb = -B log2(e), ...
+            float4 c = rec1[id];
+            c.x *= -0.5f * LOG2E, c.y *= -LOG2E, c.z *= -0.5f * LOG2E;
             sts128(dst, rec0[id]);
-            sts128(dst + 16, rec1[id]);
+            sts128(dst + 16, c);
             sts128(dst + 32, rec2[id]);
         }
         __syncthreads();
@@ -50,7 +53,9 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
             if (j < cnt) {
                 const float4 a = lds128(sbase + j * REC_BYTES);
                 const float4 c = lds128(sbase + j * REC_BYTES + 16);
-                hit = ellipse_hits_rect(a.x, a.y, a.z, c.x, c.y, c.z, bx0f, by0f, 7.0f, 3.0f);
+                constexpr float UNSCALE = -2.0f / LOG2E;  // back to (A, 2B, C) for the cull
+                hit = ellipse_hits_rect(a.x, a.y, a.z, c.x * UNSCALE, c.y * (0.5f * UNSCALE), c.z * UNSCALE, bx0f, by0f,
+                                        7.0f, 3.0f);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
             while (mask) {
@@ -58,30 +63,24 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
                 mask &= ~(0x80000000u >> lz);
                 const uint32_t jj = r + lz;
                 const uint32_t src = sbase + jj * REC_BYTES;
-                if (!done) {
-                    const float2 xy = lds64(src);
-                    const float4 c = lds128(src + 16);
-                    const float dx = xy.x - pxf, dy = xy.y - pyf;
-                    const float power = -0.5f * (c.x * dx * dx + c.z * dy * dy) - c.y * dx * dy;
-                    if (power <= 0.0f) {
-                        const float alpha = fminf(ALPHA_MAX, c.w * ex2_approx(power * LOG2E));
-                        if (alpha >= ALPHA_MIN) {
-                            const float Tn = T * (1.0f - alpha);
-                            if (Tn < T_EPS) {
-                                done = true;
-                            } else {
-                                const float4 col = lds128(src + 32);
-                                const float w = alpha * T;
-                                C0 = fmaf(col.x, w, C0);
-                                C1 = fmaf(col.y, w, C1);
-                                C2 = fmaf(col.z, w, C2);
-                                D = fmaf(col.w, w, D);
-                                T = Tn;
-                                last = (base - start) + jj + 1;
-                            }
-                        }
-                    }
-                }
+                // branch-free body: lanes that skip this Gaussian blend it with weight 0
+                const float2 xy = lds64(src);
+                const float4 c = lds128(src + 16);
+                const float4 col = lds128(src + 32);
+                const float dx = xy.x - pxf, dy = xy.y - pyf;
+                const float power2 = fmaf(dx, fmaf(c.x, dx, c.y * dy), (c.z * dy) * dy);
+                const float alpha = fminf(ALPHA_MAX, c.w * ex2_approx(power2));
+                const bool active = !done && (power2 <= 0.0f) && (alpha >= ALPHA_MIN);
+                const float Tn = T * (1.0f - alpha);
+                const bool blend = active && !(Tn < T_EPS);
+                done = done || (active && !blend);
+                const float w = blend ? alpha * T : 0.0f;
+                C0 = fmaf(col.x, w, C0);
+                C1 = fmaf(col.y, w, C1);
+                C2 = fmaf(col.z, w, C2);
+                D = fmaf(col.w, w, D);
+                T = blend ? Tn : T;
+                last = blend ? (base - start) + jj + 1 : last;
             }
             if (__all_sync(0xffffffffu, done)) break;
         }
