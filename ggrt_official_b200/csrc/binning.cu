@@ -16,8 +16,7 @@ constexpr int EMIT_THREADS = 256;
 constexpr int SORT_THREADS = 256;
 
 __global__ void __launch_bounds__(EMIT_THREADS)
-emit_kernel(View v, GeomPtrs g, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ counts,
-            uint32_t* __restrict__ cursor, unsigned long long* __restrict__ keys) {
+emit_kernel(View v, GeomPtrs g, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ keys) {
     const int i = blockIdx.x * EMIT_THREADS + threadIdx.x;
     if (i >= v.P) return;
     if (g.tiles[i] == 0) return;
@@ -26,19 +25,9 @@ emit_kernel(View v, GeomPtrs g, const uint32_t* __restrict__ starts, const uint3
     const int sub = i & (SUBS - 1);
     for (int y = r.y; y < r.w; ++y)
         for (int x = r.x; x < r.z; ++x) {
-            const int tile = y * v.gx + x;
-            const int t = (tile << SUBS_LOG2) + sub;
-            const uint32_t local = atomicAdd(&cursor[t], 1u);
-            // sub-segment offset inside the tile segment: counts of the lower sub-counters (one 64 B line)
-            const uint4* c4 = reinterpret_cast<const uint4*>(counts) + (size_t)tile * (SUBS / 4);
-            uint32_t base = starts[tile];
-#pragma unroll
-            for (int q = 0; q < SUBS / 4; ++q) {
-                const uint4 c = c4[q];
-                base += (4 * q + 0 < sub ? c.x : 0u) + (4 * q + 1 < sub ? c.y : 0u) + (4 * q + 2 < sub ? c.z : 0u) +
-                        (4 * q + 3 < sub ? c.w : 0u);
-            }
-            keys[base + local] = key;
+            // the (tile, sub-counter) segment start doubles as its allocation cursor: one returning atomic per pair
+            const uint32_t slot = atomicAdd(&cursor[((y * v.gx + x) << SUBS_LOG2) + sub], 1u);
+            keys[slot] = key;
         }
 }
 
@@ -102,8 +91,7 @@ sort_tiles_kernel(int T, const uint32_t* __restrict__ starts, unsigned long long
 
 void launch_emit(const View& v, const int*, GeomPtrs g, ImagePtrs im, BinPtrs b, cudaStream_t s) {
     if (v.P == 0) return;
-    emit_kernel<<<(v.P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, s>>>(v, g, im.starts, im.counts, im.cursor,
-                                                                                 b.keys);
+    emit_kernel<<<(v.P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, s>>>(v, g, im.cursor, b.keys);
 }
 
 void launch_sort_tiles(const View& v, ImagePtrs im, BinPtrs b, uint32_t max_tile_pairs, cudaStream_t s) {

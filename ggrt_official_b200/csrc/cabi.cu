@@ -68,7 +68,8 @@ void compute_layout(int P, int H, int W, long long N, GgrtRasterLayout* L) {
     const size_t gx = (size_t)(W + TILE - 1) / TILE, gy = (size_t)(H + TILE - 1) / TILE, T = gx * gy;
     const size_t px = (size_t)H * W;
     off = 0;
-    L->img_counts = off; off = off + T * SUBS * sizeof(uint32_t);  // counts and cursor are zeroed by one memset
+    L->img_counts = off; off = off + T * SUBS * sizeof(uint32_t);
+    L->img_partials = off; off = align_up(off + ((T + SCAN_BLOCK - 1) / SCAN_BLOCK) * sizeof(unsigned long long));
     L->img_cursor = off; off = align_up(off + T * SUBS * sizeof(uint32_t));
     L->img_starts = off; off = align_up(off + (T + 1) * sizeof(uint32_t));
     L->img_header = off; off = align_up(off + 4 * sizeof(uint32_t));
@@ -103,6 +104,7 @@ ImagePtrs image_ptrs(void* base, int H, int W) {
     char* b = static_cast<char*>(base);
     ImagePtrs im;
     im.counts = reinterpret_cast<uint32_t*>(b + L.img_counts);
+    im.partials = reinterpret_cast<unsigned long long*>(b + L.img_partials);
     im.starts = reinterpret_cast<uint32_t*>(b + L.img_starts);
     im.cursor = reinterpret_cast<uint32_t*>(b + L.img_cursor);
     im.header = reinterpret_cast<uint32_t*>(b + L.img_header);
@@ -225,7 +227,7 @@ int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, int32_t P, c
     const int dbg = settings->debug;
     GeomPtrs g = geom_ptrs(geom_buffer, P);
     ImagePtrs im = image_ptrs(image_buffer, v.H, v.W);
-    if (cudaMemsetAsync(im.counts, 0, 2 * (size_t)v.gx * v.gy * SUBS * sizeof(uint32_t), s) != cudaSuccess)
+    if (cudaMemsetAsync(im.counts, 0, reinterpret_cast<char*>(im.cursor) - reinterpret_cast<char*>(im.counts), s) != cudaSuccess)
         return check_launch("memset tile counts", 0, s);
     for (int i = 0; i < GGRT_STAGE_COUNT; ++i) g_prof.used[i] = false;
     { StageTimer t_(GGRT_STAGE_GEOMETRY, s); launch_geometry(v, means3D, cov3D_precomp, opacities, radii, g, im, s); }

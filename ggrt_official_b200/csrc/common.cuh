@@ -44,8 +44,11 @@ struct GeomPtrs {
     uint8_t* flags;    // clamp bits
 };
 
+constexpr int SCAN_BLOCK = 256;      // tiles per CTA of the tile scan
+
 struct ImagePtrs {
     uint32_t* counts;
+    unsigned long long* partials;
     uint32_t* starts;
     uint32_t* cursor;
     uint32_t* header;

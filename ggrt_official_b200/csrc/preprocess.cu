@@ -94,95 +94,85 @@ geometry_kernel(View v, const float* __restrict__ means, const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------
-// scan_tiles: per-tile totals of the SUBS pair counters and their exclusive scan (one CTA;
-// T is a few thousand, the counters are L2 resident).  Reports {N, max pairs in one tile}.
-// Each thread owns a run of whole tiles and issues all its loads before the block scan.
+// scan_tiles: exclusive scan of the T*SUBS pair counters (L2 resident).  Writes the
+// per-(tile, sub-counter) segment starts that `emit` consumes as allocation cursors, the
+// per-tile starts for sort / render, and reports {N, max pairs in a tile}.
+// One tile per thread, SCAN_BLOCK tiles per CTA; CTAs chain through a single-pass look-back:
+// each publishes {flag, max, total} and sums the totals of the CTAs before it (they are
+// scheduled in index order and never wait on later ones, so the spin cannot deadlock).
 // ---------------------------------------------------------------------------------------
-constexpr int SCAN_MAX_PER = 8;  // tiles per thread held in registers (T <= 8192); larger images loop
-
-__global__ void __launch_bounds__(1024) scan_tiles_kernel(int T, const uint32_t* __restrict__ counts,
-                                                          uint32_t* __restrict__ starts,
-                                                          uint32_t* __restrict__ header) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t max_s;
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_tiles_kernel(int T, const uint32_t* __restrict__ counts,
+                                                                uint32_t* __restrict__ starts,
+                                                                uint32_t* __restrict__ sub_starts,
+                                                                unsigned long long* partials,
+                                                                uint32_t* __restrict__ header) {
+    __shared__ uint32_t warp_sums[SCAN_BLOCK / 32], warp_max[SCAN_BLOCK / 32];
+    __shared__ uint32_t prefix_s, gmax_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) max_s = 0;
-    const int per = (T + 1023) / 1024;  // tiles per thread
-    const int t0 = min(T, tid * per), t1 = min(T, t0 + per);
-    const uint4* c4 = reinterpret_cast<const uint4*>(counts);
-    uint32_t tot[SCAN_MAX_PER];
-    uint32_t sum = 0, local_max = 0;
-    if (per <= SCAN_MAX_PER) {
-        uint4 c[SCAN_MAX_PER][SUBS / 4];
+    const int t = blockIdx.x * SCAN_BLOCK + tid;
+    const uint4* c4 = reinterpret_cast<const uint4*>(counts) + (size_t)t * (SUBS / 4);
+    uint4 c[SUBS / 4];
+    uint32_t ts = 0;
 #pragma unroll
-        for (int u = 0; u < SCAN_MAX_PER; ++u)
-#pragma unroll
-            for (int q = 0; q < SUBS / 4; ++q)
-                c[u][q] = (t0 + u < t1) ? c4[(size_t)(t0 + u) * (SUBS / 4) + q] : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int u = 0; u < SCAN_MAX_PER; ++u) {
-            uint32_t ts = 0;
-#pragma unroll
-            for (int q = 0; q < SUBS / 4; ++q) ts += c[u][q].x + c[u][q].y + c[u][q].z + c[u][q].w;
-            tot[u] = ts;
-            local_max = max(local_max, ts);
-            sum += ts;
-        }
-    } else {
-        for (int t = t0; t < t1; ++t) {
-            uint32_t ts = 0;
-            for (int q = 0; q < SUBS / 4; ++q) {
-                const uint4 c = c4[(size_t)t * (SUBS / 4) + q];
-                ts += c.x + c.y + c.z + c.w;
-            }
-            local_max = max(local_max, ts);
-            sum += ts;
-        }
+    for (int q = 0; q < SUBS / 4; ++q) {
+        c[q] = (t < T) ? c4[q] : make_uint4(0u, 0u, 0u, 0u);
+        ts += c[q].x + c[q].y + c[q].z + c[q].w;
     }
-    uint32_t x = sum;
+    uint32_t x = ts;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
         if (lane >= d) x += y;
     }
-    if (lane == 31) warp_sums[warp] = x;
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, ts);
+    if (lane == 31) warp_sums[warp] = x, warp_max[warp] = wmax;
+    if (tid == 0) prefix_s = 0, gmax_s = 0;
     __syncthreads();
-    if (warp == 0) {
-        uint32_t w = warp_sums[lane];
+    uint32_t block_total = 0, block_max = 0, warp_off = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
-            if (lane >= d) w += y;
-        }
-        warp_sums[lane] = w;
+    for (int w = 0; w < SCAN_BLOCK / 32; ++w) {
+        if (w < warp) warp_off += warp_sums[w];
+        block_total += warp_sums[w];
+        block_max = max(block_max, warp_max[w]);
     }
+    if (tid == 0) {  // publish this CTA's aggregate: bit 63 flag | 31 bits max | 32 bits total
+        const unsigned long long pack = (1ull << 63) | ((unsigned long long)(block_max & 0x7fffffffu) << 32) | block_total;
+        __threadfence();
+        atomicExch(&partials[blockIdx.x], pack);
+    }
+    // look back: sum the totals (and fold the maxima) of all earlier CTAs
+    uint32_t psum = 0, pmax = 0;
+    for (int bk = tid; bk < (int)blockIdx.x; bk += SCAN_BLOCK) {
+        unsigned long long v;
+        do {
+            v = *reinterpret_cast<volatile unsigned long long*>(&partials[bk]);
+        } while ((v >> 63) == 0);
+        psum += (uint32_t)v;
+        pmax = max(pmax, (uint32_t)(v >> 32) & 0x7fffffffu);
+    }
+    psum = __reduce_add_sync(0xffffffffu, psum);
+    pmax = __reduce_max_sync(0xffffffffu, pmax);
+    if (lane == 0 && (psum | pmax)) atomicAdd(&prefix_s, psum), atomicMax(&gmax_s, pmax);
     __syncthreads();
-    uint32_t run = (warp == 0 ? 0u : warp_sums[warp - 1]) + x - sum;  // exclusive prefix of this thread's run
-    if (per <= SCAN_MAX_PER) {
+    uint32_t run = prefix_s + warp_off + x - ts;
+    if (t < T) {
+        starts[t] = run;
+        uint4* s4 = reinterpret_cast<uint4*>(sub_starts) + (size_t)t * (SUBS / 4);
 #pragma unroll
-        for (int u = 0; u < SCAN_MAX_PER; ++u)
-            if (t0 + u < t1) {
-                starts[t0 + u] = run;
-                run += tot[u];
-            }
-    } else {
-        for (int t = t0; t < t1; ++t) {
-            uint32_t ts = 0;
-            for (int q = 0; q < SUBS / 4; ++q) {
-                const uint4 c = c4[(size_t)t * (SUBS / 4) + q];
-                ts += c.x + c.y + c.z + c.w;
-            }
-            starts[t] = run;
-            run += ts;
+        for (int q = 0; q < SUBS / 4; ++q) {
+            uint4 o;
+            o.x = run; run += c[q].x;
+            o.y = run; run += c[q].y;
+            o.z = run; run += c[q].z;
+            o.w = run; run += c[q].w;
+            s4[q] = o;
         }
     }
-    atomicMax(&max_s, local_max);
-    __syncthreads();
-    if (tid == 1023) {
-        const uint32_t total = warp_sums[31];
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) {
+        const uint32_t total = prefix_s + block_total;
         starts[T] = total;
         header[0] = total;
-        header[1] = max_s;
+        header[1] = max(gmax_s, block_max);
         header[2] = 0u;
         header[3] = 0u;
     }
@@ -344,7 +334,9 @@ void launch_geometry(const View& v, const float* means, const float* cov3d, cons
 }
 
 void launch_scan_tiles(const View& v, ImagePtrs im, cudaStream_t s) {
-    scan_tiles_kernel<<<1, 1024, 0, s>>>(v.gx * v.gy, im.counts, im.starts, im.header);
+    const int T = v.gx * v.gy;
+    scan_tiles_kernel<<<(T + SCAN_BLOCK - 1) / SCAN_BLOCK, SCAN_BLOCK, 0, s>>>(T, im.counts, im.starts, im.cursor, im.partials,
+                                                                              im.header);
 }
 
 void launch_color(const View& v, const float* means, const float* shs, const float* colors, const int* radii,

@@ -75,7 +75,9 @@ typedef struct GgrtRasterLayout {
     size_t geom_bytes;
     /* image buffer, per tile / per pixel */
     size_t img_counts;  /* uint32[T*16] pairs per (tile, sub-counter); sub-counter = gaussian idx % 16 */
-    size_t img_cursor;  /* uint32[T*16] scratch (directly after img_counts) */
+    size_t img_partials;/* uint64[ceil(T/256)] per-scan-block {flag, max, total} (directly after img_counts, zeroed with it) */
+    size_t img_cursor;  /* uint32[T*16] exclusive scan of img_counts (per (tile, sub-counter) segment starts); consumed as
+                           allocation cursors by the emit kernel */
     size_t img_starts;  /* uint32[T+1]  exclusive scan of the per-tile totals; tile t owns [starts[t], starts[t+1]); [T] == N */
     size_t img_header;  /* uint32[4]   {N, max pairs in a tile, 0, 0} */
     size_t img_final_T; /* float[H*W]  */

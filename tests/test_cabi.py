@@ -41,7 +41,7 @@ def test_abi_version_and_layout():
     assert L.bin_bytes == lib.ggrt_raster_binning_bytes(N) >= 12 * N
     offs = [L.geom_rec0, L.geom_rec1, L.geom_rec2, L.geom_rect, L.geom_tiles, L.geom_flags]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
-    assert L.img_cursor == L.img_counts + 4 * 16 * T  # zeroed by one memset
+    assert L.img_partials == L.img_counts + 4 * 16 * T and L.img_cursor > L.img_partials
     assert lib.ggrt_raster_binning_bytes(0) > 0  # never a zero-sized allocation
 
 
