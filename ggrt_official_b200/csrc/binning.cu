@@ -89,12 +89,125 @@ sort_tiles_kernel(int T, const uint32_t* __restrict__ starts, unsigned long long
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Register-resident variant for the common case (every tile <= 256*WARPS pairs): each thread
+// holds 8 consecutive keys, so compare-exchange distances 1, 2, 4 are thread-local, distances
+// 8..128 are warp shuffles, and only distances >= 256 go through shared memory + a barrier
+// (one step for 512 keys).  Same ascending-only "flip" network, same result.
+// ---------------------------------------------------------------------------------------
+constexpr int SORT_E = 8;  // keys per thread
+
+__device__ __forceinline__ void cx(unsigned long long& a, unsigned long long& b) {  // ascending compare-exchange
+    const unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
+    a = lo, b = hi;
+}
+__device__ __forceinline__ void local_tail(unsigned long long (&v)[SORT_E]) {  // distances 4, 2, 1
+    cx(v[0], v[4]), cx(v[1], v[5]), cx(v[2], v[6]), cx(v[3], v[7]);
+    cx(v[0], v[2]), cx(v[1], v[3]), cx(v[4], v[6]), cx(v[5], v[7]);
+    cx(v[0], v[1]), cx(v[2], v[3]), cx(v[4], v[5]), cx(v[6], v[7]);
+}
+// keep the minimum (lower index side) or maximum of (mine, other)
+__device__ __forceinline__ void keep(unsigned long long& mine, unsigned long long other, bool lower) {
+    if ((other < mine) == lower) mine = other;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
+sort_tiles_reg_kernel(int T, const uint32_t* __restrict__ starts, unsigned long long* __restrict__ keys,
+                      uint32_t* __restrict__ points) {
+    __shared__ unsigned long long xch[WARPS > 1 ? 256 * WARPS : 1];
+    const int tile = blockIdx.x;
+    if (tile >= T) return;
+    const uint32_t s = starts[tile], n = starts[tile + 1] - s;
+    if (n == 0) return;
+    unsigned long long* seg = keys + s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, i0 = tid * SORT_E;
+    int L = 3;  // log2 of the padded size (>= 8)
+    while ((1u << L) < n) ++L;
+    if (WARPS > 1 && L <= 8 && tid >= 32) return;  // one warp is enough and no barrier will be executed
+
+    unsigned long long v[SORT_E];
+#pragma unroll
+    for (int e = 0; e < SORT_E; ++e) v[e] = (i0 + e < n) ? seg[i0 + e] : ~0ull;
+
+    // levels 1..3 (blocks of 2, 4, 8 keys) are entirely thread-local
+    cx(v[0], v[1]), cx(v[2], v[3]), cx(v[4], v[5]), cx(v[6], v[7]);
+    cx(v[0], v[3]), cx(v[1], v[2]), cx(v[4], v[7]), cx(v[5], v[6]);
+    cx(v[0], v[1]), cx(v[2], v[3]), cx(v[4], v[5]), cx(v[6], v[7]);
+    cx(v[0], v[7]), cx(v[1], v[6]), cx(v[2], v[5]), cx(v[3], v[4]);
+    cx(v[0], v[2]), cx(v[1], v[3]), cx(v[4], v[6]), cx(v[5], v[7]);
+    cx(v[0], v[1]), cx(v[2], v[3]), cx(v[4], v[5]), cx(v[6], v[7]);
+
+    for (int lk = 4; lk <= L; ++lk) {
+        // flip step: key i pairs with i ^ (2^lk - 1): local slot e <-> 7-e in thread tid ^ (2^(lk-3) - 1)
+        {
+            const bool lower = ((tid >> (lk - 4)) & 1u) == 0;  // bit lk-1 of the key index
+            unsigned long long o[SORT_E];
+            if (WARPS == 1 || lk <= 8) {
+                const int m = (1 << (lk - 3)) - 1;
+#pragma unroll
+                for (int e = 0; e < SORT_E; ++e) o[e] = __shfl_xor_sync(0xffffffffu, v[SORT_E - 1 - e], m);
+            } else {
+#pragma unroll
+                for (int e = 0; e < SORT_E; ++e) xch[i0 + e] = v[e];
+                __syncthreads();
+                const uint32_t m = (1u << lk) - 1u;
+#pragma unroll
+                for (int e = 0; e < SORT_E; ++e) o[e] = xch[(i0 + e) ^ m];
+                __syncthreads();
+            }
+#pragma unroll
+            for (int e = 0; e < SORT_E; ++e) keep(v[e], o[e], lower);
+        }
+        // half-cleaners with distance 2^lj, lj = lk-2 .. 3 (cross-thread), then the local tail (4, 2, 1)
+        for (int lj = lk - 2; lj >= 3; --lj) {
+            const bool lower = ((tid >> (lj - 3)) & 1u) == 0;  // bit lj of the key index
+            unsigned long long o[SORT_E];
+            if (WARPS == 1 || lj < 8) {
+                const int m = 1 << (lj - 3);
+#pragma unroll
+                for (int e = 0; e < SORT_E; ++e) o[e] = __shfl_xor_sync(0xffffffffu, v[e], m);
+            } else {
+#pragma unroll
+                for (int e = 0; e < SORT_E; ++e) xch[i0 + e] = v[e];
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < SORT_E; ++e) o[e] = xch[(i0 + e) ^ (1u << lj)];
+                __syncthreads();
+            }
+#pragma unroll
+            for (int e = 0; e < SORT_E; ++e) keep(v[e], o[e], lower);
+        }
+        local_tail(v);
+    }
+#pragma unroll
+    for (int e = 0; e < SORT_E; ++e)
+        if (i0 + e < n) {
+            seg[i0 + e] = v[e];
+            points[s + i0 + e] = (uint32_t)v[e];
+        }
+    (void)lane;
+}
+
 void launch_emit(const View& v, const int*, GeomPtrs g, ImagePtrs im, BinPtrs b, cudaStream_t s) {
     if (v.P == 0) return;
     emit_kernel<<<(v.P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, s>>>(v, g, im.cursor, b.keys);
 }
 
 void launch_sort_tiles(const View& v, ImagePtrs im, BinPtrs b, uint32_t max_tile_pairs, cudaStream_t s) {
+    const int T = v.gx * v.gy;
+    if (max_tile_pairs <= 256) {
+        sort_tiles_reg_kernel<1><<<T, 32, 0, s>>>(T, im.starts, b.keys, b.points);
+        return;
+    }
+    if (max_tile_pairs <= 512) {
+        sort_tiles_reg_kernel<2><<<T, 64, 0, s>>>(T, im.starts, b.keys, b.points);
+        return;
+    }
+    if (max_tile_pairs <= 1024) {
+        sort_tiles_reg_kernel<4><<<T, 128, 0, s>>>(T, im.starts, b.keys, b.points);
+        return;
+    }
     // shared-memory capacity tier from the largest tile (reported by scan_tiles)
     uint32_t cap = 1024;
     while (cap < max_tile_pairs && cap < 16384) cap <<= 1;
