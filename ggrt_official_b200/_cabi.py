@@ -10,7 +10,7 @@ from pathlib import Path
 
 from . import build as _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 _lib = None
 
 
@@ -84,9 +84,9 @@ def lib():
     L.ggrt_raster_image_bytes.restype = sz
     L.ggrt_raster_binning_bytes.argtypes = [i64]
     L.ggrt_raster_binning_bytes.restype = sz
-    L.ggrt_raster_forward_prepare.argtypes = [C.POINTER(Settings), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ggrt_raster_forward_prepare.argtypes = [C.POINTER(Settings), i32] + [vp] * 11
     L.ggrt_raster_forward_render.argtypes = [C.POINTER(Settings), i32, i64, u32, vp, vp, vp, vp, vp, vp]
-    L.ggrt_raster_backward.argtypes = [C.POINTER(Settings), i32, i64] + [vp] * 16
+    L.ggrt_raster_backward.argtypes = [C.POINTER(Settings), i32, i64] + [vp] * 18
     L.ggrt_raster_mark_visible.argtypes = [i32, vp, vp, vp, vp]
     L.ggrt_raster_profile_enable.argtypes = [i32]
     L.ggrt_raster_profile_read.argtypes = [C.POINTER(C.c_float)]

@@ -21,7 +21,7 @@ emit_kernel(View v, GeomPtrs g, uint32_t* __restrict__ cursor, unsigned long lon
     if (i >= v.P) return;
     if (g.tiles[i] == 0) return;
     const ushort4 r = g.rect[i];
-    const unsigned long long key = ((unsigned long long)__float_as_uint(g.rec2[i].w) << 32) | (uint32_t)i;
+    const unsigned long long key = ((unsigned long long)__float_as_uint(g.rec0[i].w) << 32) | (uint32_t)i;
     const int sub = i & (SUBS - 1);
     for (int y = r.y; y < r.w; ++y)
         for (int x = r.x; x < r.z; ++x) {

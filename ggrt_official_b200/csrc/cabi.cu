@@ -211,8 +211,8 @@ size_t ggrt_raster_binning_bytes(int64_t N) {
 
 int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, int32_t P, const float* means3D,
                                 const float* cov3D_precomp, const float* opacities, const float* shs,
-                                const float* colors_precomp, int32_t* radii, void* geom_buffer, void* image_buffer,
-                                uint32_t* counts_host, ggrt_stream_t stream) {
+                                const float* colors_precomp, const float* aux, int32_t* radii, void* geom_buffer,
+                                void* image_buffer, uint32_t* counts_host, ggrt_stream_t stream) {
     View v;
     GGRT_TRY(make_view(settings, P, &v));
     if (P > 0 && (shs == nullptr) == (colors_precomp == nullptr)) {
@@ -239,7 +239,7 @@ int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, int32_t P, c
             return check_launch("copy pair counts", 0, s);
     }
     // colour evaluation does not depend on N: it runs while the host waits for the counts
-    { StageTimer t_(GGRT_STAGE_COLOR, s); launch_color(v, means3D, shs, colors_precomp, radii, g, s); }
+    { StageTimer t_(GGRT_STAGE_COLOR, s); launch_color(v, means3D, shs, colors_precomp, aux, radii, g, s); }
     GGRT_TRY(check_launch("color", dbg, s));
     return GGRT_OK;
 }
@@ -277,14 +277,19 @@ int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, in
 int ggrt_raster_backward(const GgrtRasterSettings* settings, int32_t P, int64_t num_rendered, const float* means3D,
                          const float* cov3D_precomp, const float* shs, const int32_t* radii, const void* geom_buffer,
                          const void* binning_buffer, const void* image_buffer, const float* dL_dout_color,
-                         float* grad_scratch, float* dL_dmeans2D, float* dL_dopacity, float* dL_dmeans3D,
-                         float* dL_dcov3D, float* dL_dsh, float* dL_dcolors, ggrt_stream_t stream) {
+                         const float* dL_dout_aux, float* grad_scratch, float* dL_dmeans2D, float* dL_dopacity,
+                         float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dcolors, float* dL_daux,
+                         ggrt_stream_t stream) {
     View v;
     GGRT_TRY(make_view(settings, P, &v));
     if (P == 0) return GGRT_OK;
     if (!means3D || !cov3D_precomp || !radii || !geom_buffer || !image_buffer || !dL_dout_color || !grad_scratch ||
         !dL_dmeans2D || !dL_dopacity || !dL_dmeans3D || !dL_dcov3D || (num_rendered > 0 && !binning_buffer)) {
         set_error("backward: NULL buffer");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    if ((dL_dout_aux != nullptr) != (dL_daux != nullptr)) {
+        set_error("backward: dL_dout_aux and dL_daux go together");
         return GGRT_ERR_INVALID_ARGUMENT;
     }
     if ((shs != nullptr) != (dL_dsh != nullptr) || (shs == nullptr) != (dL_dcolors != nullptr)) {
@@ -299,13 +304,13 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, int32_t P, int64_t 
     if (cudaMemsetAsync(grad_scratch, 0, (size_t)P * GRAD_STRIDE * sizeof(float), s) != cudaSuccess)
         return check_launch("memset grad scratch", 0, s);
     if (num_rendered > 0) {
-        { StageTimer t_(GGRT_STAGE_RENDER_BACKWARD, s); launch_render_backward(v, g, im, b, dL_dout_color, grad_scratch, s); }
+        { StageTimer t_(GGRT_STAGE_RENDER_BACKWARD, s); launch_render_backward(v, g, im, b, dL_dout_color, dL_dout_aux, grad_scratch, s); }
         GGRT_TRY(check_launch("render_backward", dbg, s));
     }
     {
         StageTimer t_(GGRT_STAGE_PREPROCESS_BACKWARD, s);
         launch_preprocess_backward(v, means3D, cov3D_precomp, shs, radii, g, grad_scratch, dL_dmeans2D, dL_dopacity,
-                                   dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dcolors, s);
+                                   dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dcolors, dL_daux, s);
     }
     GGRT_TRY(check_launch("preprocess_backward", dbg, s));
     return GGRT_OK;

@@ -24,7 +24,7 @@ constexpr int SUBS = 16;
 constexpr int SUBS_LOG2 = 4;
 
 // grad_scratch slot meaning (A.4): NDC-mean x,y | conic A, B(half convention), C | opacity | colour r,g,b
-enum GradSlot { G_MX = 0, G_MY = 1, G_CA = 2, G_CB = 3, G_CC = 4, G_OP = 5, G_R = 6, G_G = 7, G_B = 8 };
+enum GradSlot { G_MX = 0, G_MY = 1, G_CA = 2, G_CB = 3, G_CC = 4, G_OP = 5, G_R = 6, G_G = 7, G_B = 8, G_AUX = 9 };
 
 struct View {  // kernel-side copy of the per-call scalars (matrices stay in device memory)
     int W, H, gx, gy, P, deg, K;
@@ -36,9 +36,9 @@ struct View {  // kernel-side copy of the per-call scalars (matrices stay in dev
 };
 
 struct GeomPtrs {
-    float4* rec0;      // {pix_x, pix_y, extent_x, extent_y}
+    float4* rec0;      // {pix_x, pix_y, cull threshold, view depth}
     float4* rec1;      // {conic A, B, C, opacity}
-    float4* rec2;      // {r, g, b, depth}
+    float4* rec2;      // {r, g, b, aux}
     ushort4* rect;     // tile rect
     uint32_t* tiles;   // tiles touched
     uint8_t* flags;    // clamp bits
@@ -72,17 +72,17 @@ BinPtrs bin_ptrs(void* base, long long N);
 void launch_geometry(const View& v, const float* means, const float* cov3d, const float* opac, int* radii,
                      GeomPtrs g, ImagePtrs im, cudaStream_t s);
 void launch_scan_tiles(const View& v, ImagePtrs im, cudaStream_t s);
-void launch_color(const View& v, const float* means, const float* shs, const float* colors, const int* radii,
-                  GeomPtrs g, cudaStream_t s);
+void launch_color(const View& v, const float* means, const float* shs, const float* colors, const float* aux,
+                  const int* radii, GeomPtrs g, cudaStream_t s);
 void launch_emit(const View& v, const int* radii_or_null, GeomPtrs g, ImagePtrs im, BinPtrs b, cudaStream_t s);
 void launch_sort_tiles(const View& v, ImagePtrs im, BinPtrs b, uint32_t max_tile_pairs, cudaStream_t s);
 void launch_render_forward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, float* out_color, float* out_depth,
                            cudaStream_t s);
-void launch_render_backward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, const float* dL_dout, float* scratch,
-                            cudaStream_t s);
+void launch_render_backward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, const float* dL_dout,
+                            const float* dL_dout_aux, float* scratch, cudaStream_t s);
 void launch_preprocess_backward(const View& v, const float* means, const float* cov3d, const float* shs,
                                 const int* radii, GeomPtrs g, const float* scratch, float* dmeans2D, float* dopacity,
-                                float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, cudaStream_t s);
+                                float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, float* daux, cudaStream_t s);
 void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------

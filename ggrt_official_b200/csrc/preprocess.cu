@@ -49,7 +49,6 @@ geometry_kernel(View v, const float* __restrict__ means, const float* __restrict
     ushort4 rect = make_ushort4(0, 0, 0, 0);
     float4 r0 = make_float4(0.f, 0.f, -1.0f, 0.f);
     float4 r1 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float depth = 0.f;
 
     Geo q;
     if (geometry(v, sV, sM, px, py, pz, cv, q)) {
@@ -71,14 +70,13 @@ geometry_kernel(View v, const float* __restrict__ means, const float* __restrict
             radius = (int)radf;
             tiles = (uint32_t)area;
             rect = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
-            depth = q.tz;
             // {alpha >= 1/255} <=> q(d) = A dx^2 + 2B dx dy + C dy^2 <= tau = 2 ln(255 o).  The render kernels cull
             // (warp pixel block, Gaussian) pairs with an exact ellipse-vs-rectangle test against tau, slightly
             // inflated so that float rounding of the per-pixel power can never contradict the cull.
             float tau_c = -1.0f;  // opacity below 1/255: never visible
             const float tau = 2.0f * logf(255.0f * o);
             if (tau > 0.0f) tau_c = tau * 1.001f + 0.02f;
-            r0 = make_float4(pxx, pxy, tau_c, 0.0f);
+            r0 = make_float4(pxx, pxy, tau_c, q.tz);
             r1 = make_float4(cA, cB, cC, o);
             const int sub = i & (SUBS - 1);
             for (int y = y0; y < y1; ++y)
@@ -90,7 +88,6 @@ geometry_kernel(View v, const float* __restrict__ means, const float* __restrict
     g.rect[i] = rect;
     g.rec0[i] = r0;
     g.rec1[i] = r1;
-    g.rec2[i] = make_float4(0.f, 0.f, 0.f, depth);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -206,7 +203,7 @@ __device__ __forceinline__ void fill_slab_generic(float* slab, const float* src,
 template <int DEG>
 __global__ void __launch_bounds__(COLOR_THREADS, 3)
 color_kernel(View v, const float* __restrict__ means, const float* __restrict__ shs, const float* __restrict__ colors,
-             const int* __restrict__ radii, GeomPtrs g, int num_slabs) {
+             const float* __restrict__ aux, const int* __restrict__ radii, GeomPtrs g, int num_slabs) {
     extern __shared__ __align__(128) float slab_ring[];
     __shared__ __align__(8) unsigned long long full_bar[COLOR_STAGES];
     constexpr int KK = (DEG + 1) * (DEG + 1);
@@ -245,7 +242,7 @@ color_kernel(View v, const float* __restrict__ means, const float* __restrict__ 
         if (sl < num_slabs && i < v.P) {
             n_radius = radii[i];
             n_mx = means[3 * i], n_my = means[3 * i + 1], n_mz = means[3 * i + 2];
-            n_depth = g.rec2[i].w;
+            n_depth = aux ? aux[i] : g.rec0[i].w;  // 4th blended channel: caller's aux or the view depth
         }
     };
     prefetch(blockIdx.x);
@@ -339,8 +336,8 @@ void launch_scan_tiles(const View& v, ImagePtrs im, cudaStream_t s) {
                                                                               im.header);
 }
 
-void launch_color(const View& v, const float* means, const float* shs, const float* colors, const int* radii,
-                  GeomPtrs g, cudaStream_t s) {
+void launch_color(const View& v, const float* means, const float* shs, const float* colors, const float* aux,
+                  const int* radii, GeomPtrs g, cudaStream_t s) {
     if (v.P == 0) return;
     const size_t smem = shs ? (size_t)COLOR_STAGES * COLOR_THREADS * v.K * 3 * sizeof(float) : 0;
     const int num_slabs = (v.P + COLOR_THREADS - 1) / COLOR_THREADS;
@@ -353,7 +350,7 @@ void launch_color(const View& v, const float* means, const float* shs, const flo
     case D:                                                                                                         \
         if (smem > 32 * 1024)                                                                                       \
             cudaFuncSetAttribute(color_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
-        color_kernel<D><<<grid, COLOR_THREADS, smem, s>>>(v, means, shs, colors, radii, g, num_slabs);              \
+        color_kernel<D><<<grid, COLOR_THREADS, smem, s>>>(v, means, shs, colors, aux, radii, g, num_slabs);                     \
         break;
     switch (v.deg) {
         GGRT_LAUNCH_COLOR(0)

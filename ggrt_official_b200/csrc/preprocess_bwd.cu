@@ -30,7 +30,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
                            const uint8_t* __restrict__ flags, const float* __restrict__ scratch,
                            float* __restrict__ dmeans2D, float* __restrict__ dopacity, float* __restrict__ dmeans3D,
                            float* __restrict__ dcov3D, float* __restrict__ dsh, float* __restrict__ dcolors,
-                           int num_slabs) {
+                           float* __restrict__ daux, int num_slabs) {
     extern __shared__ __align__(128) float slab_ring[];
     __shared__ __align__(8) unsigned long long full_bar[PB_STAGES];
     __shared__ float sV[16], sM[16];
@@ -65,7 +65,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     uint32_t n_flags = 0;
     float n_mean[3] = {0.f, 0.f, 0.f}, n_cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float4 n_ga = make_float4(0.f, 0.f, 0.f, 0.f), n_gb = n_ga;
-    float n_gc = 0.f;
+    float n_gc = 0.f, n_gx = 0.f;
     auto prefetch = [&](int sl) {
         const int i = sl * PB_THREADS + threadIdx.x;
         n_radius = 0;
@@ -80,6 +80,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             n_ga = *reinterpret_cast<const float4*>(gs);
             n_gb = *reinterpret_cast<const float4*>(gs + 4);
             n_gc = gs[8];
+            if (daux) n_gx = gs[G_AUX];
         }
     };
     prefetch(blockIdx.x);
@@ -103,7 +104,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
 #pragma unroll
     for (int k = 0; k < 6; ++k) cv[k] = n_cv[k];
     const float4 ga = n_ga, gb = n_gb;
-    const float gc = n_gc;
+    const float gc = n_gc, gaux = n_gx;
     prefetch(sl + gridDim.x);
 
     // the CTA's SH slab (staged by TMA, or cooperatively when ragged); it is overwritten in place with dL/dsh
@@ -306,6 +307,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     if (valid) {
         dmeans2D[3 * i] = g2x, dmeans2D[3 * i + 1] = g2y, dmeans2D[3 * i + 2] = 0.f;
         dopacity[i] = gop;
+        if (daux) daux[i] = live ? gaux : 0.f;
 #pragma unroll
         for (int k = 0; k < 3; ++k) dmeans3D[3 * i + k] = dmean[k];
 #pragma unroll
@@ -317,7 +319,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
 
 void launch_preprocess_backward(const View& v, const float* means, const float* cov3d, const float* shs,
                                 const int* radii, GeomPtrs g, const float* scratch, float* dmeans2D, float* dopacity,
-                                float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, cudaStream_t s) {
+                                float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, float* daux, cudaStream_t s) {
     if (v.P == 0) return;
     const size_t smem = shs ? (size_t)PB_STAGES * PB_THREADS * v.K * 3 * sizeof(float) : 0;
     const int num_slabs = (v.P + PB_THREADS - 1) / PB_THREADS;
@@ -329,7 +331,7 @@ void launch_preprocess_backward(const View& v, const float* means, const float* 
     const int per_sm = smem ? max(1, min(8, (int)((220 * 1024) / (smem + 1024)))) : 8;
     const int grid = min(num_slabs, per_sm * sms);  // persistent CTAs
     preprocess_backward_kernel<<<grid, PB_THREADS, smem, s>>>(v, means, cov3d, shs, radii, g.flags, scratch, dmeans2D,
-                                                              dopacity, dmeans3D, dcov3D, dsh, dcolors, num_slabs);
+                                                              dopacity, dmeans3D, dcov3D, dsh, dcolors, daux, num_slabs);
 }
 
 }  // namespace ggrt

@@ -33,17 +33,20 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// AUX: the 4th blended channel (out_depth) also carries an upstream gradient.
+template <bool AUX>
 __global__ void __launch_bounds__(RENDER_THREADS, 3)
 render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __restrict__ rec1,
                        const float4* __restrict__ rec2, const uint32_t* __restrict__ starts,
                        const uint32_t* __restrict__ points, const float* __restrict__ final_T,
                        const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dout,
-                       float* __restrict__ scratch) {
+                       const float* __restrict__ dL_dout_aux, float* __restrict__ scratch) {
     __shared__ __align__(16) unsigned char srec[BWD_BATCH * REC_BYTES];
     __shared__ uint32_t sid[BWD_BATCH];
     __shared__ unsigned short squeue[NWARPS][BWD_BATCH];
     __shared__ float4 spix_g[NWARPS][32];   // per pixel {g_r, g_g, g_b, bits(last)}
     __shared__ float4 spix_s[NWARPS][32];   // per pixel {x, y, T behind, sum behind}
+    __shared__ float spix_a[AUX ? NWARPS : 1][32];  // per pixel gradient of the aux channel
     __shared__ uint32_t block_last_s;
 
     const uint32_t sbase = smem_addr(srec);
@@ -57,7 +60,7 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
     uint32_t last = 0;
     {
         const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
-        float Tfin = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+        float Tfin = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, da = 0.f;
         if (px < v.W && py < v.H) {
             const size_t pix = (size_t)py * v.W + px, hw = (size_t)v.H * v.W;
             Tfin = final_T[pix];
@@ -65,9 +68,11 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
             d0 = dL_dout[pix];
             d1 = dL_dout[hw + pix];
             d2 = dL_dout[2 * hw + pix];
+            if (AUX) da = dL_dout_aux[pix];
         }
         // pixels with a zero upstream gradient contribute nothing (crop training leaves most tiles empty)
-        if (d0 == 0.f && d1 == 0.f && d2 == 0.f) last = 0;
+        if (d0 == 0.f && d1 == 0.f && d2 == 0.f && da == 0.f) last = 0;
+        if (AUX) spix_a[warp][lane] = da;
         const float bg_dot = v.bg[0] * d0 + v.bg[1] * d1 + v.bg[2] * d2;
         spix_g[warp][lane] = make_float4(d0, d1, d2, __uint_as_float(last));
         spix_s[warp][lane] = make_float4((float)px, (float)py, Tfin, Tfin * bg_dot);
@@ -83,6 +88,7 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
 
     const float neg_half_w = -0.5f * (float)v.W, neg_half_h = -0.5f * (float)v.H;
     const uint32_t gaddr = smem_addr(&spix_g[warp][0]), saddr = smem_addr(&spix_s[warp][0]);
+    const float* aux_g = &spix_a[AUX ? warp : 0][0];
 
     const int nb = (int)((block_last + BWD_BATCH - 1) / BWD_BATCH);
     for (int bi = nb - 1; bi >= 0; --bi) {
@@ -130,6 +136,7 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
             // exponent of the Gaussian in base 2 with the -1/2 folded in: G = 2^(ea dx^2 + eb dx dy + ec dy^2)
             const float ea = -0.5f * LOG2E * con.x, eb = -LOG2E * con.y, ec = -0.5f * LOG2E * con.z;
             float a_op = 0.f, a_mx = 0.f, a_my = 0.f, a_A = 0.f, a_B = 0.f, a_C = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f;
+            float a_x = 0.f;  // aux channel
 
             // PIX_UNROLL pixels are processed per iteration: their scans are independent dependency chains
             // that the scheduler interleaves (the kernel is shuffle-latency bound otherwise).
@@ -163,6 +170,7 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
                     alpha[u] = act[u] ? alpha_raw : 0.f;
                     inv_om[u] = rcp_approx(1.0f - alpha[u]);
                     s[u] = fmaf(col.z, pg[u].z, fmaf(col.y, pg[u].y, col.x * pg[u].x));
+                    if (AUX) s[u] = fmaf(col.w, aux_g[p[u]], s[u]);
                     // Going back to front each Gaussian maps the running pair (T, R) to (a T, R + b T) with
                     // a = 1/(1-alpha), b = alpha (c.g)/(1-alpha).  These maps compose associatively, so ONE
                     // warp scan (lane 0 = backmost) yields every lane's transmittance and the sum behind it.
@@ -198,6 +206,7 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
                     a_r = fmaf(w, pg[u].x, a_r);
                     a_g = fmaf(w, pg[u].y, a_g);
                     a_b = fmaf(w, pg[u].z, a_b);
+                    if (AUX) a_x = fmaf(w, aux_g[p[u]], a_x);
                     if (lane == 31 && pv[u]) {  // frontmost lane holds the chunk totals: state behind the next chunk
                         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr + p[u] * 16 + 8), "f"(Ti), "f"(Rtot)
                                      : "memory");
@@ -212,16 +221,22 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
                 red_add_v4(dst + G_MX, gmx * neg_half_w, gmy * neg_half_h, -0.5f * a_A, -0.5f * a_B);
                 red_add_v4(dst + G_CC, -0.5f * a_C, a_op, a_r, a_g);
                 red_add(dst + G_B, a_b);
+                if (AUX) red_add(dst + G_AUX, a_x);
             }
         }
     }
 }
 
-void launch_render_backward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, const float* dL_dout, float* scratch,
-                            cudaStream_t s) {
+void launch_render_backward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, const float* dL_dout,
+                            const float* dL_dout_aux, float* scratch, cudaStream_t s) {
     dim3 grid(v.gx, v.gy);
-    render_backward_kernel<<<grid, RENDER_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points, im.final_T,
-                                                           im.n_contrib, dL_dout, scratch);
+    if (dL_dout_aux)
+        render_backward_kernel<true><<<grid, RENDER_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
+                                                                     im.final_T, im.n_contrib, dL_dout, dL_dout_aux,
+                                                                     scratch);
+    else
+        render_backward_kernel<false><<<grid, RENDER_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
+                                                                      im.final_T, im.n_contrib, dL_dout, nullptr, scratch);
 }
 
 }  // namespace ggrt

@@ -10,7 +10,7 @@ from typing import Optional
 import torch
 from torch import Tensor, nn
 
-from .render import DepthRenderingMode, render_cuda, render_depth_cuda
+from .render import DepthRenderingMode, render_color_and_depth_cuda, render_cuda, render_depth_cuda
 
 
 @dataclass
@@ -33,14 +33,23 @@ def _per_view(t: Tensor, v: int) -> Tensor:
 
 
 class DecoderSplattingCUDA(nn.Module):
-    def __init__(self, background_color=(0.0, 0.0, 0.0)) -> None:
+    def __init__(self, background_color=(0.0, 0.0, 0.0), fused_depth: bool = False) -> None:
+        """fused_depth: render colour and depth in one rasterization (same outputs as the reference's two
+        passes; roughly half the rasterizer work when a depth mode is requested)."""
         super().__init__()
         self.background_color = torch.tensor(background_color, dtype=torch.float32)
+        self.fused_depth = fused_depth
 
     def forward(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
                 image_shape: tuple, depth_mode: Optional[DepthRenderingMode] = None) -> DecoderOutput:
         b, v = extrinsics.shape[:2]
         bg = self.background_color.to(far.device)[None].expand(b * v, 3)
+        if self.fused_depth and depth_mode is not None:
+            color, depth = render_color_and_depth_cuda(
+                extrinsics.flatten(0, 1), intrinsics.flatten(0, 1), near.flatten(), far.flatten(), image_shape, bg,
+                _per_view(gaussians.means, v), _per_view(gaussians.covariances, v), _per_view(gaussians.harmonics, v),
+                _per_view(gaussians.opacities, v), mode=depth_mode)
+            return DecoderOutput(color.unflatten(0, (b, v)), depth.unflatten(0, (b, v)))
         color = render_cuda(extrinsics.flatten(0, 1), intrinsics.flatten(0, 1), near.flatten(), far.flatten(),
                             image_shape, bg, _per_view(gaussians.means, v), _per_view(gaussians.covariances, v),
                             _per_view(gaussians.harmonics, v), _per_view(gaussians.opacities, v))

@@ -67,7 +67,8 @@ def _ptr(t: Optional[torch.Tensor]):
 class _Call:
     """Validated, contiguous inputs + the C settings struct for one rasterization."""
 
-    def __init__(self, means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: GaussianRasterizationSettings):
+    def __init__(self, means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: GaussianRasterizationSettings,
+                 aux=None):
         if not means3D.is_cuda:
             raise RuntimeError("means3D must be a CUDA tensor: the rasterizer has no CPU path")
         dev = means3D.device
@@ -78,6 +79,11 @@ class _Call:
         self.colors = _f32c(colors_precomp, "colors_precomp", dev)
         self.opacities = _f32c(opacities, "opacities", dev).reshape(-1)
         self.cov3D = _f32c(cov3D_precomp, "cov3D_precomp", dev)
+        self.aux = _f32c(aux, "aux_precomp", dev)
+        if self.aux is not None:
+            self.aux = self.aux.reshape(-1)
+            if self.aux.numel() != self.P:
+                raise ValueError(f"aux_precomp must have P={self.P} elements, got {self.aux.numel()}")
         self.H, self.W = int(rs.image_height), int(rs.image_width)
         self.deg = int(rs.sh_degree)
         K = (self.deg + 1) ** 2
@@ -111,10 +117,12 @@ class _Call:
         self.settings = s
 
 
-def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: GaussianRasterizationSettings) -> dict:
-    """Runs the forward through the C ABI and returns outputs plus the opaque state buffers."""
+def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: GaussianRasterizationSettings,
+                aux=None) -> dict:
+    """Runs the forward through the C ABI and returns outputs plus the opaque state buffers.
+    `aux` [P]: optional extra per-Gaussian channel blended into the third output instead of the view depth."""
     L = _cabi.lib()
-    c = _Call(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs)
+    c = _Call(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs, aux)
     dev = c.device
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev)
@@ -127,8 +135,9 @@ def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: Gauss
         depth = torch.empty((c.H, c.W), dtype=torch.float32, device=dev)
         counts = _pinned_counts()
         _cabi.check(L.ggrt_raster_forward_prepare(C.byref(c.settings), c.P, _ptr(c.means3D), _ptr(c.cov3D),
-                                                  _ptr(c.opacities), _ptr(c.sh), _ptr(c.colors), _ptr(radii),
-                                                  _ptr(geom), _ptr(img), C.c_void_p(counts.data_ptr()), sp),
+                                                  _ptr(c.opacities), _ptr(c.sh), _ptr(c.colors), _ptr(c.aux),
+                                                  _ptr(radii), _ptr(geom), _ptr(img),
+                                                  C.c_void_p(counts.data_ptr()), sp),
                     "forward_prepare")
         # N sizes the caller-owned pair buffer; the colour kernel keeps the GPU busy while we wait
         ev = torch.cuda.Event()
@@ -143,9 +152,11 @@ def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: Gauss
                 max_tile_pairs=max_pairs)
 
 
-def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = None) -> dict:
+def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = None,
+                 grad_aux: Optional[torch.Tensor] = None) -> dict:
     """Runs the backward through the C ABI.  `out` may supply preallocated, contiguous float32 output
-    tensors (e.g. views into one gradient arena that is all-reduced across GPUs afterwards)."""
+    tensors (e.g. views into one gradient arena that is all-reduced across GPUs afterwards).
+    `grad_aux` [H,W]: gradient of the third output (only when the forward was given `aux`)."""
     L = _cabi.lib()
     c: _Call = state["call"]
     dev = c.device
@@ -153,6 +164,9 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
         stream = torch.cuda.current_stream(dev)
         sp = C.c_void_p(stream.cuda_stream)
         g = _f32c(grad_color, "grad_color", dev)
+        ga = _f32c(grad_aux, "grad_aux", dev)
+        if ga is not None and c.aux is None:
+            raise RuntimeError("the third output is only differentiable when aux_precomp was given")
         f32 = dict(dtype=torch.float32, device=dev)
         scratch = torch.empty((c.P, 12), **f32)
         given = out or {}
@@ -172,12 +186,14 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
             dcov3D=buf("dcov3D", (c.P, 6)),
             dsh=buf("dsh", tuple(c.sh.shape)) if c.sh is not None else None,
             dcolors=buf("dcolors", (c.P, 3)) if c.sh is None else None,
+            daux=buf("daux", (c.P,)) if ga is not None else None,
         )
         _cabi.check(L.ggrt_raster_backward(C.byref(c.settings), c.P, state["N"], _ptr(c.means3D), _ptr(c.cov3D),
                                            _ptr(c.sh), _ptr(state["radii"]), _ptr(state["geom"]),
-                                           _ptr(state["binning"]), _ptr(state["img"]), _ptr(g), _ptr(scratch),
-                                           _ptr(out["dmeans2D"]), _ptr(out["dopacity"]), _ptr(out["dmeans3D"]),
-                                           _ptr(out["dcov3D"]), _ptr(out["dsh"]), _ptr(out["dcolors"]), sp),
+                                           _ptr(state["binning"]), _ptr(state["img"]), _ptr(g), _ptr(ga),
+                                           _ptr(scratch), _ptr(out["dmeans2D"]), _ptr(out["dopacity"]),
+                                           _ptr(out["dmeans3D"]), _ptr(out["dcov3D"]), _ptr(out["dsh"]),
+                                           _ptr(out["dcolors"]), _ptr(out["daux"]), sp),
                     "backward")
     return out
 
@@ -193,9 +209,9 @@ def _dump(path: str, payload) -> None:
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings):
+                raster_settings, aux=None):
         try:
-            st = forward_raw(means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings)
+            st = forward_raw(means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings, aux)
         except Exception:
             if raster_settings.debug:
                 _dump("snapshot_fw.dump", (means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings))
@@ -206,7 +222,12 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.raster_settings = raster_settings
         ctx.sh_shape = None if sh is None else tuple(sh.shape)
         ctx.opacity_shape = tuple(opacities.shape)
-        ctx.mark_non_differentiable(st["radii"], st["depth"])
+        ctx.has_aux = aux is not None
+        ctx.aux_shape = None if aux is None else tuple(aux.shape)
+        if ctx.has_aux:  # the third output blends the caller's channel and is differentiable
+            ctx.mark_non_differentiable(st["radii"])
+        else:
+            ctx.mark_non_differentiable(st["radii"], st["depth"])
         ctx.set_materialize_grads(False)
         return st["color"], st["radii"], st["depth"]
 
@@ -214,10 +235,13 @@ class _RasterizeGaussians(torch.autograd.Function):
     def backward(ctx, grad_color, _grad_radii=None, _grad_depth=None):
         st = ctx.state
         c: _Call = st["call"]
+        grad_aux = _grad_depth if ctx.has_aux else None
+        if grad_color is None and grad_aux is None:
+            return (None,) * 10
         if grad_color is None:
-            return (None,) * 9
+            grad_color = torch.zeros((3, c.H, c.W), dtype=torch.float32, device=c.device)
         try:
-            g = backward_raw(st, grad_color)
+            g = backward_raw(st, grad_color, grad_aux=grad_aux)
         except Exception:
             if ctx.raster_settings.debug:
                 _dump("snapshot_bw.dump", (c.means3D, c.sh, c.colors, c.opacities, c.cov3D, grad_color))
@@ -227,14 +251,17 @@ class _RasterizeGaussians(torch.autograd.Function):
             full = torch.zeros(ctx.sh_shape, dtype=dsh.dtype, device=dsh.device)
             full[:, : dsh.shape[1]] = dsh
             dsh = full
+        daux = g.get("daux")
+        if daux is not None:
+            daux = daux.reshape(ctx.aux_shape)
         return (g["dmeans3D"], g["dmeans2D"], dsh, g["dcolors"], g["dopacity"].reshape(ctx.opacity_shape), None, None,
-                g["dcov3D"], None)
+                g["dcov3D"], None, daux)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings):
+                        raster_settings, aux_precomp=None):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings)
+                                     cov3Ds_precomp, raster_settings, aux_precomp)
 
 
 class GaussianRasterizer(nn.Module):
@@ -259,7 +286,10 @@ class GaussianRasterizer(nn.Module):
         return out.bool()
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None):
+                cov3D_precomp=None, aux_precomp=None):
+        """Same keywords as upstream, plus the extension `aux_precomp` [P] or [P,1]: an extra per-Gaussian scalar
+        that is alpha-blended with the colour's weights into the third output (differentiable).  Without it the
+        third output is the blended view-space depth (not differentiable).  GGRt never passes it."""
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
             raise Exception("Please provide excatly one of either SHs or precomputed colors!")
         if ((scales is None or rotations is None) and cov3D_precomp is None) or (
@@ -269,4 +299,4 @@ class GaussianRasterizer(nn.Module):
             raise NotImplementedError(
                 "scales/rotations are not supported: GGRt always passes cov3D_precomp (cuda_splatting.py:124)")
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                   self.raster_settings)
+                                   self.raster_settings, aux_precomp)

@@ -53,8 +53,9 @@ def get_projection_matrix(near: Tensor, far: Tensor, fov_x: Tensor, fov_y: Tenso
 def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple,
                 background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
                 gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor, scale_invariant: bool = True,
-                use_sh: bool = True, return_aux: bool = False):
-    """[b] views of [b,g] Gaussians -> [b,3,h,w].  With return_aux also the per-view radii and depth maps."""
+                use_sh: bool = True, return_aux: bool = False, gaussian_aux: Optional[Tensor] = None):
+    """[b] views of [b,g] Gaussians -> [b,3,h,w].  With return_aux also the per-view radii and the third
+    output: the alpha-blended `gaussian_aux` [b,g] channel when given (differentiable), else the view depth."""
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
     if scale_invariant:  # everything rescaled so that near == 1 (cuda_splatting.py:66-73)
         scale = 1 / near
@@ -89,7 +90,8 @@ def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tenso
         image, radii, depth = GaussianRasterizer(settings)(
             means3D=gaussian_means[i], means2D=mean_gradients, shs=shs[i] if use_sh else None,
             colors_precomp=None if use_sh else shs[i, :, 0, :], opacities=gaussian_opacities[i, ..., None],
-            cov3D_precomp=gaussian_covariances[i, :, row, col])
+            cov3D_precomp=gaussian_covariances[i, :, row, col],
+            aux_precomp=None if gaussian_aux is None else gaussian_aux[i])
         images.append(image)
         radii_all.append(radii)
         depths.append(depth)
@@ -105,6 +107,39 @@ def depth_to_relative_disparity(depth: Tensor, near: Tensor, far: Tensor, eps: f
     disp_far = 1 / (far + eps)
     disp = 1 / (depth + eps)
     return 1 - (disp - disp_far) / (disp_near - disp_far + eps)
+
+
+SH_C0 = 0.28209479177387814
+
+
+def depth_channel(extrinsics: Tensor, gaussian_means: Tensor, near: Tensor, far: Tensor,
+                  mode: DepthRenderingMode = "depth") -> Tensor:
+    """The per-Gaussian value GGRt's depth pass blends: camera-space z (or its disparity / log variants,
+    cuda_splatting.py:240-252) pushed through the degree-0 SH colour path, max(0, C0*z + 0.5)."""
+    hom = torch.cat([gaussian_means, torch.ones_like(gaussian_means[..., :1])], dim=-1)
+    fake = torch.einsum("bij,bgj->bgi", extrinsics.inverse(), hom)[..., 2]
+    if mode == "disparity":
+        fake = 1 / fake
+    elif mode == "relative_disparity":
+        fake = depth_to_relative_disparity(fake, near[:, None], far[:, None])
+    elif mode == "log":
+        fake = fake.minimum(near[:, None]).maximum(far[:, None]).log()
+    return (SH_C0 * fake + 0.5).clamp(min=0.0)
+
+
+def render_color_and_depth_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple,
+                                background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
+                                gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor,
+                                scale_invariant: bool = True, mode: DepthRenderingMode = "depth"):
+    """render_cuda + render_depth_cuda in ONE rasterization: the depth pass blends a
+    per-Gaussian scalar with exactly the colour pass's geometry and weights, so it rides along as the
+    rasterizer's aux channel instead of costing a second preprocess + binning + render.
+    Returns (color [b,3,h,w], depth [b,h,w]) equal to the two reference calls."""
+    aux = depth_channel(extrinsics, gaussian_means, near, far, mode)
+    color, _, depth = render_cuda(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means,
+                                  gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities,
+                                  scale_invariant=scale_invariant, return_aux=True, gaussian_aux=aux)
+    return color, depth
 
 
 def render_depth_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple,

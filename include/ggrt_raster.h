@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GGRT_RASTER_ABI_VERSION 1
+#define GGRT_RASTER_ABI_VERSION 2
 #define GGRT_RASTER_TILE 16 /* tile edge in pixels (tile ids are part of the contract) */
 #define GGRT_RASTER_SUBS 16 /* pair counters per tile (contention spreading) */
 
@@ -66,9 +66,9 @@ typedef struct GgrtRasterSettings {
 /* Byte offsets of the sub-arrays inside the caller-owned buffers (for tests / tools). */
 typedef struct GgrtRasterLayout {
     /* geometry buffer, per Gaussian */
-    size_t geom_rec0;   /* float4[P]  {pix_x, pix_y, cull threshold tau, 0} */
+    size_t geom_rec0;   /* float4[P]  {pix_x, pix_y, cull threshold tau, view_depth} */
     size_t geom_rec1;   /* float4[P]  {conic_A, conic_B, conic_C, opacity} */
-    size_t geom_rec2;   /* float4[P]  {r, g, b, view_depth} */
+    size_t geom_rec2;   /* float4[P]  {r, g, b, aux} (aux = caller's 4th channel, default view_depth) */
     size_t geom_rect;   /* uint16x4[P] {tile_x0, tile_y0, tile_x1, tile_y1} */
     size_t geom_tiles;  /* uint32[P]  tiles touched */
     size_t geom_flags;  /* uint8[P]   bit c: colour channel c was clamped at 0 */
@@ -102,36 +102,42 @@ size_t ggrt_raster_binning_bytes(int64_t num_rendered);
 /*
  * Forward, phase 1.  Exactly one of shs [P,K,3] / colors_precomp [P,3] is non-NULL
  * (K = (sh_degree+1)^2).  cov3D_precomp is [P,6] = (xx,xy,xz,yy,yz,zz).  opacities [P].
+ * aux [P] (may be NULL) is an extra per-Gaussian scalar that is alpha-blended with the same
+ * weights as the colour into out_depth (NULL: the view-space depth is used).  GGRt's depth pass
+ * (cuda_splatting.py:227-269) is such a channel, so colour and depth can share one rasterization.
  * Writes radii [P] (int32; 0 = culled), fills geom_buffer and the tile tables of
  * image_buffer, then enqueues a copy of {N, max pairs per tile} to counts_host
  * (2 x uint32 of pinned host memory; may be NULL if the caller reads img_header itself).
  */
 int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, int32_t P, const float* means3D,
                                 const float* cov3D_precomp, const float* opacities, const float* shs,
-                                const float* colors_precomp, int32_t* radii, void* geom_buffer, void* image_buffer,
-                                uint32_t* counts_host, ggrt_stream_t stream);
+                                const float* colors_precomp, const float* aux, int32_t* radii, void* geom_buffer,
+                                void* image_buffer, uint32_t* counts_host, ggrt_stream_t stream);
 
 /*
  * Forward, phase 2.  num_rendered / max_tile_pairs are the two values `prepare`
  * reported; binning_buffer holds ggrt_raster_binning_bytes(num_rendered) bytes.
- * Writes out_color [3,H,W], out_depth [H,W] (sum of view depth * alpha * T, no
- * background, no normalisation) and the per-pixel state needed by backward.
+ * Writes out_color [3,H,W], out_depth [H,W] (sum of aux * alpha * T -- view depth unless aux
+ * was given -- no background, no normalisation) and the per-pixel state needed by backward.
  */
 int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, int64_t num_rendered,
                                uint32_t max_tile_pairs, const void* geom_buffer, void* binning_buffer,
                                void* image_buffer, float* out_color, float* out_depth, ggrt_stream_t stream);
 
 /*
- * Backward.  dL_dout_color [3,H,W].  grad_scratch is [P,12] float32 scratch (zeroed
+ * Backward.  dL_dout_color [3,H,W]; dL_dout_aux [H,W] or NULL (gradient of out_depth; only
+ * meaningful when aux was given to prepare).  grad_scratch is [P,12] float32 scratch (zeroed
  * by the callee).  Outputs, all overwritten: dL_dmeans2D [P,3] (gradient w.r.t. NDC
- * xy, z = 0), dL_dopacity [P], dL_dmeans3D [P,3], dL_dcov3D [P,6], and either
- * dL_dsh [P,K,3] (when shs was given) or dL_dcolors [P,3]; the unused one is NULL.
+ * xy, z = 0), dL_dopacity [P], dL_dmeans3D [P,3], dL_dcov3D [P,6], either dL_dsh [P,K,3]
+ * (when shs was given) or dL_dcolors [P,3] (the unused one is NULL), and dL_daux [P] (NULL
+ * unless dL_dout_aux is given).
  */
 int ggrt_raster_backward(const GgrtRasterSettings* settings, int32_t P, int64_t num_rendered, const float* means3D,
                          const float* cov3D_precomp, const float* shs, const int32_t* radii, const void* geom_buffer,
                          const void* binning_buffer, const void* image_buffer, const float* dL_dout_color,
-                         float* grad_scratch, float* dL_dmeans2D, float* dL_dopacity, float* dL_dmeans3D,
-                         float* dL_dcov3D, float* dL_dsh, float* dL_dcolors, ggrt_stream_t stream);
+                         const float* dL_dout_aux, float* grad_scratch, float* dL_dmeans2D, float* dL_dopacity,
+                         float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dcolors, float* dL_daux,
+                         ggrt_stream_t stream);
 
 /* Frustum test only (upstream markVisible): present[i] = view-space z > 0.2. */
 int ggrt_raster_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present,

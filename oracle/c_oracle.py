@@ -140,8 +140,10 @@ def bin_tiles(cam: Camera, pre: dict) -> dict:
     return dict(N=N, offsets=offsets, keys=keys[:N], point_list=vals[:N], ranges=ranges)
 
 
-def render_forward(cam: Camera, pre: dict, binning: dict) -> dict:
+def render_forward(cam: Camera, pre: dict, binning: dict, aux=None) -> dict:
+    """aux [P]: optional 4th blended channel (default: the view depth)."""
     L = lib()
+    chan = pre["depth"] if aux is None else _f32(aux).reshape(-1)
     P = pre["depth"].shape[0]
     H, W = cam.H, cam.W
     out = dict(
@@ -154,17 +156,18 @@ def render_forward(cam: Camera, pre: dict, binning: dict) -> dict:
     pl = binning["point_list"] if binning["N"] > 0 else np.zeros(1, np.uint32)
     cc = cam.c(P)
     L.oracle_render_forward(C.byref(cc), _p(binning["ranges"]), _p(pl), _p(pre["xy"]), _p(pre["conic_opacity"]),
-                            _p(pre["rgb"]), _p(pre["depth"]), _p(out["color"]), _p(out["depth"]), _p(out["final_T"]),
+                            _p(pre["rgb"]), _p(chan), _p(out["color"]), _p(out["depth"]), _p(out["final_T"]),
                             _p(out["n_contrib"]), _p(out["fragile"]))
     return out
 
 
-def forward(cam: Camera, means, cov3d, opacities, sh=None, colors=None) -> dict:
+def forward(cam: Camera, means, cov3d, opacities, sh=None, colors=None, aux=None) -> dict:
     """Whole forward: returns a dict with pre / bin / img sub-dicts plus color, depth, radii."""
     pre = preprocess(cam, means, cov3d, opacities, sh=sh, colors=colors)
     b = bin_tiles(cam, pre)
-    img = render_forward(cam, pre, b)
-    return dict(pre=pre, bin=b, img=img, color=img["color"], depth=img["depth"], radii=pre["radii"])
+    img = render_forward(cam, pre, b, aux=aux)
+    return dict(pre=pre, bin=b, img=img, color=img["color"], depth=img["depth"], radii=pre["radii"],
+                aux=None if aux is None else _f32(aux).reshape(-1))
 
 
 def backward(cam: Camera, means, cov3d, opacities, fwd: dict, dL_dcolor_img, sh=None, colors=None,
@@ -187,16 +190,20 @@ def backward(cam: Camera, means, cov3d, opacities, fwd: dict, dL_dcolor_img, sh=
     )
     pl = b["point_list"] if b["N"] > 0 else np.zeros(1, np.uint32)
     cc = cam.c(P)
+    aux = fwd.get("aux")
+    chan = pre["depth"] if aux is None else aux
     L.oracle_render_backward(C.byref(cc), _p(b["ranges"]), _p(pl), _p(pre["xy"]), _p(pre["conic_opacity"]),
-                             _p(pre["rgb"]), _p(pre["depth"]), _p(img["final_T"]), _p(img["n_contrib"]), _p(dimg),
+                             _p(pre["rgb"]), _p(chan), _p(img["final_T"]), _p(img["n_contrib"]), _p(dimg),
                              _p(ddep), _p(g["dmean2D"]), _p(g["dconic"]), _p(g["dopacity"]), _p(g["dcolor"]),
                              _p(g["ddepth"]))
     g["dmeans3D"] = np.zeros((P, 3), np.float32)
     g["dcov3D"] = np.zeros((P, 6), np.float32)
     g["dsh"] = np.zeros((P, K, 3), np.float32) if sh is not None else None
     L.oracle_preprocess_backward(C.byref(cc), _p(means), _p(cov3d), _p(sh), _p(pre["radii"]), _p(pre["clamped"]),
-                                 _p(g["dmean2D"]), _p(g["dconic"]), _p(g["dcolor"]), _p(g["ddepth"]),
+                                 _p(g["dmean2D"]), _p(g["dconic"]), _p(g["dcolor"]),
+                                 _p(g["ddepth"]) if aux is None else None,  # a caller-supplied channel is a leaf
                                  _p(g["dmeans3D"]), _p(g["dcov3D"]), _p(g["dsh"]))
+    g["daux"] = g["ddepth"] if aux is not None else None
     return g
 
 

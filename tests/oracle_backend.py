@@ -27,9 +27,9 @@ def _camera(rs, deg):
                      campos=_np(rs.campos), bg=_np(rs.bg), deg=deg)
 
 
-def fake_forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs):
+def fake_forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs, aux=None):
     CALLS.append(dict(means3D=means3D, sh=sh, colors_precomp=colors_precomp, opacities=opacities,
-                      cov3D_precomp=cov3D_precomp, settings=rs))
+                      cov3D_precomp=cov3D_precomp, settings=rs, aux=aux))
     deg = int(rs.sh_degree)
     cam = _camera(rs, deg)
     shn = _np(sh)
@@ -37,24 +37,28 @@ def fake_forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs):
         shn = np.ascontiguousarray(shn[:, : (deg + 1) ** 2, :])
     inp = dict(means=_np(means3D), cov=_np(cov3D_precomp), opac=_np(opacities).reshape(-1), sh=shn,
                colors=_np(colors_precomp))
-    f = co.forward(cam, inp["means"], inp["cov"], inp["opac"], sh=inp["sh"], colors=inp["colors"])
+    auxn = None if aux is None else _np(aux).reshape(-1)
+    f = co.forward(cam, inp["means"], inp["cov"], inp["opac"], sh=inp["sh"], colors=inp["colors"], aux=auxn)
     call = SimpleNamespace(means3D=means3D, sh=sh, colors=colors_precomp, opacities=opacities, cov3D=cov3D_precomp,
-                           P=inp["means"].shape[0])
+                           P=inp["means"].shape[0], aux=aux, H=int(rs.image_height), W=int(rs.image_width),
+                           device=means3D.device)
     return dict(call=call, color=torch.from_numpy(f["color"].copy()), depth=torch.from_numpy(f["depth"].copy()),
                 radii=torch.from_numpy(f["radii"].copy()), geom=None, img=None, binning=None, N=f["bin"]["N"],
                 max_tile_pairs=0, _oracle=(cam, inp, f))
 
 
-def fake_backward_raw(state, grad_color):
+def fake_backward_raw(state, grad_color, out=None, grad_aux=None):
     cam, inp, f = state["_oracle"]
-    g = co.backward(cam, inp["means"], inp["cov"], inp["opac"], f, _np(grad_color), sh=inp["sh"], colors=inp["colors"])
+    g = co.backward(cam, inp["means"], inp["cov"], inp["opac"], f, _np(grad_color), sh=inp["sh"], colors=inp["colors"],
+                    dL_ddepth_img=_np(grad_aux))
     P = inp["means"].shape[0]
     t = torch.from_numpy
     d2 = np.zeros((P, 3), np.float32)
     d2[:, :2] = g["dmean2D"]
     return dict(dmeans2D=t(d2), dopacity=t(g["dopacity"].reshape(P, 1).copy()), dmeans3D=t(g["dmeans3D"]),
                 dcov3D=t(g["dcov3D"]), dsh=None if g["dsh"] is None else t(g["dsh"]),
-                dcolors=None if inp["colors"] is None else t(g["dcolor"]))
+                dcolors=None if inp["colors"] is None else t(g["dcolor"]),
+                daux=None if g.get("daux") is None else t(g["daux"]))
 
 
 @contextlib.contextmanager
@@ -64,9 +68,10 @@ def installed():
     R.forward_raw, R.backward_raw = fake_forward_raw, fake_backward_raw
     orig_fwd = R._RasterizeGaussians.forward
 
-    def fwd(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+    def fwd(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings,
+            aux=None):
         out = orig_fwd(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                       raster_settings)
+                       raster_settings, aux)
         ctx.state["_oracle"] = CALLS_STATE.pop()
         return out
 

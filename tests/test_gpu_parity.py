@@ -87,6 +87,34 @@ def test_colors_precomp_path():
         assert e["max_rel"] < 1e-3 and e["nonfinite"] == 0, (k, e)
 
 
+def test_aux_channel_forward_and_backward():
+    """The optional 4th blended channel (used to fuse GGRt's depth pass into the colour pass)."""
+    P, H, W = 2500, 80, 96
+    _, ri = small_case(P, H, W, 4, bg=(0.1, 0.3, 0.2), seed=21, cov_scale=6.0)
+    dev = "cuda:0"
+    rng = np.random.default_rng(4)
+    aux = rng.uniform(0.0, 3.0, P).astype(np.float32)
+    t = lambda a: torch.tensor(np.asarray(a), device=dev)
+    st = R.forward_raw(t(ri.means3D), t(ri.shs), None, t(ri.opacities), t(ri.cov3D), G.settings_from(ri, dev), aux=t(aux))
+    cam = oracle_camera(ri)
+    f = co.forward(cam, ri.means3D, ri.cov3D, ri.opacities, sh=ri.shs, aux=aux)
+    ok = f["img"]["fragile"] == 0
+    assert np.abs(st["depth"].cpu().numpy() - f["depth"])[ok].max() < 1e-4
+    assert np.abs(st["color"].cpu().numpy() - f["color"])[:, ok].max() < 1e-4
+    g = rng.standard_normal((3, H, W)).astype(np.float32)
+    ga = rng.standard_normal((H, W)).astype(np.float32)
+    got = R.backward_raw(st, t(g), grad_aux=t(ga))
+    ref = co.backward(cam, ri.means3D, ri.cov3D, ri.opacities, f, g, sh=ri.shs, dL_ddepth_img=ga)
+    errs = G.grad_errors(got, ref)
+    a, b = got["daux"].cpu().numpy().astype(np.float64), ref["daux"].astype(np.float64)
+    errs["daux"] = dict(max_rel=float(np.abs(a - b).max() / np.abs(b).max()), nonfinite=int((~np.isfinite(a)).sum()))
+    for k, e in errs.items():
+        assert e["nonfinite"] == 0 and e["max_rel"] < 1e-3, (k, errs)
+    with pytest.raises(RuntimeError, match="aux_precomp"):
+        st2 = R.forward_raw(t(ri.means3D), t(ri.shs), None, t(ri.opacities), t(ri.cov3D), G.settings_from(ri, dev))
+        R.backward_raw(st2, t(g), grad_aux=t(ga))
+
+
 def test_config1_10k_256(tmp_path):
     """BASELINE config 1: 10K Gaussians, 256x256, 1 view, forward vs the oracle."""
     ri = to_raster_inputs(make_scene(10_000, 256, 256, sh_degree=4))
