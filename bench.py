@@ -303,15 +303,36 @@ def run_ours(args, rank, world, local_rank):
     d2h = h_img.numel() * 4 + 4
     rasterizer = GaussianRasterizer(rs)
 
-    # device staging tensors are allocated once (as a training loop would) and refilled every step
-    d_in = [torch.empty_like(x, device=dev).requires_grad_() for x in (h_means, h_cov, h_opac, h_shs)]
+    # Two sets of device staging tensors, allocated once: the H2D copy of step i+1's inputs is issued on a copy
+    # stream while step i computes (the usual input prefetch of a training loop).  Every step still copies its
+    # own 102 MB from pinned host memory and reads its image + loss back, all inside the timed region.
+    d_sets = [[torch.empty_like(x, device=dev).requires_grad_() for x in (h_means, h_cov, h_opac, h_shs)]
+              for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    filled = [torch.cuda.Event(), torch.cuda.Event()]   # set k holds fresh inputs
+    free = [torch.cuda.Event(), torch.cuda.Event()]     # the step that used set k has finished with it
+    main = torch.cuda.current_stream(dev)
+    e2e_state = {"i": 0}
+
+    def prefetch(k):
+        copy_stream.wait_event(free[k])
+        with torch.cuda.stream(copy_stream), torch.no_grad():
+            for d_, h_ in zip(d_sets[k], (h_means, h_cov, h_opac, h_shs)):
+                d_.copy_(h_, non_blocking=True)
+        filled[k].record(copy_stream)
+
+    for k in range(2):
+        free[k].record(main)
+    prefetch(0)
 
     def e2e_step():
-        with torch.no_grad():
-            for d_, h_ in zip(d_in, (h_means, h_cov, h_opac, h_shs)):
-                d_.copy_(h_, non_blocking=True)
-                d_.grad = None
-        m, c, o, s = d_in
+        k = e2e_state["i"] & 1
+        e2e_state["i"] += 1
+        prefetch(k ^ 1)              # next step's inputs, overlapped with this step's kernels
+        main.wait_event(filled[k])
+        m, c, o, s = d_sets[k]
+        for d_ in d_sets[k]:
+            d_.grad = None
         m2 = torch.zeros_like(m, requires_grad=True)
         image, radii, _ = rasterizer(means3D=m, means2D=m2, shs=s, colors_precomp=None, opacities=o, cov3D_precomp=c)
         loss = (image * grad_img).sum()
@@ -319,6 +340,7 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             for p_ in (m, c, o, s):
                 dist.all_reduce(p_.grad)
+        free[k].record(main)
         h_img.copy_(image.detach(), non_blocking=True)
         h_loss.copy_(loss.detach(), non_blocking=True)
 
