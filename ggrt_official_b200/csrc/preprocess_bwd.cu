@@ -24,6 +24,7 @@ constexpr int PB_THREADS = GGRT_PB_THREADS;
 
 constexpr int PB_STAGES = GGRT_PB_STAGES;
 
+template <bool AUX>
 __global__ void __launch_bounds__(PB_THREADS, 3)
 preprocess_backward_kernel(View v, const float* __restrict__ means, const float* __restrict__ cov3d,
                            const float* __restrict__ shs, const int* __restrict__ radii,
@@ -80,7 +81,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             n_ga = *reinterpret_cast<const float4*>(gs);
             n_gb = *reinterpret_cast<const float4*>(gs + 4);
             n_gc = gs[8];
-            if (daux) n_gx = gs[G_AUX];
+            if (AUX) n_gx = gs[G_AUX];
         }
     };
     prefetch(blockIdx.x);
@@ -307,7 +308,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     if (valid) {
         dmeans2D[3 * i] = g2x, dmeans2D[3 * i + 1] = g2y, dmeans2D[3 * i + 2] = 0.f;
         dopacity[i] = gop;
-        if (daux) daux[i] = live ? gaux : 0.f;
+        if (AUX) daux[i] = live ? gaux : 0.f;
 #pragma unroll
         for (int k = 0; k < 3; ++k) dmeans3D[3 * i + k] = dmean[k];
 #pragma unroll
@@ -326,12 +327,18 @@ void launch_preprocess_backward(const View& v, const float* means, const float* 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (smem > 32 * 1024)
-        cudaFuncSetAttribute(preprocess_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 32 * 1024) {
+        cudaFuncSetAttribute(preprocess_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(preprocess_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
     const int per_sm = smem ? max(1, min(8, (int)((220 * 1024) / (smem + 1024)))) : 8;
     const int grid = min(num_slabs, per_sm * sms);  // persistent CTAs
-    preprocess_backward_kernel<<<grid, PB_THREADS, smem, s>>>(v, means, cov3d, shs, radii, g.flags, scratch, dmeans2D,
-                                                              dopacity, dmeans3D, dcov3D, dsh, dcolors, daux, num_slabs);
+    if (daux)
+        preprocess_backward_kernel<true><<<grid, PB_THREADS, smem, s>>>(
+            v, means, cov3d, shs, radii, g.flags, scratch, dmeans2D, dopacity, dmeans3D, dcov3D, dsh, dcolors, daux, num_slabs);
+    else
+        preprocess_backward_kernel<false><<<grid, PB_THREADS, smem, s>>>(
+            v, means, cov3d, shs, radii, g.flags, scratch, dmeans2D, dopacity, dmeans3D, dcov3D, dsh, dcolors, daux, num_slabs);
 }
 
 }  // namespace ggrt
