@@ -4,26 +4,38 @@
 //
 // Work decomposition ("Gaussian-parallel"): one CTA per 16x16 tile, warp w owns the 8x4
 // pixel block (w&1, w>>1) as in the forward.  A batch of up to 512 Gaussian records is
-// staged into shared memory; each warp culls it against its pixel block (bounding box of
-// {alpha >= 1/255}) into a back-to-front queue and then processes the queue 32 Gaussians
-// at a time with LANES = GAUSSIANS: for every pixel of the block the 32 lanes evaluate
-// their Gaussian's alpha, a warp prefix product of (1-alpha) recovers each Gaussian's
-// transmittance T_i from the transmittance behind the chunk, and a warp prefix sum gives
-// the colour accumulated behind it.  Every lane accumulates the 9 partial gradients of ITS
-// Gaussian over the block's pixels in registers, so there is no per-Gaussian cross-lane
-// reduction (the upstream bottleneck) -- one set of global RED.ADD.F32 per lane per chunk.
+// staged into shared memory; each warp culls it against its pixel block (exact ellipse vs
+// rectangle test on {alpha >= 1/255}) into a back-to-front queue and then consumes the queue
+// GL = 8 Gaussians at a time with LANES = (pixel slot, Gaussian slot): per step the warp
+// evaluates 8 Gaussians at 4 pixels, a segmented warp scan over the associative maps
+// (T, R) -> (aT, R + bT) recovers each Gaussian's transmittance T_i and the colour
+// accumulated behind it, and every lane accumulates the 9 partial gradients of ITS Gaussian
+// in registers.  There is no per-Gaussian reduction over 32 pixel lanes (the upstream
+// bottleneck): the 4 pixel-slot partials are folded once per chunk and committed with
+// vector RED.ADD.F32 (2 x v4 + 1 scalar per Gaussian per warp).
 //   dL/dalpha_i = T_i (c_i . g) - [ sum_{j behind i} w_j (c_j . g) + T_final (bg . g) ] / (1 - alpha_i)
 // Per-pixel running state {T behind, sum behind} lives in shared memory between chunks.
 #include "render_common.cuh"
 
 namespace ggrt {
 
-constexpr int BWD_BATCH = 512;
+#ifndef GGRT_BWD_BATCH
+#define GGRT_BWD_BATCH 512
+#endif
+#ifndef GGRT_BWD_MINBLOCKS
+#define GGRT_BWD_MINBLOCKS 4
+#endif
+constexpr int BWD_BATCH = GGRT_BWD_BATCH;
 constexpr int NWARPS = RENDER_THREADS / 32;
 #ifndef GGRT_BWD_PIX_UNROLL
 #define GGRT_BWD_PIX_UNROLL 2
 #endif
 constexpr int PIX_UNROLL = GGRT_BWD_PIX_UNROLL;
+#ifndef GGRT_BWD_GL
+#define GGRT_BWD_GL 8
+#endif
+constexpr int GL = GGRT_BWD_GL;   // Gaussians per warp step (power of two <= 32)
+constexpr int PL = 32 / GL;       // pixels per warp step
 
 __device__ __forceinline__ void red_add(float* addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
@@ -35,7 +47,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 // AUX: the 4th blended channel (out_depth) also carries an upstream gradient.
 template <bool AUX>
-__global__ void __launch_bounds__(RENDER_THREADS, 3)
+__global__ void __launch_bounds__(RENDER_THREADS, GGRT_BWD_MINBLOCKS)
 render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __restrict__ rec1,
                        const float4* __restrict__ rec2, const uint32_t* __restrict__ starts,
                        const uint32_t* __restrict__ points, const float* __restrict__ final_T,
@@ -123,10 +135,13 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
         }
         __syncwarp();
 
-        // ---- 32 queued Gaussians at a time: lane = Gaussian ----------------------------------------
-        for (uint32_t c0 = 0; c0 < qn; c0 += 32) {
-            const bool valid = c0 + lane < qn;
-            const uint32_t jj = valid ? squeue[warp][c0 + lane] : 0u;
+        // ---- GL queued Gaussians at a time.  Lane tiling: lane = (pixel slot q, Gaussian slot gl); the warp
+        // processes GL Gaussians x PL = 32/GL pixels per step, so the scan has log2(GL) levels and the per-pixel
+        // work is shared by fewer idle lanes.  The PL partial accumulators of a Gaussian are combined at the end.
+        const int gl = lane & (GL - 1), q = lane / GL;
+        for (uint32_t c0 = 0; c0 < qn; c0 += GL) {
+            const bool valid = c0 + gl < qn;
+            const uint32_t jj = valid ? squeue[warp][c0 + gl] : 0u;
             const uint32_t src = sbase + jj * REC_BYTES;
             const float2 gxy = lds64(src);
             float4 con = lds128(src + 16);
@@ -138,83 +153,77 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
             float a_op = 0.f, a_mx = 0.f, a_my = 0.f, a_A = 0.f, a_B = 0.f, a_C = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f;
             float a_x = 0.f;  // aux channel
 
-            // PIX_UNROLL pixels are processed per iteration: their scans are independent dependency chains
-            // that the scheduler interleaves (the kernel is shuffle-latency bound otherwise).
-            uint32_t pm = pmask;
-            while (pm) {
-                int p[PIX_UNROLL];
-                bool pv[PIX_UNROLL];
-#pragma unroll
-                for (int u = 0; u < PIX_UNROLL; ++u) {
-                    pv[u] = pm != 0;
-                    p[u] = pv[u] ? __ffs(pm) - 1 : p[0];
-                    pm &= pm - 1;
+            // pixel groups: group t holds pixels t*PL .. t*PL+PL-1, one per pixel slot
+#pragma unroll PIX_UNROLL
+            for (int t = 0; t < 32 / PL; ++t) {
+                if (((pmask >> (t * PL)) & ((1u << PL) - 1u)) == 0) continue;  // no pixel of the group matters
+                const int p = t * PL + q;
+                const float4 pg = lds128(gaddr + p * 16);   // {g_r, g_g, g_b, last}
+                const float4 ps = lds128(saddr + p * 16);   // {x, y, T behind, sum behind}
+                const float dx = gxy.x - ps.x, dy = gxy.y - ps.y;
+                const float dxx = dx * dx, dyy = dy * dy, dxy = dx * dy;
+                const float power2 = fmaf(ea, dxx, fmaf(ec, dyy, eb * dxy));  // log2 of the Gaussian
+                const float G = ex2_approx(power2);
+                const float alpha_raw = fminf(ALPHA_MAX, con.w * G);
+                const bool act = (pos < __float_as_uint(pg.w)) && (power2 <= 0.0f) && (alpha_raw >= ALPHA_MIN);
+                const float alpha = act ? alpha_raw : 0.f;
+                const float inv_om = rcp_approx(1.0f - alpha);
+                float sdot = fmaf(col.z, pg.z, fmaf(col.y, pg.y, col.x * pg.x));
+                float ga = 0.f;
+                if (AUX) {
+                    ga = aux_g[p];
+                    sdot = fmaf(col.w, ga, sdot);
                 }
-                float4 pg[PIX_UNROLL], ps[PIX_UNROLL];
-                float dx[PIX_UNROLL], dy[PIX_UNROLL], dxx[PIX_UNROLL], dyy[PIX_UNROLL], dxy[PIX_UNROLL];
-                float G[PIX_UNROLL], alpha[PIX_UNROLL], inv_om[PIX_UNROLL], s[PIX_UNROLL], A[PIX_UNROLL], B[PIX_UNROLL];
-                bool act[PIX_UNROLL];
+                // Going back to front each Gaussian maps the running pair (T, R) to (a T, R + b T) with
+                // a = 1/(1-alpha), b = alpha (c.g)/(1-alpha).  These maps compose associatively, so ONE
+                // segmented warp scan (slot 0 = backmost) yields every lane's transmittance and the sum behind it.
+                float A = inv_om, B = alpha * sdot * inv_om;
 #pragma unroll
-                for (int u = 0; u < PIX_UNROLL; ++u) {
-                    pg[u] = lds128(gaddr + p[u] * 16);   // {g_r, g_g, g_b, last}
-                    ps[u] = lds128(saddr + p[u] * 16);   // {x, y, T behind, sum behind}
-                }
-#pragma unroll
-                for (int u = 0; u < PIX_UNROLL; ++u) {
-                    dx[u] = gxy.x - ps[u].x, dy[u] = gxy.y - ps[u].y;
-                    dxx[u] = dx[u] * dx[u], dyy[u] = dy[u] * dy[u], dxy[u] = dx[u] * dy[u];
-                    const float power2 = fmaf(ea, dxx[u], fmaf(ec, dyy[u], eb * dxy[u]));  // log2 of the Gaussian
-                    G[u] = ex2_approx(power2);
-                    const float alpha_raw = fminf(ALPHA_MAX, con.w * G[u]);
-                    act[u] = pv[u] && (pos < __float_as_uint(pg[u].w)) && (power2 <= 0.0f) && (alpha_raw >= ALPHA_MIN);
-                    alpha[u] = act[u] ? alpha_raw : 0.f;
-                    inv_om[u] = rcp_approx(1.0f - alpha[u]);
-                    s[u] = fmaf(col.z, pg[u].z, fmaf(col.y, pg[u].y, col.x * pg[u].x));
-                    if (AUX) s[u] = fmaf(col.w, aux_g[p[u]], s[u]);
-                    // Going back to front each Gaussian maps the running pair (T, R) to (a T, R + b T) with
-                    // a = 1/(1-alpha), b = alpha (c.g)/(1-alpha).  These maps compose associatively, so ONE
-                    // warp scan (lane 0 = backmost) yields every lane's transmittance and the sum behind it.
-                    A[u] = inv_om[u];
-                    B[u] = alpha[u] * s[u] * inv_om[u];
-                }
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-                    for (int u = 0; u < PIX_UNROLL; ++u) {
-                        const float Ap = __shfl_up_sync(0xffffffffu, A[u], d);
-                        const float Bp = __shfl_up_sync(0xffffffffu, B[u], d);
-                        if (lane >= d) {
-                            B[u] = fmaf(B[u], Ap, Bp);
-                            A[u] *= Ap;
-                        }
+                for (int d = 1; d < GL; d <<= 1) {
+                    const float Ap = __shfl_up_sync(0xffffffffu, A, d, GL);
+                    const float Bp = __shfl_up_sync(0xffffffffu, B, d, GL);
+                    if (gl >= d) {
+                        B = fmaf(B, Ap, Bp);
+                        A *= Ap;
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < PIX_UNROLL; ++u) {
-                    const float Ti = ps[u].z * A[u];                    // transmittance in front of this Gaussian
-                    const float w = alpha[u] * Ti;
-                    const float Rtot = fmaf(ps[u].z, B[u], ps[u].w);   // sum behind, this Gaussian included
-                    const float dL_dalpha = fmaf(Ti, s[u], -(Rtot - w * s[u]) * inv_om[u]);
-                    const float q = act[u] ? G[u] * dL_dalpha : 0.f;
-                    const float t = con.w * q;
-                    a_op += q;
-                    a_mx = fmaf(t, dx[u], a_mx);  // first moments; the conic is applied once per chunk below
-                    a_my = fmaf(t, dy[u], a_my);
-                    a_A = fmaf(t, dxx[u], a_A);
-                    a_B = fmaf(t, dxy[u], a_B);
-                    a_C = fmaf(t, dyy[u], a_C);
-                    a_r = fmaf(w, pg[u].x, a_r);
-                    a_g = fmaf(w, pg[u].y, a_g);
-                    a_b = fmaf(w, pg[u].z, a_b);
-                    if (AUX) a_x = fmaf(w, aux_g[p[u]], a_x);
-                    if (lane == 31 && pv[u]) {  // frontmost lane holds the chunk totals: state behind the next chunk
-                        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr + p[u] * 16 + 8), "f"(Ti), "f"(Rtot)
-                                     : "memory");
-                    }
+                const float Ti = ps.z * A;                   // transmittance in front of this Gaussian
+                const float w = alpha * Ti;
+                const float Rtot = fmaf(ps.z, B, ps.w);      // sum behind, this Gaussian included
+                const float dL_dalpha = fmaf(Ti, sdot, -(Rtot - w * sdot) * inv_om);
+                const float qv = act ? G * dL_dalpha : 0.f;
+                const float tq = con.w * qv;
+                a_op += qv;
+                a_mx = fmaf(tq, dx, a_mx);  // first moments; the conic is applied once per chunk below
+                a_my = fmaf(tq, dy, a_my);
+                a_A = fmaf(tq, dxx, a_A);
+                a_B = fmaf(tq, dxy, a_B);
+                a_C = fmaf(tq, dyy, a_C);
+                a_r = fmaf(w, pg.x, a_r);
+                a_g = fmaf(w, pg.y, a_g);
+                a_b = fmaf(w, pg.z, a_b);
+                if (AUX) a_x = fmaf(w, ga, a_x);
+                if (gl == GL - 1) {  // frontmost slot holds the chunk totals: state behind the next chunk
+                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr + p * 16 + 8), "f"(Ti), "f"(Rtot)
+                                 : "memory");
                 }
             }
             __syncwarp();
-            if (valid) {
+            // combine the PL pixel-slot partials of each Gaussian (lanes gl, gl+GL, ...)
+#pragma unroll
+            for (int d = GL; d < 32; d <<= 1) {
+                a_op += __shfl_xor_sync(0xffffffffu, a_op, d);
+                a_mx += __shfl_xor_sync(0xffffffffu, a_mx, d);
+                a_my += __shfl_xor_sync(0xffffffffu, a_my, d);
+                a_A += __shfl_xor_sync(0xffffffffu, a_A, d);
+                a_B += __shfl_xor_sync(0xffffffffu, a_B, d);
+                a_C += __shfl_xor_sync(0xffffffffu, a_C, d);
+                a_r += __shfl_xor_sync(0xffffffffu, a_r, d);
+                a_g += __shfl_xor_sync(0xffffffffu, a_g, d);
+                a_b += __shfl_xor_sync(0xffffffffu, a_b, d);
+                if (AUX) a_x += __shfl_xor_sync(0xffffffffu, a_x, d);
+            }
+            if (valid && q == 0) {
                 float* dst = scratch + (size_t)sid[jj] * GRAD_STRIDE;
                 // scratch rows are 48 B (16-B aligned): slots {mx,my,A,B} {C,op,r,g} {b}
                 const float gmx = fmaf(con.x, a_mx, con.y * a_my), gmy = fmaf(con.z, a_my, con.y * a_mx);
