@@ -10,7 +10,7 @@ from pathlib import Path
 
 from . import build as _build
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 
@@ -31,6 +31,12 @@ class Settings(C.Structure):
         ("campos", C.c_void_p),
         ("bg", C.c_void_p),
     ]
+
+
+class InputLayout(C.Structure):
+    """struct GgrtRasterInputLayout"""
+
+    _fields_ = [("scene_scale", C.c_float), ("cov_full3x3", C.c_int32), ("sh_channel_major", C.c_int32)]
 
 
 class Layout(C.Structure):
@@ -84,9 +90,9 @@ def lib():
     L.ggrt_raster_image_bytes.restype = sz
     L.ggrt_raster_binning_bytes.argtypes = [i64]
     L.ggrt_raster_binning_bytes.restype = sz
-    L.ggrt_raster_forward_prepare.argtypes = [C.POINTER(Settings), i32] + [vp] * 11
+    L.ggrt_raster_forward_prepare.argtypes = [C.POINTER(Settings), C.POINTER(InputLayout), i32] + [vp] * 11
     L.ggrt_raster_forward_render.argtypes = [C.POINTER(Settings), i32, i64, u32, vp, vp, vp, vp, vp, vp]
-    L.ggrt_raster_backward.argtypes = [C.POINTER(Settings), i32, i64] + [vp] * 18
+    L.ggrt_raster_backward.argtypes = [C.POINTER(Settings), C.POINTER(InputLayout), i32, i64] + [vp] * 18
     L.ggrt_raster_mark_visible.argtypes = [i32, vp, vp, vp, vp]
     L.ggrt_raster_profile_enable.argtypes = [i32]
     L.ggrt_raster_profile_read.argtypes = [C.POINTER(C.c_float)]

@@ -123,7 +123,7 @@ BinPtrs bin_ptrs(void* base, long long N) {
     return p;
 }
 
-static int make_view(const GgrtRasterSettings* s, int P, View* v) {
+static int make_view(const GgrtRasterSettings* s, const GgrtRasterInputLayout* lay, int P, View* v) {
     if (s == nullptr) {
         set_error("settings is NULL");
         return GGRT_ERR_INVALID_ARGUMENT;
@@ -159,6 +159,18 @@ static int make_view(const GgrtRasterSettings* s, int P, View* v) {
     v->tanfovy = s->tanfovy;
     v->fx = (float)v->W / (2.0f * s->tanfovx);  // same float expression as the oracle
     v->fy = (float)v->H / (2.0f * s->tanfovy);
+    v->scale = 1.0f;
+    v->cov_stride = 6;
+    v->sh_ks = 3, v->sh_cs = 1;
+    if (lay != nullptr) {
+        if (!(lay->scene_scale > 0.f)) {
+            set_error("scene_scale must be positive");
+            return GGRT_ERR_INVALID_ARGUMENT;
+        }
+        v->scale = lay->scene_scale;
+        v->cov_stride = lay->cov_full3x3 ? 9 : 6;
+        if (lay->sh_channel_major) v->sh_ks = 1, v->sh_cs = v->K;
+    }
     v->view = s->viewmatrix;
     v->proj = s->projmatrix;
     v->campos = s->campos;
@@ -209,12 +221,13 @@ size_t ggrt_raster_binning_bytes(int64_t N) {
     return L.bin_bytes;
 }
 
-int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, int32_t P, const float* means3D,
+int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, const GgrtRasterInputLayout* layout, int32_t P,
+                                const float* means3D,
                                 const float* cov3D_precomp, const float* opacities, const float* shs,
                                 const float* colors_precomp, const float* aux, int32_t* radii, void* geom_buffer,
                                 void* image_buffer, uint32_t* counts_host, ggrt_stream_t stream) {
     View v;
-    GGRT_TRY(make_view(settings, P, &v));
+    GGRT_TRY(make_view(settings, layout, P, &v));
     if (P > 0 && (shs == nullptr) == (colors_precomp == nullptr)) {
         set_error("exactly one of shs / colors_precomp must be given");
         return GGRT_ERR_INVALID_ARGUMENT;
@@ -248,7 +261,7 @@ int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, in
                                uint32_t max_tile_pairs, const void* geom_buffer, void* binning_buffer,
                                void* image_buffer, float* out_color, float* out_depth, ggrt_stream_t stream) {
     View v;
-    GGRT_TRY(make_view(settings, P, &v));
+    GGRT_TRY(make_view(settings, nullptr, P, &v));
     if (!geom_buffer || !image_buffer || !out_color || !out_depth || num_rendered < 0 ||
         (num_rendered > 0 && !binning_buffer)) {
         set_error("forward_render: bad argument");
@@ -274,14 +287,15 @@ int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, in
     return GGRT_OK;
 }
 
-int ggrt_raster_backward(const GgrtRasterSettings* settings, int32_t P, int64_t num_rendered, const float* means3D,
+int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInputLayout* layout, int32_t P,
+                         int64_t num_rendered, const float* means3D,
                          const float* cov3D_precomp, const float* shs, const int32_t* radii, const void* geom_buffer,
                          const void* binning_buffer, const void* image_buffer, const float* dL_dout_color,
                          const float* dL_dout_aux, float* grad_scratch, float* dL_dmeans2D, float* dL_dopacity,
                          float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dcolors, float* dL_daux,
                          ggrt_stream_t stream) {
     View v;
-    GGRT_TRY(make_view(settings, P, &v));
+    GGRT_TRY(make_view(settings, layout, P, &v));
     if (P == 0) return GGRT_OK;
     if (!means3D || !cov3D_precomp || !radii || !geom_buffer || !image_buffer || !dL_dout_color || !grad_scratch ||
         !dL_dmeans2D || !dL_dopacity || !dL_dmeans3D || !dL_dcov3D || (num_rendered > 0 && !binning_buffer)) {

@@ -29,6 +29,9 @@ enum GradSlot { G_MX = 0, G_MY = 1, G_CA = 2, G_CB = 3, G_CC = 4, G_OP = 5, G_R 
 struct View {  // kernel-side copy of the per-call scalars (matrices stay in device memory)
     int W, H, gx, gy, P, deg, K;
     float tanfovx, tanfovy, fx, fy;
+    float scale;        // scene scale applied to means (s) and covariances (s*s)
+    int cov_stride;     // 6 ([P,6]) or 9 ([P,3,3])
+    int sh_ks, sh_cs;   // SH element (k, c) of a Gaussian's row lives at k*sh_ks + c*sh_cs
     const float* view;
     const float* proj;
     const float* campos;
@@ -146,6 +149,21 @@ __device__ __forceinline__ bool geometry(const View& v, const float* __restrict_
     g.det = fsub(fmul(g.a, g.c), fmul(g.b, g.b));
     if (!(g.det > 0.0f) && !(g.det < 0.0f)) return false;  // det == 0 (A.1) or NaN
     return true;
+}
+
+// the 6 upper-triangular covariance entries (xx,xy,xz,yy,yz,zz) of Gaussian i, scaled by s*s (exactly rounded,
+// matching the reference's separate `covariances * scale**2`, cuda_splatting.py:70)
+__device__ __forceinline__ void load_cov6(const View& v, const float* __restrict__ cov3d, int i, float cv[6]) {
+    const float* c = cov3d + (size_t)i * v.cov_stride;
+    if (v.cov_stride == 9) {
+        cv[0] = c[0], cv[1] = c[1], cv[2] = c[2], cv[3] = c[4], cv[4] = c[5], cv[5] = c[8];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cv[k] = c[k];
+    }
+    const float s2 = fmul(v.scale, v.scale);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cv[k] = fmul(cv[k], s2);
 }
 
 __device__ __forceinline__ int f2i_sat(float x) {

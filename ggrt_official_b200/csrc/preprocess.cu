@@ -30,18 +30,9 @@ geometry_kernel(View v, const float* __restrict__ means, const float* __restrict
     const int i = blockIdx.x * GEO_THREADS + threadIdx.x;
     if (i >= v.P) return;
 
-    const float px = means[3 * i], py = means[3 * i + 1], pz = means[3 * i + 2];
+    const float px = fmul(means[3 * i], v.scale), py = fmul(means[3 * i + 1], v.scale), pz = fmul(means[3 * i + 2], v.scale);
     float cv[6];
-    {
-        const float2* c2 = reinterpret_cast<const float2*>(cov3d) + 3 * (size_t)i;  // 24 B rows: 8 B aligned
-        if ((reinterpret_cast<uintptr_t>(cov3d) & 7) == 0) {
-            const float2 a = c2[0], b = c2[1], c = c2[2];
-            cv[0] = a.x; cv[1] = a.y; cv[2] = b.x; cv[3] = b.y; cv[4] = c.x; cv[5] = c.y;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) cv[k] = cov3d[6 * (size_t)i + k];
-        }
-    }
+    load_cov6(v, cov3d, i, cv);
     const float o = opac[i];
 
     int radius = 0;
@@ -208,6 +199,7 @@ color_kernel(View v, const float* __restrict__ means, const float* __restrict__ 
     __shared__ __align__(8) unsigned long long full_bar[COLOR_STAGES];
     constexpr int KK = (DEG + 1) * (DEG + 1);
     constexpr int row = KK * 3;
+    const int ks = v.sh_ks, cs = v.sh_cs;
     const int slab_floats = COLOR_THREADS * row;
     const bool tma_ok = shs != nullptr && (reinterpret_cast<uintptr_t>(shs) & 15) == 0;  // slab bases are 16 B multiples
 
@@ -241,7 +233,7 @@ color_kernel(View v, const float* __restrict__ means, const float* __restrict__ 
         n_radius = 0;
         if (sl < num_slabs && i < v.P) {
             n_radius = radii[i];
-            n_mx = means[3 * i], n_my = means[3 * i + 1], n_mz = means[3 * i + 2];
+            n_mx = fmul(means[3 * i], v.scale), n_my = fmul(means[3 * i + 1], v.scale), n_mz = fmul(means[3 * i + 2], v.scale);
             n_depth = aux ? aux[i] : g.rec0[i].w;  // 4th blended channel: caller's aux or the view depth
         }
     };
@@ -285,9 +277,9 @@ color_kernel(View v, const float* __restrict__ means, const float* __restrict__ 
                     rgb[0] = rgb[1] = rgb[2] = 0.5f;
 #pragma unroll
                     for (int k = 0; k < KK; ++k) {
-                        rgb[0] = fmaf(b[k], my[3 * k + 0], rgb[0]);
-                        rgb[1] = fmaf(b[k], my[3 * k + 1], rgb[1]);
-                        rgb[2] = fmaf(b[k], my[3 * k + 2], rgb[2]);
+                        rgb[0] = fmaf(b[k], my[k * ks], rgb[0]);
+                        rgb[1] = fmaf(b[k], my[k * ks + cs], rgb[1]);
+                        rgb[2] = fmaf(b[k], my[k * ks + 2 * cs], rgb[2]);
                     }
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {

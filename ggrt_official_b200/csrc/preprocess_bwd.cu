@@ -39,6 +39,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     else if (threadIdx.x < 32) sM[threadIdx.x - 16] = v.proj[threadIdx.x - 16];
 
     const int row = v.K * 3;
+    const int ks = v.sh_ks, cs = v.sh_cs;
     const int slab_floats = PB_THREADS * row;
     const bool tma_ok = shs != nullptr && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(dsh) & 15) == 0;
@@ -74,9 +75,8 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             n_radius = radii[i];
             n_flags = flags[i];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) n_mean[k] = means[3 * (size_t)i + k];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) n_cv[k] = cov3d[6 * (size_t)i + k];
+            for (int k = 0; k < 3; ++k) n_mean[k] = fmul(means[3 * (size_t)i + k], v.scale);
+            load_cov6(v, cov3d, i, n_cv);
             const float* gs = scratch + (size_t)i * GRAD_STRIDE;
             n_ga = *reinterpret_cast<const float4*>(gs);
             n_gb = *reinterpret_cast<const float4*>(gs + 4);
@@ -204,10 +204,10 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             // one SH term: accumulate dL/ddir from the stored coefficients, then overwrite them with dL/dsh
 #define GGRT_TERM(k, B, BX, BY, BZ)                                                        \
     {                                                                                      \
-        const float s_ = my[3 * (k)] * dR + my[3 * (k) + 1] * dG + my[3 * (k) + 2] * dB;   \
+        const float s_ = my[(k) * ks] * dR + my[(k) * ks + cs] * dG + my[(k) * ks + 2 * cs] * dB; \
         ddx = fmaf((BX), s_, ddx), ddy = fmaf((BY), s_, ddy), ddz = fmaf((BZ), s_, ddz);   \
         const float b_ = (B);                                                              \
-        my[3 * (k)] = b_ * dR, my[3 * (k) + 1] = b_ * dG, my[3 * (k) + 2] = b_ * dB;       \
+        my[(k) * ks] = b_ * dR, my[(k) * ks + cs] = b_ * dG, my[(k) * ks + 2 * cs] = b_ * dB; \
     }
             GGRT_TERM(0, GGRT_SH_C0, 0.f, 0.f, 0.f)
             if (v.deg > 0) {
@@ -309,10 +309,19 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
         dmeans2D[3 * i] = g2x, dmeans2D[3 * i + 1] = g2y, dmeans2D[3 * i + 2] = 0.f;
         dopacity[i] = gop;
         if (AUX) daux[i] = live ? gaux : 0.f;
+        // chain rule of the scene scale: means_used = s * means, cov_used = s^2 * cov
+        const float s1 = v.scale, s2 = v.scale * v.scale;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) dmeans3D[3 * i + k] = dmean[k];
+        for (int k = 0; k < 3; ++k) dmeans3D[3 * i + k] = s1 * dmean[k];
+        float* dc = dcov3D + (size_t)i * v.cov_stride;
+        if (v.cov_stride == 9) {  // upper triangle of the 3x3 (as the reference's triu gather does), zeros below
+            dc[0] = s2 * dS[0], dc[1] = s2 * dS[1], dc[2] = s2 * dS[2];
+            dc[3] = 0.f, dc[4] = s2 * dS[3], dc[5] = s2 * dS[4];
+            dc[6] = 0.f, dc[7] = 0.f, dc[8] = s2 * dS[5];
+        } else {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) dcov3D[6 * (size_t)i + k] = dS[k];
+            for (int k = 0; k < 6; ++k) dc[k] = s2 * dS[k];
+        }
     }
     }  // slab loop
     if (threadIdx.x == 0) bulk_wait0();  // all bulk stores of this CTA have completed

@@ -10,7 +10,8 @@ from typing import Optional
 import torch
 from torch import Tensor, nn
 
-from .render import DepthRenderingMode, render_color_and_depth_cuda, render_cuda, render_depth_cuda
+from .render import (DepthRenderingMode, render_color_and_depth_cuda, render_cuda, render_depth_cuda,
+                     render_views_fast)
 
 
 @dataclass
@@ -33,17 +34,26 @@ def _per_view(t: Tensor, v: int) -> Tensor:
 
 
 class DecoderSplattingCUDA(nn.Module):
-    def __init__(self, background_color=(0.0, 0.0, 0.0), fused_depth: bool = False) -> None:
+    def __init__(self, background_color=(0.0, 0.0, 0.0), fused_depth: bool = False, fast_glue: bool = False) -> None:
         """fused_depth: render colour and depth in one rasterization (same outputs as the reference's two
-        passes; roughly half the rasterizer work when a depth mode is requested)."""
+        passes; roughly half the rasterizer work when a depth mode is requested).
+        fast_glue: additionally skip the reference glue's per-view replication / rescale / gather / permute
+        copies and its per-view host syncs (render_views_fast); implies fused_depth."""
         super().__init__()
         self.background_color = torch.tensor(background_color, dtype=torch.float32)
-        self.fused_depth = fused_depth
+        self.fused_depth = fused_depth or fast_glue
+        self.fast_glue = fast_glue
 
     def forward(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
                 image_shape: tuple, depth_mode: Optional[DepthRenderingMode] = None) -> DecoderOutput:
         b, v = extrinsics.shape[:2]
         bg = self.background_color.to(far.device)[None].expand(b * v, 3)
+        if self.fast_glue:
+            color, depth = render_views_fast(
+                extrinsics.flatten(0, 1), intrinsics.flatten(0, 1), near.flatten(), far.flatten(), image_shape, bg,
+                gaussians.means, gaussians.covariances, gaussians.harmonics, gaussians.opacities,
+                view_to_scene=[i // v for i in range(b * v)], depth_mode=depth_mode)
+            return DecoderOutput(color.unflatten(0, (b, v)), None if depth is None else depth.unflatten(0, (b, v)))
         if self.fused_depth and depth_mode is not None:
             color, depth = render_color_and_depth_cuda(
                 extrinsics.flatten(0, 1), intrinsics.flatten(0, 1), near.flatten(), far.flatten(), image_shape, bg,

@@ -68,7 +68,7 @@ class _Call:
     """Validated, contiguous inputs + the C settings struct for one rasterization."""
 
     def __init__(self, means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: GaussianRasterizationSettings,
-                 aux=None):
+                 aux=None, layout: Optional[dict] = None):
         if not means3D.is_cuda:
             raise RuntimeError("means3D must be a CUDA tensor: the rasterizer has no CPU path")
         dev = means3D.device
@@ -87,13 +87,23 @@ class _Call:
         self.H, self.W = int(rs.image_height), int(rs.image_width)
         self.deg = int(rs.sh_degree)
         K = (self.deg + 1) ** 2
+        lay = layout or {}
+        self.scale = float(lay.get("scene_scale", 1.0))
+        self.cov9 = bool(lay.get("cov_full3x3", False))
+        self.sh_cmajor = bool(lay.get("sh_channel_major", False))
+        self.layout = None
+        if layout:
+            self.layout = _cabi.InputLayout(self.scale, int(self.cov9), int(self.sh_cmajor))
         if self.means3D.dim() != 2 or self.means3D.shape[1] != 3:
             raise ValueError(f"means3D must be [P,3], got {tuple(self.means3D.shape)}")
-        if self.cov3D.shape != (self.P, 6):
-            raise ValueError(f"cov3D_precomp must be [P,6], got {tuple(self.cov3D.shape)}")
+        if tuple(self.cov3D.shape) != ((self.P, 3, 3) if self.cov9 else (self.P, 6)):
+            raise ValueError(f"cov3D_precomp must be {'[P,3,3]' if self.cov9 else '[P,6]'}, got {tuple(self.cov3D.shape)}")
         if self.opacities.numel() != self.P:
             raise ValueError(f"opacities must have P={self.P} elements, got {self.opacities.numel()}")
-        if self.sh is not None:
+        if self.sh is not None and self.sh_cmajor:
+            if tuple(self.sh.shape) != (self.P, 3, K):
+                raise ValueError(f"channel-major shs must be [P,3,{K}], got {tuple(self.sh.shape)}")
+        elif self.sh is not None:
             if self.sh.dim() != 3 or self.sh.shape[0] != self.P or self.sh.shape[2] != 3 or self.sh.shape[1] < K:
                 raise ValueError(f"shs must be [P,>={K},3] for sh_degree {self.deg}, got {tuple(self.sh.shape)}")
             if self.sh.shape[1] != K:  # upstream reads the first (deg+1)^2 coefficients of a wider table
@@ -118,11 +128,12 @@ class _Call:
 
 
 def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: GaussianRasterizationSettings,
-                aux=None) -> dict:
+                aux=None, layout: Optional[dict] = None) -> dict:
     """Runs the forward through the C ABI and returns outputs plus the opaque state buffers.
-    `aux` [P]: optional extra per-Gaussian channel blended into the third output instead of the view depth."""
+    `aux` [P]: optional extra per-Gaussian channel blended into the third output instead of the view depth.
+    `layout`: optional {scene_scale, cov_full3x3, sh_channel_major} (struct GgrtRasterInputLayout)."""
     L = _cabi.lib()
-    c = _Call(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs, aux)
+    c = _Call(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs, aux, layout)
     dev = c.device
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev)
@@ -134,7 +145,8 @@ def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: Gauss
         color = torch.empty((3, c.H, c.W), dtype=torch.float32, device=dev)
         depth = torch.empty((c.H, c.W), dtype=torch.float32, device=dev)
         counts = _pinned_counts()
-        _cabi.check(L.ggrt_raster_forward_prepare(C.byref(c.settings), c.P, _ptr(c.means3D), _ptr(c.cov3D),
+        lay = C.byref(c.layout) if c.layout is not None else None
+        _cabi.check(L.ggrt_raster_forward_prepare(C.byref(c.settings), lay, c.P, _ptr(c.means3D), _ptr(c.cov3D),
                                                   _ptr(c.opacities), _ptr(c.sh), _ptr(c.colors), _ptr(c.aux),
                                                   _ptr(radii), _ptr(geom), _ptr(img),
                                                   C.c_void_p(counts.data_ptr()), sp),
@@ -183,12 +195,13 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
             dmeans2D=buf("dmeans2D", (c.P, 3)),
             dopacity=buf("dopacity", (c.P, 1)),
             dmeans3D=buf("dmeans3D", (c.P, 3)),
-            dcov3D=buf("dcov3D", (c.P, 6)),
+            dcov3D=buf("dcov3D", (c.P, 3, 3) if c.cov9 else (c.P, 6)),
             dsh=buf("dsh", tuple(c.sh.shape)) if c.sh is not None else None,
             dcolors=buf("dcolors", (c.P, 3)) if c.sh is None else None,
             daux=buf("daux", (c.P,)) if ga is not None else None,
         )
-        _cabi.check(L.ggrt_raster_backward(C.byref(c.settings), c.P, state["N"], _ptr(c.means3D), _ptr(c.cov3D),
+        lay = C.byref(c.layout) if c.layout is not None else None
+        _cabi.check(L.ggrt_raster_backward(C.byref(c.settings), lay, c.P, state["N"], _ptr(c.means3D), _ptr(c.cov3D),
                                            _ptr(c.sh), _ptr(state["radii"]), _ptr(state["geom"]),
                                            _ptr(state["binning"]), _ptr(state["img"]), _ptr(g), _ptr(ga),
                                            _ptr(scratch), _ptr(out["dmeans2D"]), _ptr(out["dopacity"]),
@@ -209,9 +222,9 @@ def _dump(path: str, payload) -> None:
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings, aux=None):
+                raster_settings, aux=None, layout=None):
         try:
-            st = forward_raw(means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings, aux)
+            st = forward_raw(means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings, aux, layout)
         except Exception:
             if raster_settings.debug:
                 _dump("snapshot_fw.dump", (means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings))
@@ -237,7 +250,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         c: _Call = st["call"]
         grad_aux = _grad_depth if ctx.has_aux else None
         if grad_color is None and grad_aux is None:
-            return (None,) * 10
+            return (None,) * 11
         if grad_color is None:
             grad_color = torch.zeros((3, c.H, c.W), dtype=torch.float32, device=c.device)
         try:
@@ -254,14 +267,14 @@ class _RasterizeGaussians(torch.autograd.Function):
         daux = g.get("daux")
         if daux is not None:
             daux = daux.reshape(ctx.aux_shape)
-        return (g["dmeans3D"], g["dmeans2D"], dsh, g["dcolors"], g["dopacity"].reshape(ctx.opacity_shape), None, None,
-                g["dcov3D"], None, daux)
+        return (g["dmeans3D"], g["dmeans2D"] if ctx.needs_input_grad[1] else None, dsh, g["dcolors"],
+                g["dopacity"].reshape(ctx.opacity_shape), None, None, g["dcov3D"], None, daux, None)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings, aux_precomp=None):
+                        raster_settings, aux_precomp=None, layout=None):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings, aux_precomp)
+                                     cov3Ds_precomp, raster_settings, aux_precomp, layout)
 
 
 class GaussianRasterizer(nn.Module):
@@ -286,10 +299,12 @@ class GaussianRasterizer(nn.Module):
         return out.bool()
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None, aux_precomp=None):
-        """Same keywords as upstream, plus the extension `aux_precomp` [P] or [P,1]: an extra per-Gaussian scalar
-        that is alpha-blended with the colour's weights into the third output (differentiable).  Without it the
-        third output is the blended view-space depth (not differentiable).  GGRt never passes it."""
+                cov3D_precomp=None, aux_precomp=None, layout=None):
+        """Same keywords as upstream, plus two extensions GGRt never passes: `aux_precomp` [P] or [P,1], an extra
+        per-Gaussian scalar that is alpha-blended with the colour's weights into the third output (differentiable;
+        without it the third output is the blended view-space depth, not differentiable), and `layout`, a dict
+        {scene_scale, cov_full3x3, sh_channel_major} describing inputs stored as pixelSplat's `Gaussians` holds
+        them, so the rescale / gather / permute copies of the reference glue can be skipped."""
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
             raise Exception("Please provide excatly one of either SHs or precomputed colors!")
         if ((scales is None or rotations is None) and cov3D_precomp is None) or (
@@ -299,4 +314,4 @@ class GaussianRasterizer(nn.Module):
             raise NotImplementedError(
                 "scales/rotations are not supported: GGRt always passes cov3D_precomp (cuda_splatting.py:124)")
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                   self.raster_settings, aux_precomp)
+                                   self.raster_settings, aux_precomp, layout)

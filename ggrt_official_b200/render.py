@@ -10,7 +10,7 @@ shim; tests/test_reference_caller.py checks both produce identical rasterizer ca
 from __future__ import annotations
 
 from math import isqrt
-from typing import Literal, Optional
+from typing import Literal, Optional, Sequence
 
 import torch
 from torch import Tensor
@@ -140,6 +140,56 @@ def render_color_and_depth_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Te
                                   gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities,
                                   scale_invariant=scale_invariant, return_aux=True, gaussian_aux=aux)
     return color, depth
+
+
+def render_views_fast(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple,
+                      background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
+                      gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor, view_to_scene: Sequence[int],
+                      scale_invariant: bool = True, depth_mode: Optional[DepthRenderingMode] = None):
+    """Same result as render_cuda (+ render_depth_cuda when depth_mode is given), with the per-call copies of the
+    reference glue removed:
+      * the Gaussians are NOT replicated per view (`view_to_scene[i]` picks the scene of view i) and NOT rescaled,
+        gathered or permuted in PyTorch: the rasterizer reads pixelSplat's own layout (means [g,3], covariances
+        [g,3,3], harmonics [g,3,n]) and applies the scale-invariant 1/near factor itself (`layout` argument);
+      * one host sync per call (tan(fov/2) and 1/near for all views together) instead of two per view;
+      * colour and depth share one rasterization (aux channel).
+    extrinsics / intrinsics / near / far / background_color are per view [b', ...]; the Gaussian tensors are per
+    scene [s, g, ...].  Returns (color [b',3,h,w], depth [b',h,w] or None)."""
+    nb = extrinsics.shape[0]
+    h, w = image_shape
+    n = gaussian_sh_coefficients.shape[-1]
+    degree = isqrt(n) - 1
+    aux = None
+    if depth_mode is not None:  # camera-space z of the UNSCALED scene, per view (cuda_splatting.py:240-243)
+        v2s = list(view_to_scene)
+        per_view_means = gaussian_means if v2s == list(range(gaussian_means.shape[0])) else \
+            gaussian_means[torch.as_tensor(v2s, device=gaussian_means.device)]
+        aux = depth_channel(extrinsics, per_view_means, near, far, depth_mode)
+    scale = 1 / near if scale_invariant else torch.ones_like(near)
+    extr = extrinsics.clone()
+    extr[..., :3, 3] = extr[..., :3, 3] * scale[:, None]
+    near_s, far_s = near * scale, far * scale
+    fov_x, fov_y = get_fov(intrinsics).unbind(dim=-1)
+    host = torch.stack([(0.5 * fov_x).tan(), (0.5 * fov_y).tan(), scale]).tolist()  # the single host sync
+    projection = get_projection_matrix(near_s, far_s, fov_x, fov_y, intrinsics).transpose(1, 2)
+    view = extr.inverse().transpose(1, 2)
+    full = view @ projection
+    harm = gaussian_sh_coefficients.contiguous()
+    cov = gaussian_covariances.contiguous()
+    colors, depths = [], []
+    for i in range(nb):
+        s_ = view_to_scene[i]
+        settings = GaussianRasterizationSettings(
+            image_height=h, image_width=w, tanfovx=host[0][i], tanfovy=host[1][i], bg=background_color[i],
+            scale_modifier=1.0, viewmatrix=view[i], projmatrix=full[i], sh_degree=degree, campos=extr[i, :3, 3],
+            prefiltered=False)
+        image, _, depth = GaussianRasterizer(settings)(
+            means3D=gaussian_means[s_], means2D=None, shs=harm[s_], opacities=gaussian_opacities[s_],
+            cov3D_precomp=cov[s_], aux_precomp=None if aux is None else aux[i],
+            layout=dict(scene_scale=host[2][i], cov_full3x3=True, sh_channel_major=True))
+        colors.append(image)
+        depths.append(depth)
+    return torch.stack(colors), (torch.stack(depths) if depth_mode is not None else None)
 
 
 def render_depth_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple,

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GGRT_RASTER_ABI_VERSION 2
+#define GGRT_RASTER_ABI_VERSION 3
 #define GGRT_RASTER_TILE 16 /* tile edge in pixels (tile ids are part of the contract) */
 #define GGRT_RASTER_SUBS 16 /* pair counters per tile (contention spreading) */
 
@@ -62,6 +62,19 @@ typedef struct GgrtRasterSettings {
     const float* campos;     /* [3]   device */
     const float* bg;         /* [3]   device */
 } GgrtRasterSettings;
+
+/*
+ * Optional description of how the caller stores the Gaussians, so that the copies GGRt's glue makes before
+ * every rasterization can be skipped (cuda_splatting.py:66-77,116,124: scale-invariant rescale of means and
+ * covariances, [g,3,n] -> [g,n,3] SH permute, upper-triangle gather).  NULL = the upstream layout.
+ * Gradients are returned in the same layout and with respect to the UNSCALED inputs.
+ */
+typedef struct GgrtRasterInputLayout {
+    float scene_scale;        /* means are multiplied by s, covariances by s*s before use (1.0 = none) */
+    int32_t cov_full3x3;      /* 0: cov3D_precomp is [P,6]; 1: [P,3,3] row-major (upper triangle is read; the
+                                 gradient is written to the upper triangle, zeros below) */
+    int32_t sh_channel_major; /* 0: shs is [P,K,3]; 1: [P,3,K] */
+} GgrtRasterInputLayout;
 
 /* Byte offsets of the sub-arrays inside the caller-owned buffers (for tests / tools). */
 typedef struct GgrtRasterLayout {
@@ -109,7 +122,8 @@ size_t ggrt_raster_binning_bytes(int64_t num_rendered);
  * image_buffer, then enqueues a copy of {N, max pairs per tile} to counts_host
  * (2 x uint32 of pinned host memory; may be NULL if the caller reads img_header itself).
  */
-int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, int32_t P, const float* means3D,
+int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, const GgrtRasterInputLayout* layout, int32_t P,
+                                const float* means3D,
                                 const float* cov3D_precomp, const float* opacities, const float* shs,
                                 const float* colors_precomp, const float* aux, int32_t* radii, void* geom_buffer,
                                 void* image_buffer, uint32_t* counts_host, ggrt_stream_t stream);
@@ -132,7 +146,8 @@ int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, in
  * (when shs was given) or dL_dcolors [P,3] (the unused one is NULL), and dL_daux [P] (NULL
  * unless dL_dout_aux is given).
  */
-int ggrt_raster_backward(const GgrtRasterSettings* settings, int32_t P, int64_t num_rendered, const float* means3D,
+int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInputLayout* layout, int32_t P,
+                         int64_t num_rendered, const float* means3D,
                          const float* cov3D_precomp, const float* shs, const int32_t* radii, const void* geom_buffer,
                          const void* binning_buffer, const void* image_buffer, const float* dL_dout_color,
                          const float* dL_dout_aux, float* grad_scratch, float* dL_dmeans2D, float* dL_dopacity,

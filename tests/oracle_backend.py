@@ -27,16 +27,25 @@ def _camera(rs, deg):
                      campos=_np(rs.campos), bg=_np(rs.bg), deg=deg)
 
 
-def fake_forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs, aux=None):
+def fake_forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs, aux=None, layout=None):
     CALLS.append(dict(means3D=means3D, sh=sh, colors_precomp=colors_precomp, opacities=opacities,
-                      cov3D_precomp=cov3D_precomp, settings=rs, aux=aux))
+                      cov3D_precomp=cov3D_precomp, settings=rs, aux=aux, layout=layout))
     deg = int(rs.sh_degree)
     cam = _camera(rs, deg)
+    lay = layout or {}
+    scale = np.float32(lay.get("scene_scale", 1.0))
     shn = _np(sh)
     if shn is not None:
+        if lay.get("sh_channel_major"):
+            shn = np.transpose(shn, (0, 2, 1))
         shn = np.ascontiguousarray(shn[:, : (deg + 1) ** 2, :])
-    inp = dict(means=_np(means3D), cov=_np(cov3D_precomp), opac=_np(opacities).reshape(-1), sh=shn,
-               colors=_np(colors_precomp))
+    covn = _np(cov3D_precomp)
+    if lay.get("cov_full3x3"):
+        iu = np.triu_indices(3)
+        covn = covn[:, iu[0], iu[1]]
+    covn = np.ascontiguousarray(covn * (scale * scale))
+    inp = dict(means=np.ascontiguousarray(_np(means3D) * scale), cov=covn, opac=_np(opacities).reshape(-1), sh=shn,
+               colors=_np(colors_precomp), layout=dict(lay))
     auxn = None if aux is None else _np(aux).reshape(-1)
     f = co.forward(cam, inp["means"], inp["cov"], inp["opac"], sh=inp["sh"], colors=inp["colors"], aux=auxn)
     call = SimpleNamespace(means3D=means3D, sh=sh, colors=colors_precomp, opacities=opacities, cov3D=cov3D_precomp,
@@ -55,6 +64,17 @@ def fake_backward_raw(state, grad_color, out=None, grad_aux=None):
     t = torch.from_numpy
     d2 = np.zeros((P, 3), np.float32)
     d2[:, :2] = g["dmean2D"]
+    lay = inp["layout"]
+    scale = np.float32(lay.get("scene_scale", 1.0))
+    g["dmeans3D"] = np.ascontiguousarray(g["dmeans3D"] * scale)
+    g["dcov3D"] = np.ascontiguousarray(g["dcov3D"] * (scale * scale))
+    if lay.get("cov_full3x3"):
+        full = np.zeros((P, 3, 3), np.float32)
+        iu = np.triu_indices(3)
+        full[:, iu[0], iu[1]] = g["dcov3D"]
+        g["dcov3D"] = full
+    if lay.get("sh_channel_major") and g["dsh"] is not None:
+        g["dsh"] = np.ascontiguousarray(np.transpose(g["dsh"], (0, 2, 1)))
     return dict(dmeans2D=t(d2), dopacity=t(g["dopacity"].reshape(P, 1).copy()), dmeans3D=t(g["dmeans3D"]),
                 dcov3D=t(g["dcov3D"]), dsh=None if g["dsh"] is None else t(g["dsh"]),
                 dcolors=None if inp["colors"] is None else t(g["dcolor"]),
@@ -69,9 +89,9 @@ def installed():
     orig_fwd = R._RasterizeGaussians.forward
 
     def fwd(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings,
-            aux=None):
+            aux=None, layout=None):
         out = orig_fwd(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                       raster_settings, aux)
+                       raster_settings, aux, layout)
         ctx.state["_oracle"] = CALLS_STATE.pop()
         return out
 

@@ -47,15 +47,15 @@ def test_abi_version_and_layout():
 
 def test_argument_errors_are_reported_without_touching_cuda():
     lib = _cabi.lib()
-    rc = lib.ggrt_raster_forward_prepare(None, 0, None, None, None, None, None, None, None, None, None, None, None)
+    rc = lib.ggrt_raster_forward_prepare(None, None, 0, None, None, None, None, None, None, None, None, None, None, None)
     assert rc == -1
     assert b"settings" in lib.ggrt_raster_last_error()
     s = _cabi.Settings()
     s.image_height, s.image_width, s.tanfovx, s.tanfovy, s.sh_degree = 16, 16, 1.0, 1.0, 7
     dummy = C.c_void_p(16)
     s.viewmatrix = s.projmatrix = s.campos = s.bg = 16
-    rc = lib.ggrt_raster_forward_prepare(C.byref(s), 1, dummy, dummy, dummy, dummy, None, None, dummy, dummy, dummy, None,
-                                         None)
+    rc = lib.ggrt_raster_forward_prepare(C.byref(s), None, 1, dummy, dummy, dummy, dummy, None, None, dummy, dummy, dummy,
+                                         None, None)
     assert rc == -3 and b"sh_degree" in lib.ggrt_raster_last_error()
     with pytest.raises(RuntimeError, match="sh_degree"):
         _cabi.check(rc, "forward_prepare")

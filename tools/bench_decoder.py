@@ -23,8 +23,8 @@ near, far = torch.full((1, 1), sc.near, device=dev), torch.full((1, 1), sc.far, 
 wc = torch.randn(1, 1, 3, H, W, device=dev) / (3 * H * W)
 wd = torch.randn(1, 1, H, W, device=dev) / (H * W)
 out = {}
-for name, fused in (("two_pass", False), ("fused_depth", True)):
-    dec = DecoderSplattingCUDA(fused_depth=fused)
+for name, fused, fast in (("two_pass", False, False), ("fused_depth", True, False), ("fast_glue", True, True)):
+    dec = DecoderSplattingCUDA(fused_depth=fused, fast_glue=fast)
 
     def step():
         for v in leaves.values():
@@ -45,5 +45,6 @@ for name, fused in (("two_pass", False), ("fused_depth", True)):
     ms = sorted(a.elapsed_time(b) for a, b in ev)
     out[name] = dict(ms_median=ms[len(ms) // 2], ms_min=ms[0])
     out[name + "_depth_mean"] = float(r.depth.mean())
-out["speedup"] = out["two_pass"]["ms_median"] / out["fused_depth"]["ms_median"]
+out["speedup_fused"] = out["two_pass"]["ms_median"] / out["fused_depth"]["ms_median"]
+out["speedup_fast_glue"] = out["two_pass"]["ms_median"] / out["fast_glue"]["ms_median"]
 print(json.dumps(out))
