@@ -154,8 +154,9 @@ __device__ __forceinline__ bool geometry(const View& v, const float* __restrict_
 // the 6 upper-triangular covariance entries (xx,xy,xz,yy,yz,zz) of Gaussian i, scaled by s*s (exactly rounded,
 // matching the reference's separate `covariances * scale**2`, cuda_splatting.py:70)
 __device__ __forceinline__ void load_cov6(const View& v, const float* __restrict__ cov3d, int i, float cv[6]) {
-    const float* c = cov3d + (size_t)i * v.cov_stride;
-    if (v.cov_stride == 9) {
+    const int stride = v.cov_stride;
+    const float* c = cov3d + (size_t)i * stride;
+    if (stride == 9) {
         cv[0] = c[0], cv[1] = c[1], cv[2] = c[2], cv[3] = c[4], cv[4] = c[5], cv[5] = c[8];
     } else {
 #pragma unroll

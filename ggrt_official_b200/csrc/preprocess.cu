@@ -191,7 +191,7 @@ __device__ __forceinline__ void fill_slab_generic(float* slab, const float* src,
     }
 }
 
-template <int DEG>
+template <int DEG, bool CMAJOR>
 __global__ void __launch_bounds__(COLOR_THREADS, 3)
 color_kernel(View v, const float* __restrict__ means, const float* __restrict__ shs, const float* __restrict__ colors,
              const float* __restrict__ aux, const int* __restrict__ radii, GeomPtrs g, int num_slabs) {
@@ -199,7 +199,7 @@ color_kernel(View v, const float* __restrict__ means, const float* __restrict__ 
     __shared__ __align__(8) unsigned long long full_bar[COLOR_STAGES];
     constexpr int KK = (DEG + 1) * (DEG + 1);
     constexpr int row = KK * 3;
-    const int ks = v.sh_ks, cs = v.sh_cs;
+    constexpr int ks = CMAJOR ? 1 : 3, cs = CMAJOR ? KK : 1;  // SH element (k, c) at k*ks + c*cs of the row
     const int slab_floats = COLOR_THREADS * row;
     const bool tma_ok = shs != nullptr && (reinterpret_cast<uintptr_t>(shs) & 15) == 0;  // slab bases are 16 B multiples
 
@@ -338,11 +338,15 @@ void launch_color(const View& v, const float* means, const float* shs, const flo
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int per_sm = smem ? max(1, min(8, (int)((220 * 1024) / (smem + 1024)))) : 8;
     const int grid = min(num_slabs, per_sm * sms);  // persistent CTAs, each streams slabs through its ring
+#define GGRT_LAUNCH_COLOR2(D, CM)                                                                                   \
+    {                                                                                                               \
+        if (smem > 32 * 1024)                                                                                       \
+            cudaFuncSetAttribute(color_kernel<D, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        color_kernel<D, CM><<<grid, COLOR_THREADS, smem, s>>>(v, means, shs, colors, aux, radii, g, num_slabs);     \
+    }
 #define GGRT_LAUNCH_COLOR(D)                                                                                        \
     case D:                                                                                                         \
-        if (smem > 32 * 1024)                                                                                       \
-            cudaFuncSetAttribute(color_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
-        color_kernel<D><<<grid, COLOR_THREADS, smem, s>>>(v, means, shs, colors, aux, radii, g, num_slabs);                     \
+        if (v.sh_ks == 1 && D > 0) GGRT_LAUNCH_COLOR2(D, true) else GGRT_LAUNCH_COLOR2(D, false)                     \
         break;
     switch (v.deg) {
         GGRT_LAUNCH_COLOR(0)
@@ -352,6 +356,7 @@ void launch_color(const View& v, const float* means, const float* shs, const flo
         GGRT_LAUNCH_COLOR(4)
     }
 #undef GGRT_LAUNCH_COLOR
+#undef GGRT_LAUNCH_COLOR2
 }
 
 void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t s) {

@@ -24,7 +24,7 @@ constexpr int PB_THREADS = GGRT_PB_THREADS;
 
 constexpr int PB_STAGES = GGRT_PB_STAGES;
 
-template <bool AUX>
+template <bool AUX, bool CMAJOR>
 __global__ void __launch_bounds__(PB_THREADS, 3)
 preprocess_backward_kernel(View v, const float* __restrict__ means, const float* __restrict__ cov3d,
                            const float* __restrict__ shs, const int* __restrict__ radii,
@@ -39,7 +39,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     else if (threadIdx.x < 32) sM[threadIdx.x - 16] = v.proj[threadIdx.x - 16];
 
     const int row = v.K * 3;
-    const int ks = v.sh_ks, cs = v.sh_cs;
+    const int ks = CMAJOR ? 1 : 3, cs = CMAJOR ? v.K : 1;  // SH element (k, c) at k*ks + c*cs of the row
     const int slab_floats = PB_THREADS * row;
     const bool tma_ok = shs != nullptr && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(dsh) & 15) == 0;
@@ -336,18 +336,24 @@ void launch_preprocess_backward(const View& v, const float* means, const float* 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (smem > 32 * 1024) {
-        cudaFuncSetAttribute(preprocess_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(preprocess_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
     const int per_sm = smem ? max(1, min(8, (int)((220 * 1024) / (smem + 1024)))) : 8;
     const int grid = min(num_slabs, per_sm * sms);  // persistent CTAs
-    if (daux)
-        preprocess_backward_kernel<true><<<grid, PB_THREADS, smem, s>>>(
-            v, means, cov3d, shs, radii, g.flags, scratch, dmeans2D, dopacity, dmeans3D, dcov3D, dsh, dcolors, daux, num_slabs);
-    else
-        preprocess_backward_kernel<false><<<grid, PB_THREADS, smem, s>>>(
-            v, means, cov3d, shs, radii, g.flags, scratch, dmeans2D, dopacity, dmeans3D, dcov3D, dsh, dcolors, daux, num_slabs);
+#define GGRT_LAUNCH_PB(AX, CM)                                                                                          \
+    {                                                                                                                   \
+        if (smem > 32 * 1024)                                                                                           \
+            cudaFuncSetAttribute(preprocess_backward_kernel<AX, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                 (int)smem);                                                                            \
+        preprocess_backward_kernel<AX, CM><<<grid, PB_THREADS, smem, s>>>(v, means, cov3d, shs, radii, g.flags, scratch, \
+                                                                          dmeans2D, dopacity, dmeans3D, dcov3D, dsh,    \
+                                                                          dcolors, daux, num_slabs);                    \
+    }
+    const bool cm = v.sh_ks == 1 && v.K > 1;
+    if (daux) {
+        if (cm) GGRT_LAUNCH_PB(true, true) else GGRT_LAUNCH_PB(true, false)
+    } else {
+        if (cm) GGRT_LAUNCH_PB(false, true) else GGRT_LAUNCH_PB(false, false)
+    }
+#undef GGRT_LAUNCH_PB
 }
 
 }  // namespace ggrt
