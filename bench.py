@@ -61,56 +61,60 @@ STAGE_GROUP = {
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region with NVML (a 2 ms polling thread: the timed
+    region is only tens of milliseconds long, too short for `nvidia-smi -lms`)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = {  # nvmlClocksEventReasons bit -> name used by B200_PROFILING.md
+        0x0000000000000008: "hw_slowdown",
+        0x0000000000000040: "hw_thermal_slowdown",
+        0x0000000000000020: "sw_thermal_slowdown",
+        0x0000000000000004: "sw_power_cap",
+    }
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples, self.bits = [], 0
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.max_mhz = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
-                 str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            self.err = f"NVML unavailable: {e}"
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception as e:  # pragma: no cover
+                self.err = str(e)
+                return
+            time.sleep(0.002)
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": [self.err or "not started"]}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        reasons = sorted(n for bit, n in self.REASONS.items() if self.bits & bit)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.samples), "reasons": reasons}
 
 
 def make_inputs(workload: str, rank: int):

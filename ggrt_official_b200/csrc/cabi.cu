@@ -293,7 +293,7 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
                          const void* binning_buffer, const void* image_buffer, const float* dL_dout_color,
                          const float* dL_dout_aux, float* grad_scratch, float* dL_dmeans2D, float* dL_dopacity,
                          float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dcolors, float* dL_daux,
-                         ggrt_stream_t stream) {
+                         float* dL_dcamera, ggrt_stream_t stream) {
     View v;
     GGRT_TRY(make_view(settings, layout, P, &v));
     if (P == 0) return GGRT_OK;
@@ -317,6 +317,8 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
     BinPtrs b = bin_ptrs(const_cast<void*>(binning_buffer), num_rendered);
     if (cudaMemsetAsync(grad_scratch, 0, (size_t)P * GRAD_STRIDE * sizeof(float), s) != cudaSuccess)
         return check_launch("memset grad scratch", 0, s);
+    if (dL_dcamera && cudaMemsetAsync(dL_dcamera, 0, 35 * sizeof(float), s) != cudaSuccess)
+        return check_launch("memset camera gradient", 0, s);
     if (num_rendered > 0) {
         { StageTimer t_(GGRT_STAGE_RENDER_BACKWARD, s); launch_render_backward(v, g, im, b, dL_dout_color, dL_dout_aux, grad_scratch, s); }
         GGRT_TRY(check_launch("render_backward", dbg, s));
@@ -324,7 +326,7 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
     {
         StageTimer t_(GGRT_STAGE_PREPROCESS_BACKWARD, s);
         launch_preprocess_backward(v, means3D, cov3D_precomp, shs, radii, g, grad_scratch, dL_dmeans2D, dL_dopacity,
-                                   dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dcolors, dL_daux, s);
+                                   dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dcolors, dL_daux, dL_dcamera, s);
     }
     GGRT_TRY(check_launch("preprocess_backward", dbg, s));
     return GGRT_OK;

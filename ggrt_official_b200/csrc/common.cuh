@@ -85,7 +85,8 @@ void launch_render_backward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, 
                             const float* dL_dout_aux, float* scratch, cudaStream_t s);
 void launch_preprocess_backward(const View& v, const float* means, const float* cov3d, const float* shs,
                                 const int* radii, GeomPtrs g, const float* scratch, float* dmeans2D, float* dopacity,
-                                float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, float* daux, cudaStream_t s);
+                                float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, float* daux, float* dcam,
+                                cudaStream_t s);
 void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------
@@ -151,8 +152,24 @@ __device__ __forceinline__ bool geometry(const View& v, const float* __restrict_
     return true;
 }
 
-// the 6 upper-triangular covariance entries (xx,xy,xz,yy,yz,zz) of Gaussian i, scaled by s*s (exactly rounded,
-// matching the reference's separate `covariances * scale**2`, cuda_splatting.py:70)
+// the 6 upper-triangular covariance entries (xx,xy,xz,yy,yz,zz) of Gaussian i, as stored (prefetchable: no use
+// of the loaded values); scale_cov6 applies the scene scale afterwards
+__device__ __forceinline__ void load_cov6_raw(const View& v, const float* __restrict__ cov3d, int i, float cv[6]) {
+    const int stride = v.cov_stride;
+    const float* c = cov3d + (size_t)i * stride;
+    if (stride == 9) {
+        cv[0] = c[0], cv[1] = c[1], cv[2] = c[2], cv[3] = c[4], cv[4] = c[5], cv[5] = c[8];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cv[k] = c[k];
+    }
+}
+// s*s scaling, exactly rounded, matching the reference's separate `covariances * scale**2` (cuda_splatting.py:70)
+__device__ __forceinline__ void scale_cov6(const View& v, float cv[6]) {
+    const float s2 = fmul(v.scale, v.scale);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cv[k] = fmul(cv[k], s2);
+}
 __device__ __forceinline__ void load_cov6(const View& v, const float* __restrict__ cov3d, int i, float cv[6]) {
     const int stride = v.cov_stride;
     const float* c = cov3d + (size_t)i * stride;

@@ -233,7 +233,7 @@ color_kernel(View v, const float* __restrict__ means, const float* __restrict__ 
         n_radius = 0;
         if (sl < num_slabs && i < v.P) {
             n_radius = radii[i];
-            n_mx = fmul(means[3 * i], v.scale), n_my = fmul(means[3 * i + 1], v.scale), n_mz = fmul(means[3 * i + 2], v.scale);
+            n_mx = means[3 * i], n_my = means[3 * i + 1], n_mz = means[3 * i + 2];  // raw: scaled when consumed
             n_depth = aux ? aux[i] : g.rec0[i].w;  // 4th blended channel: caller's aux or the view depth
         }
     };
@@ -249,7 +249,7 @@ color_kernel(View v, const float* __restrict__ means, const float* __restrict__ 
         const int i = base + threadIdx.x;
         const bool valid = threadIdx.x < cnt;
         const bool vis = valid && n_radius > 0;
-        const float mx = n_mx, my_ = n_my, mz = n_mz, depth = n_depth;
+        const float mx = fmul(n_mx, v.scale), my_ = fmul(n_my, v.scale), mz = fmul(n_mz, v.scale), depth = n_depth;
         prefetch(sl + gridDim.x);
         float* slab = slab_ring + st * slab_floats;
         if (shs != nullptr) {

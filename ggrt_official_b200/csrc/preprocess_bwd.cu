@@ -31,7 +31,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
                            const uint8_t* __restrict__ flags, const float* __restrict__ scratch,
                            float* __restrict__ dmeans2D, float* __restrict__ dopacity, float* __restrict__ dmeans3D,
                            float* __restrict__ dcov3D, float* __restrict__ dsh, float* __restrict__ dcolors,
-                           float* __restrict__ daux, int num_slabs) {
+                           float* __restrict__ daux, float* __restrict__ dcam, int num_slabs) {
     extern __shared__ __align__(128) float slab_ring[];
     __shared__ __align__(8) unsigned long long full_bar[PB_STAGES];
     __shared__ float sV[16], sM[16];
@@ -75,8 +75,8 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             n_radius = radii[i];
             n_flags = flags[i];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) n_mean[k] = fmul(means[3 * (size_t)i + k], v.scale);
-            load_cov6(v, cov3d, i, n_cv);
+            for (int k = 0; k < 3; ++k) n_mean[k] = means[3 * (size_t)i + k];  // raw: the scene scale is applied
+            load_cov6_raw(v, cov3d, i, n_cv);                                  // when the values are consumed
             const float* gs = scratch + (size_t)i * GRAD_STRIDE;
             n_ga = *reinterpret_cast<const float4*>(gs);
             n_gb = *reinterpret_cast<const float4*>(gs + 4);
@@ -86,6 +86,13 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     };
     prefetch(blockIdx.x);
     const float cpx = v.campos[0], cpy = v.campos[1], cpz = v.campos[2];
+
+    // opt-in camera gradients (dcam != NULL): per-thread partial sums of dL/dviewmatrix (12 entries: columns
+    // 0..2), dL/dprojmatrix (12 entries: columns 0, 1, 3) and dL/dcampos, reduced once at the end of the kernel
+    float camV[12], camM[12], camC[3];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) camV[k] = 0.f, camM[k] = 0.f;
+    camC[0] = camC[1] = camC[2] = 0.f;
 
     int it = 0;
     for (int sl = blockIdx.x; sl < num_slabs; sl += gridDim.x, ++it) {
@@ -100,10 +107,11 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     const int nfl = cnt * row;
     const bool slab_tma = tma_ok && ((nfl * 4) & 15) == 0;
     const uint32_t fl = n_flags;
-    const float mean_x = n_mean[0], mean_y = n_mean[1], mean_z = n_mean[2];
+    const float mean_x = fmul(n_mean[0], v.scale), mean_y = fmul(n_mean[1], v.scale), mean_z = fmul(n_mean[2], v.scale);
     float cv[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) cv[k] = n_cv[k];
+    scale_cov6(v, cv);
     const float4 ga = n_ga, gb = n_gb;
     const float gc = n_gc, gaux = n_gx;
     prefetch(sl + gridDim.x);
@@ -189,6 +197,28 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
                        (sM[4 * k + 0] * mw - sM[4 * k + 3] * mul1) * g2x +
                        (sM[4 * k + 1] * mw - sM[4 * k + 3] * mul2) * g2y;
         }
+        if (dcam != nullptr) {
+            // t = [p,1].V[:, :3] and hom = [p,1].M  =>  dL/dV[i][j] += p_i dL/dt_j,  dL/dM[i][j] += p_i dL/dhom_j;
+            // Tm = J.Rw with Rw[m][k] = V[k][m]    =>  dL/dV[k][m] += sum_r dTm[r][k] J[r][m]
+            const float ph[4] = {mean_x, mean_y, mean_z, 1.0f};
+            const float dt[3] = {dtx, dty, dtz};
+            const float J00 = v.fx * z1, J02 = -v.fx * q.cx * z2, J11 = v.fy * z1, J12 = -v.fy * q.cy * z2;
+            const float dhx = g2x * mw, dhy = g2y * mw, dhw = -(q.hx * g2x + q.hy * g2y) * mw * mw;
+#pragma unroll
+            for (int i2 = 0; i2 < 4; ++i2) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) camV[3 * i2 + j] = fmaf(ph[i2], dt[j], camV[3 * i2 + j]);
+                camM[3 * i2 + 0] = fmaf(ph[i2], dhx, camM[3 * i2 + 0]);
+                camM[3 * i2 + 1] = fmaf(ph[i2], dhy, camM[3 * i2 + 1]);
+                camM[3 * i2 + 2] = fmaf(ph[i2], dhw, camM[3 * i2 + 2]);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                camV[3 * k + 0] = fmaf(dTm[0][k], J00, camV[3 * k + 0]);
+                camV[3 * k + 1] = fmaf(dTm[1][k], J11, camV[3 * k + 1]);
+                camV[3 * k + 2] += dTm[0][k] * J02 + dTm[1][k] * J12;
+            }
+        }
     }
 
     if (shs != nullptr) {
@@ -264,9 +294,10 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             // through normalize(): (I |v|^2 - v v^T) / |v|^3
             const float inv3 = inv * inv * inv;
             const float dot = vx * ddx + vy * ddy + vz * ddz;
-            dmean[0] += (len2 * ddx - vx * dot) * inv3;
-            dmean[1] += (len2 * ddy - vy * dot) * inv3;
-            dmean[2] += (len2 * ddz - vz * dot) * inv3;
+            const float m0 = (len2 * ddx - vx * dot) * inv3, m1 = (len2 * ddy - vy * dot) * inv3,
+                        m2 = (len2 * ddz - vz * dot) * inv3;
+            dmean[0] += m0, dmean[1] += m1, dmean[2] += m2;
+            if (dcam != nullptr) camC[0] -= m0, camC[1] -= m1, camC[2] -= m2;  // dir = p - campos
         } else if (valid) {
             for (int k = 0; k < row; ++k) my[k] = 0.f;
         }
@@ -324,12 +355,36 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
         }
     }
     }  // slab loop
+    if (dcam != nullptr) {  // layout of dcam: viewmatrix [4,4] | projmatrix [4,4] | campos [3]
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            float a = camV[k], b = camM[k];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, d);
+                b += __shfl_xor_sync(0xffffffffu, b, d);
+            }
+            if ((threadIdx.x & 31) == 0) {
+                const int i2 = k / 3, j = k % 3;
+                atomicAdd(dcam + 4 * i2 + j, a);
+                atomicAdd(dcam + 16 + 4 * i2 + (j == 2 ? 3 : j), b);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float a = camC[k];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+            if ((threadIdx.x & 31) == 0) atomicAdd(dcam + 32 + k, a);
+        }
+    }
     if (threadIdx.x == 0) bulk_wait0();  // all bulk stores of this CTA have completed
 }
 
 void launch_preprocess_backward(const View& v, const float* means, const float* cov3d, const float* shs,
                                 const int* radii, GeomPtrs g, const float* scratch, float* dmeans2D, float* dopacity,
-                                float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, float* daux, cudaStream_t s) {
+                                float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, float* daux, float* dcam,
+                                cudaStream_t s) {
     if (v.P == 0) return;
     const size_t smem = shs ? (size_t)PB_STAGES * PB_THREADS * v.K * 3 * sizeof(float) : 0;
     const int num_slabs = (v.P + PB_THREADS - 1) / PB_THREADS;
@@ -345,7 +400,7 @@ void launch_preprocess_backward(const View& v, const float* means, const float* 
                                  (int)smem);                                                                            \
         preprocess_backward_kernel<AX, CM><<<grid, PB_THREADS, smem, s>>>(v, means, cov3d, shs, radii, g.flags, scratch, \
                                                                           dmeans2D, dopacity, dmeans3D, dcov3D, dsh,    \
-                                                                          dcolors, daux, num_slabs);                    \
+                                                                          dcolors, daux, dcam, num_slabs);              \
     }
     const bool cm = v.sh_ks == 1 && v.K > 1;
     if (daux) {

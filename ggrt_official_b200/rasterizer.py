@@ -165,10 +165,12 @@ def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: Gauss
 
 
 def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = None,
-                 grad_aux: Optional[torch.Tensor] = None) -> dict:
+                 grad_aux: Optional[torch.Tensor] = None, want_camera: bool = False) -> dict:
     """Runs the backward through the C ABI.  `out` may supply preallocated, contiguous float32 output
     tensors (e.g. views into one gradient arena that is all-reduced across GPUs afterwards).
-    `grad_aux` [H,W]: gradient of the third output (only when the forward was given `aux`)."""
+    `grad_aux` [H,W]: gradient of the third output (only when the forward was given `aux`).
+    `want_camera`: also return out["dcamera"] = dL/d(viewmatrix [16] | projmatrix [16] | campos [3]) (opt-in
+    extension; the reference treats the camera as constant)."""
     L = _cabi.lib()
     c: _Call = state["call"]
     dev = c.device
@@ -199,6 +201,7 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
             dsh=buf("dsh", tuple(c.sh.shape)) if c.sh is not None else None,
             dcolors=buf("dcolors", (c.P, 3)) if c.sh is None else None,
             daux=buf("daux", (c.P,)) if ga is not None else None,
+            dcamera=torch.zeros(35, **f32) if want_camera else None,
         )
         lay = C.byref(c.layout) if c.layout is not None else None
         _cabi.check(L.ggrt_raster_backward(C.byref(c.settings), lay, c.P, state["N"], _ptr(c.means3D), _ptr(c.cov3D),
@@ -206,7 +209,7 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
                                            _ptr(state["binning"]), _ptr(state["img"]), _ptr(g), _ptr(ga),
                                            _ptr(scratch), _ptr(out["dmeans2D"]), _ptr(out["dopacity"]),
                                            _ptr(out["dmeans3D"]), _ptr(out["dcov3D"]), _ptr(out["dsh"]),
-                                           _ptr(out["dcolors"]), _ptr(out["daux"]), sp),
+                                           _ptr(out["dcolors"]), _ptr(out["daux"]), _ptr(out["dcamera"]), sp),
                     "backward")
     return out
 
@@ -222,7 +225,9 @@ def _dump(path: str, payload) -> None:
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings, aux=None, layout=None):
+                raster_settings, aux=None, layout=None, viewmatrix=None, projmatrix=None, campos=None):
+        # viewmatrix / projmatrix / campos are the tensors of raster_settings again: passing them as explicit
+        # inputs lets autograd deliver camera gradients when (and only when) they require grad
         try:
             st = forward_raw(means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings, aux, layout)
         except Exception:
@@ -249,12 +254,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         st = ctx.state
         c: _Call = st["call"]
         grad_aux = _grad_depth if ctx.has_aux else None
+        want_cam = any(ctx.needs_input_grad[11:14])
         if grad_color is None and grad_aux is None:
-            return (None,) * 11
+            return (None,) * 14
         if grad_color is None:
             grad_color = torch.zeros((3, c.H, c.W), dtype=torch.float32, device=c.device)
         try:
-            g = backward_raw(st, grad_color, grad_aux=grad_aux)
+            g = backward_raw(st, grad_color, grad_aux=grad_aux, want_camera=want_cam)
         except Exception:
             if ctx.raster_settings.debug:
                 _dump("snapshot_bw.dump", (c.means3D, c.sh, c.colors, c.opacities, c.cov3D, grad_color))
@@ -267,14 +273,23 @@ class _RasterizeGaussians(torch.autograd.Function):
         daux = g.get("daux")
         if daux is not None:
             daux = daux.reshape(ctx.aux_shape)
+        dview = dproj = dcampos = None
+        if want_cam:
+            rs = ctx.raster_settings
+            cam = g["dcamera"]
+            dview = cam[:16].reshape(rs.viewmatrix.shape) if ctx.needs_input_grad[11] else None
+            dproj = cam[16:32].reshape(rs.projmatrix.shape) if ctx.needs_input_grad[12] else None
+            dcampos = cam[32:35].reshape(rs.campos.shape) if ctx.needs_input_grad[13] else None
         return (g["dmeans3D"], g["dmeans2D"] if ctx.needs_input_grad[1] else None, dsh, g["dcolors"],
-                g["dopacity"].reshape(ctx.opacity_shape), None, None, g["dcov3D"], None, daux, None)
+                g["dopacity"].reshape(ctx.opacity_shape), None, None, g["dcov3D"], None, daux, None, dview, dproj,
+                dcampos)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                         raster_settings, aux_precomp=None, layout=None):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings, aux_precomp, layout)
+                                     cov3Ds_precomp, raster_settings, aux_precomp, layout, raster_settings.viewmatrix,
+                                     raster_settings.projmatrix, raster_settings.campos)
 
 
 class GaussianRasterizer(nn.Module):

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GGRT_RASTER_ABI_VERSION 3
+#define GGRT_RASTER_ABI_VERSION 4
 #define GGRT_RASTER_TILE 16 /* tile edge in pixels (tile ids are part of the contract) */
 #define GGRT_RASTER_SUBS 16 /* pair counters per tile (contention spreading) */
 
@@ -144,7 +144,9 @@ int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, in
  * by the callee).  Outputs, all overwritten: dL_dmeans2D [P,3] (gradient w.r.t. NDC
  * xy, z = 0), dL_dopacity [P], dL_dmeans3D [P,3], dL_dcov3D [P,6], either dL_dsh [P,K,3]
  * (when shs was given) or dL_dcolors [P,3] (the unused one is NULL), and dL_daux [P] (NULL
- * unless dL_dout_aux is given).
+ * unless dL_dout_aux is given).  dL_dcamera (NULL, or 35 floats: dL/dviewmatrix [4,4] |
+ * dL/dprojmatrix [4,4] | dL/dcampos [3], overwritten) is an opt-in extension: the reference
+ * treats the camera as constant (poses are detached, train_ggrt_stable.py:106).
  */
 int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInputLayout* layout, int32_t P,
                          int64_t num_rendered, const float* means3D,
@@ -152,7 +154,7 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
                          const void* binning_buffer, const void* image_buffer, const float* dL_dout_color,
                          const float* dL_dout_aux, float* grad_scratch, float* dL_dmeans2D, float* dL_dopacity,
                          float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dcolors, float* dL_daux,
-                         ggrt_stream_t stream);
+                         float* dL_dcamera, ggrt_stream_t stream);
 
 /* Frustum test only (upstream markVisible): present[i] = view-space z > 0.2. */
 int ggrt_raster_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present,

@@ -56,7 +56,8 @@ def fake_forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs, 
                 max_tile_pairs=0, _oracle=(cam, inp, f))
 
 
-def fake_backward_raw(state, grad_color, out=None, grad_aux=None):
+def fake_backward_raw(state, grad_color, out=None, grad_aux=None, want_camera=False):
+    assert not want_camera, "camera gradients are only implemented on the CUDA path"
     cam, inp, f = state["_oracle"]
     g = co.backward(cam, inp["means"], inp["cov"], inp["opac"], f, _np(grad_color), sh=inp["sh"], colors=inp["colors"],
                     dL_ddepth_img=_np(grad_aux))
@@ -89,9 +90,9 @@ def installed():
     orig_fwd = R._RasterizeGaussians.forward
 
     def fwd(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings,
-            aux=None, layout=None):
+            aux=None, layout=None, viewmatrix=None, projmatrix=None, campos=None):
         out = orig_fwd(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                       raster_settings, aux, layout)
+                       raster_settings, aux, layout, viewmatrix, projmatrix, campos)
         ctx.state["_oracle"] = CALLS_STATE.pop()
         return out
 

@@ -115,6 +115,42 @@ def test_aux_channel_forward_and_backward():
         R.backward_raw(st2, t(g), grad_aux=t(ga))
 
 
+def test_camera_gradients_match_autograd_restatement():
+    """Opt-in extension (BASELINE config 3): gradients w.r.t. viewmatrix / projmatrix / campos flow when those
+    tensors require grad.  Checked against autograd of the dense PyTorch restatement (oracle/torch_ref.py)."""
+    from oracle import torch_ref as tr
+
+    P, H, W, deg = 400, 48, 64, 2
+    _, ri = small_case(P, H, W, deg, bg=(0.2, 0.1, 0.3), seed=31, cov_scale=9.0, behind_fraction=0.0)
+    dev = "cuda:0"
+    t = lambda a: torch.tensor(np.asarray(a), device=dev)
+    view, proj, campos = t(ri.viewmatrix).requires_grad_(), t(ri.projmatrix).requires_grad_(), t(ri.campos).requires_grad_()
+    rs = G.settings_from(ri, dev)._replace(viewmatrix=view, projmatrix=proj, campos=campos)
+    means = t(ri.means3D).requires_grad_()
+    img, _, _ = GaussianRasterizer(rs)(means3D=means, means2D=torch.zeros_like(means, requires_grad=True),
+                                       shs=t(ri.shs), opacities=t(ri.opacities), cov3D_precomp=t(ri.cov3D))
+    g = np.random.default_rng(8).standard_normal((3, H, W)).astype(np.float32)
+    (img * t(g)).sum().backward()
+
+    d = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)
+    v64, p64, c64, m64 = d(ri.viewmatrix).requires_grad_(), d(ri.projmatrix).requires_grad_(), \
+        d(ri.campos).requires_grad_(), d(ri.means3D).requires_grad_()
+    color, _, _ = tr.rasterize(m64, d(ri.cov3D), d(ri.opacities), view=v64, proj=p64, campos=c64, bg=d(ri.bg),
+                               tanfovx=ri.tanfovx, tanfovy=ri.tanfovy, H=H, W=W, deg=deg, sh=d(ri.shs))
+    (color * d(g)).sum().backward()
+    for name, got, ref in (("viewmatrix", view.grad, v64.grad), ("projmatrix", proj.grad, p64.grad),
+                           ("campos", campos.grad, c64.grad), ("means3D", means.grad, m64.grad)):
+        got, ref = got.cpu().double(), ref
+        err = float((got - ref).abs().max() / ref.abs().max())
+        assert err < 2e-3, (name, err, got, ref)
+    # camera tensors that do not require grad cost nothing and get no gradient
+    rs2 = G.settings_from(ri, dev)
+    img2, _, _ = GaussianRasterizer(rs2)(means3D=means, means2D=torch.zeros_like(means, requires_grad=True),
+                                         shs=t(ri.shs), opacities=t(ri.opacities), cov3D_precomp=t(ri.cov3D))
+    img2.sum().backward()
+    assert rs2.viewmatrix.grad is None
+
+
 def test_config1_10k_256(tmp_path):
     """BASELINE config 1: 10K Gaussians, 256x256, 1 view, forward vs the oracle."""
     ri = to_raster_inputs(make_scene(10_000, 256, 256, sh_degree=4))
