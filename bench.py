@@ -211,7 +211,7 @@ def run_ours(args, rank, world, local_rank):
         st = R.forward_raw(means, shs, None, opac, cov, rs)
         # the Gaussian gradients land in one contiguous arena that is summed over the per-GPU views with
         # a single NCCL all-reduce
-        grads = R.backward_raw(st, grad_img, out=arena.views if arena else None)
+        grads = R.backward_raw(st, grad_img, out=arena.views if arena else None, want_camera=args.pose_grads)
         if arena:
             arena.all_reduce()
         state["N"], state["max_tile_pairs"] = st["N"], st["max_tile_pairs"]
@@ -394,7 +394,7 @@ def run_ours(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "P": P, "H": H, "W": W, "N_pairs": int(N),
                        "max_pairs_per_tile": int(state["max_tile_pairs"]), "sh_degree": SH_DEGREE,
-                       "views_per_step": world, "l2": "flushed before every timed step (256 MiB write, then 256 MiB read so the step does not pay the flush's write-back)",
+                       "views_per_step": world, "pose_grads": bool(args.pose_grads), "l2": "flushed before every timed step (256 MiB write, then 256 MiB read so the step does not pay the flush's write-back)",
                        "parallelism": f"one target view per GPU x{world}" + (", NCCL all-reduce of Gaussian gradients"
                                                                             if world > 1 else "")},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -417,6 +417,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pose-grads", action="store_true",
+                    help="also compute dL/d(viewmatrix, projmatrix, campos) in the backward (BASELINE config 3)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

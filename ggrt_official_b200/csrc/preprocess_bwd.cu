@@ -24,7 +24,7 @@ constexpr int PB_THREADS = GGRT_PB_THREADS;
 
 constexpr int PB_STAGES = GGRT_PB_STAGES;
 
-template <bool AUX, bool CMAJOR>
+template <bool AUX, bool CMAJOR, bool POSE>
 __global__ void __launch_bounds__(PB_THREADS, 3)
 preprocess_backward_kernel(View v, const float* __restrict__ means, const float* __restrict__ cov3d,
                            const float* __restrict__ shs, const int* __restrict__ radii,
@@ -81,7 +81,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             n_ga = *reinterpret_cast<const float4*>(gs);
             n_gb = *reinterpret_cast<const float4*>(gs + 4);
             n_gc = gs[8];
-            if (AUX) n_gx = gs[G_AUX];
+            if (AUX && daux) n_gx = gs[G_AUX];
         }
     };
     prefetch(blockIdx.x);
@@ -197,7 +197,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
                        (sM[4 * k + 0] * mw - sM[4 * k + 3] * mul1) * g2x +
                        (sM[4 * k + 1] * mw - sM[4 * k + 3] * mul2) * g2y;
         }
-        if (dcam != nullptr) {
+        if (POSE) {
             // t = [p,1].V[:, :3] and hom = [p,1].M  =>  dL/dV[i][j] += p_i dL/dt_j,  dL/dM[i][j] += p_i dL/dhom_j;
             // Tm = J.Rw with Rw[m][k] = V[k][m]    =>  dL/dV[k][m] += sum_r dTm[r][k] J[r][m]
             const float ph[4] = {mean_x, mean_y, mean_z, 1.0f};
@@ -297,7 +297,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             const float m0 = (len2 * ddx - vx * dot) * inv3, m1 = (len2 * ddy - vy * dot) * inv3,
                         m2 = (len2 * ddz - vz * dot) * inv3;
             dmean[0] += m0, dmean[1] += m1, dmean[2] += m2;
-            if (dcam != nullptr) camC[0] -= m0, camC[1] -= m1, camC[2] -= m2;  // dir = p - campos
+            if (POSE) camC[0] -= m0, camC[1] -= m1, camC[2] -= m2;  // dir = p - campos
         } else if (valid) {
             for (int k = 0; k < row; ++k) my[k] = 0.f;
         }
@@ -339,7 +339,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     if (valid) {
         dmeans2D[3 * i] = g2x, dmeans2D[3 * i + 1] = g2y, dmeans2D[3 * i + 2] = 0.f;
         dopacity[i] = gop;
-        if (AUX) daux[i] = live ? gaux : 0.f;
+        if (AUX && daux) daux[i] = live ? gaux : 0.f;
         // chain rule of the scene scale: means_used = s * means, cov_used = s^2 * cov
         const float s1 = v.scale, s2 = v.scale * v.scale;
 #pragma unroll
@@ -355,7 +355,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
         }
     }
     }  // slab loop
-    if (dcam != nullptr) {  // layout of dcam: viewmatrix [4,4] | projmatrix [4,4] | campos [3]
+    if (POSE) {  // layout of dcam: viewmatrix [4,4] | projmatrix [4,4] | campos [3]
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
             float a = camV[k], b = camM[k];
@@ -393,20 +393,23 @@ void launch_preprocess_backward(const View& v, const float* means, const float* 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int per_sm = smem ? max(1, min(8, (int)((220 * 1024) / (smem + 1024)))) : 8;
     const int grid = min(num_slabs, per_sm * sms);  // persistent CTAs
-#define GGRT_LAUNCH_PB(AX, CM)                                                                                          \
+#define GGRT_LAUNCH_PB(AX, CM, PO)                                                                                      \
     {                                                                                                                   \
         if (smem > 32 * 1024)                                                                                           \
-            cudaFuncSetAttribute(preprocess_backward_kernel<AX, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+            cudaFuncSetAttribute(preprocess_backward_kernel<AX, CM, PO>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                  (int)smem);                                                                            \
-        preprocess_backward_kernel<AX, CM><<<grid, PB_THREADS, smem, s>>>(v, means, cov3d, shs, radii, g.flags, scratch, \
-                                                                          dmeans2D, dopacity, dmeans3D, dcov3D, dsh,    \
-                                                                          dcolors, daux, dcam, num_slabs);              \
+        preprocess_backward_kernel<AX, CM, PO><<<grid, PB_THREADS, smem, s>>>(v, means, cov3d, shs, radii, g.flags,     \
+                                                                              scratch, dmeans2D, dopacity, dmeans3D,    \
+                                                                              dcov3D, dsh, dcolors, daux, dcam,         \
+                                                                              num_slabs);                               \
     }
     const bool cm = v.sh_ks == 1 && v.K > 1;
-    if (daux) {
-        if (cm) GGRT_LAUNCH_PB(true, true) else GGRT_LAUNCH_PB(true, false)
+    if (dcam) {  // camera gradients are rare: one instantiation per SH layout, aux always compiled in
+        if (cm) GGRT_LAUNCH_PB(true, true, true) else GGRT_LAUNCH_PB(true, false, true)
+    } else if (daux) {
+        if (cm) GGRT_LAUNCH_PB(true, true, false) else GGRT_LAUNCH_PB(true, false, false)
     } else {
-        if (cm) GGRT_LAUNCH_PB(false, true) else GGRT_LAUNCH_PB(false, false)
+        if (cm) GGRT_LAUNCH_PB(false, true, false) else GGRT_LAUNCH_PB(false, false, false)
     }
 #undef GGRT_LAUNCH_PB
 }
