@@ -278,7 +278,7 @@ def run_ours(args, rank, world, local_rank):
     traffic, traffic_src = None, None
     try:
         prof = json.loads((ROOT / "profiles" / "r1_ncu_kernels.json").read_text())
-        if prof.get("workload", "").startswith(WORKLOADS[args.workload][3][:2]):
+        if args.gaussians == 0 and prof.get("workload", "").startswith(WORKLOADS[args.workload][3][:2]):
             members = [k for k, grp in STAGE_GROUP.items() if grp == top]
             vals = [v["dram_traffic_bytes"] for name, v in prof["kernels"].items()
                     if any(name.startswith(m + "_kernel") for m in members)]
@@ -417,9 +417,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gaussians", type=int, default=0,
+                    help="override the Gaussian count of the workload (BASELINE config 5: 50K..2M sweep at 1008x756)")
     ap.add_argument("--pose-grads", action="store_true",
                     help="also compute dL/d(viewmatrix, projmatrix, campos) in the backward (BASELINE config 3)")
     args = ap.parse_args()
+    if args.gaussians > 0:
+        P0, H0, W0, d0 = WORKLOADS[args.workload]
+        WORKLOADS[args.workload] = (args.gaussians, H0, W0, f"C5 sweep point: {args.gaussians} Gaussians, {W0}x{H0}, SH degree 4, fwd+bwd")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -208,6 +208,10 @@ void launch_sort_tiles(const View& v, ImagePtrs im, BinPtrs b, uint32_t max_tile
         sort_tiles_reg_kernel<4><<<T, 128, 0, s>>>(T, im.starts, b.keys, b.points);
         return;
     }
+    if (max_tile_pairs <= 2048) {
+        sort_tiles_reg_kernel<8><<<T, 256, 0, s>>>(T, im.starts, b.keys, b.points);
+        return;
+    }
     // shared-memory capacity tier from the largest tile (reported by scan_tiles)
     uint32_t cap = 1024;
     while (cap < max_tile_pairs && cap < 16384) cap <<= 1;

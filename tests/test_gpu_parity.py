@@ -28,7 +28,8 @@ CASES = [
     (1000, 33, 47, 3, (0.3, 0.3, 0.3), 1.0, 5),
     (500, 16, 16, 1, (0.0, 0.0, 0.0), 100.0, 6),  # single tile, heavy overlap
     (1400, 32, 32, 1, (0.0, 0.0, 0.0), 60.0, 7),  # 513..1024 pairs per tile: 4-warp register sort
-    (4000, 32, 32, 0, (0.1, 0.1, 0.1), 60.0, 8),  # > 1024 pairs per tile: shared-memory sort, multi-batch render
+    (1900, 32, 32, 0, (0.0, 0.0, 0.0), 60.0, 9),  # 1025..2048 pairs per tile: 8-warp register sort
+    (4000, 32, 32, 0, (0.1, 0.1, 0.1), 60.0, 8),  # > 2048 pairs per tile: shared-memory sort, multi-batch render
 ]
 
 
