@@ -10,7 +10,7 @@ from pathlib import Path
 
 from . import build as _build
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 _lib = None
 
 
@@ -91,7 +91,7 @@ def lib():
     L.ggrt_raster_binning_bytes.argtypes = [i64]
     L.ggrt_raster_binning_bytes.restype = sz
     L.ggrt_raster_forward_prepare.argtypes = [C.POINTER(Settings), C.POINTER(InputLayout), i32] + [vp] * 11
-    L.ggrt_raster_forward_render.argtypes = [C.POINTER(Settings), i32, i64, u32, vp, vp, vp, vp, vp, vp]
+    L.ggrt_raster_forward_render.argtypes = [C.POINTER(Settings), i32, i64, u32, i32, vp, vp, vp, vp, vp, vp]
     L.ggrt_raster_backward.argtypes = [C.POINTER(Settings), C.POINTER(InputLayout), i32, i64] + [vp] * 19
     L.ggrt_raster_mark_visible.argtypes = [i32, vp, vp, vp, vp]
     L.ggrt_raster_profile_enable.argtypes = [i32]

@@ -16,7 +16,8 @@ constexpr int EMIT_THREADS = 256;
 constexpr int SORT_THREADS = 256;
 
 __global__ void __launch_bounds__(EMIT_THREADS)
-emit_kernel(View v, GeomPtrs g, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ keys) {
+emit_kernel(View v, GeomPtrs g, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ keys,
+            uint32_t capacity) {
     const int i = blockIdx.x * EMIT_THREADS + threadIdx.x;
     if (i >= v.P) return;
     if (g.tiles[i] == 0) return;
@@ -27,7 +28,7 @@ emit_kernel(View v, GeomPtrs g, uint32_t* __restrict__ cursor, unsigned long lon
         for (int x = r.x; x < r.z; ++x) {
             // the (tile, sub-counter) segment start doubles as its allocation cursor: one returning atomic per pair
             const uint32_t slot = atomicAdd(&cursor[((y * v.gx + x) << SUBS_LOG2) + sub], 1u);
-            keys[slot] = key;
+            if (slot < capacity) keys[slot] = key;  // a too-small (speculative) buffer is detected and redone by the host
         }
 }
 
@@ -41,13 +42,13 @@ __device__ __forceinline__ void cmpxchg(unsigned long long* a, uint32_t i, uint3
 
 // Ascending-only bitonic network ("flip" formulation): every compare-exchange puts the
 // minimum at the lower index, so indices >= n behave as +inf padding and are skipped.
-__device__ __forceinline__ void bitonic_sort(unsigned long long* a, uint32_t n) {
+__device__ __forceinline__ void bitonic_sort(unsigned long long* a, uint32_t n, uint32_t nthreads = SORT_THREADS) {
     uint32_t n2 = 1;
     while (n2 < n) n2 <<= 1;
     const uint32_t half = n2 >> 1;
     for (uint32_t lk = 1; (1u << lk) <= n2; ++lk) {  // k = 2^lk: block size of this merge
         const uint32_t k = 1u << lk, hk = k >> 1;
-        for (uint32_t t = threadIdx.x; t < half; t += SORT_THREADS) {
+        for (uint32_t t = threadIdx.x; t < half; t += nthreads) {
             const uint32_t blk = t >> (lk - 1), off = t & (hk - 1);
             const uint32_t i = (blk << lk) + off, l = (blk << lk) + (k - 1 - off);
             if (l < n) cmpxchg(a, i, l);
@@ -55,7 +56,7 @@ __device__ __forceinline__ void bitonic_sort(unsigned long long* a, uint32_t n) 
         __syncthreads();
         for (int lj = (int)lk - 2; lj >= 0; --lj) {  // j = 2^lj: half-cleaner distance
             const uint32_t j = 1u << lj;
-            for (uint32_t t = threadIdx.x; t < half; t += SORT_THREADS) {
+            for (uint32_t t = threadIdx.x; t < half; t += nthreads) {
                 const uint32_t i = ((t >> lj) << (lj + 1)) + (t & (j - 1)), l = i + j;
                 if (l < n) cmpxchg(a, i, l);
             }
@@ -66,11 +67,11 @@ __device__ __forceinline__ void bitonic_sort(unsigned long long* a, uint32_t n) 
 
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_tiles_kernel(int T, const uint32_t* __restrict__ starts, unsigned long long* __restrict__ keys,
-                  uint32_t* __restrict__ points, uint32_t smem_cap) {
+                  uint32_t* __restrict__ points, uint32_t smem_cap, uint32_t capacity) {
     extern __shared__ __align__(16) unsigned long long sk[];
     const int tile = blockIdx.x;
     if (tile >= T) return;
-    const uint32_t s = starts[tile], e = starts[tile + 1], n = e - s;
+    const uint32_t s = min(starts[tile], capacity), e = min(starts[tile + 1], capacity), n = e - s;
     if (n == 0) return;
     unsigned long long* seg = keys + s;
     if (n <= smem_cap) {
@@ -114,13 +115,18 @@ __device__ __forceinline__ void keep(unsigned long long& mine, unsigned long lon
 template <int WARPS>
 __global__ void __launch_bounds__(32 * WARPS)
 sort_tiles_reg_kernel(int T, const uint32_t* __restrict__ starts, unsigned long long* __restrict__ keys,
-                      uint32_t* __restrict__ points) {
+                      uint32_t* __restrict__ points, uint32_t capacity) {
     __shared__ unsigned long long xch[WARPS > 1 ? 256 * WARPS : 1];
     const int tile = blockIdx.x;
     if (tile >= T) return;
-    const uint32_t s = starts[tile], n = starts[tile + 1] - s;
+    const uint32_t s = min(starts[tile], capacity), n = min(starts[tile + 1], capacity) - s;
     if (n == 0) return;
     unsigned long long* seg = keys + s;
+    if (n > 256u * WARPS) {  // larger than the (hinted) register capacity: same network in place in global memory
+        bitonic_sort(seg, n, 32 * WARPS);
+        for (uint32_t i = threadIdx.x; i < n; i += 32 * WARPS) points[s + i] = (uint32_t)seg[i];
+        return;
+    }
     const uint32_t tid = threadIdx.x, lane = tid & 31, i0 = tid * SORT_E;
     int L = 3;  // log2 of the padded size (>= 8)
     while ((1u << L) < n) ++L;
@@ -189,27 +195,28 @@ sort_tiles_reg_kernel(int T, const uint32_t* __restrict__ starts, unsigned long 
     (void)lane;
 }
 
-void launch_emit(const View& v, const int*, GeomPtrs g, ImagePtrs im, BinPtrs b, cudaStream_t s) {
+void launch_emit(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, uint32_t capacity, cudaStream_t s) {
     if (v.P == 0) return;
-    emit_kernel<<<(v.P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, s>>>(v, g, im.cursor, b.keys);
+    emit_kernel<<<(v.P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, s>>>(v, g, im.cursor, b.keys, capacity);
 }
 
-void launch_sort_tiles(const View& v, ImagePtrs im, BinPtrs b, uint32_t max_tile_pairs, cudaStream_t s) {
+void launch_sort_tiles(const View& v, ImagePtrs im, BinPtrs b, uint32_t max_tile_pairs, uint32_t capacity,
+                       cudaStream_t s) {
     const int T = v.gx * v.gy;
     if (max_tile_pairs <= 256) {
-        sort_tiles_reg_kernel<1><<<T, 32, 0, s>>>(T, im.starts, b.keys, b.points);
+        sort_tiles_reg_kernel<1><<<T, 32, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
         return;
     }
     if (max_tile_pairs <= 512) {
-        sort_tiles_reg_kernel<2><<<T, 64, 0, s>>>(T, im.starts, b.keys, b.points);
+        sort_tiles_reg_kernel<2><<<T, 64, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
         return;
     }
     if (max_tile_pairs <= 1024) {
-        sort_tiles_reg_kernel<4><<<T, 128, 0, s>>>(T, im.starts, b.keys, b.points);
+        sort_tiles_reg_kernel<4><<<T, 128, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
         return;
     }
     if (max_tile_pairs <= 2048) {
-        sort_tiles_reg_kernel<8><<<T, 256, 0, s>>>(T, im.starts, b.keys, b.points);
+        sort_tiles_reg_kernel<8><<<T, 256, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
         return;
     }
     // shared-memory capacity tier from the largest tile (reported by scan_tiles)
@@ -218,7 +225,7 @@ void launch_sort_tiles(const View& v, ImagePtrs im, BinPtrs b, uint32_t max_tile
     const size_t smem = (size_t)cap * sizeof(unsigned long long);
     if (smem > 32 * 1024)  // per-device attribute; cheap host-side call
         cudaFuncSetAttribute(sort_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
-    sort_tiles_kernel<<<v.gx * v.gy, SORT_THREADS, smem, s>>>(v.gx * v.gy, im.starts, b.keys, b.points, cap);
+    sort_tiles_kernel<<<v.gx * v.gy, SORT_THREADS, smem, s>>>(v.gx * v.gy, im.starts, b.keys, b.points, cap, capacity);
 }
 
 }  // namespace ggrt

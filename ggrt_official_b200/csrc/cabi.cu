@@ -245,12 +245,10 @@ int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, const GgrtRa
     for (int i = 0; i < GGRT_STAGE_COUNT; ++i) g_prof.used[i] = false;
     { StageTimer t_(GGRT_STAGE_GEOMETRY, s); launch_geometry(v, means3D, cov3D_precomp, opacities, radii, g, im, s); }
     GGRT_TRY(check_launch("geometry", dbg, s));
-    { StageTimer t_(GGRT_STAGE_SCAN_TILES, s); launch_scan_tiles(v, im, s); }
+    // {N, max pairs per tile} goes straight into the caller's mapped pinned host memory from the scan kernel:
+    // no copy node sits between the scan and the colour kernel
+    { StageTimer t_(GGRT_STAGE_SCAN_TILES, s); launch_scan_tiles(v, im, counts_host, s); }
     GGRT_TRY(check_launch("scan_tiles", dbg, s));
-    if (counts_host) {
-        if (cudaMemcpyAsync(counts_host, im.header, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess)
-            return check_launch("copy pair counts", 0, s);
-    }
     // colour evaluation does not depend on N: it runs while the host waits for the counts
     { StageTimer t_(GGRT_STAGE_COLOR, s); launch_color(v, means3D, shs, colors_precomp, aux, radii, g, s); }
     GGRT_TRY(check_launch("color", dbg, s));
@@ -258,7 +256,7 @@ int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, const GgrtRa
 }
 
 int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, int64_t num_rendered,
-                               uint32_t max_tile_pairs, const void* geom_buffer, void* binning_buffer,
+                               uint32_t max_tile_pairs, int32_t rescan, const void* geom_buffer, void* binning_buffer,
                                void* image_buffer, float* out_color, float* out_depth, ggrt_stream_t stream) {
     View v;
     GGRT_TRY(make_view(settings, nullptr, P, &v));
@@ -276,13 +274,18 @@ int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, in
     GeomPtrs g = geom_ptrs(const_cast<void*>(geom_buffer), P);
     ImagePtrs im = image_ptrs(image_buffer, v.H, v.W);
     BinPtrs b = bin_ptrs(binning_buffer, num_rendered);
+    const uint32_t capacity = (uint32_t)num_rendered;
+    if (rescan) {  // a previous speculative attempt consumed the emit cursors
+        { StageTimer t_(GGRT_STAGE_SCAN_TILES, s); launch_scan_tiles(v, im, nullptr, s); }
+        GGRT_TRY(check_launch("scan_tiles", dbg, s));
+    }
     if (num_rendered > 0) {
-        { StageTimer t_(GGRT_STAGE_EMIT, s); launch_emit(v, nullptr, g, im, b, s); }
+        { StageTimer t_(GGRT_STAGE_EMIT, s); launch_emit(v, g, im, b, capacity, s); }
         GGRT_TRY(check_launch("emit", dbg, s));
-        { StageTimer t_(GGRT_STAGE_SORT_TILES, s); launch_sort_tiles(v, im, b, max_tile_pairs, s); }
+        { StageTimer t_(GGRT_STAGE_SORT_TILES, s); launch_sort_tiles(v, im, b, max_tile_pairs, capacity, s); }
         GGRT_TRY(check_launch("sort_tiles", dbg, s));
     }
-    { StageTimer t_(GGRT_STAGE_RENDER_FORWARD, s); launch_render_forward(v, g, im, b, out_color, out_depth, s); }
+    { StageTimer t_(GGRT_STAGE_RENDER_FORWARD, s); launch_render_forward(v, g, im, b, capacity, out_color, out_depth, s); }
     GGRT_TRY(check_launch("render_forward", dbg, s));
     return GGRT_OK;
 }

@@ -74,13 +74,14 @@ BinPtrs bin_ptrs(void* base, long long N);
 // kernel launchers (each in its own translation unit)
 void launch_geometry(const View& v, const float* means, const float* cov3d, const float* opac, int* radii,
                      GeomPtrs g, ImagePtrs im, cudaStream_t s);
-void launch_scan_tiles(const View& v, ImagePtrs im, cudaStream_t s);
+void launch_scan_tiles(const View& v, ImagePtrs im, uint32_t* counts_host, cudaStream_t s);
 void launch_color(const View& v, const float* means, const float* shs, const float* colors, const float* aux,
                   const int* radii, GeomPtrs g, cudaStream_t s);
-void launch_emit(const View& v, const int* radii_or_null, GeomPtrs g, ImagePtrs im, BinPtrs b, cudaStream_t s);
-void launch_sort_tiles(const View& v, ImagePtrs im, BinPtrs b, uint32_t max_tile_pairs, cudaStream_t s);
-void launch_render_forward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, float* out_color, float* out_depth,
-                           cudaStream_t s);
+void launch_emit(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, uint32_t capacity, cudaStream_t s);
+void launch_sort_tiles(const View& v, ImagePtrs im, BinPtrs b, uint32_t max_tile_pairs, uint32_t capacity,
+                       cudaStream_t s);
+void launch_render_forward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, uint32_t capacity, float* out_color,
+                           float* out_depth, cudaStream_t s);
 void launch_render_backward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, const float* dL_dout,
                             const float* dL_dout_aux, float* scratch, cudaStream_t s);
 void launch_preprocess_backward(const View& v, const float* means, const float* cov3d, const float* shs,

@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_tiles_kernel(int T, const uin
                                                                 uint32_t* __restrict__ starts,
                                                                 uint32_t* __restrict__ sub_starts,
                                                                 unsigned long long* partials,
-                                                                uint32_t* __restrict__ header) {
+                                                                uint32_t* __restrict__ header,
+                                                                volatile uint32_t* counts_host) {
     __shared__ uint32_t warp_sums[SCAN_BLOCK / 32], warp_max[SCAN_BLOCK / 32];
     __shared__ uint32_t prefix_s, gmax_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -163,6 +164,11 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_tiles_kernel(int T, const uin
         header[1] = max(gmax_s, block_max);
         header[2] = 0u;
         header[3] = 0u;
+        if (counts_host != nullptr) {  // mapped pinned host memory: the host polls / waits on the following event
+            counts_host[0] = total;
+            counts_host[1] = max(gmax_s, block_max);
+            __threadfence_system();
+        }
     }
 }
 
@@ -322,10 +328,10 @@ void launch_geometry(const View& v, const float* means, const float* cov3d, cons
                                                                                    im.counts);
 }
 
-void launch_scan_tiles(const View& v, ImagePtrs im, cudaStream_t s) {
+void launch_scan_tiles(const View& v, ImagePtrs im, uint32_t* counts_host, cudaStream_t s) {
     const int T = v.gx * v.gy;
     scan_tiles_kernel<<<(T + SCAN_BLOCK - 1) / SCAN_BLOCK, SCAN_BLOCK, 0, s>>>(T, im.counts, im.starts, im.cursor, im.partials,
-                                                                              im.header);
+                                                                              im.header, counts_host);
 }
 
 void launch_color(const View& v, const float* means, const float* shs, const float* colors, const float* aux,

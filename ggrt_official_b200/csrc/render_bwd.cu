@@ -26,7 +26,7 @@ namespace ggrt {
 #define GGRT_BWD_MINBLOCKS 4
 #endif
 constexpr int BWD_BATCH = GGRT_BWD_BATCH;
-constexpr int NWARPS = RENDER_THREADS / 32;
+constexpr int NWARPS = BWD_WARPS;
 #ifndef GGRT_BWD_PIX_UNROLL
 #define GGRT_BWD_PIX_UNROLL 2
 #endif
@@ -47,7 +47,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 // AUX: the 4th blended channel (out_depth) also carries an upstream gradient.
 template <bool AUX>
-__global__ void __launch_bounds__(RENDER_THREADS, GGRT_BWD_MINBLOCKS)
+__global__ void __launch_bounds__(BWD_THREADS, GGRT_BWD_MINBLOCKS * 8 / BWD_WARPS)
 render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __restrict__ rec1,
                        const float4* __restrict__ rec2, const uint32_t* __restrict__ starts,
                        const uint32_t* __restrict__ points, const float* __restrict__ final_T,
@@ -64,7 +64,8 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
     const uint32_t sbase = smem_addr(srec);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.y * v.gx + blockIdx.x;
-    const int bx0 = blockIdx.x * TILE + (warp & 1) * 8, by0 = blockIdx.y * TILE + (warp >> 1) * 4;
+    const int wt = warp + blockIdx.z * BWD_WARPS;  // warp pixel block of the tile (8 per tile)
+    const int bx0 = blockIdx.x * TILE + (wt & 1) * 8, by0 = blockIdx.y * TILE + (wt >> 1) * 4;
     const float bx0f = (float)bx0, by0f = (float)by0;
     const uint32_t start = starts[tile];
 
@@ -107,7 +108,7 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
         const uint32_t boff = (uint32_t)bi * BWD_BATCH;
         const uint32_t cnt = min((uint32_t)BWD_BATCH, block_last - boff);
         __syncthreads();  // every warp is done with the previous batch before the refill
-        for (uint32_t k = tid; k < cnt; k += RENDER_THREADS) {
+        for (uint32_t k = tid; k < cnt; k += BWD_THREADS) {
             const uint32_t id = points[start + boff + k];
             sid[k] = id;
             const uint32_t dst = sbase + k * REC_BYTES;
@@ -238,13 +239,13 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
 
 void launch_render_backward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, const float* dL_dout,
                             const float* dL_dout_aux, float* scratch, cudaStream_t s) {
-    dim3 grid(v.gx, v.gy);
+    dim3 grid(v.gx, v.gy, 8 / BWD_WARPS);
     if (dL_dout_aux)
-        render_backward_kernel<true><<<grid, RENDER_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
+        render_backward_kernel<true><<<grid, BWD_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
                                                                      im.final_T, im.n_contrib, dL_dout, dL_dout_aux,
                                                                      scratch);
     else
-        render_backward_kernel<false><<<grid, RENDER_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
+        render_backward_kernel<false><<<grid, BWD_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
                                                                       im.final_T, im.n_contrib, dL_dout, nullptr, scratch);
 }
 

@@ -5,7 +5,17 @@
 
 namespace ggrt {
 
-constexpr int RENDER_THREADS = 256;
+// A tile has 8 warp pixel blocks (8x4 px each).  Each render CTA handles *_WARPS of them; splitting a tile over
+// several smaller CTAs shortens the work unit and with it the tail of the last wave.
+#ifndef GGRT_FWD_WARPS
+#define GGRT_FWD_WARPS 8
+#endif
+#ifndef GGRT_BWD_WARPS
+#define GGRT_BWD_WARPS 8
+#endif
+constexpr int FWD_WARPS = GGRT_FWD_WARPS, BWD_WARPS = GGRT_BWD_WARPS;
+constexpr int FWD_THREADS = 32 * FWD_WARPS, BWD_THREADS = 32 * BWD_WARPS;
+constexpr int FWD_BATCH = 256;
 constexpr int REC_BYTES = 48;  // {x, y, tau', - | A, B, C, opacity | r, g, b, depth}
 constexpr float LOG2E = 1.4426950408889634f;
 

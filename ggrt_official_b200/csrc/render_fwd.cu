@@ -11,32 +11,33 @@
 
 namespace ggrt {
 
-__global__ void __launch_bounds__(RENDER_THREADS, 4)
+__global__ void __launch_bounds__(FWD_THREADS, 1024 / FWD_THREADS)
 render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __restrict__ rec1,
                       const float4* __restrict__ rec2, const uint32_t* __restrict__ starts,
-                      const uint32_t* __restrict__ points, float* __restrict__ out_color,
+                      const uint32_t* __restrict__ points, uint32_t capacity, float* __restrict__ out_color,
                       float* __restrict__ out_depth, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
-    __shared__ __align__(16) unsigned char srec[RENDER_THREADS * REC_BYTES];
+    __shared__ __align__(16) unsigned char srec[FWD_BATCH * REC_BYTES];
     const uint32_t sbase = smem_addr(srec);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.y * v.gx + blockIdx.x;
-    const int bx0 = blockIdx.x * TILE + (warp & 1) * 8, by0 = blockIdx.y * TILE + (warp >> 1) * 4;
+    const int wt = warp + blockIdx.z * FWD_WARPS;  // warp pixel block of the tile (8 per tile)
+    const int bx0 = blockIdx.x * TILE + (wt & 1) * 8, by0 = blockIdx.y * TILE + (wt >> 1) * 4;
     const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
     const bool inside = px < v.W && py < v.H;
     const float pxf = (float)px, pyf = (float)py;
     const float bx0f = (float)bx0, by0f = (float)by0;
-    const uint32_t start = starts[tile], end = starts[tile + 1];
+    const uint32_t start = min(starts[tile], capacity), end = min(starts[tile + 1], capacity);
 
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
     uint32_t last = 0;
     bool done = !inside;
 
-    for (uint32_t base = start; base < end; base += RENDER_THREADS) {
+    for (uint32_t base = start; base < end; base += FWD_BATCH) {
         if (__syncthreads_and(done)) break;  // also orders the previous batch's reads before the refill
-        const uint32_t cnt = min((uint32_t)RENDER_THREADS, end - base);
-        if (tid < cnt) {
-            const uint32_t id = points[base + tid];
-            const uint32_t dst = sbase + tid * REC_BYTES;
+        const uint32_t cnt = min((uint32_t)FWD_BATCH, end - base);
+        for (uint32_t k = tid; k < cnt; k += FWD_THREADS) {
+            const uint32_t id = points[base + k];
+            const uint32_t dst = sbase + k * REC_BYTES;
             // the conic is staged pre-scaled: G = 2^(ea dx^2 + eb dx dy + ec dy^2), ea = -A log2(e)/2, eb = -B log2(e), ...
             float4 c = rec1[id];
             c.x *= -0.5f * LOG2E, c.y *= -LOG2E, c.z *= -0.5f * LOG2E;
@@ -96,10 +97,10 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
     }
 }
 
-void launch_render_forward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, float* out_color, float* out_depth,
-                           cudaStream_t s) {
-    dim3 grid(v.gx, v.gy);
-    render_forward_kernel<<<grid, RENDER_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points, out_color,
+void launch_render_forward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, uint32_t capacity, float* out_color,
+                           float* out_depth, cudaStream_t s) {
+    dim3 grid(v.gx, v.gy, 8 / FWD_WARPS);
+    render_forward_kernel<<<grid, FWD_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points, capacity, out_color,
                                                           out_depth, im.final_T, im.n_contrib);
 }
 

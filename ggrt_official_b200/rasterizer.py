@@ -39,6 +39,11 @@ class GaussianRasterizationSettings(NamedTuple):
 
 _tls = threading.local()
 
+# (device, P, H, W) -> (N, max pairs per tile) of the most recent forward of that shape (see forward_raw)
+_capacity_cache: dict = {}
+SPECULATIVE_BINNING = True
+CAPACITY_SLACK = 1.25
+
 
 def _pinned_counts() -> torch.Tensor:
     buf = getattr(_tls, "counts", None)
@@ -151,17 +156,41 @@ def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: Gauss
                                                   _ptr(radii), _ptr(geom), _ptr(img),
                                                   C.c_void_p(counts.data_ptr()), sp),
                     "forward_prepare")
-        # N sizes the caller-owned pair buffer; the colour kernel keeps the GPU busy while we wait
         ev = torch.cuda.Event()
-        ev.record(stream)
-        ev.synchronize()
-        packed = int(counts[0].item())
-        N, max_pairs = packed & 0xFFFFFFFF, (packed >> 32) & 0xFFFFFFFF
-        binning = torch.empty(L.ggrt_raster_binning_bytes(N), **u8)
-        _cabi.check(L.ggrt_raster_forward_render(C.byref(c.settings), c.P, N, max_pairs, _ptr(geom), _ptr(binning),
-                                                 _ptr(img), _ptr(color), _ptr(depth), sp), "forward_render")
+        ev.record(stream)  # after the 8-byte copy of {N, max pairs per tile}; colour evaluation follows it
+
+        def read_counts():
+            ev.synchronize()
+            packed = int(counts[0].item())
+            return packed & 0xFFFFFFFF, (packed >> 32) & 0xFFFFFFFF
+
+        def render(capacity, max_hint, rescan):
+            buf = torch.empty(L.ggrt_raster_binning_bytes(capacity), **u8)
+            _cabi.check(L.ggrt_raster_forward_render(C.byref(c.settings), c.P, capacity, max_hint, int(rescan),
+                                                     _ptr(geom), _ptr(buf), _ptr(img), _ptr(color), _ptr(depth), sp),
+                        "forward_render")
+            return buf
+
+        # N sizes the caller-owned pair buffer.  Waiting for it costs a host round trip that the colour kernel is
+        # too short to hide, so after the first call of a given shape the buffer is sized from the previous N plus
+        # slack and the remaining kernels are launched at once; N is checked afterwards (the copy finished long
+        # before) and the binning + render is redone with the exact size in the rare case the guess was too small.
+        key = (dev.index, c.P, c.H, c.W)
+        guess = _capacity_cache.get(key) if SPECULATIVE_BINNING else None
+        if guess is None:
+            N, max_pairs = read_counts()
+            cap = N
+            binning = render(cap, max_pairs, False)
+        else:
+            cap = int(guess[0] * CAPACITY_SLACK) + 1024
+            binning = render(cap, int(guess[1] * 1.05) + 4, False)  # hint only: larger tiles still sort correctly
+            N, max_pairs = read_counts()
+            if N > cap:
+                cap = N
+                binning = render(cap, max_pairs, True)
+        _capacity_cache[key] = (N, max_pairs)
     return dict(call=c, color=color, depth=depth, radii=radii, geom=geom, img=img, binning=binning, N=N,
-                max_tile_pairs=max_pairs)
+                capacity=cap, max_tile_pairs=max_pairs)
 
 
 def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = None,
@@ -204,7 +233,7 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
             dcamera=torch.zeros(35, **f32) if want_camera else None,
         )
         lay = C.byref(c.layout) if c.layout is not None else None
-        _cabi.check(L.ggrt_raster_backward(C.byref(c.settings), lay, c.P, state["N"], _ptr(c.means3D), _ptr(c.cov3D),
+        _cabi.check(L.ggrt_raster_backward(C.byref(c.settings), lay, c.P, state["capacity"], _ptr(c.means3D), _ptr(c.cov3D),
                                            _ptr(c.sh), _ptr(state["radii"]), _ptr(state["geom"]),
                                            _ptr(state["binning"]), _ptr(state["img"]), _ptr(g), _ptr(ga),
                                            _ptr(scratch), _ptr(out["dmeans2D"]), _ptr(out["dopacity"]),
@@ -236,7 +265,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             raise
         # keep only what backward needs; the outputs must not be referenced from ctx (that would be a
         # grad_fn <-> output reference cycle and the buffers would wait for the garbage collector)
-        ctx.state = {k: st[k] for k in ("call", "radii", "geom", "img", "binning", "N")}
+        ctx.state = {k: st[k] for k in ("call", "radii", "geom", "img", "binning", "N", "capacity")}
         ctx.raster_settings = raster_settings
         ctx.sh_shape = None if sh is None else tuple(sh.shape)
         ctx.opacity_shape = tuple(opacities.shape)

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GGRT_RASTER_ABI_VERSION 4
+#define GGRT_RASTER_ABI_VERSION 5
 #define GGRT_RASTER_TILE 16 /* tile edge in pixels (tile ids are part of the contract) */
 #define GGRT_RASTER_SUBS 16 /* pair counters per tile (contention spreading) */
 
@@ -119,8 +119,10 @@ size_t ggrt_raster_binning_bytes(int64_t num_rendered);
  * weights as the colour into out_depth (NULL: the view-space depth is used).  GGRt's depth pass
  * (cuda_splatting.py:227-269) is such a channel, so colour and depth can share one rasterization.
  * Writes radii [P] (int32; 0 = culled), fills geom_buffer and the tile tables of
- * image_buffer, then enqueues a copy of {N, max pairs per tile} to counts_host
- * (2 x uint32 of pinned host memory; may be NULL if the caller reads img_header itself).
+ * image_buffer, and the tile-scan kernel stores {N, max pairs per tile} directly into counts_host
+ * (2 x uint32 of MAPPED pinned host memory -- cudaHostAlloc / torch pin_memory under UVA; may be
+ * NULL if the caller reads img_header itself).  The values are valid once work enqueued on the
+ * stream after this call (e.g. an event recorded right after it) has completed.
  */
 int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, const GgrtRasterInputLayout* layout, int32_t P,
                                 const float* means3D,
@@ -129,13 +131,19 @@ int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, const GgrtRa
                                 void* image_buffer, uint32_t* counts_host, ggrt_stream_t stream);
 
 /*
- * Forward, phase 2.  num_rendered / max_tile_pairs are the two values `prepare`
- * reported; binning_buffer holds ggrt_raster_binning_bytes(num_rendered) bytes.
+ * Forward, phase 2.  binning_buffer holds ggrt_raster_binning_bytes(num_rendered) bytes.
+ * num_rendered is its CAPACITY in pairs: normally the N that `prepare` reported, but a caller
+ * that does not want to wait for N may pass a guess (e.g. the previous frame's N plus slack) and
+ * launch immediately -- every kernel stays inside the capacity -- then compare the reported N with
+ * its guess afterwards and, if N was larger, call again with rescan = 1 and a large enough buffer
+ * (rescan re-runs the tile scan, whose cursors the first attempt consumed).  max_tile_pairs is
+ * only a hint that selects the sort variant; larger tiles are still sorted correctly.  backward
+ * must be given the same num_rendered.
  * Writes out_color [3,H,W], out_depth [H,W] (sum of aux * alpha * T -- view depth unless aux
  * was given -- no background, no normalisation) and the per-pixel state needed by backward.
  */
 int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, int64_t num_rendered,
-                               uint32_t max_tile_pairs, const void* geom_buffer, void* binning_buffer,
+                               uint32_t max_tile_pairs, int32_t rescan, const void* geom_buffer, void* binning_buffer,
                                void* image_buffer, float* out_color, float* out_depth, ggrt_stream_t stream);
 
 /*

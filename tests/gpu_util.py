@@ -37,7 +37,7 @@ def unpack_state(st):
     """Views of the opaque buffers as numpy arrays (layout from ggrt_raster_layout)."""
     c = st["call"]
     P, H, W, N = c.P, c.H, c.W, st["N"]
-    L = _cabi.layout(P, H, W, N)
+    L = _cabi.layout(P, H, W, st["capacity"])  # the buffer is laid out for its capacity (>= N)
     T = ((W + 15) // 16) * ((H + 15) // 16)
     g, im, b = st["geom"], st["img"], st["binning"]
     out = dict(

@@ -53,7 +53,7 @@ def fake_forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs, 
                            device=means3D.device)
     return dict(call=call, color=torch.from_numpy(f["color"].copy()), depth=torch.from_numpy(f["depth"].copy()),
                 radii=torch.from_numpy(f["radii"].copy()), geom=None, img=None, binning=None, N=f["bin"]["N"],
-                max_tile_pairs=0, _oracle=(cam, inp, f))
+                capacity=f["bin"]["N"], max_tile_pairs=0, _oracle=(cam, inp, f))
 
 
 def fake_backward_raw(state, grad_color, out=None, grad_aux=None, want_camera=False):

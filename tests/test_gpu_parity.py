@@ -152,6 +152,33 @@ def test_camera_gradients_match_autograd_restatement():
     assert rs2.viewmatrix.grad is None
 
 
+def test_speculative_binning_overflow_is_redone():
+    """After the first call of a shape the pair buffer is sized from the previous N (no host wait).  If the next
+    scene of the same shape needs more pairs than guessed, the binning + render is redone: results stay exact."""
+    P, H, W = 3000, 96, 96
+    _, sparse = small_case(P, H, W, 2, seed=41, cov_scale=1.0)
+    _, dense = small_case(P, H, W, 2, seed=42, cov_scale=64.0)
+    R._capacity_cache.clear()
+    st0 = G.run_cuda_forward(sparse)        # first call of this shape: exact, synchronous
+    st1 = G.run_cuda_forward(dense)         # guess from the sparse scene is far too small -> redo path
+    assert st1["N"] > 2 * st0["N"] and st1["capacity"] == st1["N"]
+    _, f1 = G.oracle_forward(dense)
+    _check_forward(G.compare_forward(st1, f1), H * W)
+    st2 = G.run_cuda_forward(dense)         # now the guess is large enough: speculative path, capacity > N
+    assert st2["capacity"] > st2["N"] == st1["N"]
+    _check_forward(G.compare_forward(st2, f1), H * W)
+    g = np.random.default_rng(1).standard_normal((3, H, W)).astype(np.float32)
+    cam = oracle_camera(dense)
+    ref = co.backward(cam, dense.means3D, dense.cov3D, dense.opacities, f1, g, sh=dense.shs)
+    for st in (st1, st2):
+        got = R.backward_raw(st, torch.tensor(g, device="cuda:0"))
+        for k, e in G.grad_errors(got, ref).items():
+            assert e["nonfinite"] == 0 and e["max_rel"] < 1e-3, (k, e)
+    st3 = G.run_cuda_forward(sparse)        # shrinking scenes are fine too
+    _, f0 = G.oracle_forward(sparse)
+    _check_forward(G.compare_forward(st3, f0), H * W)
+
+
 def test_config1_10k_256(tmp_path):
     """BASELINE config 1: 10K Gaussians, 256x256, 1 view, forward vs the oracle."""
     ri = to_raster_inputs(make_scene(10_000, 256, 256, sh_degree=4))
