@@ -1,0 +1,95 @@
+"""GPU edge cases of the rasterizer boundary: saturated opacities, huge / degenerate / non-finite Gaussians,
+non-contiguous and float64 inputs, wider SH tables than the degree needs."""
+import numpy as np
+import pytest
+import torch
+
+from ggrt_official_b200 import GaussianRasterizer
+from ggrt_official_b200 import rasterizer as R
+from oracle import c_oracle as co
+from tests import gpu_util as G
+from tests.helpers import oracle_camera, small_case
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _t(a):
+    return torch.tensor(np.asarray(a), device=DEV)
+
+
+def _fwd_bwd_vs_oracle(ri, seed=0, min_ok=0.98):
+    H, W = ri.image_height, ri.image_width
+    st = G.run_cuda_forward(ri)
+    cam, f = G.oracle_forward(ri)
+    res = G.compare_forward(st, f)
+    for k in ("radii_mismatch", "rect_mismatch", "tiles_mismatch", "starts_mismatch", "point_list_mismatch"):
+        assert res.get(k, 0) == 0, (k, res)
+    assert res["color_max_err"] < 1e-4 and res["depth_max_relerr"] < 1e-4, res
+    assert (f["img"]["fragile"] == 0).mean() >= min_ok
+    g = np.random.default_rng(seed).standard_normal((3, H, W)).astype(np.float32)
+    got = R.backward_raw(st, _t(g))
+    ref = co.backward(cam, ri.means3D, ri.cov3D, ri.opacities, f, g, sh=ri.shs)
+    for k, e in G.grad_errors(got, ref).items():
+        assert e["nonfinite"] == 0 and e["max_rel"] < 1e-3, (k, e)
+    return st, f
+
+
+def test_saturated_opacities_and_early_termination():
+    """Opacities up to 1: alpha clamps at 0.99 and pixels terminate at T < 1e-4 (n_contrib < list length)."""
+    _, ri = small_case(4000, 64, 64, 1, seed=51, cov_scale=30.0, opacity_max=1.0)
+    ri.opacities = np.ascontiguousarray(np.clip(ri.opacities * 1.6, 0.0, 1.0))
+    st, f = _fwd_bwd_vs_oracle(ri, min_ok=0.95)
+    assert float(f["img"]["final_T"].min()) < 1e-3          # termination was exercised
+    assert (f["pre"]["conic_opacity"][:, 3] >= 0.99).any()  # and the clamp
+
+
+def test_huge_and_degenerate_gaussians():
+    _, ri = small_case(600, 256, 256, 0, seed=52, cov_scale=1.0, behind_fraction=0.0)
+    ri.cov3D[0] = np.array([400.0, 0, 0, 400.0, 0, 400.0], np.float32)   # covers the whole image (256 tiles)
+    ri.cov3D[1] = 0.0                                                     # zero covariance: low-pass only
+    ri.cov3D[2] = np.array([1e-12, 0, 0, 1e-12, 0, 1e-12], np.float32)
+    ri.cov3D[3] = np.array([1.0, 0, 0, 1e-8, 0, 1.0], np.float32)         # needle
+    ri.opacities[4] = 0.0                                                 # invisible
+    ri.opacities[5] = 1.0 / 255.0                                         # exactly the alpha threshold
+    st, f = _fwd_bwd_vs_oracle(ri)
+    assert int(st["radii"][0]) > 100 and st["max_tile_pairs"] >= 1
+
+
+def test_non_finite_inputs_are_culled_not_propagated():
+    _, ri = small_case(300, 48, 48, 2, seed=53, behind_fraction=0.0)
+    ri.means3D[0] = np.nan
+    ri.cov3D[1] = np.nan
+    ri.means3D[2] = np.inf
+    st = G.run_cuda_forward(ri)
+    radii = st["radii"].cpu().numpy()
+    assert radii[0] == 0 and radii[1] == 0 and radii[2] == 0
+    assert torch.isfinite(st["color"]).all() and torch.isfinite(st["depth"]).all()
+    g = R.backward_raw(st, torch.ones(3, 48, 48, device=DEV))
+    for k in ("dmeans3D", "dcov3D", "dopacity", "dsh"):
+        assert torch.isfinite(g[k][3:]).all(), k
+        assert float(g[k][:3].abs().sum()) == 0.0, k
+
+
+def test_non_contiguous_float64_and_wide_sh_table():
+    P, H, W = 1500, 64, 80
+    _, ri = small_case(P, H, W, 2, seed=54, cov_scale=4.0)
+    rs = G.settings_from(ri, DEV)
+    # reference result from well-formed float32 inputs
+    st = R.forward_raw(_t(ri.means3D), _t(ri.shs), None, _t(ri.opacities), _t(ri.cov3D), rs)
+    # the same data, badly laid out: strided means (a column slice of a wider tensor), float64 covariances,
+    # an SH table with 16 coefficients of which degree 2 uses the first 9, opacities [P] instead of [P,1]
+    wide = torch.zeros(P, 5, device=DEV)
+    wide[:, 1:4] = _t(ri.means3D)
+    means = wide[:, 1:4]
+    assert not means.is_contiguous()
+    sh16 = torch.randn(P, 16, 3, device=DEV)
+    sh16[:, :9] = _t(ri.shs)
+    sh16.requires_grad_()
+    means2D = torch.zeros(P, 3, device=DEV, requires_grad=True)
+    img, radii, _ = GaussianRasterizer(rs)(means3D=means, means2D=means2D, shs=sh16,
+                                           opacities=_t(ri.opacities).reshape(-1), cov3D_precomp=_t(ri.cov3D).double())
+    assert torch.equal(radii, st["radii"]) and torch.allclose(img, st["color"], atol=1e-6)
+    img.sum().backward()
+    assert sh16.grad.shape == (P, 16, 3) and float(sh16.grad[:, 9:].abs().max()) == 0.0
+    assert float(sh16.grad[:, :9].abs().max()) > 0.0 and means2D.grad.shape == (P, 3)
