@@ -203,17 +203,25 @@ def run_ours(args, rank, world, local_rank):
 
     state = {}
 
-    from ggrt_official_b200.view_parallel import GradientArena
+    from ggrt_official_b200.view_parallel import CompactGradientExchange, GradientArena
 
-    arena = GradientArena.allocate(P, K, dev) if world > 1 else None
+    # Sum of the per-view Gaussian gradients over the GPUs, inside the timed step:
+    #   arena   - ONE NCCL all-reduce of the contiguous [P, 3+6+1+3K] gradient arena (340 B / Gaussian)
+    #   compact - exchange the [P,3] colour gradients + all-reduce [P,10], rebuild dL/dsh locally (sh_merge.cu)
+    #   p2p     - compact over symmetric memory: in-kernel NVLink gather + NVLS multimem reduction, no NCCL
+    arena = GradientArena.allocate(P, K, dev) if world > 1 and args.exchange == "arena" else None
+    exch = None
+    if world > 1 and args.exchange != "arena":
+        exch = CompactGradientExchange(P, SH_DEGREE, dev, transport="p2p" if args.exchange == "p2p" else "nccl")
 
     def step():
         st = R.forward_raw(means, shs, None, opac, cov, rs)
-        # the Gaussian gradients land in one contiguous arena that is summed over the per-GPU views with
-        # a single NCCL all-reduce
-        grads = R.backward_raw(st, grad_img, out=arena.views if arena else None, want_camera=args.pose_grads)
-        if arena:
-            arena.all_reduce()
+        if exch is not None:
+            grads = exch.run(st, grad_img, want_camera=args.pose_grads)
+        else:
+            grads = R.backward_raw(st, grad_img, out=arena.views if arena else None, want_camera=args.pose_grads)
+            if arena:
+                arena.all_reduce()
         state["N"], state["max_tile_pairs"] = st["N"], st["max_tile_pairs"]
         return grads
 
@@ -395,11 +403,15 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": desc, "P": P, "H": H, "W": W, "N_pairs": int(N),
                        "max_pairs_per_tile": int(state["max_tile_pairs"]), "sh_degree": SH_DEGREE,
                        "views_per_step": world, "pose_grads": bool(args.pose_grads), "l2": "flushed before every timed step (256 MiB write, then 256 MiB read so the step does not pay the flush's write-back)",
-                       "parallelism": f"one target view per GPU x{world}" + (", NCCL all-reduce of Gaussian gradients"
-                                                                            if world > 1 else "")},
+                       "parallelism": f"one target view per GPU x{world}" + (
+                           "" if world == 1 else
+                           ", NCCL all-reduce of the Gaussian gradient arena" if exch is None else
+                           f", compact gradient exchange ({exch.transport}): gather [P,3] colour gradients + "
+                           "all-reduce [P,10], dL/dsh rebuilt per GPU"),
+                       "exchange_bytes": None if exch is None else exch.exchange_bytes()},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": n_e2e},
-            "gpu_launches": 8 * args.steps,
+            "gpu_launches": (8 + (1 if exch is not None else 0)) * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,
@@ -419,6 +431,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gaussians", type=int, default=0,
                     help="override the Gaussian count of the workload (BASELINE config 5: 50K..2M sweep at 1008x756)")
+    ap.add_argument("--exchange", default="compact", choices=["arena", "compact", "p2p"],
+                    help="multi-GPU gradient exchange (N>1 only), see run_ours")
     ap.add_argument("--pose-grads", action="store_true",
                     help="also compute dL/d(viewmatrix, projmatrix, campos) in the backward (BASELINE config 3)")
     args = ap.parse_args()

@@ -10,7 +10,7 @@ from pathlib import Path
 
 from . import build as _build
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 _lib = None
 
 
@@ -58,12 +58,15 @@ EXPORTS = (
     "ggrt_raster_forward_prepare",
     "ggrt_raster_forward_render",
     "ggrt_raster_backward",
+    "ggrt_raster_sh_gradient_merge",
+    "ggrt_raster_nvls_allreduce_f32",
     "ggrt_raster_mark_visible",
     "ggrt_raster_profile_enable",
     "ggrt_raster_profile_read",
     "ggrt_raster_stage_name",
 )
 STAGE_COUNT = 8
+MAX_MERGE_VIEWS = 16
 
 
 def library_path() -> Path:
@@ -93,6 +96,9 @@ def lib():
     L.ggrt_raster_forward_prepare.argtypes = [C.POINTER(Settings), C.POINTER(InputLayout), i32] + [vp] * 11
     L.ggrt_raster_forward_render.argtypes = [C.POINTER(Settings), i32, i64, u32, i32, vp, vp, vp, vp, vp, vp]
     L.ggrt_raster_backward.argtypes = [C.POINTER(Settings), C.POINTER(InputLayout), i32, i64] + [vp] * 19
+    L.ggrt_raster_sh_gradient_merge.argtypes = [i32, i32, C.POINTER(InputLayout), vp, i32, C.POINTER(vp), C.POINTER(vp),
+                                                vp, vp]
+    L.ggrt_raster_nvls_allreduce_f32.argtypes = [vp, i64, i32, i32, vp]
     L.ggrt_raster_mark_visible.argtypes = [i32, vp, vp, vp, vp]
     L.ggrt_raster_profile_enable.argtypes = [i32]
     L.ggrt_raster_profile_read.argtypes = [C.POINTER(C.c_float)]

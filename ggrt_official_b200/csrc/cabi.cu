@@ -309,8 +309,9 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
         set_error("backward: dL_dout_aux and dL_daux go together");
         return GGRT_ERR_INVALID_ARGUMENT;
     }
-    if ((shs != nullptr) != (dL_dsh != nullptr) || (shs == nullptr) != (dL_dcolors != nullptr)) {
-        set_error("backward: pass dL_dsh with shs, dL_dcolors without");
+    // with shs: dL_dsh (full SH gradient) or dL_dcolors (compact mode, see the header) -- exactly one of them
+    if ((dL_dsh != nullptr) == (dL_dcolors != nullptr) || (shs == nullptr && dL_dsh != nullptr)) {
+        set_error("backward: pass exactly one of dL_dsh (needs shs) / dL_dcolors");
         return GGRT_ERR_INVALID_ARGUMENT;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -333,6 +334,51 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
     }
     GGRT_TRY(check_launch("preprocess_backward", dbg, s));
     return GGRT_OK;
+}
+
+int ggrt_raster_sh_gradient_merge(int32_t P, int32_t sh_degree, const GgrtRasterInputLayout* layout,
+                                  const float* means3D, int32_t num_views, const float* const* drgb_views_host,
+                                  const float* const* campos_views_host, float* dL_dsh, ggrt_stream_t stream) {
+    if (P < 0 || sh_degree < 0 || sh_degree > 4 || num_views < 1 || num_views > GGRT_RASTER_MAX_MERGE_VIEWS) {
+        set_error("sh_gradient_merge: bad sizes (P=%d, sh_degree=%d, num_views=%d, at most %d views)", P, sh_degree,
+                  num_views, GGRT_RASTER_MAX_MERGE_VIEWS);
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    if (!drgb_views_host || !campos_views_host || (P > 0 && (!means3D || !dL_dsh))) {
+        set_error("sh_gradient_merge: NULL buffer");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    for (int v = 0; v < num_views; ++v)
+        if (!drgb_views_host[v] || !campos_views_host[v]) {
+            set_error("sh_gradient_merge: NULL pointer for view %d", v);
+            return GGRT_ERR_INVALID_ARGUMENT;
+        }
+    float scale = 1.0f;
+    bool cmajor = false;
+    if (layout) {
+        if (!(layout->scene_scale > 0.f)) {
+            set_error("scene_scale must be positive");
+            return GGRT_ERR_INVALID_ARGUMENT;
+        }
+        scale = layout->scene_scale;
+        cmajor = layout->sh_channel_major != 0;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    launch_sh_gradient_merge(P, sh_degree, scale, cmajor, means3D, num_views, drgb_views_host, campos_views_host,
+                             dL_dsh, s);
+    return check_launch("sh_gradient_merge", 0, s);
+}
+
+int ggrt_raster_nvls_allreduce_f32(void* multicast_ptr, int64_t count, int32_t rank, int32_t world,
+                                   ggrt_stream_t stream) {
+    if (!multicast_ptr || count < 0 || (count & 3) || world < 1 || rank < 0 || rank >= world ||
+        (reinterpret_cast<uintptr_t>(multicast_ptr) & 15)) {
+        set_error("nvls_allreduce: bad argument (count must be a multiple of 4, pointer 16-byte aligned)");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    launch_nvls_allreduce(static_cast<float*>(multicast_ptr), count, rank, world, s);
+    return check_launch("nvls_allreduce", 0, s);
 }
 
 int ggrt_raster_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present,

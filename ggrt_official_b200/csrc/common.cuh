@@ -88,6 +88,9 @@ void launch_preprocess_backward(const View& v, const float* means, const float* 
                                 const int* radii, GeomPtrs g, const float* scratch, float* dmeans2D, float* dopacity,
                                 float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, float* daux, float* dcam,
                                 cudaStream_t s);
+void launch_sh_gradient_merge(int P, int deg, float scale, bool cmajor, const float* means, int num_views,
+                              const float* const* drgb, const float* const* campos, float* dsh, cudaStream_t s);
+void launch_nvls_allreduce(float* multicast, long long count, int rank, int world, cudaStream_t s);
 void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------

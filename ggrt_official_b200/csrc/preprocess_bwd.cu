@@ -9,6 +9,11 @@
 // ring by the TMA engine (cp.async.bulk + mbarrier), overwritten in place with dL/dsh by the
 // threads (one row each, odd stride), and written back with a TMA bulk store
 // (cp.async.bulk.global.shared) while the next slab is processed.
+//
+// Compact mode (shs given, dsh == NULL, dcolors != NULL): dL/dsh of one view is the outer product
+// basis(dir) x dL/drgb, so for the view-sharded multi-GPU path only the masked colour gradient [P,3] is
+// written (12 B instead of 12K B per Gaussian) and the SH gradient of ALL views is rebuilt after the exchange
+// by sh_gradient_merge_kernel (sh_merge.cu).  The SH slab is still read: dL/dmean3D needs it.
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -39,10 +44,11 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     else if (threadIdx.x < 32) sM[threadIdx.x - 16] = v.proj[threadIdx.x - 16];
 
     const int row = v.K * 3;
+    const bool compact = shs != nullptr && dsh == nullptr;  // uniform: write dL/drgb instead of dL/dsh
     const int ks = CMAJOR ? 1 : 3, cs = CMAJOR ? v.K : 1;  // SH element (k, c) at k*ks + c*cs of the row
     const int slab_floats = PB_THREADS * row;
     const bool tma_ok = shs != nullptr && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&
-                        (reinterpret_cast<uintptr_t>(dsh) & 15) == 0;
+                        (reinterpret_cast<uintptr_t>(dsh) & 15) == 0;  // (a NULL dsh is "aligned": no store is issued)
     if (shs != nullptr && threadIdx.x == 0) {
         for (int st = 0; st < PB_STAGES; ++st) mbar_init(smem_u32(&full_bar[st]), 1);
         fence_mbar_init();
@@ -236,8 +242,10 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     {                                                                                      \
         const float s_ = my[(k) * ks] * dR + my[(k) * ks + cs] * dG + my[(k) * ks + 2 * cs] * dB; \
         ddx = fmaf((BX), s_, ddx), ddy = fmaf((BY), s_, ddy), ddz = fmaf((BZ), s_, ddz);   \
-        const float b_ = (B);                                                              \
-        my[(k) * ks] = b_ * dR, my[(k) * ks + cs] = b_ * dG, my[(k) * ks + 2 * cs] = b_ * dB; \
+        if (!compact) {                                                                    \
+            const float b_ = (B);                                                          \
+            my[(k) * ks] = b_ * dR, my[(k) * ks + cs] = b_ * dG, my[(k) * ks + 2 * cs] = b_ * dB; \
+        }                                                                                  \
     }
             GGRT_TERM(0, GGRT_SH_C0, 0.f, 0.f, 0.f)
             if (v.deg > 0) {
@@ -298,22 +306,27 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
                         m2 = (len2 * ddz - vz * dot) * inv3;
             dmean[0] += m0, dmean[1] += m1, dmean[2] += m2;
             if (POSE) camC[0] -= m0, camC[1] -= m1, camC[2] -= m2;  // dir = p - campos
-        } else if (valid) {
+        } else if (valid && !compact) {
             for (int k = 0; k < row; ++k) my[k] = 0.f;
         }
+        if (compact && valid) {  // masked colour gradient (zero for culled Gaussians and clamped channels)
+            dcolors[3 * i] = dR, dcolors[3 * i + 1] = dG, dcolors[3 * i + 2] = dB;
+        }
         // write-out of the dL/dsh slab: TMA bulk store, or coalesced stores when ragged / unaligned
-        float* dst = dsh + (size_t)base * row;
+        float* dst = compact ? nullptr : dsh + (size_t)base * row;
         if (slab_tma) {
-            fence_proxy_async();  // this thread's generic writes -> visible to the async proxy
+            if (!compact) fence_proxy_async();  // this thread's generic writes -> visible to the async proxy
             __syncthreads();
             if (threadIdx.x == 0) {
-                bulk_s2g(dst, smem_u32(slab), (uint32_t)nfl * 4u);
-                bulk_commit();
+                if (!compact) {
+                    bulk_s2g(dst, smem_u32(slab), (uint32_t)nfl * 4u);
+                    bulk_commit();
+                }
                 const int nsl = sl + PB_STAGES * gridDim.x;
                 if (nsl < num_slabs) {
                     const uint32_t nbytes = (uint32_t)min(PB_THREADS, v.P - nsl * PB_THREADS) * row * 4u;
                     if ((nbytes & 15u) == 0) {
-                        bulk_wait_read0();  // the store has drained this stage before it is refilled
+                        if (!compact) bulk_wait_read0();  // the store has drained this stage before it is refilled
                         mbar_expect_tx(smem_u32(&full_bar[st]), nbytes);
                         bulk_g2s(smem_u32(slab), shs + (size_t)nsl * slab_floats, nbytes, smem_u32(&full_bar[st]));
                     }
@@ -321,7 +334,8 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             }
         } else {
             __syncthreads();
-            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            if (compact) {
+            } else if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
                 float4* d4 = reinterpret_cast<float4*>(dst);
                 const float4* s4 = reinterpret_cast<const float4*>(slab);
                 const int n4 = nfl >> 2;

@@ -194,14 +194,19 @@ def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: Gauss
 
 
 def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = None,
-                 grad_aux: Optional[torch.Tensor] = None, want_camera: bool = False) -> dict:
+                 grad_aux: Optional[torch.Tensor] = None, want_camera: bool = False, compact: bool = False) -> dict:
     """Runs the backward through the C ABI.  `out` may supply preallocated, contiguous float32 output
     tensors (e.g. views into one gradient arena that is all-reduced across GPUs afterwards).
     `grad_aux` [H,W]: gradient of the third output (only when the forward was given `aux`).
     `want_camera`: also return out["dcamera"] = dL/d(viewmatrix [16] | projmatrix [16] | campos [3]) (opt-in
-    extension; the reference treats the camera as constant)."""
+    extension; the reference treats the camera as constant).
+    `compact` (SH inputs only): skip dL/dsh and return out["dcolors"] [P,3], the gradient w.r.t. the evaluated SH
+    colour, instead -- dL/dsh of one view is basis(dir) (x) dcolors, which `sh_gradient_merge` rebuilds for a whole
+    set of views after the (K times smaller) colour gradients have been exchanged between GPUs."""
     L = _cabi.lib()
     c: _Call = state["call"]
+    if compact and c.sh is None:
+        raise ValueError("compact=True needs SH inputs (colors_precomp already yields dcolors)")
     dev = c.device
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev)
@@ -227,8 +232,8 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
             dopacity=buf("dopacity", (c.P, 1)),
             dmeans3D=buf("dmeans3D", (c.P, 3)),
             dcov3D=buf("dcov3D", (c.P, 3, 3) if c.cov9 else (c.P, 6)),
-            dsh=buf("dsh", tuple(c.sh.shape)) if c.sh is not None else None,
-            dcolors=buf("dcolors", (c.P, 3)) if c.sh is None else None,
+            dsh=buf("dsh", tuple(c.sh.shape)) if c.sh is not None and not compact else None,
+            dcolors=buf("dcolors", (c.P, 3)) if c.sh is None or compact else None,
             daux=buf("daux", (c.P,)) if ga is not None else None,
             dcamera=torch.zeros(35, **f32) if want_camera else None,
         )
@@ -240,6 +245,52 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
                                            _ptr(out["dmeans3D"]), _ptr(out["dcov3D"]), _ptr(out["dsh"]),
                                            _ptr(out["dcolors"]), _ptr(out["daux"]), _ptr(out["dcamera"]), sp),
                     "backward")
+    return out
+
+
+def sh_gradient_merge(means3D: torch.Tensor, sh_degree: int, drgb_views, campos_views,
+                      out: Optional[torch.Tensor] = None, layout: Optional[dict] = None) -> torch.Tensor:
+    """dL/dsh [P,K,3] of a set of views of the same Gaussians from their compact colour gradients:
+    sum_v basis(normalize(scene_scale * means3D - campos_v)) (x) drgb_v   (ggrt_raster_sh_gradient_merge).
+
+    `drgb_views` / `campos_views`: per view either a float32 CUDA tensor ([P,3] / [3], contiguous) or an integer
+    device address -- e.g. a peer GPU's symmetric-memory buffer, in which case the gather over NVLink happens
+    inside the kernel; the caller is responsible for the cross-device barrier before this call."""
+    L = _cabi.lib()
+    if not means3D.is_cuda:
+        raise RuntimeError("means3D must be a CUDA tensor: the rasterizer has no CPU path")
+    dev = means3D.device
+    means = _f32c(means3D, "means3D", dev)
+    P = int(means.shape[0])
+    K = (int(sh_degree) + 1) ** 2
+    V = len(drgb_views)
+    if V != len(campos_views) or not 1 <= V <= _cabi.MAX_MERGE_VIEWS:
+        raise ValueError(f"need 1..{_cabi.MAX_MERGE_VIEWS} views with one campos each, got {V} / {len(campos_views)}")
+    lay = layout or {}
+    cmajor = bool(lay.get("sh_channel_major", False))
+    shape = (P, 3, K) if cmajor else (P, K, 3)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
+        raise ValueError(f"out must be a contiguous float32 {shape} tensor on {dev}")
+    keep = []
+
+    def address(x, name, numel):
+        if isinstance(x, int):
+            return x
+        x = _f32c(x, name, dev)
+        if x.numel() != numel:
+            raise ValueError(f"{name} must have {numel} elements, got {x.numel()}")
+        keep.append(x)
+        return x.data_ptr()
+
+    drgb = (C.c_void_p * V)(*[address(x, "drgb_views[i]", 3 * P) for x in drgb_views])
+    cams = (C.c_void_p * V)(*[address(x, "campos_views[i]", 3) for x in campos_views])
+    clay = _cabi.InputLayout(float(lay.get("scene_scale", 1.0)), int(bool(lay.get("cov_full3x3", False))), int(cmajor))
+    with torch.cuda.device(dev):
+        sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _cabi.check(L.ggrt_raster_sh_gradient_merge(P, int(sh_degree), C.byref(clay), _ptr(means), V, drgb, cams,
+                                                    _ptr(out), sp), "sh_gradient_merge")
     return out
 
 

@@ -4,14 +4,22 @@ Each target view is an independent rasterization of the same Gaussian set (the p
 loop at /root/reference/ggrt/model/pixelsplat/decoder/cuda_splatting.py:93-127 has no
 cross-iteration dependence), so rank r renders views r, r+world, ... of the replicated
 Gaussians with no data-path collective in the forward.  The only exchange step is the sum of
-the per-view Gaussian gradients: ONE all-reduce over a single contiguous arena
-[P, 3 + 6 + 1 + 3K].  One process per GPU, torch.distributed (NCCL over
-NVLink on the B200 box; gloo in the CPU tests).
+the per-view Gaussian gradients.  One process per GPU, torch.distributed (NCCL
+over NVLink on the B200 box; gloo in the CPU tests).  Two implementations of the exchange:
+
+* `GradientArena`: ONE all-reduce over a single contiguous arena [P, 3 + 6 + 1 + 3K]
+  (340 B per Gaussian at SH degree 4) -- the baseline.
+* `CompactGradientExchange`: dL/dsh of one view is the outer product basis(dir_v) (x) dL/drgb_v
+  and every rank can evaluate basis(dir_v) itself, so only the [P,3] colour gradients are
+  gathered (12 B per Gaussian and view) and the [P,10] rest is all-reduced; the summed SH
+  gradient is rebuilt locally by `sh_gradient_merge`.  With transport "p2p" the buffers are
+  symmetric memory: the merge kernel gathers straight from the peers over NVLink and the small
+  arena is summed in the NVSwitch (multimem) -- no NCCL call on the data path.
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence
+from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -76,3 +84,99 @@ def render_views_sharded(render_fn, num_views: int, rank: Optional[int] = None, 
     if world_size is None:
         world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     return {v: render_fn(v) for v in shard_views(num_views, rank, world_size)}
+
+
+class CompactGradientExchange:
+    """Sum of the per-view Gaussian gradients over ranks that moves 12 B + 2 x 40 B instead of 2 x 340 B per
+    Gaussian (SH degree 4) across NVLink; see the module docstring.  Buffers are allocated once.
+
+    run(state, grad_color) performs this rank's backward in compact mode, the exchange and the merge and
+    returns {"dmeans3D", "dcov3D", "dopacity", "dsh"} summed over all ranks plus this view's "dmeans2D".
+    `backward_fn` / `merge_fn` default to the CUDA entry points (`rasterizer.backward_raw`,
+    `rasterizer.sh_gradient_merge`); the CPU tests inject oracle-backed ones to exercise the choreography on gloo.
+    """
+
+    def __init__(self, P: int, sh_degree: int, device, group=None, transport: str = "nccl",
+                 layout: Optional[dict] = None, backward_fn: Optional[Callable] = None,
+                 merge_fn: Optional[Callable] = None):
+        if transport not in ("nccl", "p2p"):
+            raise ValueError(f"unknown transport {transport!r}")
+        on = dist.is_available() and dist.is_initialized()
+        self.group = group
+        self.world = dist.get_world_size(group) if on else 1
+        self.rank = dist.get_rank(group) if on else 0
+        self.P, self.deg, self.K = int(P), int(sh_degree), (int(sh_degree) + 1) ** 2
+        self.device = torch.device(device)
+        self.layout = layout
+        self.transport = transport if self.world > 1 else "nccl"
+        if layout and layout.get("cov_full3x3"):
+            raise NotImplementedError("CompactGradientExchange expects [P,6] covariances")
+        from . import rasterizer as R
+
+        self.backward_fn = backward_fn or R.backward_raw
+        self.merge_fn = merge_fn or R.sh_gradient_merge
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.slot = 3 * (self.P + 1)                 # [P,3] colour gradients + one row holding this view's campos
+        self.small_elems = (10 * self.P + 3) // 4 * 4  # dmeans3D | dcov3D | dopacity, padded to float4
+        self.handles = None
+        if self.transport == "p2p":
+            import torch.distributed._symmetric_memory as symm
+
+            gname = (group or dist.group.WORLD).group_name
+            self.slots = symm.empty(self.slot, **f32)
+            self.small = symm.empty(self.small_elems, **f32)
+            self.handles = (symm.rendezvous(self.slots, gname), symm.rendezvous(self.small, gname))
+            self.my_slot = self.slots
+        else:
+            self.slots = torch.empty(self.world * self.slot, **f32)
+            self.small = torch.empty(self.small_elems, **f32)
+            self.my_slot = self.slots[self.rank * self.slot: (self.rank + 1) * self.slot]
+        self.small.zero_()
+        P_ = self.P
+        self.views = {
+            "dmeans3D": self.small[: 3 * P_].view(P_, 3),
+            "dcov3D": self.small[3 * P_: 9 * P_].view(P_, 6),
+            "dopacity": self.small[9 * P_: 10 * P_].view(P_, 1),
+            "dcolors": self.my_slot[: 3 * P_].view(P_, 3),
+        }
+        shape = (P_, 3, self.K) if layout and layout.get("sh_channel_major") else (P_, self.K, 3)
+        self.dsh = torch.empty(shape, **f32)
+
+    def exchange_bytes(self) -> dict:
+        """Bytes this rank sends over the interconnect per step (ring/NVLS lower bounds), for reports."""
+        w = self.world
+        return {"gather_recv": 4 * self.slot * (w - 1), "allreduce_payload": 4 * self.small_elems,
+                "arena_allreduce_payload_replaced": 4 * self.P * (10 + 3 * self.K)}
+
+    def run(self, state: dict, grad_color: torch.Tensor, **backward_kw) -> dict:
+        P_ = self.P
+        out = self.backward_fn(state, grad_color, out=dict(self.views), compact=True, **backward_kw)
+        call = state["call"]
+        self.my_slot[3 * P_:].copy_(call.campos.reshape(3))
+        if self.world > 1 and self.transport == "p2p":
+            from . import _cabi
+            import ctypes as C
+
+            hs, hm = self.handles
+            hs.barrier(channel=0)  # every rank's colour gradients and small arena are complete
+            stream = torch.cuda.current_stream(self.device)
+            if hm.multicast_ptr:  # NVLS available: the NVSwitch does the sum
+                _cabi.check(_cabi.lib().ggrt_raster_nvls_allreduce_f32(
+                    C.c_void_p(hm.multicast_ptr), self.small_elems, self.rank, self.world,
+                    C.c_void_p(stream.cuda_stream)), "nvls_allreduce")
+            else:
+                dist.all_reduce(self.small, op=dist.ReduceOp.SUM, group=self.group)
+            bases = [int(p) for p in hs.buffer_ptrs]
+            drgb = [b for b in bases]
+            cams = [b + 4 * 3 * P_ for b in bases]
+            dsh = self.merge_fn(call.means3D, self.deg, drgb, cams, out=self.dsh, layout=self.layout)
+            hs.barrier(channel=1)  # peers have finished reading this rank's buffers; the reduced arena is visible
+        else:
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.slots, self.my_slot, group=self.group)
+                dist.all_reduce(self.small, op=dist.ReduceOp.SUM, group=self.group)
+            slots = self.slots.view(self.world, P_ + 1, 3)
+            dsh = self.merge_fn(call.means3D, self.deg, [slots[r, :P_] for r in range(self.world)],
+                                [slots[r, P_] for r in range(self.world)], out=self.dsh, layout=self.layout)
+        return {"dmeans3D": self.views["dmeans3D"], "dcov3D": self.views["dcov3D"],
+                "dopacity": self.views["dopacity"], "dsh": dsh, "dmeans2D": out["dmeans2D"]}

@@ -36,9 +36,10 @@
 extern "C" {
 #endif
 
-#define GGRT_RASTER_ABI_VERSION 5
+#define GGRT_RASTER_ABI_VERSION 6
 #define GGRT_RASTER_TILE 16 /* tile edge in pixels (tile ids are part of the contract) */
 #define GGRT_RASTER_SUBS 16 /* pair counters per tile (contention spreading) */
+#define GGRT_RASTER_MAX_MERGE_VIEWS 16 /* views per ggrt_raster_sh_gradient_merge call */
 
 #define GGRT_OK 0
 #define GGRT_ERR_INVALID_ARGUMENT (-1)
@@ -155,6 +156,13 @@ int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, in
  * unless dL_dout_aux is given).  dL_dcamera (NULL, or 35 floats: dL/dviewmatrix [4,4] |
  * dL/dprojmatrix [4,4] | dL/dcampos [3], overwritten) is an opt-in extension: the reference
  * treats the camera as constant (poses are detached, train_ggrt_stable.py:106).
+ *
+ * Compact mode (view-sharded multi-GPU path): with shs given, pass dL_dsh = NULL and dL_dcolors
+ * [P,3] instead.  dL_dcolors then receives the gradient w.r.t. the evaluated SH colour (zero for
+ * culled Gaussians and for channels clamped at 0) and no SH gradient is written; dL_dmeans3D still
+ * contains the view-direction term.  dL/dsh of one view is basis(dir) (x) dL_dcolors, so the
+ * per-view [P,3] arrays can be exchanged between GPUs instead of the K times larger SH gradients
+ * and summed into dL/dsh with ggrt_raster_sh_gradient_merge.
  */
 int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInputLayout* layout, int32_t P,
                          int64_t num_rendered, const float* means3D,
@@ -163,6 +171,32 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
                          const float* dL_dout_aux, float* grad_scratch, float* dL_dmeans2D, float* dL_dopacity,
                          float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dcolors, float* dL_daux,
                          float* dL_dcamera, ggrt_stream_t stream);
+
+/*
+ * dL_dsh[i] = sum over views v of basis(normalize(scene_scale * means3D[i] - campos_v)) (x) drgb_v[i]
+ * for num_views <= GGRT_RASTER_MAX_MERGE_VIEWS views of the same P Gaussians: the SH gradient of a
+ * multi-view step rebuilt from the compact per-view colour gradients of ggrt_raster_backward.
+ * drgb_views_host / campos_views_host are HOST arrays of num_views device pointers ([P,3] and [3]
+ * floats each); the pointers may address peer-GPU memory (P2P / symmetric memory over NVLink) -- the
+ * kernel then gathers over NVLink while it streams dL_dsh to HBM -- provided the data was published
+ * by a cross-device barrier the caller enqueued on `stream` before this call.  layout (may be NULL)
+ * gives scene_scale and the SH layout of dL_dsh ([P,K,3], or [P,3,K] when sh_channel_major).
+ * dL_dsh is overwritten.
+ */
+int ggrt_raster_sh_gradient_merge(int32_t P, int32_t sh_degree, const GgrtRasterInputLayout* layout,
+                                  const float* means3D, int32_t num_views, const float* const* drgb_views_host,
+                                  const float* const* campos_views_host, float* dL_dsh, ggrt_stream_t stream);
+
+/*
+ * In-place float32 sum over `world` GPUs of `count` floats (a multiple of 4) that every rank holds at the
+ * same offset of an NVLS multicast mapping (`multicast_ptr`: the multicast address of a symmetric
+ * allocation, e.g. torch.distributed._symmetric_memory's multicast_ptr).  Rank r reduces slice r
+ * inside the NVSwitch (multimem.ld_reduce) and broadcasts the result to all ranks (multimem.st).
+ * The caller brackets the call with cross-device barriers on `stream` (inputs complete on every
+ * rank before; results visible on every rank after).
+ */
+int ggrt_raster_nvls_allreduce_f32(void* multicast_ptr, int64_t count, int32_t rank, int32_t world,
+                                   ggrt_stream_t stream);
 
 /* Frustum test only (upstream markVisible): present[i] = view-space z > 0.2. */
 int ggrt_raster_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present,

@@ -50,7 +50,7 @@ def fake_forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs, 
     f = co.forward(cam, inp["means"], inp["cov"], inp["opac"], sh=inp["sh"], colors=inp["colors"], aux=auxn)
     call = SimpleNamespace(means3D=means3D, sh=sh, colors=colors_precomp, opacities=opacities, cov3D=cov3D_precomp,
                            P=inp["means"].shape[0], aux=aux, H=int(rs.image_height), W=int(rs.image_width),
-                           device=means3D.device)
+                           device=means3D.device, campos=rs.campos)
     return dict(call=call, color=torch.from_numpy(f["color"].copy()), depth=torch.from_numpy(f["depth"].copy()),
                 radii=torch.from_numpy(f["radii"].copy()), geom=None, img=None, binning=None, N=f["bin"]["N"],
                 capacity=f["bin"]["N"], max_tile_pairs=0, _oracle=(cam, inp, f))
@@ -112,3 +112,38 @@ def installed():
     finally:
         R.forward_raw, R.backward_raw = orig[0], orig[1]
         R._RasterizeGaussians.forward = staticmethod(orig[2])
+
+
+def fake_backward_compact(state, grad_color, out=None, compact=False, **kw):
+    """`backward_raw(..., compact=True)` on the oracle: dcolors = masked colour gradient, no dsh."""
+    g = fake_backward_raw(state, grad_color, **kw)
+    if compact:
+        cam, inp, f = state["_oracle"]
+        pre = f["pre"]
+        d = co.backward(cam, inp["means"], inp["cov"], inp["opac"], f, _np(grad_color), sh=inp["sh"])["dcolor"]
+        d = d * (pre["clamped"] == 0) * (pre["radii"] > 0)[:, None]
+        g["dcolors"], g["dsh"] = torch.from_numpy(d.astype(np.float32)), None
+    if out:
+        for k, dst in out.items():
+            if g.get(k) is not None:
+                dst.copy_(g[k].reshape(dst.shape))
+                g[k] = dst
+    return g
+
+
+def fake_sh_gradient_merge(means3D, sh_degree, drgb_views, campos_views, out=None, layout=None):
+    """`sh_gradient_merge` restated with torch on the CPU (float64 accumulate)."""
+    from oracle.torch_ref import sh_basis
+
+    scale = float((layout or {}).get("scene_scale", 1.0))
+    m = means3D.detach().double() * scale
+    acc = 0
+    for d, cpos in zip(drgb_views, campos_views):
+        dirs = m - cpos.detach().double().reshape(1, 3)
+        dirs = dirs / dirs.norm(dim=1, keepdim=True)
+        acc = acc + sh_basis(int(sh_degree), dirs)[:, :, None] * d.detach().double()[:, None, :]
+    res = acc.float()
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res

@@ -60,3 +60,19 @@ def test_argument_errors_are_reported_without_touching_cuda():
     with pytest.raises(RuntimeError, match="sh_degree"):
         _cabi.check(rc, "forward_prepare")
     assert lib.ggrt_raster_stage_name(6) == b"render_backward"
+
+
+def test_exchange_entry_points_validate_arguments():
+    lib = _cabi.lib()
+    ptrs = (C.c_void_p * 1)(16)
+    dummy = C.c_void_p(16)
+    assert lib.ggrt_raster_sh_gradient_merge(8, 4, None, dummy, 0, ptrs, ptrs, dummy, None) == -1
+    assert b"num_views" in lib.ggrt_raster_last_error()
+    assert lib.ggrt_raster_sh_gradient_merge(8, 4, None, dummy, _cabi.MAX_MERGE_VIEWS + 1, ptrs, ptrs, dummy, None) == -1
+    assert lib.ggrt_raster_sh_gradient_merge(8, 5, None, dummy, 1, ptrs, ptrs, dummy, None) == -1
+    null = (C.c_void_p * 1)(None)
+    assert lib.ggrt_raster_sh_gradient_merge(8, 4, None, dummy, 1, null, ptrs, dummy, None) == -1
+    assert b"view 0" in lib.ggrt_raster_last_error()
+    assert lib.ggrt_raster_nvls_allreduce_f32(dummy, 6, 0, 2, None) == -1  # not a multiple of 4
+    assert lib.ggrt_raster_nvls_allreduce_f32(dummy, 8, 2, 2, None) == -1  # rank outside the world
+    assert lib.ggrt_raster_nvls_allreduce_f32(None, 8, 0, 2, None) == -1
