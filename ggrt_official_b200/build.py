@@ -68,6 +68,24 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_variant(name: str, defines: dict, verbose: bool = False) -> Path:
+    """Tuning experiments: the same sources with other -D knobs -> gpurun_variants/<name>/libggrt_raster.so
+    (git-ignored, shipped to the GPU box; load it with GGRT_RASTER_LIB=<path>)."""
+    out_dir = PKG.parent / "gpurun_variants" / name
+    out_dir.mkdir(parents=True, exist_ok=True)
+    out = out_dir / "libggrt_raster.so"
+    cmd = [find_nvcc(), *NVCC_FLAGS, *[f"-D{k}={v}" for k, v in defines.items()], "-o", str(out), *map(str, sources())]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if verbose:
+        print(res.stdout, res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+    return out
+
+
 if __name__ == "__main__":
     import sys
 

@@ -1,6 +1,7 @@
 // extern "C" entry points of libggrt_raster.so (include/ggrt_raster.h) and buffer layout.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -52,6 +53,69 @@ struct StageTimer {  // RAII: records start/stop events around one launch when p
         g_prof.used[stage] = true;
     }
 };
+
+// ---- colour evaluation overlapped with binning ------------------------------------------
+// The SH colour kernel is an HBM stream (~25 us at C2) that only the render kernel consumes, while the
+// tile scan / emit / sort kernels between them are latency- and L2-bound and leave HBM idle.  `prepare`
+// therefore forks the colour kernel onto an internal per-(thread, device) side stream right after the
+// geometry kernel and `render` joins it in front of the render kernel.  The only state kept is this stream
+// and its two events; GGRT_RASTER_OVERLAP=0 (or profiling / debug mode) keeps everything on the caller's stream.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool pending = false;
+};
+constexpr int MAX_DEVICES = 64;
+static thread_local SideStream g_side[MAX_DEVICES];
+
+static bool overlap_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("GGRT_RASTER_OVERLAP");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+// returns the side stream of the current device, or nullptr when it cannot be used
+static SideStream* side_stream() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return nullptr;
+    SideStream* ss = &g_side[dev];
+    if (!ss->stream) {
+        if (cudaStreamCreateWithFlags(&ss->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ss->fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ss->join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            ss->stream = nullptr;
+            return nullptr;
+        }
+    }
+    return ss;
+}
+
+// ---- L2 prefetch of the SH table for the preprocess backward -------------------------------
+// The render backward is instruction bound and leaves HBM idle for ~170 us at C2; the preprocess backward that
+// follows is HBM bound and starts by re-reading the 12K B/Gaussian SH table (90 MB at C2, smaller than the
+// 126 MB L2).  With GGRT_RASTER_PREFETCH_SH=1 `backward` forks a TMA bulk L2 prefetch of the table
+// (cp.async.bulk.prefetch.L2) onto the side stream so that it streams in underneath the render backward.
+// Nothing depends on it (it only warms the cache), so it is never joined.
+static bool prefetch_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("GGRT_RASTER_PREFETCH_SH");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+
+__global__ void l2_prefetch_kernel(const char* base, size_t bytes) {
+    constexpr size_t CHUNK = 32 * 1024;
+    const size_t nchunks = (bytes + CHUNK - 1) / CHUNK;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += (size_t)gridDim.x * blockDim.x) {
+        const size_t off = c * CHUNK;
+        const uint32_t n = (uint32_t)((bytes - off < CHUNK ? bytes - off : CHUNK) & ~(size_t)15);
+        if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(n) : "memory");
+    }
+}
 
 void compute_layout(int P, int H, int W, long long N, GgrtRasterLayout* L) {
     memset(L, 0, sizeof(*L));
@@ -245,13 +309,24 @@ int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, const GgrtRa
     for (int i = 0; i < GGRT_STAGE_COUNT; ++i) g_prof.used[i] = false;
     { StageTimer t_(GGRT_STAGE_GEOMETRY, s); launch_geometry(v, means3D, cov3D_precomp, opacities, radii, g, im, s); }
     GGRT_TRY(check_launch("geometry", dbg, s));
-    // {N, max pairs per tile} goes straight into the caller's mapped pinned host memory from the scan kernel:
-    // no copy node sits between the scan and the colour kernel
+    // colour evaluation needs the geometry kernel's radii / depths but nothing of the binning: fork it onto the
+    // side stream so it streams the SH table from HBM while scan / emit / sort run (joined in forward_render)
+    SideStream* ss = (overlap_enabled() && !g_prof.on && !dbg && P > 0) ? side_stream() : nullptr;
+    if (ss && cudaEventRecord(ss->fork, s) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess) {
+        launch_color(v, means3D, shs, colors_precomp, aux, radii, g, ss->stream);
+        GGRT_TRY(check_launch("color", 0, ss->stream));
+        if (cudaEventRecord(ss->join, ss->stream) != cudaSuccess) return check_launch("color join", 0, s);
+        ss->pending = true;
+    } else {
+        ss = nullptr;
+    }
+    // {N, max pairs per tile} goes straight into the caller's mapped pinned host memory from the scan kernel
     { StageTimer t_(GGRT_STAGE_SCAN_TILES, s); launch_scan_tiles(v, im, counts_host, s); }
     GGRT_TRY(check_launch("scan_tiles", dbg, s));
-    // colour evaluation does not depend on N: it runs while the host waits for the counts
-    { StageTimer t_(GGRT_STAGE_COLOR, s); launch_color(v, means3D, shs, colors_precomp, aux, radii, g, s); }
-    GGRT_TRY(check_launch("color", dbg, s));
+    if (!ss) {
+        { StageTimer t_(GGRT_STAGE_COLOR, s); launch_color(v, means3D, shs, colors_precomp, aux, radii, g, s); }
+        GGRT_TRY(check_launch("color", dbg, s));
+    }
     return GGRT_OK;
 }
 
@@ -284,6 +359,14 @@ int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, in
         GGRT_TRY(check_launch("emit", dbg, s));
         { StageTimer t_(GGRT_STAGE_SORT_TILES, s); launch_sort_tiles(v, im, b, max_tile_pairs, capacity, s); }
         GGRT_TRY(check_launch("sort_tiles", dbg, s));
+    }
+    {  // join the colour kernel that `prepare` forked (a later event of the in-order side stream covers earlier ones)
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < MAX_DEVICES && g_side[dev].pending) {
+            // `pending` is never cleared: renders of interleaved prepares on other streams must wait as well, and
+            // waiting on an event that has already completed costs nothing on the device
+            if (cudaStreamWaitEvent(s, g_side[dev].join, 0) != cudaSuccess) return check_launch("color join", 0, s);
+        }
     }
     { StageTimer t_(GGRT_STAGE_RENDER_FORWARD, s); launch_render_forward(v, g, im, b, capacity, out_color, out_depth, s); }
     GGRT_TRY(check_launch("render_forward", dbg, s));
@@ -323,6 +406,15 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
         return check_launch("memset grad scratch", 0, s);
     if (dL_dcamera && cudaMemsetAsync(dL_dcamera, 0, 35 * sizeof(float), s) != cudaSuccess)
         return check_launch("memset camera gradient", 0, s);
+    if (num_rendered > 0 && shs && prefetch_enabled() && !g_prof.on && !dbg &&
+        (reinterpret_cast<uintptr_t>(shs) & 15) == 0) {
+        SideStream* ss = side_stream();
+        if (ss && cudaEventRecord(ss->fork, s) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess) {
+            l2_prefetch_kernel<<<148, 32, 0, ss->stream>>>(reinterpret_cast<const char*>(shs),
+                                                           (size_t)P * v.K * 3 * sizeof(float));
+            cudaGetLastError();  // best effort
+        }
+    }
     if (num_rendered > 0) {
         { StageTimer t_(GGRT_STAGE_RENDER_BACKWARD, s); launch_render_backward(v, g, im, b, dL_dout_color, dL_dout_aux, grad_scratch, s); }
         GGRT_TRY(check_launch("render_backward", dbg, s));

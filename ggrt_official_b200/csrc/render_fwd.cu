@@ -9,6 +9,10 @@
 // few pixels wide, so most (warp, Gaussian) pairs of a tile are culled.
 #include "render_common.cuh"
 
+#ifndef GGRT_FWD_V2
+#define GGRT_FWD_V2 0
+#endif
+
 namespace ggrt {
 
 __global__ void __launch_bounds__(FWD_THREADS, 1024 / FWD_THREADS)
@@ -28,6 +32,79 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
     const float bx0f = (float)bx0, by0f = (float)by0;
     const uint32_t start = min(starts[tile], capacity), end = min(starts[tile + 1], capacity);
 
+#if GGRT_FWD_V2
+    // The sign of T carries the per-pixel "done" flag (T > 0: live, T < 0: terminated with final transmittance |T|;
+    // a live T never drops below T_EPS), which removes the predicate bookkeeping from the blend loop: a terminated
+    // pixel yields Tn < 0 and therefore never blends again.
+    float T = inside ? 1.0f : -1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
+    uint32_t last = 0;
+
+    for (uint32_t base = start; base < end; base += FWD_BATCH) {
+        if (__syncthreads_and(T < 0.0f)) break;  // also orders the previous batch's reads before the refill
+        const uint32_t cnt = min((uint32_t)FWD_BATCH, end - base);
+        for (uint32_t k = tid; k < cnt; k += FWD_THREADS) {
+            const uint32_t id = points[base + k];
+            const uint32_t dst = sbase + k * REC_BYTES;
+            float4 c = rec1[id];
+            c.x *= -0.5f * LOG2E, c.y *= -LOG2E, c.z *= -0.5f * LOG2E;
+            sts128(dst, rec0[id]);
+            sts128(dst + 16, c);
+            sts128(dst + 32, rec2[id]);
+        }
+        __syncthreads();
+        if (__all_sync(0xffffffffu, T < 0.0f)) continue;
+        for (uint32_t r = 0; r < cnt; r += 32) {
+            // lane l tests list entry r + 31 - l: bit b of the ballot is entry r + 31 - b, the highest bit comes first
+            const uint32_t j = r + 31 - lane;
+            bool hit = false;
+            if (j < cnt) {
+                const float4 a = lds128(sbase + j * REC_BYTES);
+                const float4 c = lds128(sbase + j * REC_BYTES + 16);
+                constexpr float UNSCALE = -2.0f / LOG2E;  // back to (A, 2B, C) for the cull
+                hit = ellipse_hits_rect(a.x, a.y, a.z, c.x * UNSCALE, c.y * (0.5f * UNSCALE), c.z * UNSCALE, bx0f, by0f,
+                                        7.0f, 3.0f);
+            }
+            uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            const uint32_t top = sbase + (r + 31) * REC_BYTES;       // record of bit 0 ... minus b records for bit b
+            const uint32_t last_top = (base - start) + r + 32;       // 1-based list position of bit 0's entry ... - b
+            while (mask) {
+                uint32_t b, src;  // opaque to the optimiser, which otherwise rebuilds the index from 31 - clz
+                asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(mask));
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(src) : "r"(b), "r"(0u - (uint32_t)REC_BYTES), "r"(top));
+                mask ^= 1u << b;
+                const float2 xy = lds64(src);
+                const float4 c = lds128(src + 16);
+                const float4 col = lds128(src + 32);
+                const float dx = xy.x - pxf, dy = xy.y - pyf;
+                const float power2 = fmaf(dx, fmaf(c.x, dx, c.y * dy), (c.z * dy) * dy);
+                const float alpha = fminf(ALPHA_MAX, c.w * ex2_approx(power2));
+                const bool active = (power2 <= 0.0f) && (alpha >= ALPHA_MIN);
+                const float Tn = T * (1.0f - alpha);
+                const bool blend = active && (Tn >= T_EPS);
+                const float w = blend ? alpha * T : 0.0f;
+                C0 = fmaf(col.x, w, C0);
+                C1 = fmaf(col.y, w, C1);
+                C2 = fmaf(col.z, w, C2);
+                D = fmaf(col.w, w, D);
+                const float Tstop = active ? -fabsf(T) : T;  // a live pixel that cannot blend an active Gaussian stops
+                T = blend ? Tn : Tstop;
+                last = blend ? last_top - b : last;
+            }
+            if (__all_sync(0xffffffffu, T < 0.0f)) break;
+        }
+    }
+    if (inside) {
+        const float Tf = fabsf(T);
+        const size_t pix = (size_t)py * v.W + px, hw = (size_t)v.H * v.W;
+        out_color[pix] = fmaf(Tf, v.bg[0], C0);
+        out_color[hw + pix] = fmaf(Tf, v.bg[1], C1);
+        out_color[2 * hw + pix] = fmaf(Tf, v.bg[2], C2);
+        out_depth[pix] = D;
+        final_T[pix] = Tf;
+        n_contrib[pix] = last;
+    }
+}
+#else
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
     uint32_t last = 0;
     bool done = !inside;
@@ -96,6 +173,7 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
         n_contrib[pix] = last;
     }
 }
+#endif  // GGRT_FWD_V2
 
 void launch_render_forward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, uint32_t capacity, float* out_color,
                            float* out_depth, cudaStream_t s) {

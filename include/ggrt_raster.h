@@ -14,8 +14,13 @@
  *
  * Plain C: raw device pointers, sizes and a CUDA stream handle.  No torch / pybind
  * types cross this boundary.  The library never allocates or frees device memory and
- * keeps no state between calls; the caller owns every buffer (sizes from the
- * ggrt_raster_*_bytes functions).  All float data is float32, all pointers are device
+ * keeps no data between calls; the caller owns every buffer (sizes from the
+ * ggrt_raster_*_bytes functions).  The only internal objects are one side stream and two
+ * events per (host thread, device): forward_prepare forks the SH colour kernel onto it so that
+ * it overlaps the binning kernels, forward_render joins it in front of the render kernel
+ * (GGRT_RASTER_OVERLAP=0 in the environment keeps every kernel on the caller's stream).
+ * Consequently the inputs of forward_prepare must stay valid and unmodified until the matching
+ * forward_render has been enqueued.  All float data is float32, all pointers are device
  * pointers unless the name ends in `_host`.  Every function returns 0 on success or a
  * negative GGRT_ERR_* code; ggrt_raster_last_error() returns a thread-local message.
  *
