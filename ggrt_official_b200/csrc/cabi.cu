@@ -93,30 +93,6 @@ static SideStream* side_stream() {
     return ss;
 }
 
-// ---- L2 prefetch of the SH table for the preprocess backward -------------------------------
-// The render backward is instruction bound and leaves HBM idle for ~170 us at C2; the preprocess backward that
-// follows is HBM bound and starts by re-reading the 12K B/Gaussian SH table (90 MB at C2, smaller than the
-// 126 MB L2).  With GGRT_RASTER_PREFETCH_SH=1 `backward` forks a TMA bulk L2 prefetch of the table
-// (cp.async.bulk.prefetch.L2) onto the side stream so that it streams in underneath the render backward.
-// Nothing depends on it (it only warms the cache), so it is never joined.
-static bool prefetch_enabled() {
-    static const bool on = [] {
-        const char* e = getenv("GGRT_RASTER_PREFETCH_SH");
-        return e && e[0] == '1';
-    }();
-    return on;
-}
-
-__global__ void l2_prefetch_kernel(const char* base, size_t bytes) {
-    constexpr size_t CHUNK = 32 * 1024;
-    const size_t nchunks = (bytes + CHUNK - 1) / CHUNK;
-    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += (size_t)gridDim.x * blockDim.x) {
-        const size_t off = c * CHUNK;
-        const uint32_t n = (uint32_t)((bytes - off < CHUNK ? bytes - off : CHUNK) & ~(size_t)15);
-        if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(n) : "memory");
-    }
-}
-
 void compute_layout(int P, int H, int W, long long N, GgrtRasterLayout* L) {
     memset(L, 0, sizeof(*L));
     const size_t p = (size_t)(P > 0 ? P : 0);
@@ -406,15 +382,6 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
         return check_launch("memset grad scratch", 0, s);
     if (dL_dcamera && cudaMemsetAsync(dL_dcamera, 0, 35 * sizeof(float), s) != cudaSuccess)
         return check_launch("memset camera gradient", 0, s);
-    if (num_rendered > 0 && shs && prefetch_enabled() && !g_prof.on && !dbg &&
-        (reinterpret_cast<uintptr_t>(shs) & 15) == 0) {
-        SideStream* ss = side_stream();
-        if (ss && cudaEventRecord(ss->fork, s) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess) {
-            l2_prefetch_kernel<<<148, 32, 0, ss->stream>>>(reinterpret_cast<const char*>(shs),
-                                                           (size_t)P * v.K * 3 * sizeof(float));
-            cudaGetLastError();  // best effort
-        }
-    }
     if (num_rendered > 0) {
         { StageTimer t_(GGRT_STAGE_RENDER_BACKWARD, s); launch_render_backward(v, g, im, b, dL_dout_color, dL_dout_aux, grad_scratch, s); }
         GGRT_TRY(check_launch("render_backward", dbg, s));

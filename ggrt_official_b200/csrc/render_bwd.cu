@@ -148,7 +148,8 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
             float4 con = lds128(src + 16);
             const float4 col = lds128(src + 32);
             if (!valid) con.w = 0.f;  // zero opacity: never active
-            const uint32_t pos = valid ? boff + jj : 0xffffffffu;  // 0-based list position
+            uint32_t pos = valid ? boff + jj : 0xffffffffu;  // 0-based list position (never "behind" a pixel's last)
+            asm volatile("" : "+r"(pos));  // keep the select: otherwise `valid` is re-tested in every pixel step
             // exponent of the Gaussian in base 2 with the -1/2 folded in: G = 2^(ea dx^2 + eb dx dy + ec dy^2)
             const float ea = -0.5f * LOG2E * con.x, eb = -LOG2E * con.y, ec = -0.5f * LOG2E * con.z;
             float a_op = 0.f, a_mx = 0.f, a_my = 0.f, a_A = 0.f, a_B = 0.f, a_C = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f;

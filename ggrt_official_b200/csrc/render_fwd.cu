@@ -9,10 +9,6 @@
 // few pixels wide, so most (warp, Gaussian) pairs of a tile are culled.
 #include "render_common.cuh"
 
-#ifndef GGRT_FWD_V2
-#define GGRT_FWD_V2 0
-#endif
-
 namespace ggrt {
 
 __global__ void __launch_bounds__(FWD_THREADS, 1024 / FWD_THREADS)
@@ -32,7 +28,6 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
     const float bx0f = (float)bx0, by0f = (float)by0;
     const uint32_t start = min(starts[tile], capacity), end = min(starts[tile + 1], capacity);
 
-#if GGRT_FWD_V2
     // The sign of T carries the per-pixel "done" flag (T > 0: live, T < 0: terminated with final transmittance |T|;
     // a live T never drops below T_EPS), which removes the predicate bookkeeping from the blend loop: a terminated
     // pixel yields Tn < 0 and therefore never blends again.
@@ -104,76 +99,6 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
         n_contrib[pix] = last;
     }
 }
-#else
-    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
-    uint32_t last = 0;
-    bool done = !inside;
-
-    for (uint32_t base = start; base < end; base += FWD_BATCH) {
-        if (__syncthreads_and(done)) break;  // also orders the previous batch's reads before the refill
-        const uint32_t cnt = min((uint32_t)FWD_BATCH, end - base);
-        for (uint32_t k = tid; k < cnt; k += FWD_THREADS) {
-            const uint32_t id = points[base + k];
-            const uint32_t dst = sbase + k * REC_BYTES;
-            // the conic is staged pre-scaled: G = 2^(ea dx^2 + eb dx dy + ec dy^2), ea = -A log2(e)/2, eb = -B log2(e), ...
-            float4 c = rec1[id];
-            c.x *= -0.5f * LOG2E, c.y *= -LOG2E, c.z *= -0.5f * LOG2E;
-            sts128(dst, rec0[id]);
-            sts128(dst + 16, c);
-            sts128(dst + 32, rec2[id]);
-        }
-        __syncthreads();
-        if (__all_sync(0xffffffffu, done)) continue;
-        for (uint32_t r = 0; r < cnt; r += 32) {
-            // lane l tests list entry r + 31 - l, so the highest set bit of the ballot is the first entry
-            const uint32_t j = r + 31 - lane;
-            bool hit = false;
-            if (j < cnt) {
-                const float4 a = lds128(sbase + j * REC_BYTES);
-                const float4 c = lds128(sbase + j * REC_BYTES + 16);
-                constexpr float UNSCALE = -2.0f / LOG2E;  // back to (A, 2B, C) for the cull
-                hit = ellipse_hits_rect(a.x, a.y, a.z, c.x * UNSCALE, c.y * (0.5f * UNSCALE), c.z * UNSCALE, bx0f, by0f,
-                                        7.0f, 3.0f);
-            }
-            uint32_t mask = __ballot_sync(0xffffffffu, hit);
-            while (mask) {
-                const int lz = __clz(mask);
-                mask &= ~(0x80000000u >> lz);
-                const uint32_t jj = r + lz;
-                const uint32_t src = sbase + jj * REC_BYTES;
-                // branch-free body: lanes that skip this Gaussian blend it with weight 0
-                const float2 xy = lds64(src);
-                const float4 c = lds128(src + 16);
-                const float4 col = lds128(src + 32);
-                const float dx = xy.x - pxf, dy = xy.y - pyf;
-                const float power2 = fmaf(dx, fmaf(c.x, dx, c.y * dy), (c.z * dy) * dy);
-                const float alpha = fminf(ALPHA_MAX, c.w * ex2_approx(power2));
-                const bool active = !done && (power2 <= 0.0f) && (alpha >= ALPHA_MIN);
-                const float Tn = T * (1.0f - alpha);
-                const bool blend = active && !(Tn < T_EPS);
-                done = done || (active && !blend);
-                const float w = blend ? alpha * T : 0.0f;
-                C0 = fmaf(col.x, w, C0);
-                C1 = fmaf(col.y, w, C1);
-                C2 = fmaf(col.z, w, C2);
-                D = fmaf(col.w, w, D);
-                T = blend ? Tn : T;
-                last = blend ? (base - start) + jj + 1 : last;
-            }
-            if (__all_sync(0xffffffffu, done)) break;
-        }
-    }
-    if (inside) {
-        const size_t pix = (size_t)py * v.W + px, hw = (size_t)v.H * v.W;
-        out_color[pix] = fmaf(T, v.bg[0], C0);
-        out_color[hw + pix] = fmaf(T, v.bg[1], C1);
-        out_color[2 * hw + pix] = fmaf(T, v.bg[2], C2);
-        out_depth[pix] = D;
-        final_T[pix] = T;
-        n_contrib[pix] = last;
-    }
-}
-#endif  // GGRT_FWD_V2
 
 void launch_render_forward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, uint32_t capacity, float* out_color,
                            float* out_depth, cudaStream_t s) {
