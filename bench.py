@@ -203,16 +203,19 @@ def run_ours(args, rank, world, local_rank):
 
     state = {}
 
-    from ggrt_official_b200.view_parallel import CompactGradientExchange, GradientArena
+    from ggrt_official_b200.view_parallel import GradientArena, make_exchange
 
     # Sum of the per-view Gaussian gradients over the GPUs, inside the timed step:
     #   arena   - ONE NCCL all-reduce of the contiguous [P, 3+6+1+3K] gradient arena (340 B / Gaussian)
     #   compact - exchange the [P,3] colour gradients + all-reduce [P,10], rebuild dL/dsh locally (sh_merge.cu)
     #   p2p     - compact over symmetric memory: in-kernel NVLink gather + NVLS multimem reduction, no NCCL
+    #   auto    - p2p if every rank can set up symmetric memory, else compact (default)
     arena = GradientArena.allocate(P, K, dev) if world > 1 and args.exchange == "arena" else None
     exch = None
     if world > 1 and args.exchange != "arena":
-        exch = CompactGradientExchange(P, SH_DEGREE, dev, transport="p2p" if args.exchange == "p2p" else "nccl")
+        exch = make_exchange(P, SH_DEGREE, dev, prefer="nccl" if args.exchange == "compact" else "p2p")
+        if args.exchange == "p2p" and exch.transport != "p2p":
+            raise SystemExit("--exchange p2p: symmetric memory could not be set up on every rank")
 
     def step():
         st = R.forward_raw(means, shs, None, opac, cov, rs)
@@ -431,7 +434,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gaussians", type=int, default=0,
                     help="override the Gaussian count of the workload (BASELINE config 5: 50K..2M sweep at 1008x756)")
-    ap.add_argument("--exchange", default="compact", choices=["arena", "compact", "p2p"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "arena", "compact", "p2p"],
                     help="multi-GPU gradient exchange (N>1 only), see run_ours")
     ap.add_argument("--pose-grads", action="store_true",
                     help="also compute dL/d(viewmatrix, projmatrix, campos) in the backward (BASELINE config 3)")

@@ -57,6 +57,25 @@ sh_gradient_merge_kernel(int P, float scale, const float* __restrict__ means, Me
     __syncthreads();
     const bool aligned = (reinterpret_cast<uintptr_t>(dsh) & 15) == 0;
 
+    // The inputs of the NEXT slab (mean + the first MERGE_GROUP views' colour gradients, possibly remote: NVLink
+    // latency is microseconds) are loaded into registers while the current slab is evaluated and stored.
+    float n_m[3] = {0.f, 0.f, 0.f};
+    float n_g[MERGE_GROUP][3];
+    auto prefetch = [&](int sl) {
+        const int i = sl * MERGE_THREADS + threadIdx.x;
+        const bool ok = sl < num_slabs && i < P;
+#pragma unroll
+        for (int u = 0; u < MERGE_GROUP; ++u) {
+            n_g[u][0] = n_g[u][1] = n_g[u][2] = 0.f;
+            if (ok && u < mv.n) {
+                const float* src = mv.drgb[u] + 3 * (size_t)i;
+                n_g[u][0] = ld_sys(src), n_g[u][1] = ld_sys(src + 1), n_g[u][2] = ld_sys(src + 2);
+            }
+        }
+        if (ok) n_m[0] = means[3 * (size_t)i], n_m[1] = means[3 * (size_t)i + 1], n_m[2] = means[3 * (size_t)i + 2];
+    };
+    prefetch(blockIdx.x);
+
     int it = 0;
     for (int sl = blockIdx.x; sl < num_slabs; sl += gridDim.x, ++it) {
         float* slab = merge_ring + (it % MERGE_STAGES) * (MERGE_THREADS * ROW);
@@ -64,25 +83,26 @@ sh_gradient_merge_kernel(int P, float scale, const float* __restrict__ means, Me
         const int cnt = min(MERGE_THREADS, P - base);
         const int i = base + threadIdx.x;
         const bool valid = threadIdx.x < cnt;
+        const float mx = fmul(n_m[0], scale), my = fmul(n_m[1], scale), mz = fmul(n_m[2], scale);
+        float g[MERGE_GROUP][3];
+#pragma unroll
+        for (int u = 0; u < MERGE_GROUP; ++u) g[u][0] = n_g[u][0], g[u][1] = n_g[u][1], g[u][2] = n_g[u][2];
+        prefetch(sl + gridDim.x);
         if (threadIdx.x == 0) bulk_wait_read<MERGE_STAGES - 1>();  // the store that last used this stage has drained
         __syncthreads();
 
         float acc[ROW];
 #pragma unroll
         for (int k = 0; k < ROW; ++k) acc[k] = 0.f;
-        float mx = 0.f, my = 0.f, mz = 0.f;
-        if (valid) {
-            mx = fmul(means[3 * (size_t)i], scale), my = fmul(means[3 * (size_t)i + 1], scale),
-            mz = fmul(means[3 * (size_t)i + 2], scale);
-        }
         for (int v0 = 0; v0 < mv.n; v0 += MERGE_GROUP) {
-            float g[MERGE_GROUP][3];
+            if (v0 > 0) {  // more than MERGE_GROUP views: the later groups are loaded in place
 #pragma unroll
-            for (int u = 0; u < MERGE_GROUP; ++u) {  // all (possibly remote) loads first
-                g[u][0] = g[u][1] = g[u][2] = 0.f;
-                if (valid && v0 + u < mv.n) {
-                    const float* src = mv.drgb[v0 + u] + 3 * (size_t)i;
-                    g[u][0] = ld_sys(src), g[u][1] = ld_sys(src + 1), g[u][2] = ld_sys(src + 2);
+                for (int u = 0; u < MERGE_GROUP; ++u) {
+                    g[u][0] = g[u][1] = g[u][2] = 0.f;
+                    if (valid && v0 + u < mv.n) {
+                        const float* src = mv.drgb[v0 + u] + 3 * (size_t)i;
+                        g[u][0] = ld_sys(src), g[u][1] = ld_sys(src + 1), g[u][2] = ld_sys(src + 2);
+                    }
                 }
             }
 #pragma unroll

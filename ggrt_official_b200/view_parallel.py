@@ -119,6 +119,8 @@ class CompactGradientExchange:
         self.slot = 3 * (self.P + 1)                 # [P,3] colour gradients + one row holding this view's campos
         self.small_elems = (10 * self.P + 3) // 4 * 4  # dmeans3D | dcov3D | dopacity, padded to float4
         self.handles = None
+        self._side = None
+        self.profile, self.marks = False, []
         if self.transport == "p2p":
             import torch.distributed._symmetric_memory as symm
 
@@ -148,35 +150,86 @@ class CompactGradientExchange:
         return {"gather_recv": 4 * self.slot * (w - 1), "allreduce_payload": 4 * self.small_elems,
                 "arena_allreduce_payload_replaced": 4 * self.P * (10 + 3 * self.K)}
 
+    def _mark(self, name: str) -> None:
+        """Phase boundary for `profile = True` (diagnostics): CUDA events on the current stream."""
+        if self.profile:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(self.device))
+            self.marks.append((name, ev))
+
+    def phase_ms(self) -> dict:
+        """Durations between the marks of the last profiled run() (waits for the last event)."""
+        if not self.marks:
+            return {}
+        self.marks[-1][1].synchronize()
+        return {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(self.marks[:-1], self.marks[1:])}
+
     def run(self, state: dict, grad_color: torch.Tensor, **backward_kw) -> dict:
         P_ = self.P
+        self.marks = []
+        self._mark("start")
         out = self.backward_fn(state, grad_color, out=dict(self.views), compact=True, **backward_kw)
         call = state["call"]
         self.my_slot[3 * P_:].copy_(call.campos.reshape(3))
+        self._mark("backward_compact")
         if self.world > 1 and self.transport == "p2p":
             from . import _cabi
             import ctypes as C
 
             hs, hm = self.handles
             hs.barrier(channel=0)  # every rank's colour gradients and small arena are complete
-            stream = torch.cuda.current_stream(self.device)
+            self._mark("barrier_in")
+            main = torch.cuda.current_stream(self.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            side = self._side
+            # the NVLink-bound sum of the small arena runs beside the HBM-bound merge
+            side.wait_stream(main)
             if hm.multicast_ptr:  # NVLS available: the NVSwitch does the sum
                 _cabi.check(_cabi.lib().ggrt_raster_nvls_allreduce_f32(
                     C.c_void_p(hm.multicast_ptr), self.small_elems, self.rank, self.world,
-                    C.c_void_p(stream.cuda_stream)), "nvls_allreduce")
+                    C.c_void_p(side.cuda_stream)), "nvls_allreduce")
             else:
-                dist.all_reduce(self.small, op=dist.ReduceOp.SUM, group=self.group)
+                with torch.cuda.stream(side):
+                    dist.all_reduce(self.small, op=dist.ReduceOp.SUM, group=self.group)
             bases = [int(p) for p in hs.buffer_ptrs]
             drgb = [b for b in bases]
             cams = [b + 4 * 3 * P_ for b in bases]
             dsh = self.merge_fn(call.means3D, self.deg, drgb, cams, out=self.dsh, layout=self.layout)
+            self._mark("merge")
+            main.wait_stream(side)
+            self._mark("join_allreduce")
             hs.barrier(channel=1)  # peers have finished reading this rank's buffers; the reduced arena is visible
+            self._mark("barrier_out")
         else:
             if self.world > 1:
                 dist.all_gather_into_tensor(self.slots, self.my_slot, group=self.group)
+                self._mark("all_gather")
                 dist.all_reduce(self.small, op=dist.ReduceOp.SUM, group=self.group)
+                self._mark("all_reduce")
             slots = self.slots.view(self.world, P_ + 1, 3)
             dsh = self.merge_fn(call.means3D, self.deg, [slots[r, :P_] for r in range(self.world)],
                                 [slots[r, P_] for r in range(self.world)], out=self.dsh, layout=self.layout)
+            self._mark("merge")
         return {"dmeans3D": self.views["dmeans3D"], "dcov3D": self.views["dcov3D"],
                 "dopacity": self.views["dopacity"], "dsh": dsh, "dmeans2D": out["dmeans2D"]}
+
+
+def make_exchange(P: int, sh_degree: int, device, group=None, prefer: str = "p2p", layout: Optional[dict] = None):
+    """CompactGradientExchange with the preferred transport if EVERY rank can set it up (symmetric memory needs
+    P2P access / a fabric between all GPUs), otherwise -- decided collectively, so no rank is left waiting in a
+    rendezvous -- with the NCCL transport."""
+    on = dist.is_available() and dist.is_initialized()
+    if not on or dist.get_world_size(group) == 1 or prefer == "nccl":
+        return CompactGradientExchange(P, sh_degree, device, group=group, transport="nccl", layout=layout)
+    ex, ok = None, 1
+    try:
+        ex = CompactGradientExchange(P, sh_degree, device, group=group, transport=prefer, layout=layout)
+    except Exception:  # noqa: BLE001 - any failure means "fall back", the reason is not actionable here
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 1:
+        return ex
+    del ex
+    return CompactGradientExchange(P, sh_degree, device, group=group, transport="nccl", layout=layout)

@@ -105,9 +105,18 @@ def main():
             worst = torch.tensor([max(errs.values())], dtype=torch.float64, device=dev)
             dist.all_reduce(worst, op=dist.ReduceOp.MAX)
             ms = timed(step_compact)
+            ex.profile = True
+            phases = {}
+            for _ in range(10):
+                flush_buf.zero_()
+                step_compact()
+                for k, v in ex.phase_ms().items():
+                    phases[k] = phases.get(k, 0.0) + v / 10
+            ex.profile = False
             say({"variant": f"compact_{transport}", "world": world, "ms_per_step": ms, "max_rel_err_vs_arena": errs,
                  "worst_over_ranks": float(worst.item()), "ok": bool(worst.item() < 1e-4),
-                 "multicast": bool(ex.handles and ex.handles[1].multicast_ptr), "bytes": ex.exchange_bytes()})
+                 "multicast": bool(ex.handles and ex.handles[1].multicast_ptr), "bytes": ex.exchange_bytes(),
+                 "phase_ms_rank0": {k: round(v, 4) for k, v in phases.items()}})
         except Exception as e:  # report and carry on with the next variant
             say({"variant": f"compact_{transport}", "world": world, "error": repr(e)[:400],
                  "trace": traceback.format_exc()[-1200:]})
