@@ -39,6 +39,12 @@ class InputLayout(C.Structure):
     _fields_ = [("scene_scale", C.c_float), ("cov_full3x3", C.c_int32), ("sh_channel_major", C.c_int32)]
 
 
+class GradSinks(C.Structure):
+    """struct GgrtRasterGradSinks"""
+
+    _fields_ = [("count", C.c_int32), ("multimem", C.c_int32), ("ptr", C.c_void_p * 16)]
+
+
 class Layout(C.Structure):
     """struct GgrtRasterLayout"""
 
@@ -95,7 +101,8 @@ def lib():
     L.ggrt_raster_binning_bytes.restype = sz
     L.ggrt_raster_forward_prepare.argtypes = [C.POINTER(Settings), C.POINTER(InputLayout), i32] + [vp] * 11
     L.ggrt_raster_forward_render.argtypes = [C.POINTER(Settings), i32, i64, u32, i32, vp, vp, vp, vp, vp, vp]
-    L.ggrt_raster_backward.argtypes = [C.POINTER(Settings), C.POINTER(InputLayout), i32, i64] + [vp] * 19
+    L.ggrt_raster_backward.argtypes = ([C.POINTER(Settings), C.POINTER(InputLayout), i32, i64] + [vp] * 18
+                                       + [C.POINTER(GradSinks), vp])
     L.ggrt_raster_sh_gradient_merge.argtypes = [i32, i32, C.POINTER(InputLayout), vp, i32, C.POINTER(vp), C.POINTER(vp),
                                                 vp, vp]
     L.ggrt_raster_nvls_allreduce_f32.argtypes = [vp, i64, i32, i32, vp]

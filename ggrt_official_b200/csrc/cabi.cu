@@ -357,7 +357,7 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
                          const void* binning_buffer, const void* image_buffer, const float* dL_dout_color,
                          const float* dL_dout_aux, float* grad_scratch, float* dL_dmeans2D, float* dL_dopacity,
                          float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dcolors, float* dL_daux,
-                         float* dL_dcamera, ggrt_stream_t stream) {
+                         float* dL_dcamera, const GgrtRasterGradSinks* color_sinks, ggrt_stream_t stream) {
     View v;
     GGRT_TRY(make_view(settings, layout, P, &v));
     if (P == 0) return GGRT_OK;
@@ -370,10 +370,31 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
         set_error("backward: dL_dout_aux and dL_daux go together");
         return GGRT_ERR_INVALID_ARGUMENT;
     }
-    // with shs: dL_dsh (full SH gradient) or dL_dcolors (compact mode, see the header) -- exactly one of them
-    if ((dL_dsh != nullptr) == (dL_dcolors != nullptr) || (shs == nullptr && dL_dsh != nullptr)) {
-        set_error("backward: pass exactly one of dL_dsh (needs shs) / dL_dcolors");
+    // with shs: dL_dsh (full SH gradient) or dL_dcolors / color_sinks (compact mode, see the header)
+    const bool have_sinks = color_sinks != nullptr;
+    if ((dL_dsh != nullptr) == (dL_dcolors != nullptr || have_sinks) || (shs == nullptr && (dL_dsh != nullptr || have_sinks)) ||
+        (have_sinks && dL_dcolors != nullptr)) {
+        set_error("backward: pass exactly one of dL_dsh (needs shs) / dL_dcolors / color_sinks (needs shs)");
         return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    ColorSinks sinks;
+    memset(&sinks, 0, sizeof(sinks));
+    if (have_sinks) {
+        if (color_sinks->count < 1 || color_sinks->count > GGRT_RASTER_MAX_MERGE_VIEWS ||
+            (color_sinks->multimem && color_sinks->count != 1)) {
+            set_error("backward: color_sinks->count must be 1..%d (exactly 1 with multimem)", GGRT_RASTER_MAX_MERGE_VIEWS);
+            return GGRT_ERR_INVALID_ARGUMENT;
+        }
+        for (int k = 0; k < color_sinks->count; ++k) {
+            if (!color_sinks->ptr[k] || (reinterpret_cast<uintptr_t>(color_sinks->ptr[k]) & 15)) {
+                set_error("backward: color_sinks->ptr[%d] must be a 16-byte aligned device pointer", k);
+                return GGRT_ERR_INVALID_ARGUMENT;
+            }
+            sinks.ptr[k] = color_sinks->ptr[k];
+        }
+        sinks.n = color_sinks->count, sinks.multimem = color_sinks->multimem != 0, sinks.with_campos = 1;
+    } else if (shs != nullptr && dL_dcolors != nullptr) {
+        sinks.ptr[0] = dL_dcolors, sinks.n = 1;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int dbg = settings->debug;
@@ -391,7 +412,7 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
     {
         StageTimer t_(GGRT_STAGE_PREPROCESS_BACKWARD, s);
         launch_preprocess_backward(v, means3D, cov3D_precomp, shs, radii, g, grad_scratch, dL_dmeans2D, dL_dopacity,
-                                   dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dcolors, dL_daux, dL_dcamera, s);
+                                   dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dcolors, dL_daux, dL_dcamera, sinks, s);
     }
     GGRT_TRY(check_launch("preprocess_backward", dbg, s));
     return GGRT_OK;

@@ -64,6 +64,15 @@ struct BinPtrs {
     uint32_t* points;
 };
 
+// destinations of the compact colour gradients: [P,3] rows of dL/drgb, plus (with_campos) a row P holding the
+// view's camera centre, so that a peer can rebuild dL/dsh from the buffer alone
+struct ColorSinks {
+    float* ptr[GGRT_RASTER_MAX_MERGE_VIEWS];
+    int n;
+    int multimem;     // ptr[0] is an NVLS multicast address: use multimem.st
+    int with_campos;
+};
+
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 void compute_layout(int P, int H, int W, long long N, GgrtRasterLayout* L);
@@ -87,7 +96,7 @@ void launch_render_backward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, 
 void launch_preprocess_backward(const View& v, const float* means, const float* cov3d, const float* shs,
                                 const int* radii, GeomPtrs g, const float* scratch, float* dmeans2D, float* dopacity,
                                 float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, float* daux, float* dcam,
-                                cudaStream_t s);
+                                const ColorSinks& sinks, cudaStream_t s);
 void launch_sh_gradient_merge(int P, int deg, float scale, bool cmajor, const float* means, int num_views,
                               const float* const* drgb, const float* const* campos, float* dsh, cudaStream_t s);
 void launch_nvls_allreduce(float* multicast, long long count, int rank, int world, cudaStream_t s);

@@ -29,6 +29,22 @@ constexpr int PB_THREADS = GGRT_PB_THREADS;
 
 constexpr int PB_STAGES = GGRT_PB_STAGES;
 
+// float4 / scalar stores of the compact colour gradients: plain (local or peer memory) or NVLS multicast
+__device__ __forceinline__ void sink_store4(float* dst, float4 v, bool multimem) {
+    if (multimem)
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y),
+                     "f"(v.z), "f"(v.w)
+                     : "memory");
+    else
+        *reinterpret_cast<float4*>(dst) = v;
+}
+__device__ __forceinline__ void sink_store1(float* dst, float v, bool multimem) {
+    if (multimem)
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst), "f"(v) : "memory");
+    else
+        *dst = v;
+}
+
 template <bool AUX, bool CMAJOR, bool POSE>
 __global__ void __launch_bounds__(PB_THREADS, 3)
 preprocess_backward_kernel(View v, const float* __restrict__ means, const float* __restrict__ cov3d,
@@ -36,8 +52,10 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
                            const uint8_t* __restrict__ flags, const float* __restrict__ scratch,
                            float* __restrict__ dmeans2D, float* __restrict__ dopacity, float* __restrict__ dmeans3D,
                            float* __restrict__ dcov3D, float* __restrict__ dsh, float* __restrict__ dcolors,
-                           float* __restrict__ daux, float* __restrict__ dcam, int num_slabs) {
+                           float* __restrict__ daux, float* __restrict__ dcam, ColorSinks sinks, int num_slabs) {
     extern __shared__ __align__(128) float slab_ring[];
+    __shared__ __align__(16) float sdc[PB_THREADS * 3];  // compact mode: the slab's colour gradients, staged for
+                                                          // coalesced 16-byte (possibly remote / multicast) stores
     __shared__ __align__(8) unsigned long long full_bar[PB_STAGES];
     __shared__ float sV[16], sM[16];
     if (threadIdx.x < 16) sV[threadIdx.x] = v.view[threadIdx.x];
@@ -309,8 +327,22 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
         } else if (valid && !compact) {
             for (int k = 0; k < row; ++k) my[k] = 0.f;
         }
-        if (compact && valid) {  // masked colour gradient (zero for culled Gaussians and clamped channels)
-            dcolors[3 * i] = dR, dcolors[3 * i + 1] = dG, dcolors[3 * i + 2] = dB;
+        if (compact) {  // masked colour gradient (zero for culled Gaussians and clamped channels)
+            if (valid) sdc[3 * threadIdx.x] = dR, sdc[3 * threadIdx.x + 1] = dG, sdc[3 * threadIdx.x + 2] = dB;
+            __syncthreads();
+            const int n3 = cnt * 3, n4 = n3 >> 2;
+            for (int sk = 0; sk < sinks.n; ++sk) {  // every sink is a [P+1,3] buffer: local, a peer's, or multicast
+                float* dstc = sinks.ptr[sk] + (size_t)base * 3;  // slab offsets are multiples of 1536 B
+                const bool mm = sinks.multimem != 0;
+                if ((reinterpret_cast<uintptr_t>(dstc) & 15) == 0) {
+                    for (int k = threadIdx.x; k < n4; k += PB_THREADS)
+                        sink_store4(dstc + 4 * k, *reinterpret_cast<const float4*>(sdc + 4 * k), mm);
+                    for (int k = (n4 << 2) + threadIdx.x; k < n3; k += PB_THREADS) sink_store1(dstc + k, sdc[k], mm);
+                } else {
+                    for (int k = threadIdx.x; k < n3; k += PB_THREADS) sink_store1(dstc + k, sdc[k], mm);
+                }
+            }
+            // (the barrier in the slab write-out / refill code below orders these reads before the next slab's writes)
         }
         // write-out of the dL/dsh slab: TMA bulk store, or coalesced stores when ragged / unaligned
         float* dst = compact ? nullptr : dsh + (size_t)base * row;
@@ -392,13 +424,17 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             if ((threadIdx.x & 31) == 0) atomicAdd(dcam + 32 + k, a);
         }
     }
+    if (compact && sinks.with_campos && blockIdx.x == 0 && threadIdx.x < 3) {  // row P of every sink: this view's camera centre
+        for (int sk = 0; sk < sinks.n; ++sk)
+            sink_store1(sinks.ptr[sk] + (size_t)v.P * 3 + threadIdx.x, v.campos[threadIdx.x], sinks.multimem != 0);
+    }
     if (threadIdx.x == 0) bulk_wait0();  // all bulk stores of this CTA have completed
 }
 
 void launch_preprocess_backward(const View& v, const float* means, const float* cov3d, const float* shs,
                                 const int* radii, GeomPtrs g, const float* scratch, float* dmeans2D, float* dopacity,
                                 float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, float* daux, float* dcam,
-                                cudaStream_t s) {
+                                const ColorSinks& sinks, cudaStream_t s) {
     if (v.P == 0) return;
     const size_t smem = shs ? (size_t)PB_STAGES * PB_THREADS * v.K * 3 * sizeof(float) : 0;
     const int num_slabs = (v.P + PB_THREADS - 1) / PB_THREADS;
@@ -415,7 +451,7 @@ void launch_preprocess_backward(const View& v, const float* means, const float* 
         preprocess_backward_kernel<AX, CM, PO><<<grid, PB_THREADS, smem, s>>>(v, means, cov3d, shs, radii, g.flags,     \
                                                                               scratch, dmeans2D, dopacity, dmeans3D,    \
                                                                               dcov3D, dsh, dcolors, daux, dcam,         \
-                                                                              num_slabs);                               \
+                                                                              sinks, num_slabs);                               \
     }
     const bool cm = v.sh_ks == 1 && v.K > 1;
     if (dcam) {  // camera gradients are rare: one instantiation per SH layout, aux always compiled in

@@ -194,7 +194,8 @@ def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: Gauss
 
 
 def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = None,
-                 grad_aux: Optional[torch.Tensor] = None, want_camera: bool = False, compact: bool = False) -> dict:
+                 grad_aux: Optional[torch.Tensor] = None, want_camera: bool = False, compact: bool = False,
+                 color_sinks: Optional[dict] = None) -> dict:
     """Runs the backward through the C ABI.  `out` may supply preallocated, contiguous float32 output
     tensors (e.g. views into one gradient arena that is all-reduced across GPUs afterwards).
     `grad_aux` [H,W]: gradient of the third output (only when the forward was given `aux`).
@@ -202,9 +203,23 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
     extension; the reference treats the camera as constant).
     `compact` (SH inputs only): skip dL/dsh and return out["dcolors"] [P,3], the gradient w.r.t. the evaluated SH
     colour, instead -- dL/dsh of one view is basis(dir) (x) dcolors, which `sh_gradient_merge` rebuilds for a whole
-    set of views after the (K times smaller) colour gradients have been exchanged between GPUs."""
+    set of views after the (K times smaller) colour gradients have been exchanged between GPUs.
+    `color_sinks` = {"ptrs": [device addresses], "multimem": bool} (implies compact): the kernel itself writes the
+    [P,3] colour gradients plus a row P with the view's campos to each of the 16-byte aligned [P+1,3] buffers --
+    peer-GPU memory, or one NVLS multicast address with multimem=True (struct GgrtRasterGradSinks); no local
+    "dcolors" is returned."""
     L = _cabi.lib()
     c: _Call = state["call"]
+    sinks = None
+    if color_sinks is not None:
+        compact = True
+        ptrs = [int(p) for p in color_sinks["ptrs"]]
+        sinks = _cabi.GradSinks()
+        sinks.count, sinks.multimem = len(ptrs), int(bool(color_sinks.get("multimem", False)))
+        if not 1 <= len(ptrs) <= _cabi.MAX_MERGE_VIEWS:
+            raise ValueError(f"color_sinks needs 1..{_cabi.MAX_MERGE_VIEWS} pointers, got {len(ptrs)}")
+        for k, p in enumerate(ptrs):
+            sinks.ptr[k] = p
     if compact and c.sh is None:
         raise ValueError("compact=True needs SH inputs (colors_precomp already yields dcolors)")
     dev = c.device
@@ -233,7 +248,7 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
             dmeans3D=buf("dmeans3D", (c.P, 3)),
             dcov3D=buf("dcov3D", (c.P, 3, 3) if c.cov9 else (c.P, 6)),
             dsh=buf("dsh", tuple(c.sh.shape)) if c.sh is not None and not compact else None,
-            dcolors=buf("dcolors", (c.P, 3)) if c.sh is None or compact else None,
+            dcolors=buf("dcolors", (c.P, 3)) if c.sh is None or (compact and sinks is None) else None,
             daux=buf("daux", (c.P,)) if ga is not None else None,
             dcamera=torch.zeros(35, **f32) if want_camera else None,
         )
@@ -243,7 +258,8 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
                                            _ptr(state["binning"]), _ptr(state["img"]), _ptr(g), _ptr(ga),
                                            _ptr(scratch), _ptr(out["dmeans2D"]), _ptr(out["dopacity"]),
                                            _ptr(out["dmeans3D"]), _ptr(out["dcov3D"]), _ptr(out["dsh"]),
-                                           _ptr(out["dcolors"]), _ptr(out["daux"]), _ptr(out["dcamera"]), sp),
+                                           _ptr(out["dcolors"]), _ptr(out["daux"]), _ptr(out["dcamera"]),
+                                           C.byref(sinks) if sinks is not None else None, sp),
                     "backward")
     return out
 

@@ -116,19 +116,29 @@ class CompactGradientExchange:
         self.backward_fn = backward_fn or R.backward_raw
         self.merge_fn = merge_fn or R.sh_gradient_merge
         f32 = dict(dtype=torch.float32, device=self.device)
-        self.slot = 3 * (self.P + 1)                 # [P,3] colour gradients + one row holding this view's campos
+        self.slot = (3 * (self.P + 1) + 3) // 4 * 4  # [P,3] colour gradients + a row with the view's campos (float4-padded)
         self.small_elems = (10 * self.P + 3) // 4 * 4  # dmeans3D | dcov3D | dopacity, padded to float4
         self.handles = None
+        self.sinks = None
         self._side = None
         self.profile, self.marks = False, []
         if self.transport == "p2p":
             import torch.distributed._symmetric_memory as symm
 
+            # "push" model: every rank holds the slots of ALL views in symmetric memory and each rank's backward
+            # kernel stores its colour gradients into slot `rank` of every GPU (posted NVLink stores, or ONE
+            # multimem.st per vector when the fabric has NVLS multicast), so the merge only reads local memory
             gname = (group or dist.group.WORLD).group_name
-            self.slots = symm.empty(self.slot, **f32)
+            self.slots = symm.empty(self.world * self.slot, **f32)
             self.small = symm.empty(self.small_elems, **f32)
             self.handles = (symm.rendezvous(self.slots, gname), symm.rendezvous(self.small, gname))
-            self.my_slot = self.slots
+            self.my_slot = self.slots[self.rank * self.slot: (self.rank + 1) * self.slot]
+            hs = self.handles[0]
+            off = 4 * self.rank * self.slot
+            if hs.multicast_ptr:
+                self.sinks = {"ptrs": [int(hs.multicast_ptr) + off], "multimem": True}
+            else:
+                self.sinks = {"ptrs": [int(p) + off for p in hs.buffer_ptrs], "multimem": False}
         else:
             self.slots = torch.empty(self.world * self.slot, **f32)
             self.small = torch.empty(self.small_elems, **f32)
@@ -147,7 +157,7 @@ class CompactGradientExchange:
     def exchange_bytes(self) -> dict:
         """Bytes this rank sends over the interconnect per step (ring/NVLS lower bounds), for reports."""
         w = self.world
-        return {"gather_recv": 4 * self.slot * (w - 1), "allreduce_payload": 4 * self.small_elems,
+        return {"gather_recv": 4 * 3 * (self.P + 1) * (w - 1), "allreduce_payload": 4 * self.small_elems,
                 "arena_allreduce_payload_replaced": 4 * self.P * (10 + 3 * self.K)}
 
     def _mark(self, name: str) -> None:
@@ -168,9 +178,13 @@ class CompactGradientExchange:
         P_ = self.P
         self.marks = []
         self._mark("start")
-        out = self.backward_fn(state, grad_color, out=dict(self.views), compact=True, **backward_kw)
         call = state["call"]
-        self.my_slot[3 * P_:].copy_(call.campos.reshape(3))
+        if self.sinks is not None:  # p2p: the kernel pushes colour gradients + campos into every GPU's slot table
+            out = self.backward_fn(state, grad_color, out={k: v for k, v in self.views.items() if k != "dcolors"},
+                                   color_sinks=self.sinks, **backward_kw)
+        else:
+            out = self.backward_fn(state, grad_color, out=dict(self.views), compact=True, **backward_kw)
+            self.my_slot[3 * P_: 3 * P_ + 3].copy_(call.campos.reshape(3))
         self._mark("backward_compact")
         if self.world > 1 and self.transport == "p2p":
             from . import _cabi
@@ -192,10 +206,10 @@ class CompactGradientExchange:
             else:
                 with torch.cuda.stream(side):
                     dist.all_reduce(self.small, op=dist.ReduceOp.SUM, group=self.group)
-            bases = [int(p) for p in hs.buffer_ptrs]
-            drgb = [b for b in bases]
-            cams = [b + 4 * 3 * P_ for b in bases]
-            dsh = self.merge_fn(call.means3D, self.deg, drgb, cams, out=self.dsh, layout=self.layout)
+            slots = self.slots.view(self.world, self.slot)  # filled by the peers' kernels, local reads only
+            dsh = self.merge_fn(call.means3D, self.deg, [slots[r, : 3 * P_] for r in range(self.world)],
+                                [slots[r, 3 * P_: 3 * P_ + 3] for r in range(self.world)], out=self.dsh,
+                                layout=self.layout)
             self._mark("merge")
             main.wait_stream(side)
             self._mark("join_allreduce")
@@ -207,9 +221,10 @@ class CompactGradientExchange:
                 self._mark("all_gather")
                 dist.all_reduce(self.small, op=dist.ReduceOp.SUM, group=self.group)
                 self._mark("all_reduce")
-            slots = self.slots.view(self.world, P_ + 1, 3)
-            dsh = self.merge_fn(call.means3D, self.deg, [slots[r, :P_] for r in range(self.world)],
-                                [slots[r, P_] for r in range(self.world)], out=self.dsh, layout=self.layout)
+            slots = self.slots.view(self.world, self.slot)
+            dsh = self.merge_fn(call.means3D, self.deg, [slots[r, : 3 * P_].view(P_, 3) for r in range(self.world)],
+                                [slots[r, 3 * P_: 3 * P_ + 3] for r in range(self.world)], out=self.dsh,
+                                layout=self.layout)
             self._mark("merge")
         return {"dmeans3D": self.views["dmeans3D"], "dcov3D": self.views["dcov3D"],
                 "dopacity": self.views["dopacity"], "dsh": dsh, "dmeans2D": out["dmeans2D"]}

@@ -82,6 +82,20 @@ typedef struct GgrtRasterInputLayout {
     int32_t sh_channel_major; /* 0: shs is [P,K,3]; 1: [P,3,K] */
 } GgrtRasterInputLayout;
 
+/*
+ * Optional destinations of the compact colour gradients of ggrt_raster_backward (view-sharded multi-GPU
+ * path, "push" model): instead of one local dL_dcolors [P,3], the kernel writes the rows -- staged in shared
+ * memory and stored as coalesced 16-byte vectors -- to `count` buffers of [P+1,3] floats each, row P receiving
+ * the view's campos.  The pointers may address peer-GPU memory (stores over NVLink are posted, so the remote
+ * copies cost the kernel no latency), or, with multimem = 1, ptr[0] is an NVLS multicast address and ONE
+ * multimem.st per vector lands in every GPU's buffer.  Each pointer must be 16-byte aligned.
+ */
+typedef struct GgrtRasterGradSinks {
+    int32_t count;    /* 1..GGRT_RASTER_MAX_MERGE_VIEWS */
+    int32_t multimem; /* 0: plain stores to every ptr[i]; 1: multimem.st to ptr[0] (count must be 1) */
+    float* ptr[GGRT_RASTER_MAX_MERGE_VIEWS];
+} GgrtRasterGradSinks;
+
 /* Byte offsets of the sub-arrays inside the caller-owned buffers (for tests / tools). */
 typedef struct GgrtRasterLayout {
     /* geometry buffer, per Gaussian */
@@ -167,7 +181,8 @@ int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, in
  * culled Gaussians and for channels clamped at 0) and no SH gradient is written; dL_dmeans3D still
  * contains the view-direction term.  dL/dsh of one view is basis(dir) (x) dL_dcolors, so the
  * per-view [P,3] arrays can be exchanged between GPUs instead of the K times larger SH gradients
- * and summed into dL/dsh with ggrt_raster_sh_gradient_merge.
+ * and summed into dL/dsh with ggrt_raster_sh_gradient_merge.  color_sinks (may be NULL; compact mode
+ * only, then dL_dcolors may be NULL) redirects / replicates that [P,3] output, see GgrtRasterGradSinks.
  */
 int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInputLayout* layout, int32_t P,
                          int64_t num_rendered, const float* means3D,
@@ -175,7 +190,7 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
                          const void* binning_buffer, const void* image_buffer, const float* dL_dout_color,
                          const float* dL_dout_aux, float* grad_scratch, float* dL_dmeans2D, float* dL_dopacity,
                          float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dcolors, float* dL_daux,
-                         float* dL_dcamera, ggrt_stream_t stream);
+                         float* dL_dcamera, const GgrtRasterGradSinks* color_sinks, ggrt_stream_t stream);
 
 /*
  * dL_dsh[i] = sum over views v of basis(normalize(scene_scale * means3D[i] - campos_v)) (x) drgb_v[i]

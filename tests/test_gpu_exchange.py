@@ -125,3 +125,25 @@ def test_single_rank_exchange_object_and_argument_checks():
         st2 = R.forward_raw(st["call"].means3D, None, torch.rand(P, 3, device=DEV), st["call"].opacities,
                             st["call"].cov3D, G.settings_from(ri, DEV))
         R.backward_raw(st2, g_img, compact=True)
+
+
+@pytest.mark.parametrize("P", [1200, 1001])  # 1001: ragged last slab, scalar tail stores
+def test_color_sinks_receive_gradients_and_campos(P):
+    """Push model: the backward kernel itself replicates the compact colour gradients (+ the campos row) into
+    several [P+1,3] buffers (here two local ones; on the multi-GPU path they are the peers' symmetric buffers)."""
+    H, W, deg = 32, 48, 4
+    (ri,) = _views(P, H, W, deg, 1, seed=9)
+    st = _forward(ri)
+    g_img = torch.tensor(image_gradient(H, W, seed=2) * (3 * H * W), device=DEV)
+    comp = R.backward_raw(st, g_img, compact=True)
+    n = (3 * (P + 1) + 3) // 4 * 4
+    sinks = [torch.full((n,), float("nan"), device=DEV) for _ in range(2)]
+    out = R.backward_raw(st, g_img, color_sinks={"ptrs": [b.data_ptr() for b in sinks], "multimem": False})
+    torch.cuda.synchronize()
+    assert out["dcolors"] is None and out["dsh"] is None
+    for b in sinks:
+        assert _close(b[: 3 * P].view(P, 3), comp["dcolors"])
+        assert torch.equal(b[3 * P: 3 * P + 3], st["call"].campos)
+    assert _close(out["dmeans3D"], comp["dmeans3D"])
+    with pytest.raises(RuntimeError, match="aligned"):
+        R.backward_raw(st, g_img, color_sinks={"ptrs": [sinks[0].data_ptr() + 4], "multimem": False})
