@@ -45,6 +45,14 @@ class GradSinks(C.Structure):
     _fields_ = [("count", C.c_int32), ("multimem", C.c_int32), ("ptr", C.c_void_p * 16)]
 
 
+class AdapterParams(C.Structure):
+    """struct GgrtAdapterParams"""
+
+    _fields_ = [("num_views", C.c_int32), ("rays_per_view", C.c_int32), ("samples_per_ray", C.c_int32),
+                ("sh_degree", C.c_int32), ("image_height", C.c_int32), ("image_width", C.c_int32),
+                ("scale_min", C.c_float), ("scale_max", C.c_float), ("eps", C.c_float)]
+
+
 class Layout(C.Structure):
     """struct GgrtRasterLayout"""
 
@@ -66,6 +74,8 @@ EXPORTS = (
     "ggrt_raster_backward",
     "ggrt_raster_sh_gradient_merge",
     "ggrt_raster_nvls_allreduce_f32",
+    "ggrt_adapter_forward",
+    "ggrt_adapter_backward",
     "ggrt_raster_mark_visible",
     "ggrt_raster_profile_enable",
     "ggrt_raster_profile_read",
@@ -106,6 +116,8 @@ def lib():
     L.ggrt_raster_sh_gradient_merge.argtypes = [i32, i32, C.POINTER(InputLayout), vp, i32, C.POINTER(vp), C.POINTER(vp),
                                                 vp, vp]
     L.ggrt_raster_nvls_allreduce_f32.argtypes = [vp, i64, i32, i32, vp]
+    L.ggrt_adapter_forward.argtypes = [C.POINTER(AdapterParams)] + [vp] * 12
+    L.ggrt_adapter_backward.argtypes = [C.POINTER(AdapterParams)] + [vp] * 13
     L.ggrt_raster_mark_visible.argtypes = [i32, vp, vp, vp, vp]
     L.ggrt_raster_profile_enable.argtypes = [i32]
     L.ggrt_raster_profile_read.argtypes = [C.POINTER(C.c_float)]

@@ -463,6 +463,59 @@ int ggrt_raster_nvls_allreduce_f32(void* multicast_ptr, int64_t count, int32_t r
     return check_launch("nvls_allreduce", 0, s);
 }
 
+static int check_adapter_params(const GgrtAdapterParams* p) {
+    if (!p) {
+        set_error("adapter: params is NULL");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    if (p->num_views < 0 || p->rays_per_view < 0 || p->samples_per_ray < 0 || p->image_height <= 0 || p->image_width <= 0) {
+        set_error("adapter: bad sizes (views=%d rays/view=%d samples/ray=%d image=%dx%d)", p->num_views, p->rays_per_view,
+                  p->samples_per_ray, p->image_width, p->image_height);
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    if (p->sh_degree < 0 || p->sh_degree > 4) {
+        set_error("adapter: sh_degree %d outside 0..4", p->sh_degree);
+        return GGRT_ERR_UNSUPPORTED;
+    }
+    if ((long long)p->num_views * p->rays_per_view * (long long)(p->samples_per_ray > 0 ? p->samples_per_ray : 1) > 0x7fffffffLL) {
+        set_error("adapter: more than 2^31 Gaussians");
+        return GGRT_ERR_UNSUPPORTED;
+    }
+    return GGRT_OK;
+}
+
+int ggrt_adapter_forward(const GgrtAdapterParams* params, const float* extrinsics, const float* intrinsics,
+                         const float* sh_rotation, const float* coordinates, const float* depths, const float* raw,
+                         float* means, float* covariances, float* harmonics, float* scales_out,
+                         float* rotations_out, ggrt_stream_t stream) {
+    GGRT_TRY(check_adapter_params(params));
+    const long long G = (long long)params->num_views * params->rays_per_view * params->samples_per_ray;
+    if (G > 0 && (!extrinsics || !intrinsics || !coordinates || !depths || !raw || !means || !covariances || !harmonics)) {
+        set_error("adapter_forward: NULL buffer");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    launch_adapter_forward(*params, extrinsics, intrinsics, sh_rotation, coordinates, depths, raw, means, covariances,
+                           harmonics, scales_out, rotations_out, s);
+    return check_launch("adapter_forward", 0, s);
+}
+
+int ggrt_adapter_backward(const GgrtAdapterParams* params, const float* extrinsics, const float* intrinsics,
+                          const float* sh_rotation, const float* coordinates, const float* depths, const float* raw,
+                          const float* dL_dmeans, const float* dL_dcovariances, const float* dL_dharmonics,
+                          float* dL_dcoordinates, float* dL_ddepths, float* dL_draw, ggrt_stream_t stream) {
+    GGRT_TRY(check_adapter_params(params));
+    const long long G = (long long)params->num_views * params->rays_per_view * params->samples_per_ray;
+    if (G > 0 && (!extrinsics || !intrinsics || !coordinates || !depths || !raw || !dL_dcoordinates || !dL_ddepths || !dL_draw)) {
+        set_error("adapter_backward: NULL buffer");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    launch_adapter_backward(*params, extrinsics, intrinsics, sh_rotation, coordinates, depths, raw, dL_dmeans,
+                            dL_dcovariances, dL_dharmonics, dL_dcoordinates, dL_ddepths, dL_draw, s);
+    return check_launch("adapter_backward", 0, s);
+}
+
 int ggrt_raster_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present,
                              ggrt_stream_t stream) {
     if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) {

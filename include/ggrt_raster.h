@@ -218,6 +218,49 @@ int ggrt_raster_sh_gradient_merge(int32_t P, int32_t sh_degree, const GgrtRaster
 int ggrt_raster_nvls_allreduce_f32(void* multicast_ptr, int64_t count, int32_t rank, int32_t world,
                                    ggrt_stream_t stream);
 
+/*
+ * Fused Gaussian construction -- pixelSplat's "Gaussian adapter" (SURVEY.md 8f row 3).  Replaces the ~30 PyTorch
+ * kernels of /root/reference/ggrt/model/pixelsplat/encoder/common/gaussian_adapter.py:48-96 (+ gaussians.py:8-44,
+ * ggrt/geometry/projection.py:74-114, ggrt/misc/sh_rotation.py:10-29) by one forward and one backward kernel
+ * that write the rasterizer's inputs directly.  Flattened "b v r srf spp" indexing: view = (b, v); a ray = (view,
+ * r, srf) owns samples_per_ray Gaussians g = ray * samples_per_ray + s which share the ray's raw features and
+ * image coordinate.  K = (sh_degree + 1)^2.
+ *   extrinsics  [V,4,4]  camera-to-world          intrinsics [V,3,3]  normalised
+ *   sh_rotation [V,K,K]  per-view SH rotation; only the (2l+1)x(2l+1) diagonal blocks are read (the matrices
+ *                        e3nn's wigner_D gives the reference's rotate_sh); NULL = identity
+ *   coordinates [R,2]    raw [R, 7 + 3K] = scales(3) | quaternion xyzw(4) | sh [3,K]     (R = V * rays_per_view)
+ *   depths      [G]      (G = R * samples_per_ray)
+ * Outputs: means [G,3], covariances [G,3,3], harmonics [G,3,K]; scales_out [G,3] / rotations_out [G,4] may be
+ * NULL (the reference only uses them for .ply export).  Opacities pass through untouched and are not an argument.
+ */
+typedef struct GgrtAdapterParams {
+    int32_t num_views;
+    int32_t rays_per_view;
+    int32_t samples_per_ray;
+    int32_t sh_degree;     /* 0..4 */
+    int32_t image_height;
+    int32_t image_width;
+    float scale_min;       /* GaussianAdapterCfg.gaussian_scale_min / _max */
+    float scale_max;
+    float eps;             /* quaternion normalisation eps of GaussianAdapter.forward (1e-8) */
+} GgrtAdapterParams;
+
+int ggrt_adapter_forward(const GgrtAdapterParams* params, const float* extrinsics, const float* intrinsics,
+                         const float* sh_rotation, const float* coordinates, const float* depths, const float* raw,
+                         float* means, float* covariances, float* harmonics, float* scales_out,
+                         float* rotations_out, ggrt_stream_t stream);
+
+/*
+ * Backward of ggrt_adapter_forward: dL_dmeans [G,3], dL_dcovariances [G,3,3], dL_dharmonics [G,3,K] (any may be
+ * NULL = zero) -> dL_dcoordinates [R,2], dL_ddepths [G], dL_draw [R, 7 + 3K], all overwritten; gradients of the
+ * features a ray's samples share are summed inside the kernel (warp shuffles, no atomics).  Cameras are
+ * constants, as in the reference (poses are detached).
+ */
+int ggrt_adapter_backward(const GgrtAdapterParams* params, const float* extrinsics, const float* intrinsics,
+                          const float* sh_rotation, const float* coordinates, const float* depths, const float* raw,
+                          const float* dL_dmeans, const float* dL_dcovariances, const float* dL_dharmonics,
+                          float* dL_dcoordinates, float* dL_ddepths, float* dL_draw, ggrt_stream_t stream);
+
 /* Frustum test only (upstream markVisible): present[i] = view-space z > 0.2. */
 int ggrt_raster_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present,
                              ggrt_stream_t stream);

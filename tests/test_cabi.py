@@ -13,7 +13,7 @@ HEADER = (ROOT / "include" / "ggrt_raster.h").read_text()
 
 
 def declared_functions():
-    names = set(re.findall(r"\b(ggrt_raster_\w+)\s*\(", HEADER))
+    names = set(re.findall(r"\b(ggrt_(?:raster|adapter)_\w+)\s*\(", HEADER))
     return sorted(names)
 
 

@@ -1,0 +1,74 @@
+"""Fused Gaussian adapter (csrc/adapter.cu) against the same operator sequence in PyTorch (oracle/adapter_ref.py run on
+the GPU -- the reference classes themselves cannot travel to the GPU box), forward + backward, C2 shape:
+2 views x 50 000 rays x 3 samples = 300 000 Gaussians, SH degree 4.  Prints one JSON line."""
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from ggrt_official_b200.adapter import GaussianAdapter, GaussianAdapterCfg  # noqa: E402
+from oracle import adapter_ref  # noqa: E402  (baseline arm only)
+
+dev = torch.device("cuda:0")
+V, R, S, deg, h, w = 2, 50_000, 3, 4, 200, 250
+K = (deg + 1) ** 2
+g = torch.Generator().manual_seed(0)
+extr = torch.eye(4).repeat(V, 1, 1)
+extr[:, :3, 3] = torch.randn(V, 3, generator=g)
+intr = torch.tensor([[0.9, 0, 0.5], [0, 1.2, 0.5], [0, 0, 1.0]]).repeat(V, 1, 1)
+coords = torch.rand(V, R, 2, generator=g)
+depths = 1 + 4 * torch.rand(V, R, S, generator=g)
+raw = torch.randn(V, R, 7 + 3 * K, generator=g)
+blocks = torch.eye(K).repeat(V, 1, 1)
+up = dict(means=torch.randn(V, R, S, 3, generator=g), covariances=torch.randn(V, R, S, 3, 3, generator=g),
+          harmonics=torch.randn(V, R, S, 3, K, generator=g))
+extr, intr, coords, depths, raw, blocks = (t.to(dev) for t in (extr, intr, coords, depths, raw, blocks))
+up = {k: v.to(dev) for k, v in up.items()}
+ad = GaussianAdapter(GaussianAdapterCfg(0.5, 15.0, deg))
+
+
+def fused():
+    c, d, r = coords.clone().requires_grad_(), depths.clone().requires_grad_(), raw.clone().requires_grad_()
+    o = ad(extr[None, :, None, None, None], intr[None, :, None, None, None], c[None, :, :, None, None], d[None, :, :, None],
+           torch.ones_like(d[None, :, :, None]), r[None, :, :, None, None], (h, w), sh_rotations=blocks[None])
+    torch.autograd.backward([o.means, o.covariances, o.harmonics],
+                            [up["means"][None, :, :, None], up["covariances"][None, :, :, None], up["harmonics"][None, :, :, None]])
+    return r.grad
+
+
+def eager():
+    c, d, r = coords.clone().requires_grad_(), depths.clone().requires_grad_(), raw.clone().requires_grad_()
+    o = adapter_ref.adapter_forward(extr, intr, c, d, r, (h, w), deg, 0.5, 15.0, sh_rotations=blocks)
+    torch.autograd.backward([o["means"], o["covariances"], o["harmonics"]], [up["means"], up["covariances"], up["harmonics"]])
+    return r.grad
+
+
+def timed(fn, n=30):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+# oracle/adapter_ref.py builds its constants on the CPU: run it under a default-device context for the baseline arm
+with torch.device(dev):
+    ge = eager()
+gf = fused()
+err = float((gf - ge).abs().max() / ge.abs().max())
+with torch.device(dev):
+    t_eager = timed(eager)
+t_fused = timed(fused)
+G = V * R * S
+bytes_fwd = V * R * (7 + 3 * K + 2) * 4 + G * 4 + G * (3 + 9 + 3 * K + 3 + 4) * 4
+bytes_bwd = V * R * (7 + 3 * K + 2) * 4 * 2 + G * 4 * 2 + G * (3 + 9 + 3 * K) * 4
+print(json.dumps({"what": "Gaussian adapter fwd+bwd (incl. autograd glue and input clones)", "gaussians": G, "sh_degree": deg,
+                  "fused_ms": round(t_fused, 4), "pytorch_ops_ms": round(t_eager, 4), "speedup": round(t_eager / t_fused, 2),
+                  "algorithmic_MB": round((bytes_fwd + bytes_bwd) / 1e6, 1), "max_rel_grad_diff": err}))
