@@ -74,6 +74,7 @@ EXPORTS = (
     "ggrt_raster_backward",
     "ggrt_raster_sh_gradient_merge",
     "ggrt_raster_nvls_allreduce_f32",
+    "ggrt_raster_nvls_barrier",
     "ggrt_adapter_forward",
     "ggrt_adapter_backward",
     "ggrt_raster_mark_visible",
@@ -116,6 +117,7 @@ def lib():
     L.ggrt_raster_sh_gradient_merge.argtypes = [i32, i32, C.POINTER(InputLayout), vp, i32, C.POINTER(vp), C.POINTER(vp),
                                                 vp, vp]
     L.ggrt_raster_nvls_allreduce_f32.argtypes = [vp, i64, i32, i32, vp]
+    L.ggrt_raster_nvls_barrier.argtypes = [vp, vp, u32, vp]
     L.ggrt_adapter_forward.argtypes = [C.POINTER(AdapterParams)] + [vp] * 12
     L.ggrt_adapter_backward.argtypes = [C.POINTER(AdapterParams)] + [vp] * 13
     L.ggrt_raster_mark_visible.argtypes = [i32, vp, vp, vp, vp]

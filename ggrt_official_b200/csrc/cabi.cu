@@ -463,6 +463,18 @@ int ggrt_raster_nvls_allreduce_f32(void* multicast_ptr, int64_t count, int32_t r
     return check_launch("nvls_allreduce", 0, s);
 }
 
+int ggrt_raster_nvls_barrier(void* multicast_counter, const void* local_counter, uint32_t target, ggrt_stream_t stream) {
+    if (!multicast_counter || !local_counter || (reinterpret_cast<uintptr_t>(multicast_counter) & 3) ||
+        (reinterpret_cast<uintptr_t>(local_counter) & 3)) {
+        set_error("nvls_barrier: counters must be 4-byte aligned device pointers");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    launch_nvls_barrier(static_cast<unsigned int*>(multicast_counter), static_cast<const unsigned int*>(local_counter),
+                        target, s);
+    return check_launch("nvls_barrier", 0, s);
+}
+
 static int check_adapter_params(const GgrtAdapterParams* p) {
     if (!p) {
         set_error("adapter: params is NULL");

@@ -100,6 +100,8 @@ void launch_preprocess_backward(const View& v, const float* means, const float* 
 void launch_sh_gradient_merge(int P, int deg, float scale, bool cmajor, const float* means, int num_views,
                               const float* const* drgb, const float* const* campos, float* dsh, cudaStream_t s);
 void launch_nvls_allreduce(float* multicast, long long count, int rank, int world, cudaStream_t s);
+void launch_nvls_barrier(unsigned int* mc_counter, const unsigned int* local_counter, unsigned int target,
+                         cudaStream_t s);
 void launch_adapter_forward(const GgrtAdapterParams& p, const float* extr, const float* intr, const float* shrot,
                             const float* coords, const float* depths, const float* raw, float* means, float* cov,
                             float* harm, float* scales_out, float* rot_out, cudaStream_t s);

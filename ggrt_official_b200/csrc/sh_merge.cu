@@ -200,6 +200,23 @@ nvls_allreduce_kernel(float* __restrict__ mc, long long first4, long long n4) {
     }
 }
 
+// Cross-GPU barrier in one single-thread kernel: every rank adds 1 to ALL copies of a counter with one
+// multimem.red through the NVLS multicast mapping (release: the pushes of the preceding kernels are ordered before
+// it), then spins on its own copy until all `world` increments of this epoch have arrived (acquire).
+__global__ void nvls_barrier_kernel(unsigned int* mc_counter, const unsigned int* local_counter, unsigned int target) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_counter), "r"(1u) : "memory");
+    unsigned int v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local_counter) : "memory");
+    } while ((int)(v - target) < 0);
+}
+
+void launch_nvls_barrier(unsigned int* mc_counter, const unsigned int* local_counter, unsigned int target,
+                         cudaStream_t s) {
+    nvls_barrier_kernel<<<1, 32, 0, s>>>(mc_counter, local_counter, target);
+}
+
 void launch_nvls_allreduce(float* multicast, long long count, int rank, int world, cudaStream_t s) {
     const long long n4 = count / 4;  // count is a multiple of 4 (checked by the caller)
     const long long per = (n4 + world - 1) / world;

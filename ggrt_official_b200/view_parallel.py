@@ -98,7 +98,7 @@ class CompactGradientExchange:
 
     def __init__(self, P: int, sh_degree: int, device, group=None, transport: str = "nccl",
                  layout: Optional[dict] = None, backward_fn: Optional[Callable] = None,
-                 merge_fn: Optional[Callable] = None):
+                 merge_fn: Optional[Callable] = None, barrier: str = "torch"):
         if transport not in ("nccl", "p2p"):
             raise ValueError(f"unknown transport {transport!r}")
         on = dist.is_available() and dist.is_initialized()
@@ -122,6 +122,7 @@ class CompactGradientExchange:
         self.sinks = None
         self._side = None
         self.profile, self.marks = False, []
+        self.barrier_kind = "torch"
         if self.transport == "p2p":
             import torch.distributed._symmetric_memory as symm
 
@@ -135,6 +136,16 @@ class CompactGradientExchange:
             self.my_slot = self.slots[self.rank * self.slot: (self.rank + 1) * self.slot]
             hs = self.handles[0]
             off = 4 * self.rank * self.slot
+            # cross-GPU barrier: torch's symmetric-memory barrier kernel ("torch"), or one multimem.red + local spin
+            # in a single-thread kernel of this library ("nvls"; needs the multicast mapping)
+            self.barrier_kind = barrier if hs.multicast_ptr else "torch"
+            if self.barrier_kind == "nvls":
+                self.bar = symm.empty(4, dtype=torch.int32, device=self.device)
+                self.bar.zero_()
+                self.bar_handle = symm.rendezvous(self.bar, gname)
+                torch.cuda.synchronize(self.device)
+                hs.barrier(channel=0)  # every rank's counter is zero before anyone increments it
+                self.epoch = 0
             if hs.multicast_ptr:
                 self.sinks = {"ptrs": [int(hs.multicast_ptr) + off], "multimem": True}
             else:
@@ -159,6 +170,19 @@ class CompactGradientExchange:
         w = self.world
         return {"gather_recv": 4 * 3 * (self.P + 1) * (w - 1), "allreduce_payload": 4 * self.small_elems,
                 "arena_allreduce_payload_replaced": 4 * self.P * (10 + 3 * self.K)}
+
+    def _barrier(self, channel: int) -> None:
+        if self.barrier_kind == "nvls":
+            from . import _cabi
+            import ctypes as C
+
+            self.epoch += 1
+            stream = torch.cuda.current_stream(self.device)
+            _cabi.check(_cabi.lib().ggrt_raster_nvls_barrier(
+                C.c_void_p(self.bar_handle.multicast_ptr), C.c_void_p(self.bar.data_ptr()),
+                (self.world * self.epoch) & 0xFFFFFFFF, C.c_void_p(stream.cuda_stream)), "nvls_barrier")
+        else:
+            self.handles[0].barrier(channel=channel)
 
     def _mark(self, name: str) -> None:
         """Phase boundary for `profile = True` (diagnostics): CUDA events on the current stream."""
@@ -191,7 +215,7 @@ class CompactGradientExchange:
             import ctypes as C
 
             hs, hm = self.handles
-            hs.barrier(channel=0)  # every rank's colour gradients and small arena are complete
+            self._barrier(0)  # every rank's colour gradients and small arena are complete
             self._mark("barrier_in")
             main = torch.cuda.current_stream(self.device)
             if self._side is None:
@@ -213,7 +237,7 @@ class CompactGradientExchange:
             self._mark("merge")
             main.wait_stream(side)
             self._mark("join_allreduce")
-            hs.barrier(channel=1)  # peers have finished reading this rank's buffers; the reduced arena is visible
+            self._barrier(1)  # peers have finished reading this rank's buffers; the reduced arena is visible
             self._mark("barrier_out")
         else:
             if self.world > 1:

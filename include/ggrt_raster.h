@@ -219,6 +219,14 @@ int ggrt_raster_nvls_allreduce_f32(void* multicast_ptr, int64_t count, int32_t r
                                    ggrt_stream_t stream);
 
 /*
+ * Cross-GPU barrier on `stream` in one single-thread kernel (no host involvement): adds 1 to every GPU's copy of a
+ * 32-bit counter through its NVLS multicast address (multimem.red, release) and waits until the local copy
+ * (`local_counter`, the same symmetric allocation) has reached `target` = world * epoch, epoch = 1, 2, ... counted
+ * by the caller (acquire; wrap-around safe).  The counter must be zero on every rank before the first use.
+ */
+int ggrt_raster_nvls_barrier(void* multicast_counter, const void* local_counter, uint32_t target, ggrt_stream_t stream);
+
+/*
  * Fused Gaussian construction -- pixelSplat's "Gaussian adapter" (SURVEY.md 8f row 3).  Replaces the ~30 PyTorch
  * kernels of /root/reference/ggrt/model/pixelsplat/encoder/common/gaussian_adapter.py:48-96 (+ gaussians.py:8-44,
  * ggrt/geometry/projection.py:74-114, ggrt/misc/sh_rotation.py:10-29) by one forward and one backward kernel

@@ -88,9 +88,10 @@ def main():
 
     say({"variant": "no_exchange", "world": world, "ms_per_step": timed(step_local)})
 
-    for transport in ("nccl", "p2p"):
+    for transport in ("nccl", "p2p", "p2p+nvls_barrier"):
         try:
-            ex = CompactGradientExchange(P, bench.SH_DEGREE, dev, transport=transport)
+            ex = CompactGradientExchange(P, bench.SH_DEGREE, dev, transport=transport.split("+")[0],
+                                         barrier="nvls" if "+" in transport else "torch")
 
             def step_compact():
                 st = R.forward_raw(means, shs, None, opac, cov, rs)
