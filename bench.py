@@ -414,7 +414,9 @@ def run_ours(args, rank, world, local_rank):
                        "exchange_bytes": None if exch is None else exch.exchange_bytes()},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": n_e2e},
-            "gpu_launches": (8 + (1 if exch is not None else 0)) * args.steps,
+            # this library's kernels per step: 8 of the fwd+bwd path, + the SH-gradient merge (compact exchange), + the
+            # NVLS all-reduce kernel (p2p transport); torch / NCCL kernels (barriers, collectives) are not counted
+            "gpu_launches": (8 + (0 if exch is None else 2 if exch.transport == "p2p" else 1)) * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,

@@ -13,6 +13,7 @@ behind the C ABI of include/ggrt_raster.h.  There is no CPU or eager fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from typing import NamedTuple, Optional
 
@@ -35,6 +36,12 @@ class GaussianRasterizationSettings(NamedTuple):
     campos: torch.Tensor
     prefiltered: bool
     debug: bool = False
+
+
+def _debug_enabled(rs) -> bool:
+    """`debug=True` in the settings, or GGRT_RASTER_DEBUG=1 in the environment: synchronise and check after every
+    kernel, dump the inputs on failure (as upstream's debug mode)."""
+    return bool(getattr(rs, "debug", False)) or os.environ.get("GGRT_RASTER_DEBUG") == "1"
 
 
 _tls = threading.local()
@@ -126,7 +133,7 @@ class _Call:
         s.scale_modifier = float(rs.scale_modifier)
         s.sh_degree = self.deg
         s.prefiltered = int(bool(rs.prefiltered))
-        s.debug = int(bool(rs.debug))
+        s.debug = int(_debug_enabled(rs))
         s.viewmatrix, s.projmatrix = self.view.data_ptr(), self.proj.data_ptr()
         s.campos, s.bg = self.campos.data_ptr(), self.bg.data_ptr()
         self.settings = s
@@ -327,7 +334,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         try:
             st = forward_raw(means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings, aux, layout)
         except Exception:
-            if raster_settings.debug:
+            if _debug_enabled(raster_settings):
                 _dump("snapshot_fw.dump", (means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings))
             raise
         # keep only what backward needs; the outputs must not be referenced from ctx (that would be a
@@ -358,7 +365,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         try:
             g = backward_raw(st, grad_color, grad_aux=grad_aux, want_camera=want_cam)
         except Exception:
-            if ctx.raster_settings.debug:
+            if _debug_enabled(ctx.raster_settings):
                 _dump("snapshot_bw.dump", (c.means3D, c.sh, c.colors, c.opacities, c.cov3D, grad_color))
             raise
         dsh = g["dsh"]

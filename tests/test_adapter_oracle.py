@@ -28,9 +28,19 @@ def test_live_reference_if_present():
         "make_golden_adapter", Path(__file__).resolve().parent.parent / "tools" / "make_golden_adapter.py")
     mg = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mg)
-    mod = mg.load_reference_adapter()
-    case = mg.make_case(**mg.CASES["b"])
-    out, grads = mg.run_reference(mod, case)
+    import sys
+
+    before = set(sys.modules)
+    try:
+        mod = mg.load_reference_adapter()
+        case = mg.make_case(**mg.CASES["b"])
+        out, grads = mg.run_reference(mod, case)
+    finally:  # drop the e3nn stand-in and the partially imported reference package again
+        for name in set(sys.modules) - before:
+            del sys.modules[name]
+        for name in ("e3nn", "e3nn.o3"):
+            if name in sys.modules and not getattr(sys.modules[name], "__file__", None):
+                del sys.modules[name]
     c = load_case("b")
     assert rel(out.covariances, c["out"]["covariances"]) < 1e-6
     assert rel(grads["raw"], c["grad"]["raw"]) < 1e-5

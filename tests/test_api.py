@@ -79,3 +79,14 @@ def test_shard_views_and_arena():
     a.views["dsh"].fill_(1.0)
     assert float(a.flat.sum()) == 10 * 75 and a.views["dcov3D"].shape == (10, 6)
     assert a.all_reduce() is None  # no process group: a no-op
+
+
+def test_debug_mode_from_settings_or_environment(monkeypatch):
+    from ggrt_official_b200 import rasterizer as R
+
+    rs = R.GaussianRasterizationSettings(1, 1, 1.0, 1.0, None, 1.0, None, None, 0, None, False)
+    assert not R._debug_enabled(rs)
+    monkeypatch.setenv("GGRT_RASTER_DEBUG", "1")
+    assert R._debug_enabled(rs)
+    monkeypatch.delenv("GGRT_RASTER_DEBUG")
+    assert R._debug_enabled(rs._replace(debug=True))
