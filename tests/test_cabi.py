@@ -76,3 +76,12 @@ def test_exchange_entry_points_validate_arguments():
     assert lib.ggrt_raster_nvls_allreduce_f32(dummy, 6, 0, 2, None) == -1  # not a multiple of 4
     assert lib.ggrt_raster_nvls_allreduce_f32(dummy, 8, 2, 2, None) == -1  # rank outside the world
     assert lib.ggrt_raster_nvls_allreduce_f32(None, 8, 0, 2, None) == -1
+
+
+def test_upstream_structure_baseline_builds_and_exports():
+    """The GPU baseline (measurement aid, never imported by the product) compiles for sm_100a and links the product."""
+    from baseline import build as ub
+
+    lib = C.CDLL(str(ub.build()))
+    for name in ("upstream_forward", "upstream_backward", "upstream_last_error"):
+        assert hasattr(lib, name)
