@@ -398,6 +398,27 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": n / dt, "unit": "frames/s", "cores": co.num_threads(), "kind": "port",
                "sample": f"{n} full frames (fwd+bwd) of the same workload after one warm-up frame"}
 
+    # ---- GPU baseline: the upstream kernel STRUCTURE restated for sm_100a (baseline/upstream_structure.cu; NOT the
+    # reference binary, whose source is unavailable offline), timed on this GPU by tools/bench_upstream.py in a
+    # subprocess so that a failure there cannot disturb this process (rank 0, N=1 only) ----------------------------
+    gpu_base = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline and args.gaussians == 0:
+        try:
+            res = subprocess.run([sys.executable, str(ROOT / "tools" / "bench_upstream.py"), "--workload", args.workload,
+                                  "--steps", "20"], capture_output=True, text=True, timeout=240)
+            rows = [l for l in res.stdout.splitlines() if l.startswith("{")]
+            if res.returncode == 0 and rows:
+                d = json.loads(rows[-1])
+                gpu_base = {"kind": "upstream-structure restatement on this GPU (not the reference binary)",
+                            "value": d["upstream_structure_fps"], "unit": "frames/s", "ms_per_step": d["upstream_structure_ms"],
+                            "product_ms_same_harness": d["product_ms"], "speedup": d["speedup"],
+                            "same_results": {"radii_equal": d["radii_equal"], "color_max_abs_diff": d["color_max_abs_diff"],
+                                             "grad_max_rel_diff": max(d["grad_max_rel_diff"].values())}}
+            else:
+                gpu_base = {"error": (res.stderr or res.stdout)[-300:]}
+        except Exception as e:  # noqa: BLE001 - a measurement aid must never fail the bench
+            gpu_base = {"error": repr(e)[:300]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -419,6 +440,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": (8 + (0 if exch is None else 2 if exch.transport == "p2p" else 1)) * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "gpu_baseline": gpu_base,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -434,6 +456,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true",
+                    help="skip the upstream-structure GPU baseline (tools/bench_upstream.py, run in a subprocess)")
     ap.add_argument("--gaussians", type=int, default=0,
                     help="override the Gaussian count of the workload (BASELINE config 5: 50K..2M sweep at 1008x756)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "arena", "compact", "p2p"],

@@ -8,7 +8,7 @@ for v in $(ls gpurun_variants 2>/dev/null); do
   lib=$PWD/gpurun_variants/$v/libggrt_raster.so
   [ -f $lib ] || continue
   GGRT_RASTER_LIB=$lib timeout 600 python -m pytest $targets -x -q > $out/pytest_$v.log 2>&1; echo "variant $v pytest rc=$? $(tail -1 $out/pytest_$v.log)"
-  GGRT_RASTER_LIB=$lib timeout 300 python bench.py --steps 60 --no-cpu-baseline $BENCH_ARGS > $out/bench_$v.json 2> $out/bench_$v.err
+  GGRT_RASTER_LIB=$lib timeout 300 python bench.py --steps 60 --no-cpu-baseline --no-gpu-baseline $BENCH_ARGS > $out/bench_$v.json 2> $out/bench_$v.err
 done
 python - <<'PY' $out
 import json, sys, glob, os
