@@ -83,12 +83,13 @@ if __name__ == "__main__":
     raw, launches, out = sys.argv[1:4]
     src = sys.argv[4] if len(sys.argv) > 4 else ""
     lsrc = sys.argv[5] if len(sys.argv) > 5 else ""
+    workload = sys.argv[6] if len(sys.argv) > 6 else "C2: P=300000, 1008x756, SH degree 4, N=800306 pairs"
     kernels = read_raw(raw)
     la = read_launches(launches)
     ours = {k: v for k, v in la.items() if "_kernel" in k and not k.startswith(("void at::", "at::"))}
     total = sum(sum(v) for v in ours.values())
     doc = {
-        "source": src, "launch_list": lsrc,
+        "source": src, "launch_list": lsrc, "workload": workload,  # bench.py matches the workload prefix ("C2")
         "kernels": kernels,
         "launch_list_mean_us_per_launch": {k: round(sum(v) / len(v), 2) for k, v in ours.items()},
         "launch_list_launches": {k: len(v) for k, v in ours.items()},
