@@ -8,11 +8,12 @@
 //
 // Indexing ("b v r srf spp" flattened): ray = (view, r, srf) owns `spp` Gaussians g = ray * spp + s that share the
 // ray's raw features [7 + 3K] = scales(3) | quaternion xyzw(4) | sh (3 x K, channel-major) and its image
-// coordinate; depths are per Gaussian.  One warp per ray: the lanes stream the 3K harmonics (coalesced row loads
-// and stores; each lane applies the <= 9-term Wigner-D block of its coefficient from shared memory), lanes s < spp
-// do the geometry of Gaussian s (scale / rotation -> covariance, ray unprojection -> mean).  The backward sums the
-// spp harmonics gradients per lane, applies the transposed blocks, and reduces the geometry gradients of the
-// ray's Gaussians with warp shuffles -- no atomics.
+// coordinate; depths are per Gaussian.  A warp takes 8 consecutive rays per iteration: the lanes stream the rays'
+// 3K harmonics (coalesced row loads and stores, all loads of the group in flight together; each lane applies the
+// <= 9-term Wigner-D block of its coefficient from shared memory), then lane = (ray, sample slot) does the geometry
+// of one Gaussian (scale / rotation -> covariance, ray unprojection -> mean).  The backward sums the spp harmonics
+// gradients per lane, applies the transposed blocks, and reduces the geometry gradients of a ray's Gaussians over
+// its adjacent lanes with warp shuffles -- no atomics.
 #include "common.cuh"
 
 namespace ggrt {
@@ -114,6 +115,12 @@ __device__ __forceinline__ void load_blocks(const float* __restrict__ shrot_view
     }
 }
 
+// Rays are processed in groups of AD_RG per warp iteration.  Geometry: lane = (ray of the group, sample slot), so
+// with spp = 3 twenty-four lanes work at once instead of three; harmonics: the group's AD_RG rows are fetched
+// together (all loads in flight before the first use) and the lanes then stride over the AD_RG x 3K outputs.
+constexpr int AD_RG = 8;          // rays per warp iteration
+constexpr int AD_SL = 32 / AD_RG;  // sample slots per ray (samples s, s + AD_SL, ... of a ray go to the same lane)
+
 template <int DEG>
 __global__ void __launch_bounds__(AD_THREADS, 2)
 adapter_forward_kernel(AdapterParams p, const float* __restrict__ extr, const float* __restrict__ intr,
@@ -123,52 +130,72 @@ adapter_forward_kernel(AdapterParams p, const float* __restrict__ extr, const fl
                        float* __restrict__ rot_out) {
     constexpr int K = (DEG + 1) * (DEG + 1), ROW = 3 * K, CH = 7 + ROW;
     constexpr int NB = (DEG + 1) * (2 * DEG + 1) * (2 * DEG + 3) / 3;
-    __shared__ float s_row[AD_WARPS][ROW];
+    __shared__ float s_row[AD_WARPS][AD_RG * ROW];
     __shared__ float s_D[AD_WARPS][NB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rays = p.num_views * p.rays_per_view;
-    int cur_view = -1;
+    const int groups = (rays + AD_RG - 1) / AD_RG;
+    int geo_view = -1, sh_view = -1;  // view whose constants this lane holds / whose blocks the warp holds
     ViewConsts vc;
-    for (int ray = blockIdx.x * AD_WARPS + warp; ray < rays; ray += gridDim.x * AD_WARPS) {
-        const int view = ray / p.rays_per_view;
-        if (view != cur_view) {
-            cur_view = view;
-            load_view(extr + 16 * view, intr + 9 * view, p.image_h, p.image_w, vc);
-            __syncwarp();
-            load_blocks<DEG>(shrot ? shrot + (size_t)view * K * K : nullptr, s_D[warp], lane);
+    for (int grp = blockIdx.x * AD_WARPS + warp; grp < groups; grp += gridDim.x * AD_WARPS) {
+        const int ray0 = grp * AD_RG;
+        const int nr = min(AD_RG, rays - ray0);
+        // ---- harmonics: fetch the group's rows, then mask + per-degree Wigner block, same result for every sample ----
+        __syncwarp();  // the previous group's reads of s_row are done
+        for (int e = lane; e < nr * ROW; e += 32) {
+            const int r = e / ROW, o = e - r * ROW;
+            s_row[warp][e] = raw[(size_t)(ray0 + r) * CH + 7 + o];
         }
-        const float* rr = raw + (size_t)ray * CH;
-        __syncwarp();  // the previous ray's reads of s_row are done
-        for (int o = lane; o < ROW; o += 32) s_row[warp][o] = rr[7 + o];
         __syncwarp();
-        for (int o = lane; o < ROW; o += 32) {
-            const int c = o / K, k = o - c * K, l = isqrt_small(k), w = 2 * l + 1;
-            const float* blk = s_D[warp] + block_offset(l) + (k - l * l) * w;
-            const float* in = s_row[warp] + c * K + l * l;
-            float acc = 0.f;
-            for (int j = 0; j < w; ++j) acc = fmaf(blk[j], in[j], acc);
-            acc *= sh_mask_of(l);
-            for (int s = 0; s < p.spp; ++s) harm[((size_t)ray * p.spp + s) * ROW + o] = acc;  // same for every sample
+        for (int r = 0; r < nr; ++r) {
+            const int view = (ray0 + r) / p.rays_per_view;
+            if (view != sh_view) {  // warp-uniform
+                sh_view = view;
+                __syncwarp();
+                load_blocks<DEG>(shrot ? shrot + (size_t)view * K * K : nullptr, s_D[warp], lane);
+                __syncwarp();
+            }
+            for (int o = lane; o < ROW; o += 32) {
+                const int c = o / K, k = o - c * K, l = isqrt_small(k), w = 2 * l + 1;
+                const float* blk = s_D[warp] + block_offset(l) + (k - l * l) * w;
+                const float* in = s_row[warp] + r * ROW + c * K + l * l;
+                float acc = 0.f;
+                for (int j = 0; j < w; ++j) acc = fmaf(blk[j], in[j], acc);
+                acc *= sh_mask_of(l);
+                for (int sI = 0; sI < p.spp; ++sI) harm[((size_t)(ray0 + r) * p.spp + sI) * ROW + o] = acc;
+            }
         }
-        for (int s = lane; s < p.spp; s += 32) {
-            const size_t g = (size_t)ray * p.spp + s;
+        // ---- geometry: lane = (ray of the group, sample slot) ----
+        const int r = lane / AD_SL, ray = ray0 + r;
+        if (r < nr) {
+            const int view = ray / p.rays_per_view;
+            if (view != geo_view) {
+                geo_view = view;
+                load_view(extr + 16 * view, intr + 9 * view, p.image_h, p.image_w, vc);
+            }
+            const float* rr = raw + (size_t)ray * CH;
             float r7[7];
 #pragma unroll
             for (int k = 0; k < 7; ++k) r7[k] = rr[k];
-            const float depth = depths[g];
-            Geo3 q;
-            adapter_geometry(p, vc, r7, coords[2 * (size_t)ray], coords[2 * (size_t)ray + 1], depth, q);
+            const float cx = coords[2 * (size_t)ray], cy = coords[2 * (size_t)ray + 1];
+            for (int sI = lane % AD_SL; sI < p.spp; sI += AD_SL) {
+                const size_t g = (size_t)ray * p.spp + sI;
+                const float depth = depths[g];
+                Geo3 q;
+                adapter_geometry(p, vc, r7, cx, cy, depth, q);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) means[3 * g + i] = vc.o[i] + q.dw[i] * depth;
-            float W[9];
-            world_factor(vc, q, W);
+                for (int i = 0; i < 3; ++i) means[3 * g + i] = vc.o[i] + q.dw[i] * depth;
+                float W[9];
+                world_factor(vc, q, W);
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
+                for (int i = 0; i < 3; ++i)
 #pragma unroll
-                for (int j = 0; j < 3; ++j)
-                    cov[9 * g + 3 * i + j] = W[3 * i] * W[3 * j] + W[3 * i + 1] * W[3 * j + 1] + W[3 * i + 2] * W[3 * j + 2];
-            if (scales_out) scales_out[3 * g] = q.s[0], scales_out[3 * g + 1] = q.s[1], scales_out[3 * g + 2] = q.s[2];
-            if (rot_out) rot_out[4 * g] = q.q[0], rot_out[4 * g + 1] = q.q[1], rot_out[4 * g + 2] = q.q[2], rot_out[4 * g + 3] = q.q[3];
+                    for (int j = 0; j < 3; ++j)
+                        cov[9 * g + 3 * i + j] = W[3 * i] * W[3 * j] + W[3 * i + 1] * W[3 * j + 1] + W[3 * i + 2] * W[3 * j + 2];
+                if (scales_out) scales_out[3 * g] = q.s[0], scales_out[3 * g + 1] = q.s[1], scales_out[3 * g + 2] = q.s[2];
+                if (rot_out)
+                    rot_out[4 * g] = q.q[0], rot_out[4 * g + 1] = q.q[1], rot_out[4 * g + 2] = q.q[2], rot_out[4 * g + 3] = q.q[3];
+            }
         }
     }
 }
@@ -183,130 +210,148 @@ adapter_backward_kernel(AdapterParams p, const float* __restrict__ extr, const f
                         float* __restrict__ draw) {
     constexpr int K = (DEG + 1) * (DEG + 1), ROW = 3 * K, CH = 7 + ROW;
     constexpr int NB = (DEG + 1) * (2 * DEG + 1) * (2 * DEG + 3) / 3;
-    __shared__ float s_row[AD_WARPS][ROW];
+    __shared__ float s_row[AD_WARPS][AD_RG * ROW];
     __shared__ float s_D[AD_WARPS][NB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rays = p.num_views * p.rays_per_view;
-    int cur_view = -1;
+    const int groups = (rays + AD_RG - 1) / AD_RG;
+    int geo_view = -1, sh_view = -1;
     ViewConsts vc;
-    for (int ray = blockIdx.x * AD_WARPS + warp; ray < rays; ray += gridDim.x * AD_WARPS) {
-        const int view = ray / p.rays_per_view;
-        if (view != cur_view) {
-            cur_view = view;
-            load_view(extr + 16 * view, intr + 9 * view, p.image_h, p.image_w, vc);
-            __syncwarp();
-            load_blocks<DEG>(shrot ? shrot + (size_t)view * K * K : nullptr, s_D[warp], lane);
-        }
-        const float* rr = raw + (size_t)ray * CH;
-        float* dr = draw + (size_t)ray * CH;
-        // ---- harmonics: sum the samples' gradients, then the transposed Wigner-D block and the mask ----
+    for (int grp = blockIdx.x * AD_WARPS + warp; grp < groups; grp += gridDim.x * AD_WARPS) {
+        const int ray0 = grp * AD_RG;
+        const int nr = min(AD_RG, rays - ray0);
+        // ---- harmonics: sum the samples' gradients per ray, then the transposed Wigner block and the mask ----
         __syncwarp();
-        for (int o = lane; o < ROW; o += 32) {
+        for (int e = lane; e < nr * ROW; e += 32) {
+            const int r = e / ROW, o = e - r * ROW;
             float acc = 0.f;
             if (dharm)
-                for (int s = 0; s < p.spp; ++s) acc += dharm[((size_t)ray * p.spp + s) * ROW + o];
-            s_row[warp][o] = acc;
+                for (int sI = 0; sI < p.spp; ++sI) acc += dharm[((size_t)(ray0 + r) * p.spp + sI) * ROW + o];
+            s_row[warp][e] = acc;
         }
         __syncwarp();
-        for (int o = lane; o < ROW; o += 32) {
-            const int c = o / K, j = o - c * K, l = isqrt_small(j), w = 2 * l + 1;
-            const float* blk = s_D[warp] + block_offset(l) + (j - l * l);  // column j of the block
-            const float* in = s_row[warp] + c * K + l * l;
-            float acc = 0.f;
-            for (int k = 0; k < w; ++k) acc = fmaf(blk[k * w], in[k], acc);
-            dr[7 + o] = acc * sh_mask_of(l);
+        for (int r = 0; r < nr; ++r) {
+            const int view = (ray0 + r) / p.rays_per_view;
+            if (view != sh_view) {
+                sh_view = view;
+                __syncwarp();
+                load_blocks<DEG>(shrot ? shrot + (size_t)view * K * K : nullptr, s_D[warp], lane);
+                __syncwarp();
+            }
+            float* dr = draw + (size_t)(ray0 + r) * CH;
+            for (int o = lane; o < ROW; o += 32) {
+                const int c = o / K, j = o - c * K, l = isqrt_small(j), w = 2 * l + 1;
+                const float* blk = s_D[warp] + block_offset(l) + (j - l * l);  // column j of the block
+                const float* in = s_row[warp] + r * ROW + c * K + l * l;
+                float acc = 0.f;
+                for (int k = 0; k < w; ++k) acc = fmaf(blk[k * w], in[k], acc);
+                dr[7 + o] = acc * sh_mask_of(l);
+            }
         }
-        // ---- geometry: lane s handles Gaussian s of the ray; partial gradients of the shared features are reduced ----
+        // ---- geometry: lane = (ray of the group, sample slot); the slots of a ray are adjacent lanes ----
+        const int r = lane / AD_SL, ray = ray0 + r;
         float g_raw[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, g_xy[2] = {0.f, 0.f};
-        for (int s = lane; s < p.spp; s += 32) {
-            const size_t g = (size_t)ray * p.spp + s;
+        if (r < nr) {
+            const int view = ray / p.rays_per_view;
+            if (view != geo_view) {
+                geo_view = view;
+                load_view(extr + 16 * view, intr + 9 * view, p.image_h, p.image_w, vc);
+            }
+            const float* rr = raw + (size_t)ray * CH;
             float r7[7];
 #pragma unroll
             for (int k = 0; k < 7; ++k) r7[k] = rr[k];
-            const float depth = depths[g];
-            Geo3 q;
-            adapter_geometry(p, vc, r7, coords[2 * (size_t)ray], coords[2 * (size_t)ray + 1], depth, q);
-            float gdepth = 0.f;
-            // mean = o + dw * depth
-            float gm[3] = {0.f, 0.f, 0.f};
-            if (dmeans) gm[0] = dmeans[3 * g], gm[1] = dmeans[3 * g + 1], gm[2] = dmeans[3 * g + 2];
-            gdepth += gm[0] * q.dw[0] + gm[1] * q.dw[1] + gm[2] * q.dw[2];
-            float gd[3];  // dL/dd (camera-space unit direction) = C^T (depth * gm)
+            const float cx = coords[2 * (size_t)ray], cy = coords[2 * (size_t)ray + 1];
+            for (int sI = lane % AD_SL; sI < p.spp; sI += AD_SL) {
+                const size_t g = (size_t)ray * p.spp + sI;
+                const float depth = depths[g];
+                Geo3 q;
+                adapter_geometry(p, vc, r7, cx, cy, depth, q);
+                float gdepth = 0.f;
+                // mean = o + dw * depth
+                float gm[3] = {0.f, 0.f, 0.f};
+                if (dmeans) gm[0] = dmeans[3 * g], gm[1] = dmeans[3 * g + 1], gm[2] = dmeans[3 * g + 2];
+                gdepth += gm[0] * q.dw[0] + gm[1] * q.dw[1] + gm[2] * q.dw[2];
+                float gd[3];  // dL/dd (camera-space unit direction) = C^T (depth * gm)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) gd[j] = depth * (vc.C[j] * gm[0] + vc.C[3 + j] * gm[1] + vc.C[6 + j] * gm[2]);
-            const float dd = q.d[0] * gd[0] + q.d[1] * gd[1] + q.d[2] * gd[2];
-            float gu[3];
+                for (int j = 0; j < 3; ++j) gd[j] = depth * (vc.C[j] * gm[0] + vc.C[3 + j] * gm[1] + vc.C[6 + j] * gm[2]);
+                const float dd = q.d[0] * gd[0] + q.d[1] * gd[1] + q.d[2] * gd[2];
+                float gu[3];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) gu[j] = (gd[j] - q.d[j] * dd) / q.n;
-            g_xy[0] += vc.Ki[0] * gu[0] + vc.Ki[3] * gu[1] + vc.Ki[6] * gu[2];
-            g_xy[1] += vc.Ki[1] * gu[0] + vc.Ki[4] * gu[1] + vc.Ki[7] * gu[2];
-            // covariance = W W^T, W = C R diag(s)
-            float G[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (dcov)
+                for (int j = 0; j < 3; ++j) gu[j] = (gd[j] - q.d[j] * dd) / q.n;
+                g_xy[0] += vc.Ki[0] * gu[0] + vc.Ki[3] * gu[1] + vc.Ki[6] * gu[2];
+                g_xy[1] += vc.Ki[1] * gu[0] + vc.Ki[4] * gu[1] + vc.Ki[7] * gu[2];
+                // covariance = W W^T, W = C R diag(s)
+                float G[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (dcov)
 #pragma unroll
-                for (int k = 0; k < 9; ++k) G[k] = dcov[9 * g + k];
-            float W[9], gW[9], gM[9];
-            world_factor(vc, q, W);
+                    for (int k = 0; k < 9; ++k) G[k] = dcov[9 * g + k];
+                float W[9], gW[9], gM[9];
+                world_factor(vc, q, W);
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        float a = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) a += (G[3 * i + k] + G[3 * k + i]) * W[3 * k + j];
+                        gW[3 * i + j] = a;
+                    }
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        gM[3 * i + j] = vc.C[i] * gW[j] + vc.C[3 + i] * gW[3 + j] + vc.C[6 + i] * gW[6 + j];  // C^T gW
+                float gR[9], gs[3];
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    float a = 0.f;
+                    gs[j] = gM[j] * q.R[j] + gM[3 + j] * q.R[3 + j] + gM[6 + j] * q.R[6 + j];
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) a += (G[3 * i + k] + G[3 * k + i]) * W[3 * k + j];
-                    gW[3 * i + j] = a;
+                    for (int i = 0; i < 3; ++i) gR[3 * i + j] = gM[3 * i + j] * q.s[j];
                 }
+                // scales = base * depth * mult, base = smin + (smax - smin) sigmoid(raw)
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    gdepth += gs[j] * q.base[j] * vc.mult;
+                    g_raw[j] += gs[j] * depth * vc.mult * (p.scale_max - p.scale_min) * q.sg[j] * (1.0f - q.sg[j]);
+                }
+                // rotation matrix -> normalised quaternion (a, b, c, d) = (i, j, k, r), t = 2 / (|q|^2 + 1e-8)
+                const float a = q.q[0], b = q.q[1], c = q.q[2], d = q.q[3], t = q.t;
+                const float gt = -gR[0] * (b * b + c * c) + gR[1] * (a * b - c * d) + gR[2] * (a * c + b * d) +
+                                 gR[3] * (a * b + c * d) - gR[4] * (a * a + c * c) + gR[5] * (b * c - a * d) +
+                                 gR[6] * (a * c - b * d) + gR[7] * (b * c + a * d) - gR[8] * (a * a + b * b);
+                float gq[4];
+                gq[0] = t * (gR[1] * b + gR[2] * c + gR[3] * b - 2.0f * gR[4] * a - gR[5] * d + gR[6] * c + gR[7] * d - 2.0f * gR[8] * a);
+                gq[1] = t * (-2.0f * gR[0] * b + gR[1] * a + gR[2] * d + gR[3] * a + gR[5] * c - gR[6] * d + gR[7] * c - 2.0f * gR[8] * b);
+                gq[2] = t * (-2.0f * gR[0] * c - gR[1] * d + gR[2] * a + gR[3] * d - 2.0f * gR[4] * c + gR[5] * b + gR[6] * a + gR[7] * b);
+                gq[3] = t * (-gR[1] * c + gR[2] * b + gR[3] * c - gR[5] * a - gR[6] * b + gR[7] * a);
+                const float tt = gt * (-t * t);
 #pragma unroll
-                for (int j = 0; j < 3; ++j)
-                    gM[3 * i + j] = vc.C[i] * gW[j] + vc.C[3 + i] * gW[3 + j] + vc.C[6 + i] * gW[6 + j];  // C^T gW
-            float gR[9], gs[3];
+                for (int k = 0; k < 4; ++k) gq[k] += tt * q.q[k];
+                // q = raw / (|raw| + eps)
+                const float den = q.nq + p.eps;
+                const float dot = gq[0] * r7[3] + gq[1] * r7[4] + gq[2] * r7[5] + gq[3] * r7[6];
+                const float corr = q.nq > 0.f ? dot / (q.nq * den * den) : 0.f;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                gs[j] = gM[j] * q.R[j] + gM[3 + j] * q.R[3 + j] + gM[6 + j] * q.R[6 + j];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) gR[3 * i + j] = gM[3 * i + j] * q.s[j];
+                for (int k = 0; k < 4; ++k) g_raw[3 + k] += gq[k] / den - r7[3 + k] * corr;
+                ddepths[g] = gdepth;
             }
-            // scales = base * depth * mult, base = smin + (smax - smin) sigmoid(raw)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                gdepth += gs[j] * q.base[j] * vc.mult;
-                g_raw[j] += gs[j] * depth * vc.mult * (p.scale_max - p.scale_min) * q.sg[j] * (1.0f - q.sg[j]);
-            }
-            // rotation matrix -> normalised quaternion (a, b, c, d) = (i, j, k, r), t = 2 / (|q|^2 + 1e-8)
-            const float a = q.q[0], b = q.q[1], c = q.q[2], d = q.q[3], t = q.t;
-            const float gt = -gR[0] * (b * b + c * c) + gR[1] * (a * b - c * d) + gR[2] * (a * c + b * d) +
-                             gR[3] * (a * b + c * d) - gR[4] * (a * a + c * c) + gR[5] * (b * c - a * d) +
-                             gR[6] * (a * c - b * d) + gR[7] * (b * c + a * d) - gR[8] * (a * a + b * b);
-            float gq[4];
-            gq[0] = t * (gR[1] * b + gR[2] * c + gR[3] * b - 2.0f * gR[4] * a - gR[5] * d + gR[6] * c + gR[7] * d - 2.0f * gR[8] * a);
-            gq[1] = t * (-2.0f * gR[0] * b + gR[1] * a + gR[2] * d + gR[3] * a + gR[5] * c - gR[6] * d + gR[7] * c - 2.0f * gR[8] * b);
-            gq[2] = t * (-2.0f * gR[0] * c - gR[1] * d + gR[2] * a + gR[3] * d - 2.0f * gR[4] * c + gR[5] * b + gR[6] * a + gR[7] * b);
-            gq[3] = t * (-gR[1] * c + gR[2] * b + gR[3] * c - gR[5] * a - gR[6] * b + gR[7] * a);
-            const float tt = gt * (-t * t);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) gq[k] += tt * q.q[k];
-            // q = raw / (|raw| + eps)
-            const float den = q.nq + p.eps;
-            const float dot = gq[0] * r7[3] + gq[1] * r7[4] + gq[2] * r7[5] + gq[3] * r7[6];
-            const float corr = q.nq > 0.f ? dot / (q.nq * den * den) : 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) g_raw[3 + k] += gq[k] / den - r7[3 + k] * corr;
-            ddepths[g] = gdepth;
         }
+        // sum over the AD_SL sample slots of each ray (adjacent lanes); every lane takes part in the shuffles
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
+        for (int off = 1; off < AD_SL; off <<= 1) {
 #pragma unroll
             for (int k = 0; k < 7; ++k) g_raw[k] += __shfl_xor_sync(0xffffffffu, g_raw[k], off);
             g_xy[0] += __shfl_xor_sync(0xffffffffu, g_xy[0], off);
             g_xy[1] += __shfl_xor_sync(0xffffffffu, g_xy[1], off);
         }
+        if (r < nr && lane % AD_SL == 0) {
+            float* dr = draw + (size_t)ray * CH;
 #pragma unroll
-        for (int k = 0; k < 7; ++k)
-            if (lane == k) dr[k] = g_raw[k];
-        if (lane == 0) dcoords[2 * (size_t)ray] = g_xy[0];
-        if (lane == 1) dcoords[2 * (size_t)ray + 1] = g_xy[1];
+            for (int k = 0; k < 7; ++k) dr[k] = g_raw[k];
+            dcoords[2 * (size_t)ray] = g_xy[0];
+            dcoords[2 * (size_t)ray + 1] = g_xy[1];
+        }
     }
 }
 
@@ -314,7 +359,7 @@ static int adapter_grid(int rays) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int want = (rays + AD_WARPS - 1) / AD_WARPS;
+    const int want = ((rays + AD_RG - 1) / AD_RG + AD_WARPS - 1) / AD_WARPS;
     return want < 8 * sms ? (want > 0 ? want : 1) : 8 * sms;
 }
 
