@@ -85,3 +85,20 @@ def test_upstream_structure_baseline_builds_and_exports():
     lib = C.CDLL(str(ub.build()))
     for name in ("upstream_forward", "upstream_backward", "upstream_last_error"):
         assert hasattr(lib, name)
+
+
+def test_ctypes_signatures_have_the_arity_the_header_declares():
+    """Every prototype of include/ggrt_raster.h against the argtypes the ctypes binding registers."""
+    lib = _cabi.lib()
+    text = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    protos = re.findall(r"\b(ggrt_(?:raster|adapter)_\w+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) >= 16
+    checked = 0
+    for name, params in protos:
+        params = " ".join(params.split())
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        fn = getattr(lib, name)
+        if fn.argtypes is not None:
+            assert len(fn.argtypes) == n, (name, len(fn.argtypes), n)
+            checked += 1
+    assert checked >= 12
