@@ -19,8 +19,13 @@
 
 namespace ggrt {
 
+// EXPERIMENTAL, off by default, not yet measured on a GPU: two 4x4 half-block
+// queues per warp instead of one 8x4 queue -- the CPU step model predicts -25 % pixel steps, +49 % chunks.
+#ifndef GGRT_BWD_HALVES
+#define GGRT_BWD_HALVES 0
+#endif
 #ifndef GGRT_BWD_BATCH
-#define GGRT_BWD_BATCH 512
+#define GGRT_BWD_BATCH (GGRT_BWD_HALVES ? 384 : 512)  // the half queues need shared memory: keep 4 CTAs per SM
 #endif
 #ifndef GGRT_BWD_MINBLOCKS
 #define GGRT_BWD_MINBLOCKS 4
@@ -36,6 +41,8 @@ constexpr int PIX_UNROLL = GGRT_BWD_PIX_UNROLL;
 #endif
 constexpr int GL = GGRT_BWD_GL;   // Gaussians per warp step (power of two <= 32)
 constexpr int PL = 32 / GL;       // pixels per warp step
+constexpr int NHALF = GGRT_BWD_HALVES ? 2 : 1;  // queues per warp
+static_assert(!GGRT_BWD_HALVES || PL == 4, "half-block queues assume 4-pixel groups (one half-row each)");
 
 __device__ __forceinline__ void red_add(float* addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
@@ -56,6 +63,7 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
     __shared__ __align__(16) unsigned char srec[BWD_BATCH * REC_BYTES];
     __shared__ uint32_t sid[BWD_BATCH];
     __shared__ unsigned short squeue[NWARPS][BWD_BATCH];
+    __shared__ unsigned short shalf[GGRT_BWD_HALVES ? NWARPS : 1][2][GGRT_BWD_HALVES ? BWD_BATCH : 1];
     __shared__ float4 spix_g[NWARPS][32];   // per pixel {g_r, g_g, g_b, bits(last)}
     __shared__ float4 spix_s[NWARPS][32];   // per pixel {x, y, T behind, sum behind}
     __shared__ float spix_a[AUX ? NWARPS : 1][32];  // per pixel gradient of the aux channel
@@ -140,9 +148,36 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
         // processes GL Gaussians x PL = 32/GL pixels per step, so the scan has log2(GL) levels and the per-pixel
         // work is shared by fewer idle lanes.  The PL partial accumulators of a Gaussian are combined at the end.
         const int gl = lane & (GL - 1), q = lane / GL;
-        for (uint32_t c0 = 0; c0 < qn; c0 += GL) {
-            const bool valid = c0 + gl < qn;
-            const uint32_t jj = valid ? squeue[warp][c0 + gl] : 0u;
+        uint32_t qh0 = 0, qh1 = 0;
+        if (GGRT_BWD_HALVES) {
+            // second-level cull, over the survivors only: which of the two 4x4 half blocks does each queued Gaussian
+            // reach?  Order (back to front) is preserved.  A Gaussian that misses a half is inactive at every pixel of
+            // it, i.e. the identity of the (T, R) recurrence there, so leaving it out of that half's queue is exact.
+            for (uint32_t e0 = 0; e0 < qn; e0 += 32) {
+                const uint32_t e = e0 + lane;
+                bool hit_l = false, hit_r = false;
+                unsigned short j = 0;
+                if (e < qn) {
+                    j = squeue[warp][e];
+                    const float4 a = lds128(sbase + (uint32_t)j * REC_BYTES);
+                    const float4 c = lds128(sbase + (uint32_t)j * REC_BYTES + 16);
+                    hit_l = ellipse_hits_rect(a.x, a.y, a.z, c.x, c.y, c.z, bx0f, by0f, 3.0f, 3.0f);
+                    hit_r = ellipse_hits_rect(a.x, a.y, a.z, c.x, c.y, c.z, bx0f + 4.0f, by0f, 3.0f, 3.0f);
+                }
+                const uint32_t ml = __ballot_sync(0xffffffffu, hit_l), mr = __ballot_sync(0xffffffffu, hit_r);
+                const uint32_t below = (1u << lane) - 1u;
+                if (hit_l) shalf[GGRT_BWD_HALVES ? warp : 0][0][qh0 + __popc(ml & below)] = j;
+                if (hit_r) shalf[GGRT_BWD_HALVES ? warp : 0][1][qh1 + __popc(mr & below)] = j;
+                qh0 += __popc(ml), qh1 += __popc(mr);
+            }
+            __syncwarp();
+        }
+        for (int half = 0; half < NHALF; ++half) {
+        const unsigned short* queue = GGRT_BWD_HALVES ? shalf[GGRT_BWD_HALVES ? warp : 0][half] : squeue[warp];
+        const uint32_t qcount = GGRT_BWD_HALVES ? (half == 0 ? qh0 : qh1) : qn;
+        for (uint32_t c0 = 0; c0 < qcount; c0 += GL) {
+            const bool valid = c0 + gl < qcount;
+            const uint32_t jj = valid ? queue[c0 + gl] : 0u;
             const uint32_t src = sbase + jj * REC_BYTES;
             const float2 gxy = lds64(src);
             float4 con = lds128(src + 16);
@@ -155,9 +190,11 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
             float a_op = 0.f, a_mx = 0.f, a_my = 0.f, a_A = 0.f, a_B = 0.f, a_C = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f;
             float a_x = 0.f;  // aux channel
 
-            // pixel groups: group t holds pixels t*PL .. t*PL+PL-1, one per pixel slot
+            // pixel groups: group t holds pixels t*PL .. t*PL+PL-1, one per pixel slot (with half-block queues the
+            // even groups are the left 4x4 half, the odd ones the right half)
 #pragma unroll PIX_UNROLL
-            for (int t = 0; t < 32 / PL; ++t) {
+            for (int tt = 0; tt < 32 / PL / NHALF; ++tt) {
+                const int t = tt * NHALF + half;
                 if (((pmask >> (t * PL)) & ((1u << PL) - 1u)) == 0) continue;  // no pixel of the group matters
                 const int p = t * PL + q;
                 const float4 pg = lds128(gaddr + p * 16);   // {g_r, g_g, g_b, last}
@@ -235,6 +272,7 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
                 if (AUX) red_add(dst + G_AUX, a_x);
             }
         }
+        }  // half
     }
 }
 
