@@ -149,3 +149,28 @@ def test_mark_visible():
     tz = ri.means3D @ ri.viewmatrix[:3, 2] + ri.viewmatrix[3, 2]
     assert 0.5 < vis.mean() < 0.9
     assert np.array_equal(vis[np.abs(tz - 0.2) > 1e-4], (tz > 0.2)[np.abs(tz - 0.2) > 1e-4])
+
+
+def test_oracle_reproduces_its_frozen_c1_golden():
+    """BASELINE config 1 (10K Gaussians, 256x256): the oracle against its own frozen outputs -- guards the target of
+    the GPU parity tests against silent drift (tools/make_golden_c1.py)."""
+    import importlib.util
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    spec = importlib.util.spec_from_file_location("make_golden_c1", root / "tools" / "make_golden_c1.py")
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    got = mg.compute()
+    z = np.load(root / "tests" / "golden" / "c1_oracle.npz")
+    for k in ("N", "radii", "tiles_touched", "ranges", "fragile"):
+        assert np.array_equal(got[k], z[k]), k
+    for k in ("point_list_sha", "keys_sha", "n_contrib_sha"):
+        assert str(got[k]) == str(z[k]), k
+    for k in ("color_grid", "depth_grid", "final_T_grid"):
+        np.testing.assert_allclose(got[k], z[k], rtol=0, atol=1e-6, err_msg=k)
+    assert abs(float(got["color_sum"]) - float(z["color_sum"])) <= 1e-6 * abs(float(z["color_sum"]))
+    for k in ("dmeans3D_head", "dcov3D_head", "dopacity_head", "dsh_head"):
+        scale = max(float(np.abs(z[k]).max()), 1e-30)
+        assert float(np.abs(got[k] - z[k]).max()) <= 1e-5 * scale, k
+    assert abs(float(got["dsh_abs_sum"]) - float(z["dsh_abs_sum"])) <= 1e-5 * float(z["dsh_abs_sum"])
