@@ -128,37 +128,48 @@ def make_inputs(workload: str, rank: int):
     return to_raster_inputs(scene), image_gradient(H, W, seed=SEED + rank)
 
 
+def base_config(args, N_pairs, max_pairs):
+    """The workload description both arms print (identical key set, so the driver can compare the lines)."""
+    P, H, W, desc = WORKLOADS[args.workload]
+    return {"workload": desc, "P": P, "H": H, "W": W, "N_pairs": int(N_pairs), "max_pairs_per_tile": int(max_pairs),
+            "sh_degree": SH_DEGREE, "views_per_step": 1, "pose_grads": bool(args.pose_grads)}
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the oracle port (the reference's rasterizer is CUDA-only and not vendored), all host threads."""
+    """CPU arm: the oracle port (the reference's rasterizer is CUDA-only and not vendored), all host threads.
+    Under torchrun rank 0 alone runs it; torchrun exports OMP_NUM_THREADS=1, which is overridden here."""
     if rank != 0:
         return
     from oracle import c_oracle as co
 
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    co.set_num_threads(ncpu)
     ri, g = make_inputs(args.workload, 0)
     cam = co.Camera(W=ri.image_width, H=ri.image_height, tanfovx=ri.tanfovx, tanfovy=ri.tanfovy, view=ri.viewmatrix,
                     proj=ri.projmatrix, campos=ri.campos, bg=ri.bg, deg=ri.sh_degree)
 
     def step():
         f = co.forward(cam, ri.means3D, ri.cov3D, ri.opacities, sh=ri.shs)
-        co.backward(cam, ri.means3D, ri.cov3D, ri.opacities, f, g, sh=ri.shs)
-        return f["bin"]["N"]
+        co.backward(cam, ri.means3D, ri.cov3D, ri.opacities, f, g, sh=ri.shs, want_camera=args.pose_grads)
+        cnt = f["bin"]["ranges"][:, 1] - f["bin"]["ranges"][:, 0]
+        return f["bin"]["N"], int(cnt.max())
 
     for _ in range(args.warmup):
-        N = step()
+        N, mx = step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        N = step()
+        N, mx = step()
     dt = time.perf_counter() - t0
     fps = args.steps / dt
-    P, H, W, desc = WORKLOADS[args.workload]
     sample = f"{args.steps} full frames (fwd+bwd) of the same workload, one frame per step"
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "P": P, "H": H, "W": W, "N_pairs": int(N), "sh_degree": SH_DEGREE,
-                   "note": "CPU oracle port (oracle/raster_oracle.c, OpenMP): the reference rasterizer is an "
-                           "un-vendored CUDA-only package, no reference binary exists on this box"},
+        "config": base_config(args, N, mx),
+        "details": {"note": "CPU oracle port (oracle/raster_oracle.c, OpenMP): the reference rasterizer is an "
+                            "un-vendored CUDA-only package, no reference binary exists on this box",
+                    "gpus_used": 0, "host_threads": co.num_threads()},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": co.num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -167,12 +178,29 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def time_loop(fn, n, dev, before=None):
+    """n calls of fn, each bracketed by CUDA events on the current stream (`before` runs untimed in front of each);
+    returns the per-call milliseconds."""
+    import torch
+
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+    for a, b in evs:
+        if before is not None:
+            before()
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize(dev)
+    return [a.elapsed_time(b) for a, b in evs]
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
     from ggrt_official_b200 import GaussianRasterizationSettings, GaussianRasterizer, _cabi
     from ggrt_official_b200 import rasterizer as R
+    from ggrt_official_b200.graph import CapturedStep
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the rasterizer has no CPU path")
@@ -201,14 +229,12 @@ def run_ours(args, rank, world, local_rank):
         flush_buf.zero_()
         flush_sink.copy_(flush_src.sum())
 
-    state = {}
-
-    from ggrt_official_b200.view_parallel import GradientArena, make_exchange
+    from ggrt_official_b200.view_parallel import GradientArena, ViewParallelRasterizer, make_exchange
 
     # Sum of the per-view Gaussian gradients over the GPUs, inside the timed step:
     #   arena   - ONE NCCL all-reduce of the contiguous [P, 3+6+1+3K] gradient arena (340 B / Gaussian)
     #   compact - exchange the [P,3] colour gradients + all-reduce [P,10], rebuild dL/dsh locally (sh_merge.cu)
-    #   p2p     - compact over symmetric memory: in-kernel NVLink gather + NVLS multimem reduction, no NCCL
+    #   p2p     - compact over symmetric memory: in-kernel NVLink push + NVLS multimem reduction, no NCCL
     #   auto    - p2p if every rank can set up symmetric memory, else compact (default)
     arena = GradientArena.allocate(P, K, dev) if world > 1 and args.exchange == "arena" else None
     exch = None
@@ -217,22 +243,44 @@ def run_ours(args, rank, world, local_rank):
         if args.exchange == "p2p" and exch.transport != "p2p":
             raise SystemExit("--exchange p2p: symmetric memory could not be set up on every rank")
 
-    def step():
-        st = R.forward_raw(means, shs, None, opac, cov, rs)
-        if exch is not None:
-            grads = exch.run(st, grad_img, want_camera=args.pose_grads)
-        else:
-            grads = R.backward_raw(st, grad_img, out=arena.views if arena else None, want_camera=args.pose_grads)
-            if arena:
-                arena.all_reduce()
-        state["N"], state["max_tile_pairs"] = st["N"], st["max_tile_pairs"]
-        return grads
-
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    # ---- the step: forward + backward (+ exchange).  Default: captured once into a CUDA graph (graph.CapturedStep),
+    # one launch per step and no host wait; --launch eager issues the same kernels call by call with the pair-buffer
+    # check deferred (check="lazy"), so the host does not wait for the device there either -------------------------
+    st0 = R.forward_raw(means, shs, None, opac, cov, rs)  # exact first frame: sizes the pair buffer estimate
+    N, max_pairs = st0["N"], st0["max_tile_pairs"]
+    del st0
+    launch, cap, cap_err = args.launch, None, None
+    if launch == "graph" and arena is None:
+        try:
+            cap = CapturedStep(means, shs, None, opac, cov, rs, grad_img, exchange=exch, want_camera=args.pose_grads)
+        except Exception as e:  # noqa: BLE001 - fall back to eager launches, and say so in the line
+            cap_err, cap = repr(e)[:300], None
+            torch.cuda.synchronize()
+    ok = torch.tensor([1 if (cap is not None or launch != "graph" or arena is not None) else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 0:
+        cap = None
+    if cap is None:
+        launch = "eager"
+
+    def step():
+        if cap is not None:
+            cap.replay()
+            return
+        st = R.forward_raw(means, shs, None, opac, cov, rs, check="lazy")
+        if exch is not None:
+            exch.run(st, grad_img, want_camera=args.pose_grads)
+        else:
+            R.backward_raw(st, grad_img, out=arena.views if arena else None, want_camera=args.pose_grads)
+            if arena:
+                arena.all_reduce()
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -242,23 +290,30 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync_all()
-    for a, b in evs:
-        flush_l2()
-        a.record()
-        step()
-        b.record()
+    w0 = time.perf_counter()
+    per_step = time_loop(step, args.steps, dev, before=flush_l2)
+    wall_ms = 1e3 * (time.perf_counter() - w0)
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if cap is not None:
+        N, max_pairs = cap.check()  # raises if a replay overflowed the captured pair buffer
+    else:
+        R.check_pending(block=True)
+    total_ms = sum(per_step)
+    rank_ms = [total_ms]
+    rank_wall = [wall_ms]
     if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms = float(tt.item())
+        tt = torch.tensor([total_ms, wall_ms], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(allt, tt)
+        rank_ms = [float(x[0]) for x in allt]
+        rank_wall = [float(x[1]) for x in allt]
+    total_ms = max(rank_ms)
     fps = world * args.steps / (total_ms * 1e-3)
 
-    # ---- per-kernel durations (same process, same inputs, CUDA events inside the library) ---------
+    # ---- per-kernel durations (same process, same inputs, CUDA events inside the library, eager launches with the
+    # colour kernel back on the main stream) ------------------------------------------------------------------
     stage_ms = {}
     _cabi.profile_enable(True)
     nprof = min(args.steps, 20)
@@ -272,7 +327,6 @@ def run_ours(args, rank, world, local_rank):
             v = fw[k] if k not in ("render_backward", "preprocess_backward") else bw[k]
             stage_ms[k] = stage_ms.get(k, 0.0) + v / nprof
     _cabi.profile_enable(False)
-    N = state["N"]
     ab = alg_bytes(P, N, H, W, K)
     group_ms = {}
     for k, v in stage_ms.items():
@@ -287,16 +341,19 @@ def run_ours(args, rank, world, local_rank):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     # measured DRAM traffic of the same kernel(s) from the committed ncu --set full capture (per launch)
     traffic, traffic_src = None, None
-    try:
-        prof = json.loads((ROOT / "profiles" / "r1_ncu_kernels.json").read_text())
-        if args.gaussians == 0 and prof.get("workload", "").startswith(WORKLOADS[args.workload][3][:2]):
-            members = [k for k, grp in STAGE_GROUP.items() if grp == top]
-            vals = [v["dram_traffic_bytes"] for name, v in prof["kernels"].items()
-                    if any(name.startswith(m + "_kernel") for m in members)]
-            if vals:
-                traffic, traffic_src = int(sum(vals)), "profiles/r1_ncu_kernels.json (dram__bytes_read.sum + dram__bytes_write.sum)"
-    except Exception:
-        pass
+    for prof_name in ("r2_ncu_kernels.json", "r1_ncu_kernels.json"):
+        try:
+            prof = json.loads((ROOT / "profiles" / prof_name).read_text())
+            if args.gaussians == 0 and prof.get("workload", "").startswith(WORKLOADS[args.workload][3][:2]):
+                members = [k for k, grp in STAGE_GROUP.items() if grp == top]
+                vals = [v["dram_traffic_bytes"] for name, v in prof["kernels"].items()
+                        if any(name.startswith(m + "_kernel") for m in members)]
+                if vals:
+                    traffic = int(sum(vals))
+                    traffic_src = f"profiles/{prof_name} (dram__bytes_read.sum + dram__bytes_write.sum)"
+                    break
+        except Exception:
+            pass
     achieved = ab[top] / (group_ms[top] * 1e-3) / 1e9
     path_bytes = sum(ab.values())
     kernel_sum_ms = sum(stage_ms.values())
@@ -309,19 +366,29 @@ def run_ours(args, rank, world, local_rank):
                        "frac": path_bytes / (total_ms / args.steps * 1e-3) / 1e9 / peak},
     }
 
-    # ---- end to end: host buffers -> GaussianRasterizer (autograd) -> image back on the host -------
+    # ---- end to end: pinned host buffers -> public API (autograd) -> image + loss back on the host ---------------
+    # N = 1: GaussianRasterizer, every step copies its 102 MB of Gaussians from pinned memory.
+    # N > 1: the Gaussians are the same for every rank, so rank r uploads rows [r P/N, (r+1) P/N) over ITS PCIe link
+    # and the ranks all-gather the shards over NVLink (in place, on the copy stream, overlapped with the previous
+    # step); the step itself is ViewParallelRasterizer: forward, backward and the compact gradient exchange.
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    h_means, h_cov, h_opac, h_shs = pin(ri.means3D), pin(ri.cov3D), pin(ri.opacities), pin(ri.shs)
+    host_full = (ri.means3D, ri.cov3D, ri.opacities, ri.shs)
+    chunk = (P + world - 1) // world
+    lo, hi = rank * chunk, min(P, (rank + 1) * chunk)
+    h_in = [pin(a[lo:hi]) for a in host_full]
     h_img = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
     h_loss = torch.empty((), dtype=torch.float32).pin_memory()
-    h2d = sum(x.numel() * 4 for x in (h_means, h_cov, h_opac, h_shs))
+    h2d = sum(x.numel() * 4 for x in h_in)
     d2h = h_img.numel() * 4 + 4
-    rasterizer = GaussianRasterizer(rs)
+    if world > 1:
+        rasterizer = ViewParallelRasterizer(rs, exch) if exch is not None else GaussianRasterizer(rs)
+    else:
+        rasterizer = GaussianRasterizer(rs)
 
-    # Two sets of device staging tensors, allocated once: the H2D copy of step i+1's inputs is issued on a copy
-    # stream while step i computes (the usual input prefetch of a training loop).  Every step still copies its
-    # own 102 MB from pinned host memory and reads its image + loss back, all inside the timed region.
-    d_sets = [[torch.empty_like(x, device=dev).requires_grad_() for x in (h_means, h_cov, h_opac, h_shs)]
+    # Two sets of device staging tensors, allocated once (padded to world * chunk rows so that the all-gather has
+    # equal shards): the upload of step i+1 is issued on a copy stream while step i computes (the usual input
+    # prefetch of a training loop).  Every step still moves its own bytes and reads its image + loss back.
+    d_sets = [[torch.empty((world * chunk,) + tuple(a.shape[1:]), dtype=torch.float32, device=dev) for a in host_full]
               for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     filled = [torch.cuda.Event(), torch.cuda.Event()]   # set k holds fresh inputs
@@ -332,8 +399,11 @@ def run_ours(args, rank, world, local_rank):
     def prefetch(k):
         copy_stream.wait_event(free[k])
         with torch.cuda.stream(copy_stream), torch.no_grad():
-            for d_, h_ in zip(d_sets[k], (h_means, h_cov, h_opac, h_shs)):
-                d_.copy_(h_, non_blocking=True)
+            for d_, h_ in zip(d_sets[k], h_in):
+                d_[lo:hi].copy_(h_, non_blocking=True)
+            if world > 1:
+                for d_ in d_sets[k]:
+                    dist.all_gather_into_tensor(d_, d_[rank * chunk:(rank + 1) * chunk])
         filled[k].record(copy_stream)
 
     for k in range(2):
@@ -345,14 +415,16 @@ def run_ours(args, rank, world, local_rank):
         e2e_state["i"] += 1
         prefetch(k ^ 1)              # next step's inputs, overlapped with this step's kernels
         main.wait_event(filled[k])
-        m, c, o, s = d_sets[k]
-        for d_ in d_sets[k]:
-            d_.grad = None
-        m2 = torch.zeros_like(m, requires_grad=True)
-        image, radii, _ = rasterizer(means3D=m, means2D=m2, shs=s, colors_precomp=None, opacities=o, cov3D_precomp=c)
+        m, c, o, s = [d_[:P].detach().requires_grad_() for d_ in d_sets[k]]
+        if isinstance(rasterizer, ViewParallelRasterizer):
+            image, radii, _ = rasterizer(means3D=m, opacities=o, shs=s, cov3D_precomp=c)
+        else:
+            m2 = torch.zeros_like(m, requires_grad=True)
+            image, radii, _ = rasterizer(means3D=m, means2D=m2, shs=s, colors_precomp=None, opacities=o,
+                                         cov3D_precomp=c)
         loss = (image * grad_img).sum()
         loss.backward()
-        if world > 1:
+        if world > 1 and exch is None:
             for p_ in (m, c, o, s):
                 dist.all_reduce(p_.grad)
         free[k].record(main)
@@ -363,17 +435,16 @@ def run_ours(args, rank, world, local_rank):
         e2e_step()
     sync_all()
     n_e2e = min(args.steps, 20)
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_e2e)]
-    for a, b in ev2:
-        a.record()
-        e2e_step()
-        b.record()
+    e2e_ms = sum(time_loop(e2e_step, n_e2e, dev))
     sync_all()
-    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
     t2 = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_fps = world * n_e2e / (float(t2.item()) * 1e-3)
+
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = measure_extras(args, ri, g_np, dev, flush_l2)
 
     # ---- CPU baseline: the oracle port on a bounded sample (rank 0, N=1 only) ----------------------
     cpu = None
@@ -420,32 +491,123 @@ def run_ours(args, rank, world, local_rank):
             gpu_base = {"error": repr(e)[:300]}
 
     if rank == 0:
+        cfg = base_config(args, N, max_pairs)
+        cfg["views_per_step"] = world
+        n_exch = 0 if exch is None else exch.kernels_per_step()
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "P": P, "H": H, "W": W, "N_pairs": int(N),
-                       "max_pairs_per_tile": int(state["max_tile_pairs"]), "sh_degree": SH_DEGREE,
-                       "views_per_step": world, "pose_grads": bool(args.pose_grads), "l2": "flushed before every timed step (256 MiB write, then 256 MiB read so the step does not pay the flush's write-back)",
-                       "parallelism": f"one target view per GPU x{world}" + (
-                           "" if world == 1 else
-                           ", NCCL all-reduce of the Gaussian gradient arena" if exch is None else
-                           f", compact gradient exchange ({exch.transport}): gather [P,3] colour gradients + "
-                           "all-reduce [P,10], dL/dsh rebuilt per GPU"),
-                       "exchange_bytes": None if exch is None else exch.exchange_bytes()},
+            "config": cfg,
+            "details": {
+                "launch": ("one CUDA graph replay per step (graph.CapturedStep: forward + backward"
+                           + (" + gradient exchange" if exch is not None else "") + ")") if cap is not None else
+                          "eager kernel launches, pair-buffer check deferred (check='lazy')",
+                "graph_capture_error": cap_err,
+                "l2": "flushed before every timed step (256 MiB write, then 256 MiB read so the step does not pay "
+                      "the flush's write-back)",
+                "parallelism": f"one target view per GPU x{world}" + (
+                    "" if world == 1 else
+                    ", NCCL all-reduce of the Gaussian gradient arena" if exch is None else
+                    f", compact gradient exchange ({exch.transport}): push [P,3] colour gradients + "
+                    "all-reduce [P,10], dL/dsh rebuilt per GPU"),
+                "exchange_bytes": None if exch is None else exch.exchange_bytes(),
+                # skew between the ranks: device time of the timed steps vs the host's wall clock around them
+                "rank_gpu_ms_per_step": [round(x / args.steps, 5) for x in rank_ms],
+                "rank_wall_ms_per_step_incl_l2_flush": [round(x / args.steps, 5) for x in rank_wall],
+                "e2e_api": type(rasterizer).__name__ + (
+                    "" if world == 1 else ": per-rank upload of a 1/N shard + NVLink all-gather (NCCL) of the inputs"),
+            },
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": n_e2e},
-            # this library's kernels per step: 8 of the fwd+bwd path, + the SH-gradient merge (compact exchange), + the
-            # NVLS all-reduce kernel (p2p transport); torch / NCCL kernels (barriers, collectives) are not counted
-            "gpu_launches": (8 + (0 if exch is None else 2 if exch.transport == "p2p" else 1)) * args.steps,
+            # this library's kernels per step: 8 of the fwd+bwd path + the exchange's; torch / NCCL kernels
+            # (collectives, L2 flush) are not counted
+            "gpu_launches": (8 + n_exch) * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "gpu_baseline": gpu_base,
             "clocks": clocks,
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_extras(args, ri, g_np, dev, flush_l2):
+    """The two extra lines SURVEY.md 8d asks for, at N=1: the depth pass (degree-0 rasterization, fwd+bwd through the
+    C ABI) and the path THROUGH THE CALLER -- the decoder-level mirror of the unmodified reference glue
+    (render_cuda + render_depth_cuda incl. their host syncs and copies, cuda_splatting.py:49-128, :227-269), plus
+    this package's fused and copy-free variants of it.  Frames/s, fwd+bwd, CUDA events."""
+    import torch
+
+    from ggrt_official_b200 import rasterizer as R
+    from ggrt_official_b200.decoder import DecoderSplattingCUDA, Gaussians
+    from ggrt_official_b200.synthetic import SEED, make_scene
+
+    P, H, W, _ = WORKLOADS[args.workload]
+    out = {}
+    n = 20
+    t = lambda a: torch.tensor(np.asarray(a), device=dev)
+    try:
+        # depth pass: what render_depth_cuda rasterizes -- SH degree 0 "colours" (K = 1) of the same geometry
+        from ggrt_official_b200 import GaussianRasterizationSettings
+
+        means, cov, opac = t(ri.means3D), t(ri.cov3D), t(ri.opacities)
+        sh0 = t(np.ascontiguousarray(np.repeat(ri.shs[:, :1, :1], 3, axis=2)))
+        rs0 = GaussianRasterizationSettings(
+            image_height=H, image_width=W, tanfovx=ri.tanfovx, tanfovy=ri.tanfovy, bg=t(np.zeros(3, np.float32)),
+            scale_modifier=1.0, viewmatrix=t(ri.viewmatrix), projmatrix=t(ri.projmatrix), sh_degree=0,
+            campos=t(ri.campos), prefiltered=False)
+        g = t(g_np)
+
+        def depth_step():
+            st = R.forward_raw(means, sh0, None, opac, cov, rs0, check="lazy")
+            R.backward_raw(st, g)
+
+        R.forward_raw(means, sh0, None, opac, cov, rs0)
+        for _ in range(3):
+            depth_step()
+        ms = time_loop(depth_step, n, dev, before=flush_l2)
+        R.check_pending(block=True)
+        out["depth_pass"] = {"value": 1e3 * n / sum(ms), "unit": "frames/s", "ms_per_step": sum(ms) / n,
+                             "what": "SH degree 0 (K=1) rasterization of the same Gaussians, fwd+bwd, C ABI, L2 flushed"}
+    except Exception as e:  # noqa: BLE001
+        out["depth_pass"] = {"error": repr(e)[:300]}
+    try:
+        sc = make_scene(P, H, W, sh_degree=SH_DEGREE, seed=SEED)
+        leaves = dict(means=t(sc.means)[None].requires_grad_(), covariances=t(sc.covariances)[None].requires_grad_(),
+                      harmonics=t(sc.harmonics)[None].requires_grad_(), opacities=t(sc.opacities)[None].requires_grad_())
+        extr, intr = t(sc.extrinsics)[None, None], t(sc.intrinsics)[None, None]
+        near, far = torch.full((1, 1), sc.near, device=dev), torch.full((1, 1), sc.far, device=dev)
+        wc = t(g_np)[None, None]
+        wd = torch.randn(1, 1, H, W, device=dev) / (H * W)
+        res = {}
+        for name, fused, fast, mode in (("color_only", False, False, None), ("color_and_depth_two_pass", False, False, "depth"),
+                                        ("color_and_depth_fused", True, False, "depth"),
+                                        ("color_and_depth_fast_glue", True, True, "depth")):
+            dec = DecoderSplattingCUDA(fused_depth=fused, fast_glue=fast)
+
+            def dstep():
+                for v in leaves.values():
+                    v.grad = None
+                r = dec(Gaussians(**leaves), extr, intr, near, far, (H, W), depth_mode=mode)
+                loss = (r.color * wc).sum()
+                if mode is not None:
+                    loss = loss + (r.depth * wd).sum()
+                loss.backward()
+
+            for _ in range(3):
+                dstep()
+            ms = time_loop(dstep, n, dev)
+            res[name] = {"value": 1e3 * n / sum(ms), "unit": "frames/s", "ms_per_step": sum(ms) / n}
+        res["what"] = ("DecoderSplattingCUDA (mirror of decoder_splatting_cuda.py:29-85 driving render_cuda / "
+                       "render_depth_cuda, same host syncs and copies as the reference glue), 1 view, fwd+bwd through "
+                       "autograd, inputs resident, no L2 flush")
+        out["through_caller"] = res
+    except Exception as e:  # noqa: BLE001
+        out["through_caller"] = {"error": repr(e)[:300]}
+    return out
 
 
 def main():
@@ -462,6 +624,9 @@ def main():
                     help="override the Gaussian count of the workload (BASELINE config 5: 50K..2M sweep at 1008x756)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "arena", "compact", "p2p"],
                     help="multi-GPU gradient exchange (N>1 only), see run_ours")
+    ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
+                    help="how the timed step is issued: one CUDA graph replay (default) or eager kernel launches")
+    ap.add_argument("--no-extras", action="store_true", help="skip the depth-pass / through-the-caller lines (N=1)")
     ap.add_argument("--pose-grads", action="store_true",
                     help="also compute dL/d(viewmatrix, projmatrix, campos) in the backward (BASELINE config 3)")
     args = ap.parse_args()

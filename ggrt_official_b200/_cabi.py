@@ -10,7 +10,7 @@ from pathlib import Path
 
 from . import build as _build
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 _lib = None
 
 
@@ -71,6 +71,7 @@ EXPORTS = (
     "ggrt_raster_binning_bytes",
     "ggrt_raster_forward_prepare",
     "ggrt_raster_forward_render",
+    "ggrt_raster_join",
     "ggrt_raster_backward",
     "ggrt_raster_sh_gradient_merge",
     "ggrt_raster_nvls_allreduce_f32",
@@ -112,6 +113,7 @@ def lib():
     L.ggrt_raster_binning_bytes.restype = sz
     L.ggrt_raster_forward_prepare.argtypes = [C.POINTER(Settings), C.POINTER(InputLayout), i32] + [vp] * 11
     L.ggrt_raster_forward_render.argtypes = [C.POINTER(Settings), i32, i64, u32, i32, vp, vp, vp, vp, vp, vp]
+    L.ggrt_raster_join.argtypes = [vp]
     L.ggrt_raster_backward.argtypes = ([C.POINTER(Settings), C.POINTER(InputLayout), i32, i64] + [vp] * 18
                                        + [C.POINTER(GradSinks), vp])
     L.ggrt_raster_sh_gradient_merge.argtypes = [i32, i32, C.POINTER(InputLayout), vp, i32, C.POINTER(vp), C.POINTER(vp),

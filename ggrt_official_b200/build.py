@@ -50,21 +50,43 @@ def is_stale() -> bool:
     return STAMP.read_text().strip() != source_hash()
 
 
+def _replace_atomically(path: Path, data: str) -> None:
+    tmp = path.with_name(f".{path.name}.{os.getpid()}.tmp")
+    tmp.write_text(data)
+    os.replace(tmp, path)
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile the library if the sources changed.  Safe under torchrun: every rank calls this lazily, so the
+    staleness check + compile run under an exclusive file lock, nvcc writes to a private temporary file that is
+    renamed into place (a concurrent CDLL never sees a half-written .so), and the stamp is replaced the same way
+    after the library."""
     if not force and not is_stale():
         return LIB
+    import fcntl
+
     LIB_DIR.mkdir(exist_ok=True)
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", str(LIB), *map(str, sources())]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
-    if verbose:
-        print(res.stdout, res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
-    STAMP.write_text(source_hash())
+    with open(LIB_DIR / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():  # another process built it while this one waited for the lock
+                return LIB
+            tmp = LIB_DIR / f".libggrt_raster.{os.getpid()}.so.tmp"
+            cmd = [find_nvcc(), *NVCC_FLAGS, "-o", str(tmp), *map(str, sources())]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd))
+            env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+            res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+            if verbose:
+                print(res.stdout, res.stderr)
+            if res.returncode != 0:
+                tmp.unlink(missing_ok=True)
+                raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+            os.replace(tmp, LIB)
+            _replace_atomically(STAMP, source_hash())
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

@@ -109,7 +109,7 @@ void compute_layout(int P, int H, int W, long long N, GgrtRasterLayout* L) {
     const size_t px = (size_t)H * W;
     off = 0;
     L->img_counts = off; off = off + T * SUBS * sizeof(uint32_t);
-    L->img_partials = off; off = align_up(off + ((T + SCAN_BLOCK - 1) / SCAN_BLOCK) * sizeof(unsigned long long));
+    L->img_partials = off; off = align_up(off + 2 * ((T + SCAN_BLOCK - 1) / SCAN_BLOCK) * sizeof(unsigned long long));
     L->img_cursor = off; off = align_up(off + T * SUBS * sizeof(uint32_t));
     L->img_starts = off; off = align_up(off + (T + 1) * sizeof(uint32_t));
     L->img_header = off; off = align_up(off + 4 * sizeof(uint32_t));
@@ -348,6 +348,17 @@ int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, in
     }
     { StageTimer t_(GGRT_STAGE_RENDER_FORWARD, s); launch_render_forward(v, g, im, b, capacity, out_color, out_depth, s); }
     GGRT_TRY(check_launch("render_forward", dbg, s));
+    return GGRT_OK;
+}
+
+int ggrt_raster_join(ggrt_stream_t stream) {
+    // Makes `stream` wait for the colour kernel a forward_prepare of this thread forked onto the internal side
+    // stream.  forward_render does this itself; a caller that abandons a frame between prepare and render (an
+    // allocation failure, say) calls it so that the buffers prepare was given can be released safely.
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return check_launch("join", 0, nullptr);
+    if (g_side[dev].pending && cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), g_side[dev].join, 0) != cudaSuccess)
+        return check_launch("join", 0, static_cast<cudaStream_t>(stream));
     return GGRT_OK;
 }
 

@@ -95,56 +95,68 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_tiles_kernel(int T, const uin
                                                                 unsigned long long* partials,
                                                                 uint32_t* __restrict__ header,
                                                                 volatile uint32_t* counts_host) {
-    __shared__ uint32_t warp_sums[SCAN_BLOCK / 32], warp_max[SCAN_BLOCK / 32];
-    __shared__ uint32_t prefix_s, gmax_s;
+    // Running sums are 64-bit: the pair lists are indexed with 32 bits everywhere downstream, so a total of 2^32 or
+    // more cannot be rendered -- but it must be DETECTED (header[2] / counts_host[2] carry the high word, the host
+    // raises GGRT_ERR_UNSUPPORTED) instead of wrapping silently.
+    __shared__ unsigned long long warp_sums[SCAN_BLOCK / 32];
+    __shared__ uint32_t warp_max[SCAN_BLOCK / 32];
+    __shared__ unsigned long long prefix_s;
+    __shared__ uint32_t gmax_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = blockIdx.x * SCAN_BLOCK + tid;
     const uint4* c4 = reinterpret_cast<const uint4*>(counts) + (size_t)t * (SUBS / 4);
     uint4 c[SUBS / 4];
-    uint32_t ts = 0;
+    unsigned long long ts = 0;
 #pragma unroll
     for (int q = 0; q < SUBS / 4; ++q) {
         c[q] = (t < T) ? c4[q] : make_uint4(0u, 0u, 0u, 0u);
-        ts += c[q].x + c[q].y + c[q].z + c[q].w;
+        ts += (unsigned long long)c[q].x + c[q].y + c[q].z + c[q].w;
     }
-    uint32_t x = ts;
+    unsigned long long x = ts;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
         if (lane >= d) x += y;
     }
-    const uint32_t wmax = __reduce_max_sync(0xffffffffu, ts);
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, (uint32_t)min(ts, 0x7fffffffull));
     if (lane == 31) warp_sums[warp] = x, warp_max[warp] = wmax;
     if (tid == 0) prefix_s = 0, gmax_s = 0;
     __syncthreads();
-    uint32_t block_total = 0, block_max = 0, warp_off = 0;
+    unsigned long long block_total = 0, warp_off = 0;
+    uint32_t block_max = 0;
 #pragma unroll
     for (int w = 0; w < SCAN_BLOCK / 32; ++w) {
         if (w < warp) warp_off += warp_sums[w];
         block_total += warp_sums[w];
         block_max = max(block_max, warp_max[w]);
     }
-    if (tid == 0) {  // publish this CTA's aggregate: bit 63 flag | 31 bits max | 32 bits total
-        const unsigned long long pack = (1ull << 63) | ((unsigned long long)(block_max & 0x7fffffffu) << 32) | block_total;
+    // publish this CTA's aggregate: {bit 63 flag | 63 bits total} in partials[b], the maximum in partials[nb + b]
+    const int nb = gridDim.x;
+    if (tid == 0) {
+        *reinterpret_cast<volatile unsigned long long*>(&partials[nb + blockIdx.x]) = block_max;
         __threadfence();
-        atomicExch(&partials[blockIdx.x], pack);
+        atomicExch(&partials[blockIdx.x], (1ull << 63) | (block_total & 0x7fffffffffffffffull));
     }
     // look back: sum the totals (and fold the maxima) of all earlier CTAs
-    uint32_t psum = 0, pmax = 0;
+    unsigned long long psum = 0;
+    uint32_t pmax = 0;
     for (int bk = tid; bk < (int)blockIdx.x; bk += SCAN_BLOCK) {
         unsigned long long v;
         do {
             v = *reinterpret_cast<volatile unsigned long long*>(&partials[bk]);
         } while ((v >> 63) == 0);
-        psum += (uint32_t)v;
-        pmax = max(pmax, (uint32_t)(v >> 32) & 0x7fffffffu);
+        __threadfence();
+        psum += v & 0x7fffffffffffffffull;
+        pmax = max(pmax, (uint32_t) * reinterpret_cast<volatile unsigned long long*>(&partials[nb + bk]));
     }
-    psum = __reduce_add_sync(0xffffffffu, psum);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, d);
     pmax = __reduce_max_sync(0xffffffffu, pmax);
     if (lane == 0 && (psum | pmax)) atomicAdd(&prefix_s, psum), atomicMax(&gmax_s, pmax);
     __syncthreads();
-    uint32_t run = prefix_s + warp_off + x - ts;
+    unsigned long long run64 = prefix_s + warp_off + x - ts;
     if (t < T) {
+        uint32_t run = (uint32_t)run64;
         starts[t] = run;
         uint4* s4 = reinterpret_cast<uint4*>(sub_starts) + (size_t)t * (SUBS / 4);
 #pragma unroll
@@ -158,15 +170,18 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_tiles_kernel(int T, const uin
         }
     }
     if (blockIdx.x == gridDim.x - 1 && tid == 0) {
-        const uint32_t total = prefix_s + block_total;
-        starts[T] = total;
-        header[0] = total;
-        header[1] = max(gmax_s, block_max);
-        header[2] = 0u;
+        const unsigned long long total = prefix_s + block_total;
+        const uint32_t lo = (uint32_t)total, hi = (uint32_t)(total >> 32), mx = max(gmax_s, block_max);
+        starts[T] = lo;
+        header[0] = lo;
+        header[1] = mx;
+        header[2] = hi;  // non-zero: more than 2^32 - 1 pairs (unsupported)
         header[3] = 0u;
         if (counts_host != nullptr) {  // mapped pinned host memory: the host polls / waits on the following event
-            counts_host[0] = total;
-            counts_host[1] = max(gmax_s, block_max);
+            counts_host[0] = lo;
+            counts_host[1] = mx;
+            counts_host[2] = hi;
+            counts_host[3] = 0u;
             __threadfence_system();
         }
     }

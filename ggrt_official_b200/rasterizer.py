@@ -50,14 +50,98 @@ _tls = threading.local()
 _capacity_cache: dict = {}
 SPECULATIVE_BINNING = True
 CAPACITY_SLACK = 1.25
+# how GaussianRasterizer (the autograd path) verifies the speculative pair buffer: "sync" (exact: one host wait per
+# forward, like the reference, whose caller synchronises twice per view anyway) or "lazy" (no host wait; an overflow
+# surfaces as BinningOverflow in backward / the next forward).  GGRT_RASTER_CHECK=lazy selects the latter.
+AUTOGRAD_CHECK = "lazy" if os.environ.get("GGRT_RASTER_CHECK", "sync").lower() == "lazy" else "sync"
 
 
-def _pinned_counts() -> torch.Tensor:
-    buf = getattr(_tls, "counts", None)
-    if buf is None:
-        buf = torch.zeros(2, dtype=torch.int64).pin_memory()  # 2 x uint32 live in the first 8 bytes
-        _tls.counts = buf
-    return buf
+class BinningOverflow(RuntimeError):
+    """A forward that ran with a deferred check (`check="lazy"` / a captured step) needed more tile-Gaussian
+    pairs than its pair buffer held: that frame's outputs are invalid.  The capacity has been raised; redo it."""
+
+
+class _Counts:
+    """{N, max pairs per tile, N >> 32, 0}: 16 bytes of mapped pinned host memory the tile-scan kernel stores into."""
+
+    def __init__(self):
+        self.buf = torch.zeros(2, dtype=torch.int64).pin_memory()
+        self.ptr = C.c_void_p(self.buf.data_ptr())
+
+    def read(self):
+        lo, hi = int(self.buf[0].item()), int(self.buf[1].item())
+        if hi & 0xFFFFFFFF:
+            raise RuntimeError("libggrt_raster forward failed (code -3): more than 2^32 - 1 tile-Gaussian pairs")
+        return lo & 0xFFFFFFFF, (lo >> 32) & 0xFFFFFFFF
+
+
+def _pinned_counts() -> "_Counts":
+    """A ring of pinned slots per thread: with deferred checks several forwards can be in flight, and each needs
+    the slot its scan kernel writes to stay untouched until it has been read."""
+    ring = getattr(_tls, "ring", None)
+    if ring is None:
+        ring = _tls.ring = [[_Counts() for _ in range(8)], 0]
+    ring[1] = (ring[1] + 1) % len(ring[0])
+    return ring[0][ring[1]]
+
+
+class Workspace:
+    """Every buffer one rasterization of a fixed shape needs, allocated once: state (geometry, image tables, pair
+    lists for `capacity` pairs), outputs (radii, colour, depth), the backward scratch and a private pinned slot for
+    {N, max}.  A forward given a workspace performs no allocation, which makes the whole forward + backward a fixed
+    launch sequence over fixed addresses -- what a CUDA graph needs (graph.CapturedStep) -- and spares the
+    per-call allocator traffic in training loops that render the same shape every step."""
+
+    def __init__(self, device, P: int, H: int, W: int, capacity: int):
+        L = _cabi.lib()
+        self.device = torch.device(device)
+        self.P, self.H, self.W = int(P), int(H), int(W)
+        u8 = dict(dtype=torch.uint8, device=self.device)
+        self.radii = torch.empty(self.P, dtype=torch.int32, device=self.device)
+        self.geom = torch.empty(L.ggrt_raster_geom_bytes(self.P), **u8)
+        self.img = torch.empty(L.ggrt_raster_image_bytes(self.H, self.W), **u8)
+        self.color = torch.empty((3, self.H, self.W), dtype=torch.float32, device=self.device)
+        self.depth = torch.empty((self.H, self.W), dtype=torch.float32, device=self.device)
+        self.scratch = torch.empty((self.P, 12), dtype=torch.float32, device=self.device)
+        self.counts = _Counts()
+        self.capacity = 0
+        self.binning = None
+        self.grow(capacity)
+
+    def grow(self, capacity: int) -> None:
+        if capacity > self.capacity:
+            self.capacity = int(capacity)
+            self.binning = torch.empty(_cabi.lib().ggrt_raster_binning_bytes(self.capacity), dtype=torch.uint8,
+                                       device=self.device)
+
+
+# forwards whose {N <= capacity} check was deferred: (event, counts slot, capacity, cache key)
+def _pending() -> list:
+    p = getattr(_tls, "pending", None)
+    if p is None:
+        p = _tls.pending = []
+    return p
+
+
+def check_pending(block: bool = True) -> None:
+    """Verifies the deferred checks of earlier `check="lazy"` forwards of this thread (waiting for them if `block`);
+    raises BinningOverflow if one of them overflowed its pair buffer."""
+    p = _pending()
+    bad = None
+    while p:
+        ev, counts, cap, key = p[0]
+        if not block and len(p) < 6 and not ev.query():  # never more than 6 frames in flight: the pinned ring has 8 slots
+            break
+        ev.synchronize()
+        p.pop(0)
+        N, mx = counts.read()
+        if key is not None:
+            _capacity_cache[key] = (N, mx)
+        if N > cap:
+            bad = (N, cap)
+    if bad:
+        raise BinningOverflow(f"a frame needed {bad[0]} tile-Gaussian pairs but its buffer held {bad[1]}; its outputs "
+                              "are invalid -- the capacity estimate has been raised, redo the step")
 
 
 def _f32c(t: Optional[torch.Tensor], name: str, device) -> Optional[torch.Tensor]:
@@ -140,64 +224,103 @@ class _Call:
 
 
 def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: GaussianRasterizationSettings,
-                aux=None, layout: Optional[dict] = None) -> dict:
+                aux=None, layout: Optional[dict] = None, workspace: Optional[Workspace] = None,
+                check: str = "sync") -> dict:
     """Runs the forward through the C ABI and returns outputs plus the opaque state buffers.
     `aux` [P]: optional extra per-Gaussian channel blended into the third output instead of the view depth.
-    `layout`: optional {scene_scale, cov_full3x3, sh_channel_major} (struct GgrtRasterInputLayout)."""
+    `layout`: optional {scene_scale, cov_full3x3, sh_channel_major} (struct GgrtRasterInputLayout).
+    `workspace`: preallocated buffers (no allocation in this call; outputs live in the workspace).
+    `check`: how {N <= capacity of the pair buffer} is verified --
+      "sync"  wait for N inside this call and redo the binning if a speculative buffer was too small (exact, default);
+      "lazy"  do not wait: the host returns at once and can queue further work; the check happens at the next
+              forward of this thread (or check_pending()) and raises BinningOverflow after the fact;
+      "none"  no check is scheduled (a captured CUDA graph: the owner reads workspace.counts after replays)."""
+    if check not in ("sync", "lazy", "none"):
+        raise ValueError(f"check must be 'sync', 'lazy' or 'none', got {check!r}")
     L = _cabi.lib()
     c = _Call(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs, aux, layout)
     dev = c.device
+    ws = workspace
+    if ws is not None and (ws.device != dev or (ws.P, ws.H, ws.W) != (c.P, c.H, c.W)):
+        raise ValueError(f"workspace is for P={ws.P}, {ws.H}x{ws.W} on {ws.device}; this call has P={c.P}, "
+                         f"{c.H}x{c.W} on {dev}")
+    if check != "none":
+        check_pending(block=(check == "sync"))  # surfaces an overflow of an earlier lazy frame; updates the estimates
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev)
         sp = C.c_void_p(stream.cuda_stream)
         u8 = dict(dtype=torch.uint8, device=dev)
-        radii = torch.empty(c.P, dtype=torch.int32, device=dev)
-        geom = torch.empty(L.ggrt_raster_geom_bytes(c.P), **u8)
-        img = torch.empty(L.ggrt_raster_image_bytes(c.H, c.W), **u8)
-        color = torch.empty((3, c.H, c.W), dtype=torch.float32, device=dev)
-        depth = torch.empty((c.H, c.W), dtype=torch.float32, device=dev)
-        counts = _pinned_counts()
+        if ws is None:
+            radii = torch.empty(c.P, dtype=torch.int32, device=dev)
+            geom = torch.empty(L.ggrt_raster_geom_bytes(c.P), **u8)
+            img = torch.empty(L.ggrt_raster_image_bytes(c.H, c.W), **u8)
+            color = torch.empty((3, c.H, c.W), dtype=torch.float32, device=dev)
+            depth = torch.empty((c.H, c.W), dtype=torch.float32, device=dev)
+            counts = _pinned_counts()
+        else:
+            radii, geom, img, color, depth, counts = ws.radii, ws.geom, ws.img, ws.color, ws.depth, ws.counts
         lay = C.byref(c.layout) if c.layout is not None else None
         _cabi.check(L.ggrt_raster_forward_prepare(C.byref(c.settings), lay, c.P, _ptr(c.means3D), _ptr(c.cov3D),
                                                   _ptr(c.opacities), _ptr(c.sh), _ptr(c.colors), _ptr(c.aux),
-                                                  _ptr(radii), _ptr(geom), _ptr(img),
-                                                  C.c_void_p(counts.data_ptr()), sp),
+                                                  _ptr(radii), _ptr(geom), _ptr(img), counts.ptr, sp),
                     "forward_prepare")
-        ev = torch.cuda.Event()
-        ev.record(stream)  # after the 8-byte copy of {N, max pairs per tile}; colour evaluation follows it
+        try:
+            ev = None
+            if check != "none":
+                ev = torch.cuda.Event()
+                ev.record(stream)  # after the scan kernel's store of {N, max pairs per tile}; colour evaluation follows it
 
-        def read_counts():
-            ev.synchronize()
-            packed = int(counts[0].item())
-            return packed & 0xFFFFFFFF, (packed >> 32) & 0xFFFFFFFF
+            def read_counts():
+                ev.synchronize()
+                return counts.read()
 
-        def render(capacity, max_hint, rescan):
-            buf = torch.empty(L.ggrt_raster_binning_bytes(capacity), **u8)
-            _cabi.check(L.ggrt_raster_forward_render(C.byref(c.settings), c.P, capacity, max_hint, int(rescan),
-                                                     _ptr(geom), _ptr(buf), _ptr(img), _ptr(color), _ptr(depth), sp),
-                        "forward_render")
-            return buf
+            def render(capacity, max_hint, rescan):
+                if ws is None:
+                    buf = torch.empty(L.ggrt_raster_binning_bytes(capacity), **u8)
+                else:
+                    ws.grow(capacity)
+                    buf, capacity = ws.binning, ws.capacity
+                _cabi.check(L.ggrt_raster_forward_render(C.byref(c.settings), c.P, capacity, max_hint, int(rescan),
+                                                         _ptr(geom), _ptr(buf), _ptr(img), _ptr(color), _ptr(depth), sp),
+                            "forward_render")
+                return buf, capacity
 
-        # N sizes the caller-owned pair buffer.  Waiting for it costs a host round trip that the colour kernel is
-        # too short to hide, so after the first call of a given shape the buffer is sized from the previous N plus
-        # slack and the remaining kernels are launched at once; N is checked afterwards (the copy finished long
-        # before) and the binning + render is redone with the exact size in the rare case the guess was too small.
-        key = (dev.index, c.P, c.H, c.W)
-        guess = _capacity_cache.get(key) if SPECULATIVE_BINNING else None
-        if guess is None:
-            N, max_pairs = read_counts()
-            cap = N
-            binning = render(cap, max_pairs, False)
-        else:
-            cap = int(guess[0] * CAPACITY_SLACK) + 1024
-            binning = render(cap, int(guess[1] * 1.05) + 4, False)  # hint only: larger tiles still sort correctly
-            N, max_pairs = read_counts()
-            if N > cap:
-                cap = N
-                binning = render(cap, max_pairs, True)
-        _capacity_cache[key] = (N, max_pairs)
+            # N sizes the caller-owned pair buffer.  Waiting for it costs a host round trip that the colour kernel is
+            # too short to hide, so after the first call of a given shape the buffer is sized from the previous N plus
+            # slack and the remaining kernels are launched at once; N is checked afterwards and the binning + render is
+            # redone with the exact size in the rare case the guess was too small ("sync"), or the check is left to
+            # the next call so that the host never waits for the device ("lazy").
+            key = (dev.index, c.P, c.H, c.W)
+            guess = _capacity_cache.get(key) if SPECULATIVE_BINNING else None
+            if guess is None and check != "sync":
+                if ws is None or ws.capacity == 0:
+                    raise RuntimeError("check='lazy'/'none' needs a capacity estimate: run one check='sync' forward of "
+                                       "this shape first (or pass a workspace with a capacity)")
+                guess = (ws.capacity, 0)
+            if guess is None:
+                N, max_pairs = read_counts()
+                binning, cap = render(N, max_pairs, False)
+            else:
+                want = int(guess[0] * CAPACITY_SLACK) + 1024 if ws is None or ws.capacity == 0 else ws.capacity
+                hint = int(guess[1] * 1.05) + 4 if guess[1] else 0xFFFFFF  # unknown: the general sort tier
+                binning, cap = render(want, hint, False)  # hint only: larger tiles still sort correctly
+                if check == "sync":
+                    N, max_pairs = read_counts()
+                    if N > cap:
+                        binning, cap = render(N, max_pairs, True)
+                else:
+                    N, max_pairs = guess
+                    if check == "lazy":
+                        _pending().append((ev, counts, cap, key))
+            if check == "sync":
+                _capacity_cache[key] = (N, max_pairs)
+        except Exception:
+            # the colour kernel forked by `prepare` may still be running on the library's side stream: order the
+            # caller's stream (and with it the release of geom / radii to the caching allocator) after it
+            L.ggrt_raster_join(sp)
+            raise
     return dict(call=c, color=color, depth=depth, radii=radii, geom=geom, img=img, binning=binning, N=N,
-                capacity=cap, max_tile_pairs=max_pairs)
+                capacity=cap, max_tile_pairs=max_pairs, workspace=ws)
 
 
 def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = None,
@@ -238,7 +361,8 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
         if ga is not None and c.aux is None:
             raise RuntimeError("the third output is only differentiable when aux_precomp was given")
         f32 = dict(dtype=torch.float32, device=dev)
-        scratch = torch.empty((c.P, 12), **f32)
+        ws = state.get("workspace")
+        scratch = ws.scratch if ws is not None else torch.empty((c.P, 12), **f32)
         given = out or {}
 
         def buf(name, shape):
@@ -332,7 +456,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         # viewmatrix / projmatrix / campos are the tensors of raster_settings again: passing them as explicit
         # inputs lets autograd deliver camera gradients when (and only when) they require grad
         try:
-            st = forward_raw(means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings, aux, layout)
+            st = forward_raw(means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings, aux, layout,
+                             check=AUTOGRAD_CHECK)
         except Exception:
             if _debug_enabled(raster_settings):
                 _dump("snapshot_fw.dump", (means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings))
@@ -362,6 +487,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             return (None,) * 14
         if grad_color is None:
             grad_color = torch.zeros((3, c.H, c.W), dtype=torch.float32, device=c.device)
+        if AUTOGRAD_CHECK == "lazy":
+            check_pending(block=True)  # the forward of this frame has long finished: costs nothing, raises on overflow
         try:
             g = backward_raw(st, grad_color, grad_aux=grad_aux, want_camera=want_cam)
         except Exception:

@@ -171,6 +171,14 @@ class CompactGradientExchange:
         return {"gather_recv": 4 * 3 * (self.P + 1) * (w - 1), "allreduce_payload": 4 * self.small_elems,
                 "arena_allreduce_payload_replaced": 4 * self.P * (10 + 3 * self.K)}
 
+    def kernels_per_step(self) -> int:
+        """Kernels of this library the exchange adds to a step (the SH-gradient merge, + the NVLS all-reduce and,
+        with barrier="nvls", two barrier kernels on the p2p transport); torch / NCCL kernels are not counted."""
+        if self.world == 1 or self.transport != "p2p":
+            return 1
+        n = 1 + (1 if self.handles[1].multicast_ptr else 0)
+        return n + (2 if self.barrier_kind == "nvls" else 0)
+
     def _barrier(self, channel: int) -> None:
         if self.barrier_kind == "nvls":
             from . import _cabi
@@ -272,3 +280,54 @@ def make_exchange(P: int, sh_degree: int, device, group=None, prefer: str = "p2p
         return ex
     del ex
     return CompactGradientExchange(P, sh_degree, device, group=group, transport="nccl", layout=layout)
+
+
+class _ViewParallelRasterize(torch.autograd.Function):
+    """This rank's view through the rasterizer; the backward sums the Gaussian gradients over all ranks' views
+    (compact exchange) before handing them to autograd."""
+
+    @staticmethod
+    def forward(ctx, means3D, shs, opacities, cov3D_precomp, raster_settings, exchange, check):
+        from . import rasterizer as R
+
+        st = R.forward_raw(means3D, shs, None, opacities, cov3D_precomp, raster_settings, check=check)
+        ctx.state = {k: st[k] for k in ("call", "radii", "geom", "img", "binning", "N", "capacity", "workspace")}
+        ctx.exchange, ctx.check = exchange, check
+        ctx.opacity_shape = tuple(opacities.shape)
+        ctx.mark_non_differentiable(st["radii"], st["depth"])
+        ctx.set_materialize_grads(False)
+        return st["color"], st["radii"], st["depth"]
+
+    @staticmethod
+    def backward(ctx, grad_color, _grad_radii=None, _grad_depth=None):
+        from . import rasterizer as R
+
+        c = ctx.state["call"]
+        if grad_color is None:  # every rank must still take part in the exchange
+            grad_color = torch.zeros((3, c.H, c.W), dtype=torch.float32, device=c.device)
+        if ctx.check == "lazy":
+            R.check_pending(block=True)
+        g = ctx.exchange.run(ctx.state, grad_color)
+        return g["dmeans3D"], g["dsh"], g["dopacity"].reshape(ctx.opacity_shape), g["dcov3D"], None, None, None
+
+
+class ViewParallelRasterizer(torch.nn.Module):
+    """`GaussianRasterizer` for view-sharded training: every rank holds the same Gaussians and renders
+    ITS target view (`raster_settings` differ per rank); `backward()` returns the gradients summed over the views of
+    all ranks, exchanged by `exchange` (a CompactGradientExchange, see make_exchange) inside the backward -- no
+    separate all-reduce of the 340 B/Gaussian gradient set afterwards.  Inputs as GGRt passes them: `shs` [P,K,3] and
+    `cov3D_precomp` [P,6].  The returned gradient tensors are the exchange's own buffers, valid until the next
+    backward through the same exchange (use them / step the optimiser before that, as a training loop does)."""
+
+    def __init__(self, raster_settings, exchange: CompactGradientExchange, check: str = "lazy"):
+        super().__init__()
+        self.raster_settings, self.exchange, self.check = raster_settings, exchange, check
+
+    def forward(self, means3D, opacities, shs, cov3D_precomp):
+        from . import rasterizer as R
+
+        key = (means3D.device.index, int(means3D.shape[0]), int(self.raster_settings.image_height),
+               int(self.raster_settings.image_width))
+        check = self.check if key in R._capacity_cache else "sync"  # the first frame of a shape sizes the pair buffer
+        return _ViewParallelRasterize.apply(means3D, shs, opacities, cov3D_precomp, self.raster_settings,
+                                            self.exchange, check)

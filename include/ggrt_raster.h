@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GGRT_RASTER_ABI_VERSION 6
+#define GGRT_RASTER_ABI_VERSION 7
 #define GGRT_RASTER_TILE 16 /* tile edge in pixels (tile ids are part of the contract) */
 #define GGRT_RASTER_SUBS 16 /* pair counters per tile (contention spreading) */
 #define GGRT_RASTER_MAX_MERGE_VIEWS 16 /* views per ggrt_raster_sh_gradient_merge call */
@@ -139,10 +139,12 @@ size_t ggrt_raster_binning_bytes(int64_t num_rendered);
  * weights as the colour into out_depth (NULL: the view-space depth is used).  GGRt's depth pass
  * (cuda_splatting.py:227-269) is such a channel, so colour and depth can share one rasterization.
  * Writes radii [P] (int32; 0 = culled), fills geom_buffer and the tile tables of
- * image_buffer, and the tile-scan kernel stores {N, max pairs per tile} directly into counts_host
- * (2 x uint32 of MAPPED pinned host memory -- cudaHostAlloc / torch pin_memory under UVA; may be
- * NULL if the caller reads img_header itself).  The values are valid once work enqueued on the
- * stream after this call (e.g. an event recorded right after it) has completed.
+ * image_buffer, and the tile-scan kernel stores {N (low 32 bits), max pairs per tile, N >> 32, 0}
+ * directly into counts_host (4 x uint32 of MAPPED pinned host memory -- cudaHostAlloc / torch
+ * pin_memory under UVA; may be NULL if the caller reads img_header itself, which holds the same four
+ * words).  A non-zero third word means N >= 2^32: such a frame cannot be rendered (pair lists are
+ * indexed with 32 bits) and the caller must not call forward_render for it.  The values are valid once
+ * work enqueued on the stream after this call (e.g. an event recorded right after it) has completed.
  */
 int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, const GgrtRasterInputLayout* layout, int32_t P,
                                 const float* means3D,
@@ -165,6 +167,14 @@ int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, const GgrtRa
 int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, int64_t num_rendered,
                                uint32_t max_tile_pairs, int32_t rescan, const void* geom_buffer, void* binning_buffer,
                                void* image_buffer, float* out_color, float* out_depth, ggrt_stream_t stream);
+
+/*
+ * Orders `stream` after the colour kernel that the most recent forward_prepare of this host thread forked onto
+ * the library's side stream.  Only needed by a caller that abandons a frame between prepare and render
+ * (forward_render joins by itself): after this call, work enqueued on `stream` -- including the release of the
+ * buffers prepare was given to a stream-ordered allocator -- cannot overtake that kernel.
+ */
+int ggrt_raster_join(ggrt_stream_t stream);
 
 /*
  * Backward.  dL_dout_color [3,H,W]; dL_dout_aux [H,W] or NULL (gradient of out_depth; only

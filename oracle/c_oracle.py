@@ -171,8 +171,10 @@ def forward(cam: Camera, means, cov3d, opacities, sh=None, colors=None, aux=None
 
 
 def backward(cam: Camera, means, cov3d, opacities, fwd: dict, dL_dcolor_img, sh=None, colors=None,
-             dL_ddepth_img=None) -> dict:
-    """Whole backward. Returns grads in the layout of upstream's autograd outputs."""
+             dL_ddepth_img=None, want_camera: bool = False) -> dict:
+    """Whole backward. Returns grads in the layout of upstream's autograd outputs.
+    want_camera: also g["dcamera"] = dL/d(viewmatrix [16] | projmatrix [16] | campos [3]) as float64 [35]
+    (the opt-in pose-gradient extension of BASELINE config 3)."""
     L = lib()
     means, cov3d, sh = _f32(means), _f32(cov3d), _f32(sh)
     P = means.shape[0]
@@ -199,10 +201,11 @@ def backward(cam: Camera, means, cov3d, opacities, fwd: dict, dL_dcolor_img, sh=
     g["dmeans3D"] = np.zeros((P, 3), np.float32)
     g["dcov3D"] = np.zeros((P, 6), np.float32)
     g["dsh"] = np.zeros((P, K, 3), np.float32) if sh is not None else None
+    g["dcamera"] = np.zeros(35, np.float64) if want_camera else None
     L.oracle_preprocess_backward(C.byref(cc), _p(means), _p(cov3d), _p(sh), _p(pre["radii"]), _p(pre["clamped"]),
                                  _p(g["dmean2D"]), _p(g["dconic"]), _p(g["dcolor"]),
                                  _p(g["ddepth"]) if aux is None else None,  # a caller-supplied channel is a leaf
-                                 _p(g["dmeans3D"]), _p(g["dcov3D"]), _p(g["dsh"]))
+                                 _p(g["dmeans3D"]), _p(g["dcov3D"]), _p(g["dsh"]), _p(g["dcamera"]))
     g["daux"] = g["ddepth"] if aux is not None else None
     return g
 

@@ -560,12 +560,24 @@ static void sh_backward(int deg, const float* sh, float x, float y, float z, con
 void oracle_preprocess_backward(const OracleCam* cam, const float* means, const float* cov3d, const float* sh,
                                 const int* radii, const uint8_t* clamped, const float* dL_dmean2D,
                                 const float* dL_dconic, const float* dL_dcolor, const float* dL_ddepth,
-                                float* dL_dmeans, float* dL_dcov3d, float* dL_dsh) {
+                                float* dL_dmeans, float* dL_dcov3d, float* dL_dsh, double* dL_dcam) {
+    /* dL_dcam (optional, 35 doubles): gradient w.r.t. the camera tensors of the settings, laid out
+     * viewmatrix [4,4] | projmatrix [4,4] | campos [3] -- the opt-in extension for BASELINE config 3
+     * ("through the projection into camera pose").  With row-vector maths t = [p,1].V[:, :3],
+     * hom = [p,1].M and Tm = J.Rw (Rw[m][k] = V[k][m]):
+     *   dL/dV[i][j] += p_i dL/dt_j  (i = 0..3, p_3 = 1)     dL/dV[k][m] += sum_r dL/dTm[r][k] J[r][m]
+     *   dL/dM[i][j] += p_i dL/dhom_j (j = 0, 1, 3)          dL/dcampos  -= dL/d(p - campos)
+     * Accumulated in double, per thread, merged at the end (deterministic up to the merge order). */
     const int P = cam->P;
     const int K = (cam->deg + 1) * (cam->deg + 1);
     const float* V = cam->view;
     const float* M = cam->proj;
-#pragma omp parallel for schedule(static)
+    if (dL_dcam) memset(dL_dcam, 0, 35 * sizeof(double));
+#pragma omp parallel
+    {
+    double camacc[35];
+    memset(camacc, 0, sizeof(camacc));
+#pragma omp for schedule(static)
     for (int i = 0; i < P; ++i) {
         for (int k = 0; k < 3; ++k) dL_dmeans[3 * i + k] = 0.0f;
         for (int k = 0; k < 6; ++k) dL_dcov3d[6 * i + k] = 0.0f;
@@ -627,6 +639,24 @@ void oracle_preprocess_backward(const OracleCam* cam, const float* means, const 
         float g2x = dL_dmean2D[2 * i], g2y = dL_dmean2D[2 * i + 1];
         for (int k = 0; k < 3; ++k)
             dmean[k] += (M[4 * k + 0] * mw - M[4 * k + 3] * mul1) * g2x + (M[4 * k + 1] * mw - M[4 * k + 3] * mul2) * g2y;
+        if (dL_dcam) {
+            const double ph[4] = {means[3 * i], means[3 * i + 1], means[3 * i + 2], 1.0};
+            const double dt[3] = {dtx, dty, dtz};
+            const double J00 = g.fx * z1, J02 = -g.fx * g.cx * z2, J11 = g.fy * z1, J12 = -g.fy * g.cy * z2;
+            const double dhx = (double)g2x * mw, dhy = (double)g2y * mw;
+            const double dhw = -((double)g.hx * g2x + (double)g.hy * g2y) * mw * mw;
+            for (int r = 0; r < 4; ++r) {
+                for (int j = 0; j < 3; ++j) camacc[4 * r + j] += ph[r] * dt[j];
+                camacc[16 + 4 * r + 0] += ph[r] * dhx;
+                camacc[16 + 4 * r + 1] += ph[r] * dhy;
+                camacc[16 + 4 * r + 3] += ph[r] * dhw;
+            }
+            for (int k = 0; k < 3; ++k) {
+                camacc[4 * k + 0] += (double)dTm[0][k] * J00;
+                camacc[4 * k + 1] += (double)dTm[1][k] * J11;
+                camacc[4 * k + 2] += (double)dTm[0][k] * J02 + (double)dTm[1][k] * J12;
+            }
+        }
 
         /* colour -> SH and view direction */
         if (dL_dsh) {
@@ -641,12 +671,20 @@ void oracle_preprocess_backward(const OracleCam* cam, const float* means, const 
             /* through normalize(): (I |v|^2 - v v^T) / |v|^3 . ddir */
             float inv3 = inv * inv * inv;
             float dot = dx * ddir[0] + dy * ddir[1] + dz * ddir[2];
-            dmean[0] += (len2 * ddir[0] - dx * dot) * inv3;
-            dmean[1] += (len2 * ddir[1] - dy * dot) * inv3;
-            dmean[2] += (len2 * ddir[2] - dz * dot) * inv3;
+            const float m0 = (len2 * ddir[0] - dx * dot) * inv3, m1 = (len2 * ddir[1] - dy * dot) * inv3,
+                        m2 = (len2 * ddir[2] - dz * dot) * inv3;
+            dmean[0] += m0;
+            dmean[1] += m1;
+            dmean[2] += m2;
+            if (dL_dcam) camacc[32] -= m0, camacc[33] -= m1, camacc[34] -= m2;
         }
         for (int k = 0; k < 3; ++k) dL_dmeans[3 * i + k] = dmean[k];
     }
+    if (dL_dcam) {
+#pragma omp critical
+        for (int k = 0; k < 35; ++k) dL_dcam[k] += camacc[k];
+    }
+    }  /* omp parallel */
 }
 
 /* A.? mark_visible: the frustum test alone (upstream checkFrustum; unused by GGRt). */

@@ -103,8 +103,46 @@ def compare_forward(st, f, depth_scale=None):
     return res
 
 
-def grad_errors(got: dict, ref: dict, use_sh=True):
-    """max |got-ref| / max |ref| per gradient tensor, and the fraction of elements outside 1e-3 rel + floor."""
+# Gradient bar (BASELINE.json north_star: "1e-3 rel on gradients"), applied ELEMENTWISE:
+#     |got - ref| <= GRAD_REL * |ref| + GRAD_ABS_FLOOR * max|ref over the tensor|
+# The absolute floor covers float32 summation-order noise of elements that are themselves sums of
+# hundreds of cancelling per-pixel terms (the GPU adds them in another order than the oracle).
+# Gaussians that reach a pixel the oracle flags "fragile" (a hard threshold within rounding of its
+# boundary, see compare_forward) may legitimately gain or lose one whole pixel contribution; they are
+# held to the tensor-level bar only (max|diff| <= GRAD_REL * max|ref|) and must be few.
+GRAD_REL = 1e-3
+GRAD_ABS_FLOOR = 1e-5
+
+
+def fragile_allowance(n_pixels: int, n_pairs: int, n_tiles: int, dense: bool = False) -> int:
+    """Upper bound on oracle-flagged fragile pixels: the flag rate is proportional to the number of
+    threshold tests per pixel (= the tile's list length).  Measured on the BASELINE scenes (C1..C5):
+    1.0e-6 * pixels * pairs/tile; the bound is twice that (8e-6 for the inflated-covariance unit cases,
+    whose Gaussians cover many more pixels each)."""
+    per_tile = n_pairs / max(n_tiles, 1)
+    return max(16, int((8e-6 if dense else 2e-6) * n_pixels * per_tile))
+
+
+def fragile_gaussians(f: dict, H: int, W: int) -> np.ndarray:
+    """bool [P]: Gaussians whose bounding square (centre +- radius) contains a fragile pixel of a tile
+    that lists them -- the only ones whose gradients a threshold flip at that pixel can change."""
+    pre, b, img = f["pre"], f["bin"], f["img"]
+    P = pre["radii"].shape[0]
+    hit = np.zeros(P, bool)
+    ys, xs = np.nonzero(img["fragile"])
+    gx = (W + 15) // 16
+    for y, x in zip(ys.tolist(), xs.tolist()):
+        s, e = b["ranges"][(y // 16) * gx + x // 16]
+        ids = b["point_list"][int(s): int(e)].astype(np.int64)
+        d = np.abs(pre["xy"][ids] - np.array([x, y], np.float32)).max(axis=1)
+        hit[ids[d <= pre["radii"][ids] + 1]] = True
+    return hit
+
+
+def grad_errors(got: dict, ref: dict, use_sh=True, fragile=None):
+    """Per gradient tensor: max_rel = max|got-ref| / max|ref| (tensor level), worst = the largest
+    |got-ref| / (GRAD_REL |ref| + GRAD_ABS_FLOOR max|ref|) over the elements of non-fragile Gaussians
+    (<= 1 means the elementwise bar holds everywhere), n_bad = how many exceed it, frac_fragile."""
     pairs = dict(dmeans3D=(got["dmeans3D"], ref["dmeans3D"]), dcov3D=(got["dcov3D"], ref["dcov3D"]),
                  dopacity=(got["dopacity"].reshape(-1), ref["dopacity"]),
                  dmeans2D=(got["dmeans2D"][:, :2], ref["dmean2D"]))
@@ -116,8 +154,24 @@ def grad_errors(got: dict, ref: dict, use_sh=True):
     for k, (a, b) in pairs.items():
         a = a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
         a64, b64 = a.astype(np.float64), np.asarray(b, np.float64)
-        scale = max(np.abs(b64).max(), 1e-30)
-        bad = np.abs(a64 - b64) > 1e-3 * np.abs(b64) + 1e-5 * scale
-        out[k] = dict(max_rel=float(np.abs(a64 - b64).max() / scale), frac_bad=float(bad.mean()),
+        P = a64.shape[0]
+        a64, b64 = a64.reshape(P, -1), b64.reshape(P, -1)
+        scale = max(np.abs(b64).max(), 1e-30) if b64.size else 1.0
+        ratio = np.abs(a64 - b64) / (GRAD_REL * np.abs(b64) + GRAD_ABS_FLOOR * scale)
+        strict = np.ones(P, bool) if fragile is None else ~fragile
+        rs = ratio[strict]
+        out[k] = dict(max_rel=float(np.abs(a64 - b64).max() / scale) if b64.size else 0.0,
+                      worst=float(rs.max()) if rs.size else 0.0, n_bad=int((rs > 1.0).sum()),
+                      frac_bad=float((ratio > 1.0).mean()) if ratio.size else 0.0,
+                      frac_fragile=float(1.0 - strict.mean()) if P else 0.0,
                       nonfinite=int((~np.isfinite(a64)).sum()))
     return out
+
+
+def assert_grads(errs: dict, what="", max_fragile=0.05):
+    """The gradient bar of the parity tests (see GRAD_REL / GRAD_ABS_FLOOR above)."""
+    for k, e in errs.items():
+        assert e["nonfinite"] == 0, (what, k, e)
+        assert e["max_rel"] < GRAD_REL, (what, k, errs)        # tensor level, fragile Gaussians included
+        assert e["worst"] <= 1.0, (what, k, errs)               # elementwise, every non-fragile Gaussian
+        assert e["frac_fragile"] < max_fragile, (what, k, e)

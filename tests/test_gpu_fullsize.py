@@ -29,12 +29,11 @@ def test_config2_full_parity_forward_and_backward():
         assert res[k] == 0, (k, res)
     assert res["N"][0] == res["N"][1] > 2 * P
     assert res["color_max_err"] < 1e-4 and res["depth_max_relerr"] < 1e-4, res
-    assert res["fragile_pixels"] < H * W // 1000, res
+    assert res["fragile_pixels"] <= G.fragile_allowance(H * W, res["N"][1], 63 * 48), res
     g = image_gradient(H, W)
     got = R.backward_raw(st, torch.tensor(g, device="cuda:0"))
     ref = co.backward(cam, ri.means3D, ri.cov3D, ri.opacities, f, g, sh=ri.shs)
-    for k, e in G.grad_errors(got, ref).items():
-        assert e["nonfinite"] == 0 and e["max_rel"] < 1e-3 and e["frac_bad"] < 1e-3, (k, e)
+    G.assert_grads(G.grad_errors(got, ref, fragile=G.fragile_gaussians(f, H, W)), "C2")
 
 
 def test_config3_size_properties():

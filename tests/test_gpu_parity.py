@@ -33,7 +33,7 @@ CASES = [
 ]
 
 
-def _check_forward(res, n_pixels):
+def _check_forward(res, H, W, dense=True):
     for k in ("radii_mismatch", "rect_mismatch", "tiles_mismatch", "xy_bits_mismatch", "conic_bits_mismatch",
               "depth_bits_mismatch", "starts_mismatch"):
         assert res[k] == 0, (k, res)
@@ -46,7 +46,8 @@ def _check_forward(res, n_pixels):
     assert res["depth_max_relerr"] < 1e-4, res
     assert res["final_T_max_err"] < 1e-5, res
     assert res["n_contrib_mismatch"] == 0, res
-    assert res["fragile_pixels"] <= max(16, n_pixels // 250), res
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    assert res["fragile_pixels"] <= G.fragile_allowance(H * W, res["N"][1], T, dense=dense), res
     assert res["color_max_err_fragile"] < 2e-2, res  # a flipped 1/255 contribution is bounded
 
 
@@ -55,7 +56,7 @@ def test_forward_matches_oracle(P, H, W, deg, bg, cov_scale, seed):
     _, ri = small_case(P, H, W, deg, bg=bg, seed=seed, cov_scale=cov_scale)
     st = G.run_cuda_forward(ri, debug=True)
     _, f = G.oracle_forward(ri)
-    _check_forward(G.compare_forward(st, f), H * W)
+    _check_forward(G.compare_forward(st, f), H, W)
 
 
 @pytest.mark.parametrize("P,H,W,deg,bg,cov_scale,seed", CASES)
@@ -67,11 +68,7 @@ def test_backward_matches_oracle(P, H, W, deg, bg, cov_scale, seed):
     got = R.backward_raw(st, torch.tensor(g, device="cuda:0"))
     torch.cuda.synchronize()
     ref = co.backward(cam, ri.means3D, ri.cov3D, ri.opacities, f, g, sh=ri.shs)
-    errs = G.grad_errors(got, ref)
-    for k, e in errs.items():
-        assert e["nonfinite"] == 0, (k, e)
-        assert e["max_rel"] < 1e-3, (k, errs)
-        assert e["frac_bad"] < 2e-3, (k, errs)
+    G.assert_grads(G.grad_errors(got, ref, fragile=G.fragile_gaussians(f, H, W)))
 
 
 def test_colors_precomp_path():
@@ -84,8 +81,7 @@ def test_colors_precomp_path():
     g = np.random.default_rng(0).standard_normal((3, 64, 64)).astype(np.float32)
     got = R.backward_raw(st, torch.tensor(g, device="cuda:0"))
     ref = co.backward(cam, ri.means3D, ri.cov3D, ri.opacities, f, g, colors=colors)
-    for k, e in G.grad_errors(got, ref, use_sh=False).items():
-        assert e["max_rel"] < 1e-3 and e["nonfinite"] == 0, (k, e)
+    G.assert_grads(G.grad_errors(got, ref, use_sh=False, fragile=G.fragile_gaussians(f, 64, 64)))
 
 
 def test_aux_channel_forward_and_backward():
@@ -106,11 +102,9 @@ def test_aux_channel_forward_and_backward():
     ga = rng.standard_normal((H, W)).astype(np.float32)
     got = R.backward_raw(st, t(g), grad_aux=t(ga))
     ref = co.backward(cam, ri.means3D, ri.cov3D, ri.opacities, f, g, sh=ri.shs, dL_ddepth_img=ga)
-    errs = G.grad_errors(got, ref)
+    G.assert_grads(G.grad_errors(got, ref, fragile=G.fragile_gaussians(f, H, W)))
     a, b = got["daux"].cpu().numpy().astype(np.float64), ref["daux"].astype(np.float64)
-    errs["daux"] = dict(max_rel=float(np.abs(a - b).max() / np.abs(b).max()), nonfinite=int((~np.isfinite(a)).sum()))
-    for k, e in errs.items():
-        assert e["nonfinite"] == 0 and e["max_rel"] < 1e-3, (k, errs)
+    assert np.isfinite(a).all() and np.abs(a - b).max() < 1e-3 * np.abs(b).max()
     with pytest.raises(RuntimeError, match="aux_precomp"):
         st2 = R.forward_raw(t(ri.means3D), t(ri.shs), None, t(ri.opacities), t(ri.cov3D), G.settings_from(ri, dev))
         R.backward_raw(st2, t(g), grad_aux=t(ga))
@@ -163,20 +157,19 @@ def test_speculative_binning_overflow_is_redone():
     st1 = G.run_cuda_forward(dense)         # guess from the sparse scene is far too small -> redo path
     assert st1["N"] > 2 * st0["N"] and st1["capacity"] == st1["N"]
     _, f1 = G.oracle_forward(dense)
-    _check_forward(G.compare_forward(st1, f1), H * W)
+    _check_forward(G.compare_forward(st1, f1), H, W)
     st2 = G.run_cuda_forward(dense)         # now the guess is large enough: speculative path, capacity > N
     assert st2["capacity"] > st2["N"] == st1["N"]
-    _check_forward(G.compare_forward(st2, f1), H * W)
+    _check_forward(G.compare_forward(st2, f1), H, W)
     g = np.random.default_rng(1).standard_normal((3, H, W)).astype(np.float32)
     cam = oracle_camera(dense)
     ref = co.backward(cam, dense.means3D, dense.cov3D, dense.opacities, f1, g, sh=dense.shs)
     for st in (st1, st2):
         got = R.backward_raw(st, torch.tensor(g, device="cuda:0"))
-        for k, e in G.grad_errors(got, ref).items():
-            assert e["nonfinite"] == 0 and e["max_rel"] < 1e-3, (k, e)
+        G.assert_grads(G.grad_errors(got, ref, fragile=G.fragile_gaussians(f1, H, W)))
     st3 = G.run_cuda_forward(sparse)        # shrinking scenes are fine too
     _, f0 = G.oracle_forward(sparse)
-    _check_forward(G.compare_forward(st3, f0), H * W)
+    _check_forward(G.compare_forward(st3, f0), H, W)
 
 
 def test_config1_10k_256(tmp_path):
@@ -184,7 +177,7 @@ def test_config1_10k_256(tmp_path):
     ri = to_raster_inputs(make_scene(10_000, 256, 256, sh_degree=4))
     st = G.run_cuda_forward(ri)
     _, f = G.oracle_forward(ri)
-    _check_forward(G.compare_forward(st, f), 256 * 256)
+    _check_forward(G.compare_forward(st, f), 256, 256, dense=False)
 
 
 def test_autograd_module_end_to_end():
@@ -213,8 +206,7 @@ def test_autograd_module_end_to_end():
     ok = f["img"]["fragile"] == 0
     assert np.abs(image.detach().cpu().numpy() - f["color"])[:, ok].max() < 1e-4
     got = dict(dmeans3D=means.grad, dcov3D=cov.grad, dopacity=opac.grad, dmeans2D=means2D.grad, dsh=shs.grad)
-    for k, e in G.grad_errors(got, ref).items():
-        assert e["max_rel"] < 1e-3 and e["nonfinite"] == 0, (k, e)
+    G.assert_grads(G.grad_errors(got, ref, fragile=G.fragile_gaussians(f, H, W)))
 
 
 def test_empty_and_culled_inputs():

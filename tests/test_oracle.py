@@ -64,6 +64,30 @@ def test_c_oracle_matches_autograd_restatement(P, H, W, deg, bg, use_sh, seed):
         assert rel_err(b["dcolor"], col.grad.numpy()) < 2e-5
 
 
+@pytest.mark.parametrize("P,H,W,deg,seed", [(200, 40, 56, 2, 11), (300, 48, 64, 4, 12), (120, 32, 32, 0, 13)])
+def test_c_oracle_camera_gradients_match_autograd(P, H, W, deg, seed):
+    """The hand-derived dL/d(viewmatrix, projmatrix, campos) of the C oracle (pose gradients of BASELINE
+    config 3) against autograd of the dense float64 restatement.  Pins the target of the GPU pose tests."""
+    _, ri = small_case(P, H, W, deg, bg=(0.2, 0.1, 0.3), seed=seed, cov_scale=9.0, behind_fraction=0.0)
+    cam = oracle_camera(ri)
+    f = co.forward(cam, ri.means3D, ri.cov3D, ri.opacities, sh=ri.shs)
+    g = np.random.default_rng(seed).standard_normal((3, H, W)).astype(np.float32)
+    b = co.backward(cam, ri.means3D, ri.cov3D, ri.opacities, f, g, sh=ri.shs, want_camera=True)
+    v64, p64, c64 = _t(ri.viewmatrix).requires_grad_(), _t(ri.projmatrix).requires_grad_(), _t(ri.campos).requires_grad_()
+    color, _, _ = tr.rasterize(_t(ri.means3D), _t(ri.cov3D), _t(ri.opacities), view=v64, proj=p64, campos=c64,
+                               bg=_t(ri.bg), tanfovx=ri.tanfovx, tanfovy=ri.tanfovy, H=H, W=W, deg=deg, sh=_t(ri.shs))
+    (color * _t(g)).sum().backward()
+    cam_g = b["dcamera"]
+    assert rel_err(cam_g[:16].reshape(4, 4), v64.grad.numpy()) < 1e-4
+    assert rel_err(cam_g[16:32].reshape(4, 4), p64.grad.numpy()) < 1e-4
+    if deg > 0:
+        assert rel_err(cam_g[32:35], c64.grad.numpy()) < 1e-4
+    else:  # degree 0 has no view-direction dependence
+        assert c64.grad is None and np.abs(cam_g[32:35]).max() == 0.0
+    # without the flag nothing is computed
+    assert co.backward(cam, ri.means3D, ri.cov3D, ri.opacities, f, g, sh=ri.shs)["dcamera"] is None
+
+
 def test_sh_basis_is_orthonormal():
     """Degree 0..4 real SH basis (A.1 constants) integrates to the identity on the sphere."""
     n = 64
