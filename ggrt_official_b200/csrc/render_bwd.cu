@@ -6,44 +6,44 @@
 // pixel block (w&1, w>>1) as in the forward.  A batch of up to 512 Gaussian records is
 // staged into shared memory; each warp culls it against its pixel block (exact ellipse vs
 // rectangle test on {alpha >= 1/255}) into a back-to-front queue and then consumes the queue
-// GL = 8 Gaussians at a time with LANES = (pixel slot, Gaussian slot): per step the warp
-// evaluates 8 Gaussians at 4 pixels, a segmented warp scan over the associative maps
+// 8 Gaussians at a time with LANES = (pixel slot q, Gaussian slot gl).  Per step a lane evaluates
+// ITS Gaussian at the TWO pixels (q, row) and (q + 4, row) of one row of the block, so the warp covers
+// 8 Gaussians x 8 pixels; a segmented warp scan over the associative maps
 // (T, R) -> (aT, R + bT) recovers each Gaussian's transmittance T_i and the colour
 // accumulated behind it, and every lane accumulates the 9 partial gradients of ITS Gaussian
 // in registers.  There is no per-Gaussian reduction over 32 pixel lanes (the upstream
-// bottleneck): the 4 pixel-slot partials are folded once per chunk and committed with
+// bottleneck): the pixel-slot partials are folded once per chunk and committed with
 // vector RED.ADD.F32 (2 x v4 + 1 scalar per Gaussian per warp).
-//   dL/dalpha_i = T_i (c_i . g) - [ sum_{j behind i} w_j (c_j . g) + T_final (bg . g) ] / (1 - alpha_i)
-// Per-pixel running state {T behind, sum behind} lives in shared memory between chunks.
+//   dL/dalpha_i = [ T_i (c_i . g) - sum_{j behind i, j included} w_j (c_j . g) - T_final (bg . g) ] / (1 - alpha_i)
+// Per-pixel running state {T behind, -(sum behind)} lives in shared memory between chunks.
+//
+// The kernel is instruction-issue bound (ncu round 1: 140 M warp instructions, DRAM 3 %).  Two things cut the
+// instruction count of the pixel step almost in half:
+//   * the two pixels of a lane share dy and their dx differ by the constant 4, so dx, dx^2 and the dx^2 term of
+//     the exponent are per-CHUNK constants, and the y moments are accumulated once for the pair;
+//   * everything else runs on packed FP32 pairs (FFMA2 / FMUL2 / FADD2, f32x2.cuh): one issue slot per two
+//     float operations, including the scan's combine step.
+// Signs are arranged so that no negation is ever issued: the opacity is negated once per chunk (n_alpha = -alpha
+// falls out of the multiply), the state carries -R, and the colour sums come out negated and are fixed at commit.
+#include "f32x2.cuh"
 #include "render_common.cuh"
 
 namespace ggrt {
 
-// EXPERIMENTAL, off by default: two 4x4 half-block queues per warp instead of
-// one 8x4 queue -- the CPU step model predicts -25 % pixel steps, +49 % chunks; measured once at C2: 174.0 -> 167.5 us,
-// parity + edge-case tests green.  To become the default it still needs the full GPU suite.
-#ifndef GGRT_BWD_HALVES
-#define GGRT_BWD_HALVES 0
-#endif
 #ifndef GGRT_BWD_BATCH
-#define GGRT_BWD_BATCH (GGRT_BWD_HALVES ? 384 : 512)  // the half queues need shared memory: keep 4 CTAs per SM
+#define GGRT_BWD_BATCH 512
 #endif
 #ifndef GGRT_BWD_MINBLOCKS
 #define GGRT_BWD_MINBLOCKS 4
 #endif
 constexpr int BWD_BATCH = GGRT_BWD_BATCH;
 constexpr int NWARPS = BWD_WARPS;
-#ifndef GGRT_BWD_PIX_UNROLL
-#define GGRT_BWD_PIX_UNROLL 2
+#ifndef GGRT_BWD_ROW_UNROLL
+#define GGRT_BWD_ROW_UNROLL 2
 #endif
-constexpr int PIX_UNROLL = GGRT_BWD_PIX_UNROLL;
-#ifndef GGRT_BWD_GL
-#define GGRT_BWD_GL 8
-#endif
-constexpr int GL = GGRT_BWD_GL;   // Gaussians per warp step (power of two <= 32)
-constexpr int PL = 32 / GL;       // pixels per warp step
-constexpr int NHALF = GGRT_BWD_HALVES ? 2 : 1;  // queues per warp
-static_assert(!GGRT_BWD_HALVES || PL == 4, "half-block queues assume 4-pixel groups (one half-row each)");
+constexpr int ROW_UNROLL = GGRT_BWD_ROW_UNROLL;
+constexpr int GL = 8;  // Gaussians per warp step
+constexpr int QL = 4;  // pixel slots per warp step (each slot = the pixel pair (q, q + 4) of one row)
 
 __device__ __forceinline__ void red_add(float* addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
@@ -52,7 +52,46 @@ __device__ __forceinline__ void red_add(float* addr, float v) {
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+__device__ __forceinline__ f2 lds_f2(uint32_t a) {
+    f2 v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v.v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lds_2f2(uint32_t a, f2& x, f2& y) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(x.v), "=l"(y.v) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void sts_2f2(uint32_t a, f2 x, f2 y) {
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(a), "l"(x.v), "l"(y.v) : "memory");
+}
 
+// One level of the segmented scan over the GL = 8 Gaussian slots (consecutive lanes): (A, nB) <- (A Ap, nB Ap + nBp)
+// where (Ap, nBp) come from the lane d slots further back; lanes without such a lane keep their values (the shuffle's
+// in-range predicate drives the two packed operations, no compare, no select).
+__device__ __forceinline__ void scan_step(f2& A, f2& nB, int d, int gl) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 alo, ahi, blo, bhi;\n\t"
+        ".reg .b64 ap, bp;\n\t"
+        "mov.b64 {alo, ahi}, %0;\n\t"
+        "mov.b64 {blo, bhi}, %1;\n\t"
+        "setp.ge.s32 p, %3, %2;\n\t"
+        "shfl.sync.up.b32 alo, alo, %2, 0x1800, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 ahi, ahi, %2, 0x1800, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 blo, blo, %2, 0x1800, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 bhi, bhi, %2, 0x1800, 0xffffffff;\n\t"
+        "mov.b64 ap, {alo, ahi};\n\t"
+        "mov.b64 bp, {blo, bhi};\n\t"
+        "@p fma.rn.f32x2 %1, %1, ap, bp;\n\t"
+        "@p mul.rn.f32x2 %0, %0, ap;\n\t"
+        "}"
+        : "+l"(A.v), "+l"(nB.v)
+        : "r"(d), "r"(gl));
+}
+
+// Per-warp pixel tables, indexed by pair slot j = row * 4 + q (pixels (q, row) = "A" and (q + 4, row) = "B"):
+//   spix[j] = {g_r A, g_r B, g_g A, g_g B | g_b A, g_b B, last A (bits), last B (bits) |
+//              T behind A, T behind B, -(sum behind) A, -(sum behind) B}          sga[j] = {g_aux A, g_aux B}
 // AUX: the 4th blended channel (out_depth) also carries an upstream gradient.
 template <bool AUX>
 __global__ void __launch_bounds__(BWD_THREADS, GGRT_BWD_MINBLOCKS * 8 / BWD_WARPS)
@@ -64,10 +103,8 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
     __shared__ __align__(16) unsigned char srec[BWD_BATCH * REC_BYTES];
     __shared__ uint32_t sid[BWD_BATCH];
     __shared__ unsigned short squeue[NWARPS][BWD_BATCH];
-    __shared__ unsigned short shalf[GGRT_BWD_HALVES ? NWARPS : 1][2][GGRT_BWD_HALVES ? BWD_BATCH : 1];
-    __shared__ float4 spix_g[NWARPS][32];   // per pixel {g_r, g_g, g_b, bits(last)}
-    __shared__ float4 spix_s[NWARPS][32];   // per pixel {x, y, T behind, sum behind}
-    __shared__ float spix_a[AUX ? NWARPS : 1][32];  // per pixel gradient of the aux channel
+    __shared__ __align__(16) float spix[NWARPS][16][12];  // per pair slot: sg0 | sg1 | sst (48 B, one base register)
+    __shared__ __align__(8) float sga[AUX ? NWARPS : 1][16][2];
     __shared__ uint32_t block_last_s;
 
     const uint32_t sbase = smem_addr(srec);
@@ -81,7 +118,8 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
     // ---- per-pixel constants / initial state (lane = pixel here) -------------------------------
     uint32_t last = 0;
     {
-        const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+        const int lx = lane & 7, ly = lane >> 3;
+        const int px = bx0 + lx, py = by0 + ly;
         float Tfin = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, da = 0.f;
         if (px < v.W && py < v.H) {
             const size_t pix = (size_t)py * v.W + px, hw = (size_t)v.H * v.W;
@@ -94,10 +132,13 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
         }
         // pixels with a zero upstream gradient contribute nothing (crop training leaves most tiles empty)
         if (d0 == 0.f && d1 == 0.f && d2 == 0.f && da == 0.f) last = 0;
-        if (AUX) spix_a[warp][lane] = da;
         const float bg_dot = v.bg[0] * d0 + v.bg[1] * d1 + v.bg[2] * d2;
-        spix_g[warp][lane] = make_float4(d0, d1, d2, __uint_as_float(last));
-        spix_s[warp][lane] = make_float4((float)px, (float)py, Tfin, Tfin * bg_dot);
+        const int j = ly * 4 + (lx & 3), h = lx >> 2;  // pair slot, half (0 = A, 1 = B)
+        float* sp = spix[warp][j];
+        sp[h] = d0, sp[2 + h] = d1;
+        sp[4 + h] = d2, sp[6 + h] = __uint_as_float(last);
+        sp[8 + h] = Tfin, sp[10 + h] = -(Tfin * bg_dot);
+        if (AUX) sga[warp][j][h] = da;
     }
     if (tid == 0) block_last_s = 0;
     __syncthreads();
@@ -106,11 +147,13 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
     __syncthreads();
     const uint32_t block_last = block_last_s;
     if (block_last == 0) return;
-    const uint32_t pmask = __ballot_sync(0xffffffffu, last > 0);  // pixels of this warp that matter
+    const uint32_t pmask = __ballot_sync(0xffffffffu, last > 0);  // pixels of this warp that matter (bit = ly*8 + lx)
 
     const float neg_half_w = -0.5f * (float)v.W, neg_half_h = -0.5f * (float)v.H;
-    const uint32_t gaddr = smem_addr(&spix_g[warp][0]), saddr = smem_addr(&spix_s[warp][0]);
-    const float* aux_g = &spix_a[AUX ? warp : 0][0];
+    const int gl = lane & (GL - 1), q = lane / GL;
+    const uint32_t paddr = smem_addr(&spix[warp][q][0]);  // + row * 192 (4 pair slots of 48 B per row)
+    const float* aux_g = &sga[AUX ? warp : 0][q][0];
+    const float xq = bx0f + (float)q;  // x of this lane's pixel A; pixel B is 4 to the right
 
     const int nb = (int)((block_last + BWD_BATCH - 1) / BWD_BATCH);
     for (int bi = nb - 1; bi >= 0; --bi) {
@@ -145,39 +188,10 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
         }
         __syncwarp();
 
-        // ---- GL queued Gaussians at a time.  Lane tiling: lane = (pixel slot q, Gaussian slot gl); the warp
-        // processes GL Gaussians x PL = 32/GL pixels per step, so the scan has log2(GL) levels and the per-pixel
-        // work is shared by fewer idle lanes.  The PL partial accumulators of a Gaussian are combined at the end.
-        const int gl = lane & (GL - 1), q = lane / GL;
-        uint32_t qh0 = 0, qh1 = 0;
-        if (GGRT_BWD_HALVES) {
-            // second-level cull, over the survivors only: which of the two 4x4 half blocks does each queued Gaussian
-            // reach?  Order (back to front) is preserved.  A Gaussian that misses a half is inactive at every pixel of
-            // it, i.e. the identity of the (T, R) recurrence there, so leaving it out of that half's queue is exact.
-            for (uint32_t e0 = 0; e0 < qn; e0 += 32) {
-                const uint32_t e = e0 + lane;
-                bool hit_l = false, hit_r = false;
-                unsigned short j = 0;
-                if (e < qn) {
-                    j = squeue[warp][e];
-                    const float4 a = lds128(sbase + (uint32_t)j * REC_BYTES);
-                    const float4 c = lds128(sbase + (uint32_t)j * REC_BYTES + 16);
-                    hit_l = ellipse_hits_rect(a.x, a.y, a.z, c.x, c.y, c.z, bx0f, by0f, 3.0f, 3.0f);
-                    hit_r = ellipse_hits_rect(a.x, a.y, a.z, c.x, c.y, c.z, bx0f + 4.0f, by0f, 3.0f, 3.0f);
-                }
-                const uint32_t ml = __ballot_sync(0xffffffffu, hit_l), mr = __ballot_sync(0xffffffffu, hit_r);
-                const uint32_t below = (1u << lane) - 1u;
-                if (hit_l) shalf[GGRT_BWD_HALVES ? warp : 0][0][qh0 + __popc(ml & below)] = j;
-                if (hit_r) shalf[GGRT_BWD_HALVES ? warp : 0][1][qh1 + __popc(mr & below)] = j;
-                qh0 += __popc(ml), qh1 += __popc(mr);
-            }
-            __syncwarp();
-        }
-        for (int half = 0; half < NHALF; ++half) {
-        const unsigned short* queue = GGRT_BWD_HALVES ? shalf[GGRT_BWD_HALVES ? warp : 0][half] : squeue[warp];
-        const uint32_t qcount = GGRT_BWD_HALVES ? (half == 0 ? qh0 : qh1) : qn;
-        for (uint32_t c0 = 0; c0 < qcount; c0 += GL) {
-            const bool valid = c0 + gl < qcount;
+        // ---- 8 queued Gaussians at a time; lane = (pixel slot q, Gaussian slot gl) ------------------
+        const unsigned short* queue = squeue[warp];
+        for (uint32_t c0 = 0; c0 < qn; c0 += GL) {
+            const bool valid = c0 + gl < qn;
             const uint32_t jj = valid ? queue[c0 + gl] : 0u;
             const uint32_t src = sbase + jj * REC_BYTES;
             const float2 gxy = lds64(src);
@@ -188,68 +202,75 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
             asm volatile("" : "+r"(pos));  // keep the select: otherwise `valid` is re-tested in every pixel step
             // exponent of the Gaussian in base 2 with the -1/2 folded in: G = 2^(ea dx^2 + eb dx dy + ec dy^2)
             const float ea = -0.5f * LOG2E * con.x, eb = -LOG2E * con.y, ec = -0.5f * LOG2E * con.z;
-            float a_op = 0.f, a_mx = 0.f, a_my = 0.f, a_A = 0.f, a_B = 0.f, a_C = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f;
-            float a_x = 0.f;  // aux channel
+            const float ncw = -con.w;
+            // per-chunk constants of this lane's pixel pair: dx (B is 4 px to the right of A), dx^2, ea dx^2
+            const float dxa = gxy.x - xq;
+            const f2 dx2 = pk(dxa, dxa - 4.0f);
+            const f2 pa2 = mul2(bc(ea), mul2(dx2, dx2));
+            const float gyr = gxy.y - by0f;
+            f2 a_op2 = bc(0.f), a_mx2 = bc(0.f), a_A2 = bc(0.f), a_B2 = bc(0.f);
+            f2 a_r2 = bc(0.f), a_g2 = bc(0.f), a_b2 = bc(0.f), a_x2 = bc(0.f);  // colour sums come out NEGATED
+            float a_my = 0.f, a_C = 0.f;
 
-            // pixel groups: group t holds pixels t*PL .. t*PL+PL-1, one per pixel slot (with half-block queues the
-            // even groups are the left 4x4 half, the odd ones the right half)
-#pragma unroll PIX_UNROLL
-            for (int tt = 0; tt < 32 / PL / NHALF; ++tt) {
-                const int t = tt * NHALF + half;
-                if (((pmask >> (t * PL)) & ((1u << PL) - 1u)) == 0) continue;  // no pixel of the group matters
-                const int p = t * PL + q;
-                const float4 pg = lds128(gaddr + p * 16);   // {g_r, g_g, g_b, last}
-                const float4 ps = lds128(saddr + p * 16);   // {x, y, T behind, sum behind}
-                const float dx = gxy.x - ps.x, dy = gxy.y - ps.y;
-                const float dxx = dx * dx, dyy = dy * dy, dxy = dx * dy;
-                const float power2 = fmaf(ea, dxx, fmaf(ec, dyy, eb * dxy));  // log2 of the Gaussian
-                const float G = ex2_approx(power2);
-                const float alpha_raw = fminf(ALPHA_MAX, con.w * G);
-                const bool act = (pos < __float_as_uint(pg.w)) && (power2 <= 0.0f) && (alpha_raw >= ALPHA_MIN);
-                const float alpha = act ? alpha_raw : 0.f;
-                const float inv_om = rcp_approx(1.0f - alpha);
-                float sdot = fmaf(col.z, pg.z, fmaf(col.y, pg.y, col.x * pg.x));
-                float ga = 0.f;
-                if (AUX) {
-                    ga = aux_g[p];
-                    sdot = fmaf(col.w, ga, sdot);
-                }
-                // Going back to front each Gaussian maps the running pair (T, R) to (a T, R + b T) with
-                // a = 1/(1-alpha), b = alpha (c.g)/(1-alpha).  These maps compose associatively, so ONE
-                // segmented warp scan (slot 0 = backmost) yields every lane's transmittance and the sum behind it.
-                float A = inv_om, B = alpha * sdot * inv_om;
 #pragma unroll
-                for (int d = 1; d < GL; d <<= 1) {
-                    const float Ap = __shfl_up_sync(0xffffffffu, A, d, GL);
-                    const float Bp = __shfl_up_sync(0xffffffffu, B, d, GL);
-                    if (gl >= d) {
-                        B = fmaf(B, Ap, Bp);
-                        A *= Ap;
-                    }
+            for (int row = 0; row < 4; ++row) {
+                if (((pmask >> (row * 8)) & 0xffu) == 0) continue;  // no pixel of the row matters
+                const uint32_t off = paddr + (uint32_t)row * 192u;  // an immediate offset once the loop is unrolled
+                f2 gr2, gg2, gb2, last2, Tb2, nRb2;
+                lds_2f2(off, gr2, gg2);
+                lds_2f2(off + 16, gb2, last2);
+                lds_2f2(off + 32, Tb2, nRb2);
+                const float dy = gyr - (float)row;
+                // log2 of the Gaussian at both pixels: ea dx^2 + (eb dx + ec dy) dy
+                const f2 pw2 = fma2(fma2(bc(eb), dx2, bc(ec * dy)), bc(dy), pa2);
+                const float pwa = lo(pw2), pwb = hi(pw2);
+                const float Ga = ex2_approx(pwa), Gb = ex2_approx(pwb);
+                const f2 G2 = pk(Ga, Gb);
+                const f2 arn2 = mul2(bc(ncw), G2);  // -(opacity * G)
+                const float arna = fmaxf(-ALPHA_MAX, lo(arn2)), arnb = fmaxf(-ALPHA_MAX, hi(arn2));
+                const bool acta = (pos < __float_as_uint(lo(last2))) && (pwa <= 0.0f) && (arna <= -ALPHA_MIN);
+                const bool actb = (pos < __float_as_uint(hi(last2))) && (pwb <= 0.0f) && (arnb <= -ALPHA_MIN);
+                const f2 nal2 = pk(acta ? arna : 0.f, actb ? arnb : 0.f);  // -alpha
+                const f2 om2 = add2(bc(1.0f), nal2);
+                const f2 io2 = pk(rcp_approx(lo(om2)), rcp_approx(hi(om2)));  // 1 / (1 - alpha)
+                f2 sdot2 = fma2(bc(col.z), gb2, fma2(bc(col.y), gg2, mul2(bc(col.x), gr2)));
+                f2 ga2 = bc(0.f);
+                if (AUX) {
+                    ga2 = lds_f2(smem_addr(aux_g) + (uint32_t)row * 32u);
+                    sdot2 = fma2(bc(col.w), ga2, sdot2);
                 }
-                const float Ti = ps.z * A;                   // transmittance in front of this Gaussian
-                const float w = alpha * Ti;
-                const float Rtot = fmaf(ps.z, B, ps.w);      // sum behind, this Gaussian included
-                const float dL_dalpha = fmaf(Ti, sdot, -(Rtot - w * sdot) * inv_om);
-                const float qv = act ? G * dL_dalpha : 0.f;
-                const float tq = con.w * qv;
-                a_op += qv;
-                a_mx = fmaf(tq, dx, a_mx);  // first moments; the conic is applied once per chunk below
-                a_my = fmaf(tq, dy, a_my);
-                a_A = fmaf(tq, dxx, a_A);
-                a_B = fmaf(tq, dxy, a_B);
-                a_C = fmaf(tq, dyy, a_C);
-                a_r = fmaf(w, pg.x, a_r);
-                a_g = fmaf(w, pg.y, a_g);
-                a_b = fmaf(w, pg.z, a_b);
-                if (AUX) a_x = fmaf(w, ga, a_x);
-                if (gl == GL - 1) {  // frontmost slot holds the chunk totals: state behind the next chunk
-                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr + p * 16 + 8), "f"(Ti), "f"(Rtot)
-                                 : "memory");
-                }
+                // Going back to front each Gaussian maps the running pair (T, -R) to (a T, -R + nb T) with
+                // a = 1/(1-alpha), nb = -alpha (c.g)/(1-alpha).  These maps compose associatively, so ONE
+                // segmented warp scan (slot 0 = backmost) yields every lane's transmittance and the sum behind it.
+                f2 A2 = io2, nB2 = mul2(mul2(nal2, sdot2), io2);
+#pragma unroll
+                for (int d = 1; d < GL; d <<= 1) scan_step(A2, nB2, d, gl);
+                const f2 Ti2 = mul2(Tb2, A2);            // transmittance in front of this Gaussian
+                const f2 nRt2 = fma2(Tb2, nB2, nRb2);    // -(sum behind, this Gaussian included)
+                const f2 dLa2 = mul2(fma2(Ti2, sdot2, nRt2), io2);  // dL/dalpha
+                const f2 qg2 = mul2(G2, dLa2);
+                const f2 qv2 = pk(acta ? lo(qg2) : 0.f, actb ? hi(qg2) : 0.f);
+                const f2 tq2 = mul2(bc(con.w), qv2);
+                const f2 nw2 = mul2(nal2, Ti2);          // -(blend weight)
+                a_op2 = add2(a_op2, qv2);
+                const f2 inc2 = mul2(tq2, dx2);          // first x moment; the conic is applied once per chunk below
+                a_mx2 = add2(a_mx2, inc2);
+                a_B2 = fma2(inc2, bc(dy), a_B2);
+                a_A2 = fma2(inc2, dx2, a_A2);
+                const float sd = (lo(tq2) + hi(tq2)) * dy;  // the pair shares dy: y moments once for both pixels
+                a_my += sd;
+                a_C = fmaf(sd, dy, a_C);
+                a_r2 = fma2(nw2, gr2, a_r2);
+                a_g2 = fma2(nw2, gg2, a_g2);
+                a_b2 = fma2(nw2, gb2, a_b2);
+                if (AUX) a_x2 = fma2(nw2, ga2, a_x2);
+                if (gl == GL - 1) sts_2f2(off + 32, Ti2, nRt2);  // frontmost slot: state behind the next chunk
             }
             __syncwarp();
-            // combine the PL pixel-slot partials of each Gaussian (lanes gl, gl+GL, ...)
+            // fold the pair, then the QL pixel-slot partials of each Gaussian (lanes gl, gl+GL, ...)
+            float a_op = lo(a_op2) + hi(a_op2), a_mx = lo(a_mx2) + hi(a_mx2), a_A = lo(a_A2) + hi(a_A2),
+                  a_B = lo(a_B2) + hi(a_B2), a_r = lo(a_r2) + hi(a_r2), a_g = lo(a_g2) + hi(a_g2),
+                  a_b = lo(a_b2) + hi(a_b2), a_x = lo(a_x2) + hi(a_x2);
 #pragma unroll
             for (int d = GL; d < 32; d <<= 1) {
                 a_op += __shfl_xor_sync(0xffffffffu, a_op, d);
@@ -268,12 +289,11 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
                 // scratch rows are 48 B (16-B aligned): slots {mx,my,A,B} {C,op,r,g} {b}
                 const float gmx = fmaf(con.x, a_mx, con.y * a_my), gmy = fmaf(con.z, a_my, con.y * a_mx);
                 red_add_v4(dst + G_MX, gmx * neg_half_w, gmy * neg_half_h, -0.5f * a_A, -0.5f * a_B);
-                red_add_v4(dst + G_CC, -0.5f * a_C, a_op, a_r, a_g);
-                red_add(dst + G_B, a_b);
-                if (AUX) red_add(dst + G_AUX, a_x);
+                red_add_v4(dst + G_CC, -0.5f * a_C, a_op, -a_r, -a_g);
+                red_add(dst + G_B, -a_b);
+                if (AUX) red_add(dst + G_AUX, -a_x);
             }
         }
-        }  // half
     }
 }
 
