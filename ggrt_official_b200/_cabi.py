@@ -42,7 +42,9 @@ class InputLayout(C.Structure):
 class GradSinks(C.Structure):
     """struct GgrtRasterGradSinks"""
 
-    _fields_ = [("count", C.c_int32), ("multimem", C.c_int32), ("ptr", C.c_void_p * 16)]
+    _fields_ = [("count", C.c_int32), ("multimem", C.c_int32), ("ptr", C.c_void_p * 16),
+                ("epoch", C.c_void_p), ("done_counter", C.c_void_p), ("parity_stride", C.c_int64),
+                ("arrive_count", C.c_int32), ("reserved", C.c_int32), ("arrive", C.c_void_p * 16)]
 
 
 class AdapterParams(C.Structure):
@@ -74,7 +76,9 @@ EXPORTS = (
     "ggrt_raster_join",
     "ggrt_raster_backward",
     "ggrt_raster_sh_gradient_merge",
+    "ggrt_raster_sh_gradient_merge_signalled",
     "ggrt_raster_nvls_allreduce_f32",
+    "ggrt_raster_nvls_allreduce_signalled",
     "ggrt_raster_nvls_barrier",
     "ggrt_adapter_forward",
     "ggrt_adapter_backward",
@@ -118,7 +122,10 @@ def lib():
                                        + [C.POINTER(GradSinks), vp])
     L.ggrt_raster_sh_gradient_merge.argtypes = [i32, i32, C.POINTER(InputLayout), vp, i32, C.POINTER(vp), C.POINTER(vp),
                                                 vp, vp]
+    L.ggrt_raster_sh_gradient_merge_signalled.argtypes = [i32, i32, C.POINTER(InputLayout), vp, i32, vp, i64, i64, vp, vp,
+                                                          vp, vp]
     L.ggrt_raster_nvls_allreduce_f32.argtypes = [vp, i64, i32, i32, vp]
+    L.ggrt_raster_nvls_allreduce_signalled.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp]
     L.ggrt_raster_nvls_barrier.argtypes = [vp, vp, u32, vp]
     L.ggrt_adapter_forward.argtypes = [C.POINTER(AdapterParams)] + [vp] * 12
     L.ggrt_adapter_backward.argtypes = [C.POINTER(AdapterParams)] + [vp] * 13

@@ -64,7 +64,20 @@ struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
     bool pending = false;
+    unsigned long long capture_id = 0;  // stream-capture sequence the join event was last recorded in (0: none)
 };
+
+// id of the CUDA-graph capture `s` is part of (0 when it is not capturing).  An event recorded inside a capture can
+// only be waited on inside the same capture and vice versa, so the fork/join of the colour kernel is matched by id.
+static unsigned long long capture_id_of(cudaStream_t s) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    unsigned long long id = 0;
+    if (cudaStreamGetCaptureInfo(s, &st, &id) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return st == cudaStreamCaptureStatusActive ? (id ? id : 1ull) : 0ull;
+}
 constexpr int MAX_DEVICES = 64;
 static thread_local SideStream g_side[MAX_DEVICES];
 
@@ -295,6 +308,7 @@ int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, const GgrtRa
         GGRT_TRY(check_launch("color", 0, ss->stream));
         if (cudaEventRecord(ss->join, ss->stream) != cudaSuccess) return check_launch("color join", 0, s);
         ss->pending = true;
+        ss->capture_id = capture_id_of(s);
     } else {
         ss = nullptr;
     }
@@ -340,9 +354,12 @@ int ggrt_raster_forward_render(const GgrtRasterSettings* settings, int32_t P, in
     }
     {  // join the colour kernel that `prepare` forked (a later event of the in-order side stream covers earlier ones)
         int dev = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < MAX_DEVICES && g_side[dev].pending) {
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < MAX_DEVICES && g_side[dev].pending &&
+            g_side[dev].capture_id == capture_id_of(s)) {
             // `pending` is never cleared: renders of interleaved prepares on other streams must wait as well, and
-            // waiting on an event that has already completed costs nothing on the device
+            // waiting on an event that has already completed costs nothing on the device.  (An event last recorded
+            // inside another graph capture -- or outside, while `s` is capturing -- belongs to a frame that is not
+            // this one: nothing to wait for, and waiting across a capture boundary is an error.)
             if (cudaStreamWaitEvent(s, g_side[dev].join, 0) != cudaSuccess) return check_launch("color join", 0, s);
         }
     }
@@ -357,7 +374,8 @@ int ggrt_raster_join(ggrt_stream_t stream) {
     // allocation failure, say) calls it so that the buffers prepare was given can be released safely.
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return check_launch("join", 0, nullptr);
-    if (g_side[dev].pending && cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), g_side[dev].join, 0) != cudaSuccess)
+    if (g_side[dev].pending && g_side[dev].capture_id == capture_id_of(static_cast<cudaStream_t>(stream)) &&
+        cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), g_side[dev].join, 0) != cudaSuccess)
         return check_launch("join", 0, static_cast<cudaStream_t>(stream));
     return GGRT_OK;
 }
@@ -404,6 +422,24 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
             sinks.ptr[k] = color_sinks->ptr[k];
         }
         sinks.n = color_sinks->count, sinks.multimem = color_sinks->multimem != 0, sinks.with_campos = 1;
+        if (color_sinks->epoch != nullptr) {  // in-kernel step signalling
+            const int na = color_sinks->arrive_count;
+            if (!color_sinks->done_counter || na < 1 || na > GGRT_RASTER_MAX_MERGE_VIEWS ||
+                (color_sinks->multimem && na != 1) || color_sinks->parity_stride < 0 || (color_sinks->parity_stride & 3)) {
+                set_error("backward: signalling needs done_counter, 1..%d arrival counters (1 with multimem) and a "
+                          "parity_stride that is a non-negative multiple of 4 floats", GGRT_RASTER_MAX_MERGE_VIEWS);
+                return GGRT_ERR_INVALID_ARGUMENT;
+            }
+            for (int k = 0; k < na; ++k) {
+                if (!color_sinks->arrive[k] || (reinterpret_cast<uintptr_t>(color_sinks->arrive[k]) & 3)) {
+                    set_error("backward: color_sinks->arrive[%d] must be a 4-byte aligned device pointer", k);
+                    return GGRT_ERR_INVALID_ARGUMENT;
+                }
+                sinks.arrive[k] = color_sinks->arrive[k];
+            }
+            sinks.epoch = color_sinks->epoch, sinks.done = color_sinks->done_counter;
+            sinks.parity_stride = color_sinks->parity_stride, sinks.n_arrive = na;
+        }
     } else if (shs != nullptr && dL_dcolors != nullptr) {
         sinks.ptr[0] = dL_dcolors, sinks.n = 1;
     }
@@ -458,8 +494,46 @@ int ggrt_raster_sh_gradient_merge(int32_t P, int32_t sh_degree, const GgrtRaster
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     launch_sh_gradient_merge(P, sh_degree, scale, cmajor, means3D, num_views, drgb_views_host, campos_views_host,
-                             dL_dsh, s);
+                             dL_dsh, MergeSignal(), s);
     return check_launch("sh_gradient_merge", 0, s);
+}
+
+int ggrt_raster_sh_gradient_merge_signalled(int32_t P, int32_t sh_degree, const GgrtRasterInputLayout* layout,
+                                            const float* means3D, int32_t world, const float* slots,
+                                            int64_t slot_stride, int64_t parity_stride, const uint32_t* epoch,
+                                            const uint32_t* arrive, float* dL_dsh, ggrt_stream_t stream) {
+    if (P < 0 || sh_degree < 0 || sh_degree > 4 || world < 1 || world > GGRT_RASTER_MAX_MERGE_VIEWS ||
+        slot_stride < 3LL * (P + 1) || parity_stride < slot_stride * world) {
+        set_error("sh_gradient_merge_signalled: bad sizes (P=%d, sh_degree=%d, world=%d, at most %d ranks; slots are "
+                  "[P+1,3] floats)", P, sh_degree, world, GGRT_RASTER_MAX_MERGE_VIEWS);
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    if (!slots || !epoch || !arrive || (P > 0 && (!means3D || !dL_dsh))) {
+        set_error("sh_gradient_merge_signalled: NULL buffer");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    float scale = 1.0f;
+    bool cmajor = false;
+    if (layout) {
+        if (!(layout->scene_scale > 0.f)) {
+            set_error("scene_scale must be positive");
+            return GGRT_ERR_INVALID_ARGUMENT;
+        }
+        scale = layout->scene_scale;
+        cmajor = layout->sh_channel_major != 0;
+    }
+    const float* drgb[GGRT_RASTER_MAX_MERGE_VIEWS];
+    const float* campos[GGRT_RASTER_MAX_MERGE_VIEWS];
+    for (int v = 0; v < world; ++v) drgb[v] = slots + (size_t)v * slot_stride, campos[v] = drgb[v] + 3 * (size_t)P;
+    MergeSignal sig;
+    sig.epoch = epoch, sig.arrive = arrive, sig.world = world, sig.parity_stride = parity_stride;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (P == 0) {
+        set_error("sh_gradient_merge_signalled: P = 0 is not supported (the kernel is the step's wait)");
+        return GGRT_ERR_UNSUPPORTED;
+    }
+    launch_sh_gradient_merge(P, sh_degree, scale, cmajor, means3D, world, drgb, campos, dL_dsh, sig, s);
+    return check_launch("sh_gradient_merge_signalled", 0, s);
 }
 
 int ggrt_raster_nvls_allreduce_f32(void* multicast_ptr, int64_t count, int32_t rank, int32_t world,
@@ -470,8 +544,25 @@ int ggrt_raster_nvls_allreduce_f32(void* multicast_ptr, int64_t count, int32_t r
         return GGRT_ERR_INVALID_ARGUMENT;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    launch_nvls_allreduce(static_cast<float*>(multicast_ptr), count, rank, world, s);
+    launch_nvls_allreduce(static_cast<float*>(multicast_ptr), count, rank, world, nullptr, nullptr, nullptr, nullptr,
+                          nullptr, s);
     return check_launch("nvls_allreduce", 0, s);
+}
+
+int ggrt_raster_nvls_allreduce_signalled(void* multicast_ptr, int64_t count, int32_t rank, int32_t world,
+                                         const uint32_t* epoch, const uint32_t* arrive_in, void* arrive_out_multicast,
+                                         const uint32_t* arrive_out, uint32_t* done_counter, ggrt_stream_t stream) {
+    if (!multicast_ptr || count < 0 || (count & 3) || world < 1 || rank < 0 || rank >= world ||
+        (reinterpret_cast<uintptr_t>(multicast_ptr) & 15) || !epoch || !arrive_in || !arrive_out_multicast || !arrive_out ||
+        !done_counter) {
+        set_error("nvls_allreduce_signalled: bad argument (count must be a multiple of 4, pointers non-NULL, data "
+                  "pointer 16-byte aligned)");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    launch_nvls_allreduce(static_cast<float*>(multicast_ptr), count, rank, world, epoch, arrive_in,
+                          static_cast<uint32_t*>(arrive_out_multicast), arrive_out, done_counter, s);
+    return check_launch("nvls_allreduce_signalled", 0, s);
 }
 
 int ggrt_raster_nvls_barrier(void* multicast_counter, const void* local_counter, uint32_t target, ggrt_stream_t stream) {

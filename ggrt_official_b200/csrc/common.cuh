@@ -71,7 +71,39 @@ struct ColorSinks {
     int n;
     int multimem;     // ptr[0] is an NVLS multicast address: use multimem.st
     int with_campos;
+    // step signalling (GgrtRasterGradSinks.epoch): see include/ggrt_raster.h
+    uint32_t* epoch;
+    uint32_t* done;
+    long long parity_stride;
+    int n_arrive;
+    uint32_t* arrive[GGRT_RASTER_MAX_MERGE_VIEWS];
 };
+
+// ---- cross-GPU signalling primitives (system scope) -------------------------------------------------------------
+__device__ __forceinline__ void signal_add(uint32_t* counter, bool multimem) {
+    if (multimem)
+        asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+    else
+        asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+}
+__device__ __forceinline__ void wait_reached(const uint32_t* counter, uint32_t target) {
+    uint32_t v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while ((int)(v - target) < 0);  // wrap-around safe
+}
+// Called by every thread of every CTA at the end of a kernel whose global stores must be published to other GPUs:
+// returns true in thread 0 of the LAST CTA to get here, after all CTAs' stores have been fenced at system scope.
+__device__ __forceinline__ bool last_cta_done(uint32_t* done_counter) {
+    __syncthreads();
+    if (threadIdx.x != 0) return false;
+    __threadfence_system();
+    const uint32_t total = gridDim.x * gridDim.y * gridDim.z;
+    if (atomicAdd(done_counter, 1u) != total - 1u) return false;
+    *done_counter = 0u;  // ready for the next launch
+    __threadfence_system();
+    return true;
+}
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
@@ -97,9 +129,18 @@ void launch_preprocess_backward(const View& v, const float* means, const float* 
                                 const int* radii, GeomPtrs g, const float* scratch, float* dmeans2D, float* dopacity,
                                 float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, float* daux, float* dcam,
                                 const ColorSinks& sinks, cudaStream_t s);
+struct MergeSignal {  // signalled exchange: wait for world * *epoch arrivals, read half (*epoch - 1) & 1
+    const uint32_t* epoch = nullptr;
+    const uint32_t* arrive = nullptr;
+    int world = 0;
+    long long parity_stride = 0;
+};
 void launch_sh_gradient_merge(int P, int deg, float scale, bool cmajor, const float* means, int num_views,
-                              const float* const* drgb, const float* const* campos, float* dsh, cudaStream_t s);
-void launch_nvls_allreduce(float* multicast, long long count, int rank, int world, cudaStream_t s);
+                              const float* const* drgb, const float* const* campos, float* dsh, const MergeSignal& sig,
+                              cudaStream_t s);
+void launch_nvls_allreduce(float* multicast, long long count, int rank, int world, const uint32_t* epoch,
+                           const uint32_t* arrive_in, uint32_t* arrive_out_mc, const uint32_t* arrive_out,
+                           uint32_t* done_counter, cudaStream_t s);
 void launch_nvls_barrier(unsigned int* mc_counter, const unsigned int* local_counter, unsigned int target,
                          cudaStream_t s);
 void launch_adapter_forward(const GgrtAdapterParams& p, const float* extr, const float* intr, const float* shrot,

@@ -61,6 +61,10 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     if (threadIdx.x < 16) sV[threadIdx.x] = v.view[threadIdx.x];
     else if (threadIdx.x < 32) sM[threadIdx.x - 16] = v.proj[threadIdx.x - 16];
 
+    // signalled exchange: this step pushes into half (epoch & 1) of every sink
+    const long long poff = sinks.epoch != nullptr
+                               ? (long long)(*reinterpret_cast<volatile uint32_t*>(sinks.epoch) & 1u) * sinks.parity_stride
+                               : 0ll;
     const int row = v.K * 3;
     const bool compact = shs != nullptr && dsh == nullptr;  // uniform: write dL/drgb instead of dL/dsh
     const int ks = CMAJOR ? 1 : 3, cs = CMAJOR ? v.K : 1;  // SH element (k, c) at k*ks + c*cs of the row
@@ -332,7 +336,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             __syncthreads();
             const int n3 = cnt * 3, n4 = n3 >> 2;
             for (int sk = 0; sk < sinks.n; ++sk) {  // every sink is a [P+1,3] buffer: local, a peer's, or multicast
-                float* dstc = sinks.ptr[sk] + (size_t)base * 3;  // slab offsets are multiples of 1536 B
+                float* dstc = sinks.ptr[sk] + poff + (size_t)base * 3;  // slab offsets are multiples of 1536 B
                 const bool mm = sinks.multimem != 0;
                 if ((reinterpret_cast<uintptr_t>(dstc) & 15) == 0) {
                     for (int k = threadIdx.x; k < n4; k += PB_THREADS)
@@ -426,9 +430,14 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     }
     if (compact && sinks.with_campos && blockIdx.x == 0 && threadIdx.x < 3) {  // row P of every sink: this view's camera centre
         for (int sk = 0; sk < sinks.n; ++sk)
-            sink_store1(sinks.ptr[sk] + (size_t)v.P * 3 + threadIdx.x, v.campos[threadIdx.x], sinks.multimem != 0);
+            sink_store1(sinks.ptr[sk] + poff + (size_t)v.P * 3 + threadIdx.x, v.campos[threadIdx.x], sinks.multimem != 0);
     }
     if (threadIdx.x == 0) bulk_wait0();  // all bulk stores of this CTA have completed
+    if (sinks.epoch != nullptr && last_cta_done(sinks.done)) {
+        // every CTA's pushes and plain outputs are fenced: advance the step counter and tell the receivers
+        *reinterpret_cast<volatile uint32_t*>(sinks.epoch) = *reinterpret_cast<volatile uint32_t*>(sinks.epoch) + 1u;
+        for (int k = 0; k < sinks.n_arrive; ++k) signal_add(sinks.arrive[k], sinks.multimem != 0);
+    }
 }
 
 void launch_preprocess_backward(const View& v, const float* means, const float* cov3d, const float* shs,

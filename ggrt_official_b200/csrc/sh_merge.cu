@@ -47,13 +47,28 @@ __device__ __forceinline__ void bulk_wait_read() {
 template <int DEG, bool CMAJOR>
 __global__ void __launch_bounds__(MERGE_THREADS, 3)
 sh_gradient_merge_kernel(int P, float scale, const float* __restrict__ means, MergeViews mv, float* __restrict__ dsh,
-                         int num_slabs) {
+                         int num_slabs, MergeSignal sig) {
     constexpr int K = (DEG + 1) * (DEG + 1);
     constexpr int ROW = 3 * K;
     constexpr int KS = CMAJOR ? 1 : 3, CS = CMAJOR ? K : 1;  // element (k, c) of a row lives at k*KS + c*CS
     extern __shared__ __align__(128) float merge_ring[];
     __shared__ float scam[GGRT_RASTER_MAX_MERGE_VIEWS][3];
-    if (threadIdx.x < 3 * mv.n) scam[threadIdx.x / 3][threadIdx.x % 3] = ld_sys(mv.campos[threadIdx.x / 3] + threadIdx.x % 3);
+    __shared__ long long poff_s;
+    // Signalled exchange: the slots are filled by the peers' backward kernels (pushed over NVLink); wait until all
+    // `world` ranks have signalled the step this GPU's own backward just completed (*epoch), then read that half.
+    if (threadIdx.x == 0) {
+        long long poff = 0;
+        if (sig.epoch != nullptr) {
+            const uint32_t e = *reinterpret_cast<const volatile uint32_t*>(sig.epoch);
+            wait_reached(sig.arrive, e * (uint32_t)sig.world);
+            poff = (long long)((e - 1u) & 1u) * sig.parity_stride;
+        }
+        poff_s = poff;
+    }
+    __syncthreads();
+    const long long poff = poff_s;
+    if (threadIdx.x < 3 * mv.n)
+        scam[threadIdx.x / 3][threadIdx.x % 3] = ld_sys(mv.campos[threadIdx.x / 3] + poff + threadIdx.x % 3);
     __syncthreads();
     const bool aligned = (reinterpret_cast<uintptr_t>(dsh) & 15) == 0;
 
@@ -68,7 +83,7 @@ sh_gradient_merge_kernel(int P, float scale, const float* __restrict__ means, Me
         for (int u = 0; u < MERGE_GROUP; ++u) {
             n_g[u][0] = n_g[u][1] = n_g[u][2] = 0.f;
             if (ok && u < mv.n) {
-                const float* src = mv.drgb[u] + 3 * (size_t)i;
+                const float* src = mv.drgb[u] + poff + 3 * (size_t)i;
                 n_g[u][0] = ld_sys(src), n_g[u][1] = ld_sys(src + 1), n_g[u][2] = ld_sys(src + 2);
             }
         }
@@ -100,7 +115,7 @@ sh_gradient_merge_kernel(int P, float scale, const float* __restrict__ means, Me
                 for (int u = 0; u < MERGE_GROUP; ++u) {
                     g[u][0] = g[u][1] = g[u][2] = 0.f;
                     if (valid && v0 + u < mv.n) {
-                        const float* src = mv.drgb[v0 + u] + 3 * (size_t)i;
+                        const float* src = mv.drgb[v0 + u] + poff + 3 * (size_t)i;
                         g[u][0] = ld_sys(src), g[u][1] = ld_sys(src + 1), g[u][2] = ld_sys(src + 2);
                     }
                 }
@@ -146,7 +161,7 @@ sh_gradient_merge_kernel(int P, float scale, const float* __restrict__ means, Me
 
 template <int DEG>
 static void launch_merge_deg(int P, float scale, bool cmajor, const float* means, const MergeViews& mv, float* dsh,
-                             cudaStream_t s) {
+                             const MergeSignal& sig, cudaStream_t s) {
     constexpr int K = (DEG + 1) * (DEG + 1);
     const size_t smem = (size_t)MERGE_STAGES * MERGE_THREADS * 3 * K * sizeof(float);
     const int num_slabs = (P + MERGE_THREADS - 1) / MERGE_THREADS;
@@ -158,16 +173,17 @@ static void launch_merge_deg(int P, float scale, bool cmajor, const float* means
     if (cmajor && K > 1) {
         if (smem > 32 * 1024)
             cudaFuncSetAttribute(sh_gradient_merge_kernel<DEG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sh_gradient_merge_kernel<DEG, true><<<grid, MERGE_THREADS, smem, s>>>(P, scale, means, mv, dsh, num_slabs);
+        sh_gradient_merge_kernel<DEG, true><<<grid, MERGE_THREADS, smem, s>>>(P, scale, means, mv, dsh, num_slabs, sig);
     } else {
         if (smem > 32 * 1024)
             cudaFuncSetAttribute(sh_gradient_merge_kernel<DEG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sh_gradient_merge_kernel<DEG, false><<<grid, MERGE_THREADS, smem, s>>>(P, scale, means, mv, dsh, num_slabs);
+        sh_gradient_merge_kernel<DEG, false><<<grid, MERGE_THREADS, smem, s>>>(P, scale, means, mv, dsh, num_slabs, sig);
     }
 }
 
 void launch_sh_gradient_merge(int P, int deg, float scale, bool cmajor, const float* means, int num_views,
-                              const float* const* drgb, const float* const* campos, float* dsh, cudaStream_t s) {
+                              const float* const* drgb, const float* const* campos, float* dsh, const MergeSignal& sig,
+                              cudaStream_t s) {
     if (P == 0) return;
     MergeViews mv;
     mv.n = num_views;
@@ -176,17 +192,29 @@ void launch_sh_gradient_merge(int P, int deg, float scale, bool cmajor, const fl
         mv.campos[v] = v < num_views ? campos[v] : nullptr;
     }
     switch (deg) {
-        case 0: launch_merge_deg<0>(P, scale, cmajor, means, mv, dsh, s); break;
-        case 1: launch_merge_deg<1>(P, scale, cmajor, means, mv, dsh, s); break;
-        case 2: launch_merge_deg<2>(P, scale, cmajor, means, mv, dsh, s); break;
-        case 3: launch_merge_deg<3>(P, scale, cmajor, means, mv, dsh, s); break;
-        default: launch_merge_deg<4>(P, scale, cmajor, means, mv, dsh, s); break;
+        case 0: launch_merge_deg<0>(P, scale, cmajor, means, mv, dsh, sig, s); break;
+        case 1: launch_merge_deg<1>(P, scale, cmajor, means, mv, dsh, sig, s); break;
+        case 2: launch_merge_deg<2>(P, scale, cmajor, means, mv, dsh, sig, s); break;
+        case 3: launch_merge_deg<3>(P, scale, cmajor, means, mv, dsh, sig, s); break;
+        default: launch_merge_deg<4>(P, scale, cmajor, means, mv, dsh, sig, s); break;
     }
 }
 
 // ---- in-place sum over ranks through an NVLS multicast mapping (two-shot: reduce my slice, broadcast it) ----
+// Signalled form (epoch != NULL): both cross-GPU waits are inside the kernel -- it starts when every rank's inputs
+// are complete (arrive_in reached world * *epoch) and its last CTA returns when every rank has broadcast its slice.
 __global__ void __launch_bounds__(512)
-nvls_allreduce_kernel(float* __restrict__ mc, long long first4, long long n4) {
+nvls_allreduce_kernel(float* __restrict__ mc, long long first4, long long n4, const uint32_t* epoch, int world,
+                      const uint32_t* arrive_in, uint32_t* arrive_out_mc, const uint32_t* arrive_out,
+                      uint32_t* done_counter) {
+    uint32_t target = 0;
+    if (epoch != nullptr) {
+        if (threadIdx.x == 0) {
+            target = *reinterpret_cast<const volatile uint32_t*>(epoch) * (uint32_t)world;
+            wait_reached(arrive_in, target);
+        }
+        __syncthreads();
+    }
     float4* p = reinterpret_cast<float4*>(mc) + first4;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n4; k += (long long)gridDim.x * blockDim.x) {
         float4 v;
@@ -197,6 +225,10 @@ nvls_allreduce_kernel(float* __restrict__ mc, long long first4, long long n4) {
         asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + k), "f"(v.x), "f"(v.y),
                      "f"(v.z), "f"(v.w)
                      : "memory");
+    }
+    if (epoch != nullptr && last_cta_done(done_counter)) {
+        signal_add(arrive_out_mc, true);    // this rank's slice is in every GPU's buffer
+        wait_reached(arrive_out, target);   // ... and so are the slices of all other ranks
     }
 }
 
@@ -217,17 +249,20 @@ void launch_nvls_barrier(unsigned int* mc_counter, const unsigned int* local_cou
     nvls_barrier_kernel<<<1, 32, 0, s>>>(mc_counter, local_counter, target);
 }
 
-void launch_nvls_allreduce(float* multicast, long long count, int rank, int world, cudaStream_t s) {
+void launch_nvls_allreduce(float* multicast, long long count, int rank, int world, const uint32_t* epoch,
+                           const uint32_t* arrive_in, uint32_t* arrive_out_mc, const uint32_t* arrive_out,
+                           uint32_t* done_counter, cudaStream_t s) {
     const long long n4 = count / 4;  // count is a multiple of 4 (checked by the caller)
     const long long per = (n4 + world - 1) / world;
     const long long first = per * rank < n4 ? per * rank : n4, last = per * (rank + 1) < n4 ? per * (rank + 1) : n4;
-    if (last <= first) return;
+    if (last <= first && epoch == nullptr) return;  // (a signalled call must still signal with an empty slice)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long want = (last - first + 511) / 512;
+    const long long want = last > first ? (last - first + 511) / 512 : 1;
     const int grid = (int)(want < 2LL * sms ? want : 2LL * sms);
-    nvls_allreduce_kernel<<<grid, 512, 0, s>>>(multicast, first, last - first);
+    nvls_allreduce_kernel<<<grid, 512, 0, s>>>(multicast, first, last > first ? last - first : 0, epoch, world, arrive_in,
+                                               arrive_out_mc, arrive_out, done_counter);
 }
 
 }  // namespace ggrt

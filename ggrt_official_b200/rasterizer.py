@@ -337,7 +337,8 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
     `color_sinks` = {"ptrs": [device addresses], "multimem": bool} (implies compact): the kernel itself writes the
     [P,3] colour gradients plus a row P with the view's campos to each of the 16-byte aligned [P+1,3] buffers --
     peer-GPU memory, or one NVLS multicast address with multimem=True (struct GgrtRasterGradSinks); no local
-    "dcolors" is returned."""
+    "dcolors" is returned.  Optional keys "epoch", "done", "parity_stride", "arrive" switch on the in-kernel step
+    signalling of the same struct (view_parallel.CompactGradientExchange uses it)."""
     L = _cabi.lib()
     c: _Call = state["call"]
     sinks = None
@@ -350,6 +351,12 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
             raise ValueError(f"color_sinks needs 1..{_cabi.MAX_MERGE_VIEWS} pointers, got {len(ptrs)}")
         for k, p in enumerate(ptrs):
             sinks.ptr[k] = p
+        if color_sinks.get("epoch"):  # in-kernel step signalling (struct GgrtRasterGradSinks)
+            arrive = [int(a) for a in color_sinks["arrive"]]
+            sinks.epoch, sinks.done_counter = int(color_sinks["epoch"]), int(color_sinks["done"])
+            sinks.parity_stride, sinks.arrive_count = int(color_sinks["parity_stride"]), len(arrive)
+            for k, a in enumerate(arrive):
+                sinks.arrive[k] = a
     if compact and c.sh is None:
         raise ValueError("compact=True needs SH inputs (colors_precomp already yields dcolors)")
     dev = c.device

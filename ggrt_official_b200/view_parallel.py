@@ -98,7 +98,7 @@ class CompactGradientExchange:
 
     def __init__(self, P: int, sh_degree: int, device, group=None, transport: str = "nccl",
                  layout: Optional[dict] = None, backward_fn: Optional[Callable] = None,
-                 merge_fn: Optional[Callable] = None, barrier: str = "torch"):
+                 merge_fn: Optional[Callable] = None, barrier: str = "signal"):
         if transport not in ("nccl", "p2p"):
             raise ValueError(f"unknown transport {transport!r}")
         on = dist.is_available() and dist.is_initialized()
@@ -123,6 +123,7 @@ class CompactGradientExchange:
         self._side = None
         self.profile, self.marks = False, []
         self.barrier_kind = "torch"
+        self.signalled = False
         if self.transport == "p2p":
             import torch.distributed._symmetric_memory as symm
 
@@ -130,26 +131,40 @@ class CompactGradientExchange:
             # kernel stores its colour gradients into slot `rank` of every GPU (posted NVLink stores, or ONE
             # multimem.st per vector when the fabric has NVLS multicast), so the merge only reads local memory
             gname = (group or dist.group.WORLD).group_name
-            self.slots = symm.empty(self.world * self.slot, **f32)
+            probe = symm.empty(4, dtype=torch.int32, device=self.device)
+            has_mc = bool(symm.rendezvous(probe, gname).multicast_ptr)
+            # Synchronisation between the ranks: with NVLS multicast the kernels signal and wait themselves
+            # ("signal": arrival counters bumped with multimem.red by the last CTA of the producing kernel, polled by
+            # the first instruction of the consuming one -- no barrier kernels, no host, double-buffered slots);
+            # otherwise torch's symmetric-memory barrier kernel ("torch") or the single-thread barrier kernel of this
+            # library ("nvls") brackets the exchange.
+            if barrier == "signal" and not has_mc:
+                barrier = "torch"
+            self.signalled = barrier == "signal"
+            self.halves = 2 if self.signalled else 1
+            self.slots = symm.empty(self.halves * self.world * self.slot, **f32)
             self.small = symm.empty(self.small_elems, **f32)
             self.handles = (symm.rendezvous(self.slots, gname), symm.rendezvous(self.small, gname))
             self.my_slot = self.slots[self.rank * self.slot: (self.rank + 1) * self.slot]
             hs = self.handles[0]
             off = 4 * self.rank * self.slot
-            # cross-GPU barrier: torch's symmetric-memory barrier kernel ("torch"), or one multimem.red + local spin
-            # in a single-thread kernel of this library ("nvls"; needs the multicast mapping)
             self.barrier_kind = barrier if hs.multicast_ptr else "torch"
-            if self.barrier_kind == "nvls":
-                self.bar = symm.empty(4, dtype=torch.int32, device=self.device)
+            if self.barrier_kind in ("nvls", "signal"):
+                self.bar = symm.empty(8, dtype=torch.int32, device=self.device)  # [0] push arrivals, [1] reduce arrivals
                 self.bar.zero_()
                 self.bar_handle = symm.rendezvous(self.bar, gname)
+                self.ctrl = torch.zeros(4, dtype=torch.int32, device=self.device)  # [0] epoch, [1], [2] CTA counters
                 torch.cuda.synchronize(self.device)
-                hs.barrier(channel=0)  # every rank's counter is zero before anyone increments it
+                hs.barrier(channel=0)  # every rank's counters are zero before anyone increments them
+                torch.cuda.synchronize(self.device)
                 self.epoch = 0
             if hs.multicast_ptr:
                 self.sinks = {"ptrs": [int(hs.multicast_ptr) + off], "multimem": True}
             else:
                 self.sinks = {"ptrs": [int(p) + off for p in hs.buffer_ptrs], "multimem": False}
+            if self.signalled:
+                self.sinks.update(epoch=self.ctrl.data_ptr(), done=self.ctrl.data_ptr() + 4,
+                                  parity_stride=self.world * self.slot, arrive=[int(self.bar_handle.multicast_ptr)])
         else:
             self.slots = torch.empty(self.world * self.slot, **f32)
             self.small = torch.empty(self.small_elems, **f32)
@@ -176,6 +191,8 @@ class CompactGradientExchange:
         with barrier="nvls", two barrier kernels on the p2p transport); torch / NCCL kernels are not counted."""
         if self.world == 1 or self.transport != "p2p":
             return 1
+        if self.signalled:
+            return 2  # merge + all-reduce, both with their waits inside
         n = 1 + (1 if self.handles[1].multicast_ptr else 0)
         return n + (2 if self.barrier_kind == "nvls" else 0)
 
@@ -218,7 +235,37 @@ class CompactGradientExchange:
             out = self.backward_fn(state, grad_color, out=dict(self.views), compact=True, **backward_kw)
             self.my_slot[3 * P_: 3 * P_ + 3].copy_(call.campos.reshape(3))
         self._mark("backward_compact")
-        if self.world > 1 and self.transport == "p2p":
+        if self.signalled:
+            from . import _cabi
+            import ctypes as C
+
+            L = _cabi.lib()
+            hs, hm = self.handles
+            main = torch.cuda.current_stream(self.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            side = self._side
+            ctrl, bar, bar_mc = self.ctrl.data_ptr(), self.bar.data_ptr(), int(self.bar_handle.multicast_ptr)
+            # the NVLink-bound sum of the small arena runs beside the HBM-bound merge; both kernels wait by themselves
+            # for the arrival counter the ranks' backward kernels bump, the all-reduce also for its own completion
+            side.wait_stream(main)
+            _cabi.check(L.ggrt_raster_nvls_allreduce_signalled(
+                C.c_void_p(hm.multicast_ptr), self.small_elems, self.rank, self.world, C.c_void_p(ctrl),
+                C.c_void_p(bar), C.c_void_p(bar_mc + 4), C.c_void_p(bar + 4), C.c_void_p(ctrl + 8),
+                C.c_void_p(side.cuda_stream)), "nvls_allreduce_signalled")
+            clay = None
+            if self.layout:
+                clay = C.byref(_cabi.InputLayout(float(self.layout.get("scene_scale", 1.0)), 0,
+                                                 int(bool(self.layout.get("sh_channel_major", False)))))
+            _cabi.check(L.ggrt_raster_sh_gradient_merge_signalled(
+                P_, self.deg, clay, C.c_void_p(call.means3D.data_ptr()), self.world, C.c_void_p(self.slots.data_ptr()),
+                self.slot, self.world * self.slot, C.c_void_p(ctrl), C.c_void_p(bar), C.c_void_p(self.dsh.data_ptr()),
+                C.c_void_p(main.cuda_stream)), "sh_gradient_merge_signalled")
+            dsh = self.dsh
+            self._mark("merge")
+            main.wait_stream(side)
+            self._mark("join_allreduce")
+        elif self.world > 1 and self.transport == "p2p":
             from . import _cabi
             import ctypes as C
 

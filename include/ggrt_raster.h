@@ -89,11 +89,26 @@ typedef struct GgrtRasterInputLayout {
  * the view's campos.  The pointers may address peer-GPU memory (stores over NVLink are posted, so the remote
  * copies cost the kernel no latency), or, with multimem = 1, ptr[0] is an NVLS multicast address and ONE
  * multimem.st per vector lands in every GPU's buffer.  Each pointer must be 16-byte aligned.
+ *
+ * Step signalling (epoch != NULL; the multi-GPU exchange without barrier kernels and without the host): `epoch` is a
+ * LOCAL device word counting completed pushes.  The kernel reads e = *epoch, pushes into half (e & 1) of every sink
+ * (ptr[i] + (e & 1) * parity_stride floats: the receivers may still be reading the other half), and when its last
+ * CTA has finished -- all stores fenced at system scope -- stores e + 1 to *epoch and adds 1 to every arrival
+ * counter in `arrive` (release, system scope; arrive[0] is a multicast address when multimem).  A receiver that has
+ * seen world * (e + 1) arrivals on its copy of the counter may read half (e & 1) of its sinks and, on every rank,
+ * the plain outputs dL_dmeans3D / dL_dcov3D / dL_dopacity of this call (see ggrt_raster_sh_gradient_merge_signalled,
+ * ggrt_raster_nvls_allreduce_signalled).  done_counter: a LOCAL device word, zero before the first launch.
  */
 typedef struct GgrtRasterGradSinks {
     int32_t count;    /* 1..GGRT_RASTER_MAX_MERGE_VIEWS */
     int32_t multimem; /* 0: plain stores to every ptr[i]; 1: multimem.st to ptr[0] (count must be 1) */
     float* ptr[GGRT_RASTER_MAX_MERGE_VIEWS];
+    uint32_t* epoch;        /* NULL: no signalling (the fields below are ignored) */
+    uint32_t* done_counter;
+    int64_t parity_stride;  /* floats */
+    int32_t arrive_count;   /* 1 with multimem, else one counter per receiving GPU */
+    int32_t reserved;
+    uint32_t* arrive[GGRT_RASTER_MAX_MERGE_VIEWS];
 } GgrtRasterGradSinks;
 
 /* Byte offsets of the sub-arrays inside the caller-owned buffers (for tests / tools). */
@@ -218,6 +233,18 @@ int ggrt_raster_sh_gradient_merge(int32_t P, int32_t sh_degree, const GgrtRaster
                                   const float* const* campos_views_host, float* dL_dsh, ggrt_stream_t stream);
 
 /*
+ * The same merge for the signalled exchange (GgrtRasterGradSinks.epoch): the views are the `world` slots of THIS
+ * GPU's slot table -- view v at slots + half * parity_stride + v * slot_stride floats, each slot [P+1,3] with the
+ * view's campos in row P -- which the peers' backward kernels push into.  The kernel itself waits (acquire, system
+ * scope) until `arrive` (this GPU's copy of the arrival counter) has reached world * *epoch, then reads half
+ * (*epoch - 1) & 1.  Enqueue it after this rank's ggrt_raster_backward of the same step on the same stream.
+ */
+int ggrt_raster_sh_gradient_merge_signalled(int32_t P, int32_t sh_degree, const GgrtRasterInputLayout* layout,
+                                            const float* means3D, int32_t world, const float* slots,
+                                            int64_t slot_stride, int64_t parity_stride, const uint32_t* epoch,
+                                            const uint32_t* arrive, float* dL_dsh, ggrt_stream_t stream);
+
+/*
  * In-place float32 sum over `world` GPUs of `count` floats (a multiple of 4) that every rank holds at the
  * same offset of an NVLS multicast mapping (`multicast_ptr`: the multicast address of a symmetric
  * allocation, e.g. torch.distributed._symmetric_memory's multicast_ptr).  Rank r reduces slice r
@@ -227,6 +254,17 @@ int ggrt_raster_sh_gradient_merge(int32_t P, int32_t sh_degree, const GgrtRaster
  */
 int ggrt_raster_nvls_allreduce_f32(void* multicast_ptr, int64_t count, int32_t rank, int32_t world,
                                    ggrt_stream_t stream);
+
+/*
+ * ggrt_raster_nvls_allreduce_f32 for the signalled exchange, with both waits inside the kernel: it starts reducing
+ * when `arrive_in` (local copy) has reached world * *epoch -- every rank's backward outputs are complete -- and
+ * returns when `arrive_out` has reached the same value, i.e. when every rank has broadcast its slice (its last CTA
+ * adds 1 to all copies of arrive_out through `arrive_out_multicast` after its own slice).  done_counter: a LOCAL
+ * device word, zero before the first launch.  May run beside the merge kernel on another stream.
+ */
+int ggrt_raster_nvls_allreduce_signalled(void* multicast_ptr, int64_t count, int32_t rank, int32_t world,
+                                         const uint32_t* epoch, const uint32_t* arrive_in, void* arrive_out_multicast,
+                                         const uint32_t* arrive_out, uint32_t* done_counter, ggrt_stream_t stream);
 
 /*
  * Cross-GPU barrier on `stream` in one single-thread kernel (no host involvement): adds 1 to every GPU's copy of a

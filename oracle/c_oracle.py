@@ -152,12 +152,13 @@ def render_forward(cam: Camera, pre: dict, binning: dict, aux=None) -> dict:
         final_T=np.zeros((H, W), np.float32),
         n_contrib=np.zeros((H, W), np.uint32),
         fragile=np.zeros((H, W), np.uint8),
+        fragile_gaussian=np.zeros(P, np.uint8),
     )
     pl = binning["point_list"] if binning["N"] > 0 else np.zeros(1, np.uint32)
     cc = cam.c(P)
     L.oracle_render_forward(C.byref(cc), _p(binning["ranges"]), _p(pl), _p(pre["xy"]), _p(pre["conic_opacity"]),
                             _p(pre["rgb"]), _p(chan), _p(out["color"]), _p(out["depth"]), _p(out["final_T"]),
-                            _p(out["n_contrib"]), _p(out["fragile"]))
+                            _p(out["n_contrib"]), _p(out["fragile"]), _p(out["fragile_gaussian"]))
     return out
 
 

@@ -322,7 +322,11 @@ static inline int near_rel(float v, float thr) { return fabsf(v - thr) <= FRAGIL
 
 void oracle_render_forward(const OracleCam* cam, const uint32_t* ranges, const uint32_t* point_list, const float* xy,
                            const float* conic_opacity, const float* rgb, const float* depth, float* out_color,
-                           float* out_depth, float* final_T, uint32_t* n_contrib, uint8_t* fragile) {
+                           float* out_depth, float* final_T, uint32_t* n_contrib, uint8_t* fragile,
+                           uint8_t* fragile_gaussian) {
+    /* fragile_gaussian[P] (u8, may be NULL, zeroed by the caller): set for the Gaussian whose own threshold test was
+     * within the band at some pixel -- the one whose contribution an implementation with another rounding may
+     * gain or lose there.  Several threads may store the same 1 concurrently; that is benign. */
     const int W = cam->W, H = cam->H;
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
 #pragma omp parallel for schedule(dynamic, 4)
@@ -344,14 +348,22 @@ void oracle_render_forward(const OracleCam* cam, const uint32_t* ranges, const u
                     float cA = conic_opacity[4 * g], cB = conic_opacity[4 * g + 1], cC = conic_opacity[4 * g + 2],
                           o = conic_opacity[4 * g + 3];
                     float power = -0.5f * (cA * dx * dx + cC * dy * dy) - cB * dx * dy;
-                    if (fabsf(power) <= 1.0e-6f) frag = 1;
+                    uint8_t fg = 0;
+                    if (fabsf(power) <= 1.0e-6f) fg = 1;
+                    float oG = power > 0.0f ? 0.0f : o * expf(power);
+                    if (power <= 0.0f && (near_rel(oG, ALPHA_MAX) || near_rel(oG, ALPHA_MIN))) fg = 1;
+                    if (fg) {
+                        frag = 1;
+                        if (fragile_gaussian) fragile_gaussian[g] = 1;
+                    }
                     if (power > 0.0f) continue;
-                    float oG = o * expf(power);
-                    if (near_rel(oG, ALPHA_MAX) || near_rel(oG, ALPHA_MIN)) frag = 1;
                     float alpha = fminf(ALPHA_MAX, oG);
                     if (alpha < ALPHA_MIN) continue;
                     float Tn = T * (1.0f - alpha);
-                    if (near_rel(Tn, T_EPS)) frag = 1;
+                    if (near_rel(Tn, T_EPS)) {
+                        frag = 1;
+                        if (fragile_gaussian) fragile_gaussian[g] = 1;
+                    }
                     if (Tn < T_EPS) break;
                     float w = alpha * T;
                     for (int c = 0; c < 3; ++c) C[c] += rgb[3 * g + c] * w;

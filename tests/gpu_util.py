@@ -107,11 +107,14 @@ def compare_forward(st, f, depth_scale=None):
 #     |got - ref| <= GRAD_REL * |ref| + GRAD_ABS_FLOOR * max|ref over the tensor|
 # The absolute floor covers float32 summation-order noise of elements that are themselves sums of
 # hundreds of cancelling per-pixel terms (the GPU adds them in another order than the oracle).
-# Gaussians that reach a pixel the oracle flags "fragile" (a hard threshold within rounding of its
-# boundary, see compare_forward) may legitimately gain or lose one whole pixel contribution; they are
-# held to the tensor-level bar only (max|diff| <= GRAD_REL * max|ref|) and must be few.
+# Measured on B200 (round 2, tools/grad_diag.py, C2): the worst element sits at 0.03 of this bar (0.23 with a floor
+# of 1e-6).  A Gaussian whose own hard-threshold test sits within rounding of its boundary at some pixel (the
+# oracle flags it, see fragile_gaussians) may legitimately gain or lose that one pixel contribution -- up to
+# alpha*T ~ 4e-3 of a pixel's weight; those few (at most one per fragile pixel) are held to
+# max|diff| <= GRAD_FRAGILE_REL * max|ref| instead.
 GRAD_REL = 1e-3
 GRAD_ABS_FLOOR = 1e-5
+GRAD_FRAGILE_REL = 1e-2
 
 
 def fragile_allowance(n_pixels: int, n_pairs: int, n_tiles: int, dense: bool = False) -> int:
@@ -123,20 +126,11 @@ def fragile_allowance(n_pixels: int, n_pairs: int, n_tiles: int, dense: bool = F
     return max(16, int((8e-6 if dense else 2e-6) * n_pixels * per_tile))
 
 
-def fragile_gaussians(f: dict, H: int, W: int) -> np.ndarray:
-    """bool [P]: Gaussians whose bounding square (centre +- radius) contains a fragile pixel of a tile
-    that lists them -- the only ones whose gradients a threshold flip at that pixel can change."""
-    pre, b, img = f["pre"], f["bin"], f["img"]
-    P = pre["radii"].shape[0]
-    hit = np.zeros(P, bool)
-    ys, xs = np.nonzero(img["fragile"])
-    gx = (W + 15) // 16
-    for y, x in zip(ys.tolist(), xs.tolist()):
-        s, e = b["ranges"][(y // 16) * gx + x // 16]
-        ids = b["point_list"][int(s): int(e)].astype(np.int64)
-        d = np.abs(pre["xy"][ids] - np.array([x, y], np.float32)).max(axis=1)
-        hit[ids[d <= pre["radii"][ids] + 1]] = True
-    return hit
+def fragile_gaussians(f: dict, H: int = 0, W: int = 0) -> np.ndarray:
+    """bool [P]: Gaussians whose OWN threshold test (alpha >= 1/255, alpha = 0.99, power = 0, T < 1e-4) fell within
+    the oracle's rounding band at some pixel -- the ones that may legitimately gain or lose one whole pixel
+    contribution in an implementation with another exp() / fma rounding (oracle_render_forward flags them)."""
+    return f["img"]["fragile_gaussian"] != 0
 
 
 def grad_errors(got: dict, ref: dict, use_sh=True, fragile=None):
@@ -168,10 +162,10 @@ def grad_errors(got: dict, ref: dict, use_sh=True, fragile=None):
     return out
 
 
-def assert_grads(errs: dict, what="", max_fragile=0.05):
+def assert_grads(errs: dict, what="", max_fragile=0.02):
     """The gradient bar of the parity tests (see GRAD_REL / GRAD_ABS_FLOOR above)."""
     for k, e in errs.items():
         assert e["nonfinite"] == 0, (what, k, e)
-        assert e["max_rel"] < GRAD_REL, (what, k, errs)        # tensor level, fragile Gaussians included
+        assert e["max_rel"] < GRAD_FRAGILE_REL, (what, k, errs)  # tensor level, fragile Gaussians included
         assert e["worst"] <= 1.0, (what, k, errs)               # elementwise, every non-fragile Gaussian
         assert e["frac_fragile"] < max_fragile, (what, k, e)
