@@ -24,12 +24,26 @@ emit_kernel(View v, GeomPtrs g, uint32_t* __restrict__ cursor, unsigned long lon
     const ushort4 r = g.rect[i];
     const unsigned long long key = ((unsigned long long)__float_as_uint(g.rec0[i].w) << 32) | (uint32_t)i;
     const int sub = i & (SUBS - 1);
-    for (int y = r.y; y < r.w; ++y)
-        for (int x = r.x; x < r.z; ++x) {
-            // the (tile, sub-counter) segment start doubles as its allocation cursor: one returning atomic per pair
-            const uint32_t slot = atomicAdd(&cursor[((y * v.gx + x) << SUBS_LOG2) + sub], 1u);
-            if (slot < capacity) keys[slot] = key;  // a too-small (speculative) buffer is detected and redone by the host
+    // The (tile, sub-counter) segment start doubles as its allocation cursor: one returning atomic per pair.  The
+    // kernel is pure L2-atomic latency, so the claims of a Gaussian are issued TOGETHER, four at a time (GGRt's
+    // splats touch 1-4 tiles; 2x2 is the common rect), and only then the dependent stores: four round trips in
+    // flight per thread instead of one.
+    const int w = r.z - r.x, n = w * (r.w - r.y);
+    for (int t0 = 0; t0 < n; t0 += 4) {
+        uint32_t slot[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u;
+            slot[u] = 0xffffffffu;
+            if (t < n) {
+                const int y = r.y + t / w, x = r.x + t % w;
+                slot[u] = atomicAdd(&cursor[((y * v.gx + x) << SUBS_LOG2) + sub], 1u);
+            }
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (slot[u] < capacity) keys[slot[u]] = key;  // a too-small (speculative) buffer is detected and redone by the host
+    }
 }
 
 __device__ __forceinline__ void cmpxchg(unsigned long long* a, uint32_t i, uint32_t l) {
@@ -65,7 +79,7 @@ __device__ __forceinline__ void bitonic_sort(unsigned long long* a, uint32_t n, 
     }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(1024)
 sort_tiles_kernel(int T, const uint32_t* __restrict__ starts, unsigned long long* __restrict__ keys,
                   uint32_t* __restrict__ points, uint32_t smem_cap, uint32_t capacity) {
     extern __shared__ __align__(16) unsigned long long sk[];
@@ -73,20 +87,21 @@ sort_tiles_kernel(int T, const uint32_t* __restrict__ starts, unsigned long long
     if (tile >= T) return;
     const uint32_t s = min(starts[tile], capacity), e = min(starts[tile + 1], capacity), n = e - s;
     if (n == 0) return;
+    const uint32_t nt = blockDim.x;  // 256, or 1024 when some tile exceeds the shared-memory tier
     unsigned long long* seg = keys + s;
     if (n <= smem_cap) {
-        for (uint32_t i = threadIdx.x; i < n; i += SORT_THREADS) sk[i] = seg[i];
+        for (uint32_t i = threadIdx.x; i < n; i += nt) sk[i] = seg[i];
         __syncthreads();
-        bitonic_sort(sk, n);
-        for (uint32_t i = threadIdx.x; i < n; i += SORT_THREADS) {
+        bitonic_sort(sk, n, nt);
+        for (uint32_t i = threadIdx.x; i < n; i += nt) {
             const unsigned long long k = sk[i];
             seg[i] = k;
             points[s + i] = (uint32_t)k;
         }
     } else {  // oversized tile: same network directly on the global segment (block-scope visibility via the barriers)
         __syncthreads();
-        bitonic_sort(seg, n);
-        for (uint32_t i = threadIdx.x; i < n; i += SORT_THREADS) points[s + i] = (uint32_t)seg[i];
+        bitonic_sort(seg, n, nt);
+        for (uint32_t i = threadIdx.x; i < n; i += nt) points[s + i] = (uint32_t)seg[i];
     }
 }
 
@@ -99,7 +114,14 @@ sort_tiles_kernel(int T, const uint32_t* __restrict__ starts, unsigned long long
 constexpr int SORT_E = 8;  // keys per thread
 
 __device__ __forceinline__ void cx(unsigned long long& a, unsigned long long& b) {  // ascending compare-exchange
-    const unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
+    // one 64-bit compare, four selects (written out: the compiler otherwise emits a second compare for the maximum)
+    unsigned long long lo, hi;
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.lt.u64 p, %2, %3;\n\t"
+        "selp.b64 %0, %2, %3, p;\n\t"
+        "selp.b64 %1, %3, %2, p;\n\t}"
+        : "=l"(lo), "=l"(hi)
+        : "l"(a), "l"(b));
     a = lo, b = hi;
 }
 __device__ __forceinline__ void local_tail(unsigned long long (&v)[SORT_E]) {  // distances 4, 2, 1
@@ -225,7 +247,9 @@ void launch_sort_tiles(const View& v, ImagePtrs im, BinPtrs b, uint32_t max_tile
     const size_t smem = (size_t)cap * sizeof(unsigned long long);
     if (smem > 32 * 1024)  // per-device attribute; cheap host-side call
         cudaFuncSetAttribute(sort_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
-    sort_tiles_kernel<<<v.gx * v.gy, SORT_THREADS, smem, s>>>(v.gx * v.gy, im.starts, b.keys, b.points, cap, capacity);
+    // a tile beyond the shared-memory tier is sorted in place in global memory by its CTA: give it the largest CTA
+    const int threads = max_tile_pairs > 16384 ? 1024 : SORT_THREADS;
+    sort_tiles_kernel<<<v.gx * v.gy, threads, smem, s>>>(v.gx * v.gy, im.starts, b.keys, b.points, cap, capacity);
 }
 
 }  // namespace ggrt

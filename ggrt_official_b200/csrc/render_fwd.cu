@@ -11,13 +11,31 @@
 
 namespace ggrt {
 
+// ASYNC (north_star: "TMA/cp.async staging of per-tile Gaussian records into shared memory"): the records of batch
+// b+1 are gathered with cp.async (SASS: LDGSTS, 3 x 16 B per record, no register round trip) into the other half
+// of a double buffer while batch b is culled and blended; the list index a thread needs for that gather is itself
+// loaded one batch ahead.  The conic is rescaled for the ex2 exponent by a short in-place pass once a batch has
+// landed.  Measured against the synchronous fill in DESIGN.md section 8.
+#ifndef GGRT_FWD_ASYNC
+#define GGRT_FWD_ASYNC 1
+#endif
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <bool ASYNC>
 __global__ void __launch_bounds__(FWD_THREADS, 1024 / FWD_THREADS)
 render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __restrict__ rec1,
                       const float4* __restrict__ rec2, const uint32_t* __restrict__ starts,
                       const uint32_t* __restrict__ points, uint32_t capacity, float* __restrict__ out_color,
                       float* __restrict__ out_depth, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
-    __shared__ __align__(16) unsigned char srec[FWD_BATCH * REC_BYTES];
-    const uint32_t sbase = smem_addr(srec);
+    __shared__ __align__(16) unsigned char srec[(ASYNC ? 2 : 1) * FWD_BATCH * REC_BYTES];
+    uint32_t sbase = smem_addr(srec);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.y * v.gx + blockIdx.x;
     const int wt = warp + blockIdx.z * FWD_WARPS;  // warp pixel block of the tile (8 per tile)
@@ -34,17 +52,47 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
     float T = inside ? 1.0f : -1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
     uint32_t last = 0;
 
-    for (uint32_t base = start; base < end; base += FWD_BATCH) {
+    static_assert(FWD_THREADS == FWD_BATCH, "one record per thread and batch");
+    // ASYNC: gather of batch `b` into half `h` of the double buffer; nid = this thread's list entry of the batch after
+    uint32_t nid = 0;
+    auto gather = [&](uint32_t b, uint32_t h) {
+        if (b + tid < end) {
+            const uint32_t dst = smem_addr(srec) + h * (FWD_BATCH * REC_BYTES) + tid * REC_BYTES;
+            cp_async16(dst, rec0 + nid);
+            cp_async16(dst + 16, rec1 + nid);
+            cp_async16(dst + 32, rec2 + nid);
+        }
+        cp_async_commit();
+        const uint32_t nn = b + FWD_BATCH + tid;
+        if (nn < end) nid = points[nn];
+    };
+    if (ASYNC) {
+        if (start + tid < end) nid = points[start + tid];
+        gather(start, 0);
+    }
+    uint32_t half = 0;
+    for (uint32_t base = start; base < end; base += FWD_BATCH, half ^= 1u) {
         if (__syncthreads_and(T < 0.0f)) break;  // also orders the previous batch's reads before the refill
         const uint32_t cnt = min((uint32_t)FWD_BATCH, end - base);
-        for (uint32_t k = tid; k < cnt; k += FWD_THREADS) {
-            const uint32_t id = points[base + k];
-            const uint32_t dst = sbase + k * REC_BYTES;
-            float4 c = rec1[id];
-            c.x *= -0.5f * LOG2E, c.y *= -LOG2E, c.z *= -0.5f * LOG2E;
-            sts128(dst, rec0[id]);
-            sts128(dst + 16, c);
-            sts128(dst + 32, rec2[id]);
+        if (ASYNC) {
+            sbase = smem_addr(srec) + half * (FWD_BATCH * REC_BYTES);
+            gather(base + FWD_BATCH, half ^ 1u);   // the next batch streams in under this one's blend loop
+            cp_async_wait<1>();                    // this thread's copies of the current batch have landed ...
+            if (tid < cnt) {                       // ... rescale its record's conic for the ex2 exponent, in place
+                float4 c = lds128(sbase + tid * REC_BYTES + 16);
+                c.x *= -0.5f * LOG2E, c.y *= -LOG2E, c.z *= -0.5f * LOG2E;
+                sts128(sbase + tid * REC_BYTES + 16, c);
+            }
+        } else {
+            for (uint32_t k = tid; k < cnt; k += FWD_THREADS) {
+                const uint32_t id = points[base + k];
+                const uint32_t dst = sbase + k * REC_BYTES;
+                float4 c = rec1[id];
+                c.x *= -0.5f * LOG2E, c.y *= -LOG2E, c.z *= -0.5f * LOG2E;
+                sts128(dst, rec0[id]);
+                sts128(dst + 16, c);
+                sts128(dst + 32, rec2[id]);
+            }
         }
         __syncthreads();
         if (__all_sync(0xffffffffu, T < 0.0f)) continue;
@@ -88,6 +136,7 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
             if (__all_sync(0xffffffffu, T < 0.0f)) break;
         }
     }
+    if (ASYNC) cp_async_wait<0>();  // nothing may still be in flight into this CTA's shared memory when it exits
     if (inside) {
         const float Tf = fabsf(T);
         const size_t pix = (size_t)py * v.W + px, hw = (size_t)v.H * v.W;
@@ -103,8 +152,9 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
 void launch_render_forward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, uint32_t capacity, float* out_color,
                            float* out_depth, cudaStream_t s) {
     dim3 grid(v.gx, v.gy, 8 / FWD_WARPS);
-    render_forward_kernel<<<grid, FWD_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points, capacity, out_color,
-                                                          out_depth, im.final_T, im.n_contrib);
+    render_forward_kernel<GGRT_FWD_ASYNC != 0><<<grid, FWD_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
+                                                                             capacity, out_color, out_depth, im.final_T,
+                                                                             im.n_contrib);
 }
 
 }  // namespace ggrt

@@ -324,9 +324,12 @@ void oracle_render_forward(const OracleCam* cam, const uint32_t* ranges, const u
                            const float* conic_opacity, const float* rgb, const float* depth, float* out_color,
                            float* out_depth, float* final_T, uint32_t* n_contrib, uint8_t* fragile,
                            uint8_t* fragile_gaussian) {
-    /* fragile_gaussian[P] (u8, may be NULL, zeroed by the caller): set for the Gaussian whose own threshold test was
-     * within the band at some pixel -- the one whose contribution an implementation with another rounding may
-     * gain or lose there.  Several threads may store the same 1 concurrently; that is benign. */
+    /* fragile_gaussian[P] (u8, may be NULL, zeroed by the caller): bit 0 is set for the Gaussian whose own threshold
+     * test was within the band at some pixel -- the one whose contribution an implementation with another rounding
+     * may gain or lose there -- and bit 1 for every Gaussian that contributes to such a pixel: if the flagged one
+     * flips, the transmittance in front of the ones behind it and the colour accumulated behind the ones in front of
+     * it change by up to alpha ~ 0.4 %, which is more than the 1e-3 gradient bar for a splat that covers only a
+     * pixel or two.  Several threads may OR the same bits concurrently; that is benign. */
     const int W = cam->W, H = cam->H;
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
 #pragma omp parallel for schedule(dynamic, 4)
@@ -340,7 +343,7 @@ void oracle_render_forward(const OracleCam* cam, const uint32_t* ranges, const u
                 float pxf = (float)x, pyf = (float)y;
                 float T = 1.0f, C[3] = {0, 0, 0}, D = 0.0f;
                 uint32_t contributor = 0, last = 0;
-                uint8_t frag = 0;
+                uint8_t frag = 0, frag_alpha = 0;
                 for (uint32_t j = r0; j < r1; ++j) {
                     ++contributor;
                     uint32_t g = point_list[j];
@@ -354,7 +357,8 @@ void oracle_render_forward(const OracleCam* cam, const uint32_t* ranges, const u
                     if (power <= 0.0f && (near_rel(oG, ALPHA_MAX) || near_rel(oG, ALPHA_MIN))) fg = 1;
                     if (fg) {
                         frag = 1;
-                        if (fragile_gaussian) fragile_gaussian[g] = 1;
+                        frag_alpha = 1;
+                        if (fragile_gaussian) fragile_gaussian[g] |= 1;
                     }
                     if (power > 0.0f) continue;
                     float alpha = fminf(ALPHA_MAX, oG);
@@ -362,7 +366,7 @@ void oracle_render_forward(const OracleCam* cam, const uint32_t* ranges, const u
                     float Tn = T * (1.0f - alpha);
                     if (near_rel(Tn, T_EPS)) {
                         frag = 1;
-                        if (fragile_gaussian) fragile_gaussian[g] = 1;
+                        if (fragile_gaussian) fragile_gaussian[g] |= 1;
                     }
                     if (Tn < T_EPS) break;
                     float w = alpha * T;
@@ -377,6 +381,17 @@ void oracle_render_forward(const OracleCam* cam, const uint32_t* ranges, const u
                 final_T[pix] = T;
                 n_contrib[pix] = last;
                 if (fragile) fragile[pix] = frag;
+                if (frag_alpha && fragile_gaussian) { /* flag every contributor of this pixel (bit 1) */
+                    for (uint32_t j = r0; j < r1 && j < r0 + last + 1; ++j) {
+                        uint32_t g = point_list[j];
+                        float dx = xy[2 * g] - pxf, dy = xy[2 * g + 1] - pyf;
+                        float power = -0.5f * (conic_opacity[4 * g] * dx * dx + conic_opacity[4 * g + 2] * dy * dy) -
+                                      conic_opacity[4 * g + 1] * dx * dy;
+                        if (power > 0.0f) continue;
+                        if (conic_opacity[4 * g + 3] * expf(power) >= ALPHA_MIN * (1.0f - FRAGILE_REL))
+                            fragile_gaussian[g] |= 2;
+                    }
+                }
             }
     }
 }

@@ -108,10 +108,10 @@ def compare_forward(st, f, depth_scale=None):
 # The absolute floor covers float32 summation-order noise of elements that are themselves sums of
 # hundreds of cancelling per-pixel terms (the GPU adds them in another order than the oracle).
 # Measured on B200 (round 2, tools/grad_diag.py, C2): the worst element sits at 0.03 of this bar (0.23 with a floor
-# of 1e-6).  A Gaussian whose own hard-threshold test sits within rounding of its boundary at some pixel (the
-# oracle flags it, see fragile_gaussians) may legitimately gain or lose that one pixel contribution -- up to
-# alpha*T ~ 4e-3 of a pixel's weight; those few (at most one per fragile pixel) are held to
-# max|diff| <= GRAD_FRAGILE_REL * max|ref| instead.
+# of 1e-6).  Gaussians that contribute to a pixel with a hard-threshold test within rounding of its boundary (the
+# oracle flags them, see fragile_gaussians: ~23 per fragile pixel, 1.5 % of the Gaussians at C2) may legitimately
+# gain or lose that pixel's contribution, or see it scaled by (1 - alpha) ~ 0.4 %; they are held to
+# max|diff| <= GRAD_FRAGILE_REL * max|ref| instead, and their share is bounded (assert_grads).
 GRAD_REL = 1e-3
 GRAD_ABS_FLOOR = 1e-5
 GRAD_FRAGILE_REL = 1e-2
@@ -127,9 +127,12 @@ def fragile_allowance(n_pixels: int, n_pairs: int, n_tiles: int, dense: bool = F
 
 
 def fragile_gaussians(f: dict, H: int = 0, W: int = 0) -> np.ndarray:
-    """bool [P]: Gaussians whose OWN threshold test (alpha >= 1/255, alpha = 0.99, power = 0, T < 1e-4) fell within
-    the oracle's rounding band at some pixel -- the ones that may legitimately gain or lose one whole pixel
-    contribution in an implementation with another exp() / fma rounding (oracle_render_forward flags them)."""
+    """bool [P]: Gaussians that contribute to a pixel where some Gaussian's hard-threshold test (alpha >= 1/255,
+    alpha = 0.99, power = 0, T < 1e-4) fell within the oracle's rounding band (oracle_render_forward flags them).
+    An implementation with another exp() / fma rounding may legitimately take the other branch there: the flagged
+    Gaussian gains or loses that pixel's contribution, and every other contributor of the pixel sees its
+    transmittance / the colour behind it move by up to alpha ~ 0.4 % -- beyond the 1e-3 bar for splats that cover a
+    pixel or two."""
     return f["img"]["fragile_gaussian"] != 0
 
 
@@ -162,7 +165,7 @@ def grad_errors(got: dict, ref: dict, use_sh=True, fragile=None):
     return out
 
 
-def assert_grads(errs: dict, what="", max_fragile=0.02):
+def assert_grads(errs: dict, what="", max_fragile=0.05):
     """The gradient bar of the parity tests (see GRAD_REL / GRAD_ABS_FLOOR above)."""
     for k, e in errs.items():
         assert e["nonfinite"] == 0, (what, k, e)

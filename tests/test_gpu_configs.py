@@ -22,7 +22,7 @@ EXACT = ("radii_mismatch", "rect_mismatch", "tiles_mismatch", "xy_bits_mismatch"
          "n_contrib_mismatch")
 
 
-def _full_parity(P, H, W, seed, what, grad=None, want_camera=False):
+def _full_parity(P, H, W, seed, what, grad=None, want_camera=False, max_fragile=0.05):
     ri = to_raster_inputs(make_scene(P, H, W, sh_degree=4, seed=seed))
     st = G.run_cuda_forward(ri)
     cam, f = G.oracle_forward(ri)
@@ -39,7 +39,7 @@ def _full_parity(P, H, W, seed, what, grad=None, want_camera=False):
     got = R.backward_raw(st, torch.tensor(g, device=DEV), want_camera=want_camera)
     torch.cuda.synchronize()
     ref = co.backward(cam, ri.means3D, ri.cov3D, ri.opacities, f, g, sh=ri.shs, want_camera=want_camera)
-    G.assert_grads(G.grad_errors(got, ref, fragile=G.fragile_gaussians(f, H, W)), what)
+    G.assert_grads(G.grad_errors(got, ref, fragile=G.fragile_gaussians(f, H, W)), what, max_fragile=max_fragile)
     return ri, st, f, got, ref, res
 
 
@@ -71,7 +71,8 @@ def test_config4_shape_full_parity():
 def test_config5_sweep_endpoints_full_parity(P):
     """BASELINE config 5 endpoints: 50K (44 pairs/tile, launch-bound) and 2M (1763 pairs/tile: 8-warp register
     sort, multi-batch render kernels)."""
-    _, st, _, _, _, _ = _full_parity(P, 756, 1008, 3407, f"C5/{P}")
+    # at 2M Gaussians a pixel has ~150 contributors, so the 1342 fragile pixels touch ~10 % of the Gaussians
+    _, st, _, _, _, _ = _full_parity(P, 756, 1008, 3407, f"C5/{P}", max_fragile=0.2 if P > 1_000_000 else 0.05)
     if P == 2_000_000:
         assert st["max_tile_pairs"] > 1024
 
