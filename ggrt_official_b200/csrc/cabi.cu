@@ -4,11 +4,22 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>  // header-only: resolves the tools library lazily, a no-op without a profiler attached
+
 #include "common.cuh"
 
 namespace ggrt {
 
 static thread_local char g_err[512] = "";
+
+struct NvtxRange {  // RAII NVTX range around a launch
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
+static const char* const kStageNames[GGRT_STAGE_COUNT] = {"geometry",       "scan_tiles",      "color",
+                                                          "emit",           "sort_tiles",      "render_forward",
+                                                          "render_backward", "preprocess_backward"};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -40,6 +51,7 @@ struct StageTimer {  // RAII: records start/stop events around one launch when p
     int stage;
     cudaStream_t s;
     StageTimer(int stage_, cudaStream_t s_) : stage(stage_), s(s_) {
+        nvtxRangePushA(kStageNames[stage]);  // one NVTX range per kernel launch (nsys / ncu --nvtx), SURVEY.md section 5
         if (!g_prof.on) return;
         if (!g_prof.made) {
             for (int i = 0; i < GGRT_STAGE_COUNT; ++i) cudaEventCreate(&g_prof.a[i]), cudaEventCreate(&g_prof.b[i]);
@@ -48,6 +60,7 @@ struct StageTimer {  // RAII: records start/stop events around one launch when p
         cudaEventRecord(g_prof.a[stage], s);
     }
     ~StageTimer() {
+        nvtxRangePop();
         if (!g_prof.on) return;
         cudaEventRecord(g_prof.b[stage], s);
         g_prof.used[stage] = true;
@@ -304,7 +317,9 @@ int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, const GgrtRa
     // evaluating every Gaussian and deriving the depth itself, was measured too and is no faster: 0.378 ms.)
     SideStream* ss = (overlap_enabled() && !g_prof.on && !dbg && P > 0) ? side_stream() : nullptr;
     if (ss && cudaEventRecord(ss->fork, s) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess) {
+        nvtxRangePushA("color (side stream)");
         launch_color(v, means3D, shs, colors_precomp, aux, radii, g, ss->stream);
+        nvtxRangePop();
         GGRT_TRY(check_launch("color", 0, ss->stream));
         if (cudaEventRecord(ss->join, ss->stream) != cudaSuccess) return check_launch("color join", 0, s);
         ss->pending = true;
@@ -493,6 +508,7 @@ int ggrt_raster_sh_gradient_merge(int32_t P, int32_t sh_degree, const GgrtRaster
         cmajor = layout->sh_channel_major != 0;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    NvtxRange nvtx_("sh_gradient_merge");
     launch_sh_gradient_merge(P, sh_degree, scale, cmajor, means3D, num_views, drgb_views_host, campos_views_host,
                              dL_dsh, MergeSignal(), s);
     return check_launch("sh_gradient_merge", 0, s);
@@ -532,6 +548,7 @@ int ggrt_raster_sh_gradient_merge_signalled(int32_t P, int32_t sh_degree, const 
         set_error("sh_gradient_merge_signalled: P = 0 is not supported (the kernel is the step's wait)");
         return GGRT_ERR_UNSUPPORTED;
     }
+    NvtxRange nvtx_("sh_gradient_merge (signalled)");
     launch_sh_gradient_merge(P, sh_degree, scale, cmajor, means3D, world, drgb, campos, dL_dsh, sig, s);
     return check_launch("sh_gradient_merge_signalled", 0, s);
 }
@@ -544,6 +561,7 @@ int ggrt_raster_nvls_allreduce_f32(void* multicast_ptr, int64_t count, int32_t r
         return GGRT_ERR_INVALID_ARGUMENT;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    NvtxRange nvtx_("nvls_allreduce");
     launch_nvls_allreduce(static_cast<float*>(multicast_ptr), count, rank, world, nullptr, nullptr, nullptr, nullptr,
                           nullptr, s);
     return check_launch("nvls_allreduce", 0, s);
@@ -560,6 +578,7 @@ int ggrt_raster_nvls_allreduce_signalled(void* multicast_ptr, int64_t count, int
         return GGRT_ERR_INVALID_ARGUMENT;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    NvtxRange nvtx_("nvls_allreduce (signalled)");
     launch_nvls_allreduce(static_cast<float*>(multicast_ptr), count, rank, world, epoch, arrive_in,
                           static_cast<uint32_t*>(arrive_out_multicast), arrive_out, done_counter, s);
     return check_launch("nvls_allreduce_signalled", 0, s);
@@ -609,6 +628,7 @@ int ggrt_adapter_forward(const GgrtAdapterParams* params, const float* extrinsic
         return GGRT_ERR_INVALID_ARGUMENT;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    NvtxRange nvtx_("adapter_forward");
     launch_adapter_forward(*params, extrinsics, intrinsics, sh_rotation, coordinates, depths, raw, means, covariances,
                            harmonics, scales_out, rotations_out, s);
     return check_launch("adapter_forward", 0, s);
@@ -625,6 +645,7 @@ int ggrt_adapter_backward(const GgrtAdapterParams* params, const float* extrinsi
         return GGRT_ERR_INVALID_ARGUMENT;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    NvtxRange nvtx_("adapter_backward");
     launch_adapter_backward(*params, extrinsics, intrinsics, sh_rotation, coordinates, depths, raw, dL_dmeans,
                             dL_dcovariances, dL_dharmonics, dL_dcoordinates, dL_ddepths, dL_draw, s);
     return check_launch("adapter_backward", 0, s);
@@ -666,9 +687,7 @@ int ggrt_raster_profile_read(float* ms_out) {
 }
 
 const char* ggrt_raster_stage_name(int32_t stage) {
-    static const char* names[GGRT_STAGE_COUNT] = {"geometry", "scan_tiles", "color", "emit", "sort_tiles",
-                                                  "render_forward", "render_backward", "preprocess_backward"};
-    return (stage >= 0 && stage < GGRT_STAGE_COUNT) ? names[stage] : "?";
+    return (stage >= 0 && stage < GGRT_STAGE_COUNT) ? kStageNames[stage] : "?";
 }
 
 }  // extern "C"

@@ -26,6 +26,9 @@ namespace ggrt {
 #define GGRT_PB_STAGES 2
 #endif
 constexpr int PB_THREADS = GGRT_PB_THREADS;
+#ifndef GGRT_PB_MINBLOCKS
+#define GGRT_PB_MINBLOCKS 3
+#endif
 
 constexpr int PB_STAGES = GGRT_PB_STAGES;
 
@@ -46,7 +49,7 @@ __device__ __forceinline__ void sink_store1(float* dst, float v, bool multimem) 
 }
 
 template <bool AUX, bool CMAJOR, bool POSE>
-__global__ void __launch_bounds__(PB_THREADS, 3)
+__global__ void __launch_bounds__(PB_THREADS, GGRT_PB_MINBLOCKS)
 preprocess_backward_kernel(View v, const float* __restrict__ means, const float* __restrict__ cov3d,
                            const float* __restrict__ shs, const int* __restrict__ radii,
                            const uint8_t* __restrict__ flags, const float* __restrict__ scratch,
@@ -450,8 +453,9 @@ void launch_preprocess_backward(const View& v, const float* means, const float* 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int per_sm = smem ? max(1, min(8, (int)((220 * 1024) / (smem + 1024)))) : 8;
-    const int grid = min(num_slabs, per_sm * sms);  // persistent CTAs
+    // persistent CTAs: as many per SM as shared memory AND the register budget of __launch_bounds__ allow
+    const int per_sm = smem ? max(1, min(GGRT_PB_MINBLOCKS, (int)((220 * 1024) / (smem + 1024)))) : 8;
+    const int grid = min(num_slabs, per_sm * sms);
 #define GGRT_LAUNCH_PB(AX, CM, PO)                                                                                      \
     {                                                                                                                   \
         if (smem > 32 * 1024)                                                                                           \

@@ -160,14 +160,16 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
         const uint32_t boff = (uint32_t)bi * BWD_BATCH;
         const uint32_t cnt = min((uint32_t)BWD_BATCH, block_last - boff);
         __syncthreads();  // every warp is done with the previous batch before the refill
-        for (uint32_t k = tid; k < cnt; k += BWD_THREADS) {
+        for (uint32_t k = tid; k < cnt; k += BWD_THREADS) {  // gather the batch's records with cp.async (LDGSTS)
             const uint32_t id = points[start + boff + k];
             sid[k] = id;
             const uint32_t dst = sbase + k * REC_BYTES;
-            sts128(dst, rec0[id]);
-            sts128(dst + 16, rec1[id]);
-            sts128(dst + 32, rec2[id]);
+            cp_async16(dst, rec0 + id);
+            cp_async16(dst + 16, rec1 + id);
+            cp_async16(dst + 32, rec2 + id);
         }
+        cp_async_commit();
+        cp_async_wait<0>();
         __syncthreads();
         if (warp_last <= boff) continue;
 

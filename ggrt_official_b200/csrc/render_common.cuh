@@ -44,6 +44,16 @@ __device__ __forceinline__ void sts128(uint32_t a, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// cp.async (SASS: LDGSTS): 16-byte global -> shared copies without a register round trip, tracked in commit groups
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // Exact (conservative) test: does the ellipse {q(p - g) <= tau'} reach the pixel rectangle
 // [x0, x0+w] x [y0, y0+h]?  q is convex with its minimum at g, so its minimum over the rectangle is 0 when g is
 // inside and otherwise lies on an edge facing g: minimise the 1-D quadratic along the (at most two) facing edges.

@@ -19,15 +19,6 @@ namespace ggrt {
 #ifndef GGRT_FWD_ASYNC
 #define GGRT_FWD_ASYNC 1
 #endif
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 template <bool ASYNC>
 __global__ void __launch_bounds__(FWD_THREADS, 1024 / FWD_THREADS)
 render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __restrict__ rec1,

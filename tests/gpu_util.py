@@ -126,14 +126,18 @@ def fragile_allowance(n_pixels: int, n_pairs: int, n_tiles: int, dense: bool = F
     return max(16, int((8e-6 if dense else 2e-6) * n_pixels * per_tile))
 
 
-def fragile_gaussians(f: dict, H: int = 0, W: int = 0) -> np.ndarray:
-    """bool [P]: Gaussians that contribute to a pixel where some Gaussian's hard-threshold test (alpha >= 1/255,
-    alpha = 0.99, power = 0, T < 1e-4) fell within the oracle's rounding band (oracle_render_forward flags them).
-    An implementation with another exp() / fma rounding may legitimately take the other branch there: the flagged
-    Gaussian gains or loses that pixel's contribution, and every other contributor of the pixel sees its
-    transmittance / the colour behind it move by up to alpha ~ 0.4 % -- beyond the 1e-3 bar for splats that cover a
-    pixel or two."""
-    return f["img"]["fragile_gaussian"] != 0
+def fragile_gaussians(f: dict, H: int = 0, W: int = 0, contributors: bool = False) -> np.ndarray:
+    """bool [P]: Gaussians whose gradient an implementation with another exp() / fma rounding may legitimately change
+    by more than the elementwise bar, as flagged by oracle_render_forward:
+      * always: a Gaussian whose OWN hard-threshold test (alpha >= 1/255, alpha = 0.99, power = 0, T < 1e-4) fell
+        within the oracle's rounding band at some pixel -- it gains or loses that pixel's contribution;
+      * with contributors=True (the BASELINE scenes, whose splats cover a handful of pixels so that one pixel is a
+        large share of a gradient full of cancellation): every Gaussian contributing to such a pixel -- if the
+        flagged one flips, their transmittance / the colour behind them moves by up to alpha ~ 0.4 % there.  For
+        the inflated-covariance unit cases (hundreds of pixels per splat) that effect is far inside the bar and the
+        strict bar is kept for them (measured: worst element at 0.03 of the bar)."""
+    fg = f["img"]["fragile_gaussian"]
+    return (fg != 0) if contributors else ((fg & 1) != 0)
 
 
 def grad_errors(got: dict, ref: dict, use_sh=True, fragile=None):

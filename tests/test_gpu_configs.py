@@ -39,7 +39,7 @@ def _full_parity(P, H, W, seed, what, grad=None, want_camera=False, max_fragile=
     got = R.backward_raw(st, torch.tensor(g, device=DEV), want_camera=want_camera)
     torch.cuda.synchronize()
     ref = co.backward(cam, ri.means3D, ri.cov3D, ri.opacities, f, g, sh=ri.shs, want_camera=want_camera)
-    G.assert_grads(G.grad_errors(got, ref, fragile=G.fragile_gaussians(f, H, W)), what, max_fragile=max_fragile)
+    G.assert_grads(G.grad_errors(got, ref, fragile=G.fragile_gaussians(f, H, W, contributors=True)), what, max_fragile=max_fragile)
     return ri, st, f, got, ref, res
 
 

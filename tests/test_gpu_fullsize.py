@@ -33,7 +33,7 @@ def test_config2_full_parity_forward_and_backward():
     g = image_gradient(H, W)
     got = R.backward_raw(st, torch.tensor(g, device="cuda:0"))
     ref = co.backward(cam, ri.means3D, ri.cov3D, ri.opacities, f, g, sh=ri.shs)
-    G.assert_grads(G.grad_errors(got, ref, fragile=G.fragile_gaussians(f, H, W)), "C2")
+    G.assert_grads(G.grad_errors(got, ref, fragile=G.fragile_gaussians(f, H, W, contributors=True)), "C2")
 
 
 def test_config3_size_properties():
