@@ -44,8 +44,7 @@ class GradSinks(C.Structure):
 
     _fields_ = [("count", C.c_int32), ("multimem", C.c_int32), ("ptr", C.c_void_p * 16),
                 ("epoch", C.c_void_p), ("done_counter", C.c_void_p), ("parity_stride", C.c_int64),
-                ("arrive_count", C.c_int32), ("early_push", C.c_int32), ("arrive", C.c_void_p * 16),
-                ("pushed_event", C.c_void_p), ("done_counter2", C.c_void_p), ("arrive_outputs", C.c_void_p * 16)]
+                ("arrive_count", C.c_int32), ("reserved", C.c_int32), ("arrive", C.c_void_p * 16)]
 
 
 class AdapterParams(C.Structure):

@@ -454,20 +454,6 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
             }
             sinks.epoch = color_sinks->epoch, sinks.done = color_sinks->done_counter;
             sinks.parity_stride = color_sinks->parity_stride, sinks.n_arrive = na;
-            if (color_sinks->early_push) {
-                if (!color_sinks->done_counter2) {
-                    set_error("backward: early_push needs done_counter2");
-                    return GGRT_ERR_INVALID_ARGUMENT;
-                }
-                for (int k = 0; k < na; ++k)
-                    if (!color_sinks->arrive_outputs[k] || (reinterpret_cast<uintptr_t>(color_sinks->arrive_outputs[k]) & 3)) {
-                        set_error("backward: color_sinks->arrive_outputs[%d] must be a 4-byte aligned device pointer", k);
-                        return GGRT_ERR_INVALID_ARGUMENT;
-                    }
-            }
-        } else if (color_sinks->early_push) {
-            set_error("backward: early_push needs the signalling fields (epoch, ...)");
-            return GGRT_ERR_INVALID_ARGUMENT;
         }
     } else if (shs != nullptr && dL_dcolors != nullptr) {
         sinks.ptr[0] = dL_dcolors, sinks.n = 1;
@@ -484,21 +470,6 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
     if (num_rendered > 0) {
         { StageTimer t_(GGRT_STAGE_RENDER_BACKWARD, s); launch_render_backward(v, g, im, b, dL_dout_color, dL_dout_aux, grad_scratch, s); }
         GGRT_TRY(check_launch("render_backward", dbg, s));
-    }
-    if (have_sinks && color_sinks->early_push) {
-        // the colour gradients are final: push them to the other GPUs now, signal, and let the per-Gaussian kernel
-        // below run without any colour / SH output (it signals the completion of the plain outputs instead)
-        {
-            NvtxRange nvtx_("push_color_gradients");
-            launch_push_color_gradients(P, grad_scratch, radii, g.flags, v.campos, sinks, s);
-        }
-        GGRT_TRY(check_launch("push_color_gradients", dbg, s));
-        if (color_sinks->pushed_event &&
-            cudaEventRecord(static_cast<cudaEvent_t>(color_sinks->pushed_event), s) != cudaSuccess)
-            return check_launch("record pushed_event", 0, s);
-        sinks.n = 0, sinks.with_campos = 0, sinks.signal_only = 1;
-        sinks.done = color_sinks->done_counter2;
-        for (int k = 0; k < sinks.n_arrive; ++k) sinks.arrive[k] = color_sinks->arrive_outputs[k];
     }
     {
         StageTimer t_(GGRT_STAGE_PREPROCESS_BACKWARD, s);

@@ -77,7 +77,6 @@ struct ColorSinks {
     long long parity_stride;
     int n_arrive;
     uint32_t* arrive[GGRT_RASTER_MAX_MERGE_VIEWS];
-    int signal_only;  // 1: do not read / advance the epoch, just signal `arrive` when the kernel is done
 };
 
 // ---- cross-GPU signalling primitives (system scope) -------------------------------------------------------------
@@ -136,8 +135,6 @@ struct MergeSignal {  // signalled exchange: wait for world * *epoch arrivals, r
     int world = 0;
     long long parity_stride = 0;
 };
-void launch_push_color_gradients(int P, const float* scratch, const int* radii, const uint8_t* flags, const float* campos,
-                                 const ColorSinks& sinks, cudaStream_t s);
 void launch_sh_gradient_merge(int P, int deg, float scale, bool cmajor, const float* means, int num_views,
                               const float* const* drgb, const float* const* campos, float* dsh, const MergeSignal& sig,
                               cudaStream_t s);

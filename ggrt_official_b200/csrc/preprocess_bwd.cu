@@ -65,7 +65,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     else if (threadIdx.x < 32) sM[threadIdx.x - 16] = v.proj[threadIdx.x - 16];
 
     // signalled exchange: this step pushes into half (epoch & 1) of every sink
-    const long long poff = (sinks.epoch != nullptr && !sinks.signal_only)
+    const long long poff = sinks.epoch != nullptr
                                ? (long long)(*reinterpret_cast<volatile uint32_t*>(sinks.epoch) & 1u) * sinks.parity_stride
                                : 0ll;
     const int row = v.K * 3;
@@ -334,7 +334,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
         } else if (valid && !compact) {
             for (int k = 0; k < row; ++k) my[k] = 0.f;
         }
-        if (compact && sinks.n > 0) {  // masked colour gradient (zero for culled Gaussians and clamped channels)
+        if (compact) {  // masked colour gradient (zero for culled Gaussians and clamped channels)
             if (valid) sdc[3 * threadIdx.x] = dR, sdc[3 * threadIdx.x + 1] = dG, sdc[3 * threadIdx.x + 2] = dB;
             __syncthreads();
             const int n3 = cnt * 3, n4 = n3 >> 2;
@@ -436,61 +436,11 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             sink_store1(sinks.ptr[sk] + poff + (size_t)v.P * 3 + threadIdx.x, v.campos[threadIdx.x], sinks.multimem != 0);
     }
     if (threadIdx.x == 0) bulk_wait0();  // all bulk stores of this CTA have completed
-    if (sinks.n_arrive > 0 && last_cta_done(sinks.done)) {
+    if (sinks.epoch != nullptr && last_cta_done(sinks.done)) {
         // every CTA's pushes and plain outputs are fenced: advance the step counter and tell the receivers
-        if (!sinks.signal_only)
-            *reinterpret_cast<volatile uint32_t*>(sinks.epoch) = *reinterpret_cast<volatile uint32_t*>(sinks.epoch) + 1u;
+        *reinterpret_cast<volatile uint32_t*>(sinks.epoch) = *reinterpret_cast<volatile uint32_t*>(sinks.epoch) + 1u;
         for (int k = 0; k < sinks.n_arrive; ++k) signal_add(sinks.arrive[k], sinks.multimem != 0);
     }
-}
-
-// ---------------------------------------------------------------------------------------
-// Early push of the compact colour gradients (view-sharded multi-GPU exchange, GgrtRasterGradSinks.early_push).
-// dL/drgb of a Gaussian is final when the render backward kernel has finished -- it is the colour slot of the
-// gradient scratch, masked by the clamp bits -- so it can travel to the other GPUs while the per-Gaussian backward
-// kernel still runs.  256 Gaussians per CTA, rows staged in shared memory and stored as 16-byte vectors to every
-// sink (one multimem.st per vector with NVLS); row P of a sink receives the view's camera centre.  The last CTA
-// advances the epoch and signals the receivers.
-// ---------------------------------------------------------------------------------------
-constexpr int PUSH_THREADS = 256;
-
-__global__ void __launch_bounds__(PUSH_THREADS)
-push_color_gradients_kernel(int P, const float* __restrict__ scratch, const int* __restrict__ radii,
-                            const uint8_t* __restrict__ flags, const float* __restrict__ campos, ColorSinks sinks) {
-    __shared__ __align__(16) float sdc[PUSH_THREADS * 3];
-    const long long poff = (long long)(*reinterpret_cast<volatile uint32_t*>(sinks.epoch) & 1u) * sinks.parity_stride;
-    const int base = blockIdx.x * PUSH_THREADS, i = base + threadIdx.x;
-    const int cnt = min(PUSH_THREADS, P - base);
-    float dR = 0.f, dG = 0.f, dB = 0.f;
-    if (i < P && radii[i] > 0) {
-        const float* gs = scratch + (size_t)i * GRAD_STRIDE;
-        const uint32_t fl = flags[i];
-        dR = (fl & 1) ? 0.f : gs[G_R];
-        dG = (fl & 2) ? 0.f : gs[G_G];
-        dB = (fl & 4) ? 0.f : gs[G_B];
-    }
-    sdc[3 * threadIdx.x] = dR, sdc[3 * threadIdx.x + 1] = dG, sdc[3 * threadIdx.x + 2] = dB;
-    __syncthreads();
-    const int n3 = cnt * 3, n4 = n3 >> 2;
-    const bool mm = sinks.multimem != 0;
-    for (int sk = 0; sk < sinks.n; ++sk) {
-        float* dst = sinks.ptr[sk] + poff + (size_t)base * 3;  // CTA offsets are multiples of 3072 B
-        for (int k = threadIdx.x; k < n4; k += PUSH_THREADS)
-            sink_store4(dst + 4 * k, *reinterpret_cast<const float4*>(sdc + 4 * k), mm);
-        for (int k = (n4 << 2) + threadIdx.x; k < n3; k += PUSH_THREADS) sink_store1(dst + k, sdc[k], mm);
-        if (blockIdx.x == 0 && threadIdx.x < 3)
-            sink_store1(sinks.ptr[sk] + poff + (size_t)P * 3 + threadIdx.x, campos[threadIdx.x], mm);
-    }
-    if (last_cta_done(sinks.done)) {
-        *reinterpret_cast<volatile uint32_t*>(sinks.epoch) = *reinterpret_cast<volatile uint32_t*>(sinks.epoch) + 1u;
-        for (int k = 0; k < sinks.n_arrive; ++k) signal_add(sinks.arrive[k], mm);
-    }
-}
-
-void launch_push_color_gradients(int P, const float* scratch, const int* radii, const uint8_t* flags, const float* campos,
-                                 const ColorSinks& sinks, cudaStream_t s) {
-    const int grid = max(1, (P + PUSH_THREADS - 1) / PUSH_THREADS);
-    push_color_gradients_kernel<<<grid, PUSH_THREADS, 0, s>>>(P, scratch, radii, flags, campos, sinks);
 }
 
 void launch_preprocess_backward(const View& v, const float* means, const float* cov3d, const float* shs,

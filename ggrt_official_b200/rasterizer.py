@@ -357,12 +357,6 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
             sinks.parity_stride, sinks.arrive_count = int(color_sinks["parity_stride"]), len(arrive)
             for k, a in enumerate(arrive):
                 sinks.arrive[k] = a
-            if color_sinks.get("early_push"):
-                sinks.early_push = 1
-                sinks.done_counter2 = int(color_sinks["done2"])
-                sinks.pushed_event = int(color_sinks.get("pushed_event") or 0) or None
-                for k, a in enumerate(color_sinks["arrive_outputs"]):
-                    sinks.arrive_outputs[k] = int(a)
     if compact and c.sh is None:
         raise ValueError("compact=True needs SH inputs (colors_precomp already yields dcolors)")
     dev = c.device

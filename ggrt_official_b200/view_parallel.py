@@ -192,7 +192,7 @@ class CompactGradientExchange:
         if self.world == 1 or self.transport != "p2p":
             return 1
         if self.signalled:
-            return 3  # colour push + merge + all-reduce, with their waits / signals inside
+            return 2  # merge + all-reduce, both with their waits inside
         n = 1 + (1 if self.handles[1].multicast_ptr else 0)
         return n + (2 if self.barrier_kind == "nvls" else 0)
 
@@ -228,17 +228,7 @@ class CompactGradientExchange:
         self.marks = []
         self._mark("start")
         call = state["call"]
-        if self.signalled:  # p2p + in-kernel signalling: early push of the colour gradients inside the backward call
-            if self._side is None:
-                self._side = torch.cuda.Stream(device=self.device)
-                self._pushed = torch.cuda.Event()
-                self._pushed.record(torch.cuda.current_stream(self.device))  # creates the underlying CUDA event
-            bar_mc = int(self.bar_handle.multicast_ptr)
-            sinks = dict(self.sinks, early_push=True, done2=self.ctrl.data_ptr() + 12,
-                         pushed_event=self._pushed.cuda_event, arrive_outputs=[bar_mc + 8])
-            out = self.backward_fn(state, grad_color, out={k: v for k, v in self.views.items() if k != "dcolors"},
-                                   color_sinks=sinks, **backward_kw)
-        elif self.sinks is not None:  # p2p: the kernel pushes colour gradients + campos into every GPU's slot table
+        if self.sinks is not None:  # p2p: the kernel pushes colour gradients + campos into every GPU's slot table
             out = self.backward_fn(state, grad_color, out={k: v for k, v in self.views.items() if k != "dcolors"},
                                    color_sinks=self.sinks, **backward_kw)
         else:
@@ -252,12 +242,17 @@ class CompactGradientExchange:
             L = _cabi.lib()
             hs, hm = self.handles
             main = torch.cuda.current_stream(self.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
             side = self._side
             ctrl, bar, bar_mc = self.ctrl.data_ptr(), self.bar.data_ptr(), int(self.bar_handle.multicast_ptr)
-            # The push kernel inside backward_fn has signalled bar[0]; the merge (HBM-bound: it writes dL/dsh) runs on
-            # the side stream from that point on, beside this rank's per-Gaussian backward kernel, and waits by itself
-            # for the other ranks' pushes.
-            side.wait_event(self._pushed)
+            # the NVLink-bound sum of the small arena runs beside the HBM-bound merge; both kernels wait by themselves
+            # for the arrival counter the ranks' backward kernels bump, the all-reduce also for its own completion
+            side.wait_stream(main)
+            _cabi.check(L.ggrt_raster_nvls_allreduce_signalled(
+                C.c_void_p(hm.multicast_ptr), self.small_elems, self.rank, self.world, C.c_void_p(ctrl),
+                C.c_void_p(bar), C.c_void_p(bar_mc + 4), C.c_void_p(bar + 4), C.c_void_p(ctrl + 8),
+                C.c_void_p(side.cuda_stream)), "nvls_allreduce_signalled")
             clay = None
             if self.layout:
                 clay = C.byref(_cabi.InputLayout(float(self.layout.get("scene_scale", 1.0)), 0,
@@ -265,18 +260,11 @@ class CompactGradientExchange:
             _cabi.check(L.ggrt_raster_sh_gradient_merge_signalled(
                 P_, self.deg, clay, C.c_void_p(call.means3D.data_ptr()), self.world, C.c_void_p(self.slots.data_ptr()),
                 self.slot, self.world * self.slot, C.c_void_p(ctrl), C.c_void_p(bar), C.c_void_p(self.dsh.data_ptr()),
-                C.c_void_p(side.cuda_stream)), "sh_gradient_merge_signalled")
-            self._mark("merge_launch")
-            # the small arena is summed inside the NVSwitch once every rank's per-Gaussian kernel has signalled bar[2];
-            # the kernel returns when every rank has broadcast its slice (bar[1])
-            _cabi.check(L.ggrt_raster_nvls_allreduce_signalled(
-                C.c_void_p(hm.multicast_ptr), self.small_elems, self.rank, self.world, C.c_void_p(ctrl),
-                C.c_void_p(bar + 8), C.c_void_p(bar_mc + 4), C.c_void_p(bar + 4), C.c_void_p(ctrl + 8),
-                C.c_void_p(main.cuda_stream)), "nvls_allreduce_signalled")
-            self._mark("allreduce")
+                C.c_void_p(main.cuda_stream)), "sh_gradient_merge_signalled")
             dsh = self.dsh
+            self._mark("merge")
             main.wait_stream(side)
-            self._mark("join_merge")
+            self._mark("join_allreduce")
         elif self.world > 1 and self.transport == "p2p":
             from . import _cabi
             import ctypes as C

@@ -107,18 +107,8 @@ typedef struct GgrtRasterGradSinks {
     uint32_t* done_counter;
     int64_t parity_stride;  /* floats */
     int32_t arrive_count;   /* 1 with multimem, else one counter per receiving GPU */
-    int32_t early_push;     /* see below */
+    int32_t reserved;
     uint32_t* arrive[GGRT_RASTER_MAX_MERGE_VIEWS];
-    /* early_push = 1 (needs epoch): the colour gradients are final as soon as the render backward kernel has
-     * finished, so a small kernel pushes them (and signals `arrive`, advances *epoch) BEFORE the per-Gaussian
-     * backward kernel runs; `pushed_event` (a cudaEvent_t, may be NULL) is recorded on the stream right after it, so
-     * that the caller can start ggrt_raster_sh_gradient_merge_signalled on another stream beside the per-Gaussian
-     * kernel.  That kernel then writes no colour / SH gradient at all and, when its last CTA is done, adds 1 to
-     * `arrive_outputs` (count and multimem as `arrive`; done_counter2: another zeroed LOCAL word): the plain outputs
-     * dL_dmeans3D / dL_dcov3D / dL_dopacity of every rank are complete when it reaches world * *epoch. */
-    void* pushed_event;
-    uint32_t* done_counter2;
-    uint32_t* arrive_outputs[GGRT_RASTER_MAX_MERGE_VIEWS];
 } GgrtRasterGradSinks;
 
 /* Byte offsets of the sub-arrays inside the caller-owned buffers (for tests / tools). */
