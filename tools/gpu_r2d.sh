@@ -16,10 +16,14 @@ for v in $(ls gpurun_variants 2>/dev/null); do
   ts "variant $v: bench"
   GGRT_RASTER_LIB=$lib timeout 300 python bench.py --steps 40 --no-cpu-baseline --no-gpu-baseline --no-extras > $out/bench_$v.json 2> $out/bench_$v.err
 done
+ts "exchange kernels (virtual views)"
+timeout 300 python tools/bench_merge.py > $out/bench_merge.json 2> $out/bench_merge.err
+ts "ncu full: merge kernel"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'sh_gradient_merge' -s 20 -c 1 -o $out/prof_merge python tools/bench_merge.py > $out/ncu_merge.log 2>&1
 ts "ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $out/launches.csv python bench.py --launch eager --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-extras > $out/ncu_bench.log 2>&1
 ts "ncu full: render kernels"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'render_(backward|forward)' -s 8 -c 2 -o $out/prof_render python bench.py --launch eager --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-extras > $out/ncu_render.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'render_(backward|forward)|preprocess_backward|emit|sort_tiles' -s 40 -c 5 -o $out/prof_render python bench.py --launch eager --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-extras > $out/ncu_render.log 2>&1
 ts done
 python - <<'PY' $out
 import json, sys, glob, os
