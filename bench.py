@@ -256,6 +256,8 @@ def run_ours(args, rank, world, local_rank):
     N, max_pairs = st0["N"], st0["max_tile_pairs"]
     del st0
     launch, cap, cap_err = args.launch, None, None
+    if launch == "auto":
+        launch = "graph" if world == 1 else "eager"
     if launch == "graph" and arena is None:
         try:
             cap = CapturedStep(means, shs, None, opac, cov, rs, grad_img, exchange=exch, want_camera=args.pose_grads)
@@ -585,8 +587,9 @@ def measure_extras(args, ri, g_np, dev, flush_l2):
         res = {}
         for name, fused, fast, mode in (("color_only", False, False, None), ("color_and_depth_two_pass", False, False, "depth"),
                                         ("color_and_depth_fused", True, False, "depth"),
-                                        ("color_and_depth_fast_glue", True, True, "depth")):
-            dec = DecoderSplattingCUDA(fused_depth=fused, fast_glue=fast)
+                                        ("color_and_depth_fast_glue", True, True, "depth"),
+                                        ("color_and_depth_device_glue", True, "device", "depth")):
+            dec = DecoderSplattingCUDA(fused_depth=fused, fast_glue=bool(fast), device_glue=(fast == "device"))
 
             def dstep():
                 for v in leaves.values():
@@ -624,8 +627,10 @@ def main():
                     help="override the Gaussian count of the workload (BASELINE config 5: 50K..2M sweep at 1008x756)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "arena", "compact", "p2p"],
                     help="multi-GPU gradient exchange (N>1 only), see run_ours")
-    ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
-                    help="how the timed step is issued: one CUDA graph replay (default) or eager kernel launches")
+    ap.add_argument("--launch", default="auto", choices=["auto", "graph", "eager"],
+                    help="how the timed step is issued: one CUDA graph replay, or eager kernel launches with the "
+                         "pair-buffer check deferred; auto (default) = graph at N=1, eager at N>1 (measured on 8xB200, "
+                         "DESIGN.md section 6: 0.355 vs 0.369 ms at N=1, 0.470 vs 0.438 ms at N=8)")
     ap.add_argument("--no-extras", action="store_true", help="skip the depth-pass / through-the-caller lines (N=1)")
     ap.add_argument("--pose-grads", action="store_true",
                     help="also compute dL/d(viewmatrix, projmatrix, campos) in the backward (BASELINE config 3)")

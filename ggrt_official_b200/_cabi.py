@@ -10,7 +10,7 @@ from pathlib import Path
 
 from . import build as _build
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 _lib = None
 
 
@@ -30,6 +30,9 @@ class Settings(C.Structure):
         ("projmatrix", C.c_void_p),
         ("campos", C.c_void_p),
         ("bg", C.c_void_p),
+        ("device_params", C.c_void_p),
+        ("aux_mode", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -82,6 +85,7 @@ EXPORTS = (
     "ggrt_raster_nvls_barrier",
     "ggrt_adapter_forward",
     "ggrt_adapter_backward",
+    "ggrt_camera_setup",
     "ggrt_raster_mark_visible",
     "ggrt_raster_profile_enable",
     "ggrt_raster_profile_read",
@@ -89,6 +93,7 @@ EXPORTS = (
 )
 STAGE_COUNT = 8
 MAX_MERGE_VIEWS = 16
+CAMERA_FLOATS = 48
 
 
 def library_path() -> Path:
@@ -129,6 +134,7 @@ def lib():
     L.ggrt_raster_nvls_barrier.argtypes = [vp, vp, u32, vp]
     L.ggrt_adapter_forward.argtypes = [C.POINTER(AdapterParams)] + [vp] * 12
     L.ggrt_adapter_backward.argtypes = [C.POINTER(AdapterParams)] + [vp] * 13
+    L.ggrt_camera_setup.argtypes = [i32, vp, vp, vp, vp, i32, vp, vp]
     L.ggrt_raster_mark_visible.argtypes = [i32, vp, vp, vp, vp]
     L.ggrt_raster_profile_enable.argtypes = [i32]
     L.ggrt_raster_profile_read.argtypes = [C.POINTER(C.c_float)]

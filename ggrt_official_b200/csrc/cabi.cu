@@ -202,9 +202,13 @@ static int make_view(const GgrtRasterSettings* s, const GgrtRasterInputLayout* l
         set_error("sh_degree %d outside 0..4", s->sh_degree);
         return GGRT_ERR_UNSUPPORTED;
     }
-    if (!(s->tanfovx > 0.f) || !(s->tanfovy > 0.f)) {
+    if (s->device_params == nullptr && (!(s->tanfovx > 0.f) || !(s->tanfovy > 0.f))) {
         set_error("tanfov must be positive");
         return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    if (s->aux_mode != 0 && s->aux_mode != 1) {
+        set_error("aux_mode %d unknown", s->aux_mode);
+        return GGRT_ERR_UNSUPPORTED;
     }
     if (!s->viewmatrix || !s->projmatrix || !s->campos || !s->bg) {
         set_error("viewmatrix / projmatrix / campos / bg must be device pointers");
@@ -241,6 +245,11 @@ static int make_view(const GgrtRasterSettings* s, const GgrtRasterInputLayout* l
     v->proj = s->projmatrix;
     v->campos = s->campos;
     v->bg = s->bg;
+    v->dparams = s->device_params;
+    v->aux_mode = s->aux_mode;
+    if (s->device_params != nullptr) {  // the kernels read tanfov / scene scale themselves (resolve_device_params)
+        v->tanfovx = v->tanfovy = v->fx = v->fy = 0.0f;
+    }
     return GGRT_OK;
 }
 
@@ -410,10 +419,12 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
         set_error("backward: NULL buffer");
         return GGRT_ERR_INVALID_ARGUMENT;
     }
-    if ((dL_dout_aux != nullptr) != (dL_daux != nullptr)) {
-        set_error("backward: dL_dout_aux and dL_daux go together");
+    if (settings->aux_mode == 1 ? dL_daux != nullptr : (dL_dout_aux != nullptr) != (dL_daux != nullptr)) {
+        set_error("backward: dL_dout_aux and dL_daux go together (aux_mode 1: dL_daux must be NULL, the gradient of the "
+                  "depth channel flows into dL_dmeans3D)");
         return GGRT_ERR_INVALID_ARGUMENT;
     }
+    if (dL_dout_aux == nullptr) v.aux_mode = 0;  // no gradient for the channel: the per-Gaussian kernel need not know it
     // with shs: dL_dsh (full SH gradient) or dL_dcolors / color_sinks (compact mode, see the header)
     const bool have_sinks = color_sinks != nullptr;
     if ((dL_dsh != nullptr) == (dL_dcolors != nullptr || have_sinks) || (shs == nullptr && (dL_dsh != nullptr || have_sinks)) ||
@@ -649,6 +660,18 @@ int ggrt_adapter_backward(const GgrtAdapterParams* params, const float* extrinsi
     launch_adapter_backward(*params, extrinsics, intrinsics, sh_rotation, coordinates, depths, raw, dL_dmeans,
                             dL_dcovariances, dL_dharmonics, dL_dcoordinates, dL_ddepths, dL_draw, s);
     return check_launch("adapter_backward", 0, s);
+}
+
+int ggrt_camera_setup(int32_t num_views, const float* extrinsics, const float* intrinsics, const float* near,
+                      const float* far, int32_t scale_invariant, float* cameras_out, ggrt_stream_t stream) {
+    if (num_views < 0 || (num_views > 0 && (!extrinsics || !intrinsics || !near || !far || !cameras_out))) {
+        set_error("camera_setup: bad argument");
+        return GGRT_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    NvtxRange nvtx_("camera_setup");
+    launch_camera_setup(num_views, extrinsics, intrinsics, near, far, scale_invariant, cameras_out, s);
+    return check_launch("camera_setup", 0, s);
 }
 
 int ggrt_raster_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present,

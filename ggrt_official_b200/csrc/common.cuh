@@ -36,6 +36,8 @@ struct View {  // kernel-side copy of the per-call scalars (matrices stay in dev
     const float* proj;
     const float* campos;
     const float* bg;
+    const float* dparams;  // device {tanfovx, tanfovy, scene_scale} overriding the host copies above (or NULL)
+    int aux_mode;          // 1: aux channel = max(0, C0 z + 0.5) of the unscaled view depth (GGRt's depth pass)
 };
 
 struct GeomPtrs {
@@ -312,6 +314,22 @@ __device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, flo
     b[24] = GGRT_SH_C4_8 * (xx * (xx - 3.0f * yy) - yy * (3.0f * xx - yy));
 }
 
+// Kernels whose maths uses the camera scalars call this first: with a device-resident camera (View::dparams) the
+// host never saw tanfov / scene scale, so they are read here; fx, fy are derived exactly as the host derives them.
+__device__ __forceinline__ void resolve_device_params(View& v) {
+    if (v.dparams != nullptr) {
+        v.tanfovx = v.dparams[0], v.tanfovy = v.dparams[1], v.scale = v.dparams[2];
+        v.fx = fdiv((float)v.W, fmul(2.0f, v.tanfovx));
+        v.fy = fdiv((float)v.H, fmul(2.0f, v.tanfovy));
+    }
+}
+// GGRt's depth channel: the degree-0 SH "colour" of the unscaled camera-space depth (cuda_splatting.py:256-268)
+__device__ __forceinline__ float ggrt_depth_channel(float tz, float scale) {
+    return fmaxf(0.0f, fadd(fmul(GGRT_SH_C0, fdiv(tz, scale)), 0.5f));
+}
+
+void launch_camera_setup(int n, const float* extr, const float* intr, const float* near, const float* far,
+                         int scale_invariant, float* out, cudaStream_t s);
 void set_error(const char* fmt, ...);
 int check_launch(const char* what, int debug, cudaStream_t s);
 

@@ -26,6 +26,7 @@ geometry_kernel(View v, const float* __restrict__ means, const float* __restrict
     __shared__ float sV[16], sM[16];
     if (threadIdx.x < 16) sV[threadIdx.x] = v.view[threadIdx.x];
     else if (threadIdx.x < 32) sM[threadIdx.x - 16] = v.proj[threadIdx.x - 16];
+    resolve_device_params(v);
     __syncthreads();
     const int i = blockIdx.x * GEO_THREADS + threadIdx.x;
     if (i >= v.P) return;
@@ -221,6 +222,7 @@ color_kernel(View v, const float* __restrict__ means, const float* __restrict__ 
     constexpr int KK = (DEG + 1) * (DEG + 1);
     constexpr int row = KK * 3;
     constexpr int ks = CMAJOR ? 1 : 3, cs = CMAJOR ? KK : 1;  // SH element (k, c) at k*ks + c*cs of the row
+    resolve_device_params(v);
     const int slab_floats = COLOR_THREADS * row;
     const bool tma_ok = shs != nullptr && (reinterpret_cast<uintptr_t>(shs) & 15) == 0;  // slab bases are 16 B multiples
 
@@ -255,7 +257,8 @@ color_kernel(View v, const float* __restrict__ means, const float* __restrict__ 
         if (sl < num_slabs && i < v.P) {
             n_radius = radii[i];
             n_mx = means[3 * i], n_my = means[3 * i + 1], n_mz = means[3 * i + 2];  // raw: scaled when consumed
-            n_depth = aux ? aux[i] : g.rec0[i].w;  // 4th blended channel: caller's aux or the view depth
+            n_depth = aux ? aux[i] : g.rec0[i].w;  // 4th blended channel: caller's aux or the view depth ...
+            if (v.aux_mode == 1) n_depth = ggrt_depth_channel(n_depth, v.scale);  // ... or GGRt's depth channel of it
         }
     };
     prefetch(blockIdx.x);
@@ -326,6 +329,111 @@ color_kernel(View v, const float* __restrict__ means, const float* __restrict__ 
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// camera_setup: one thread per view, float32 arithmetic in the order of the reference glue where that matters for
+// the result (projection entries, tan(fov/2)); the rigid inverse is evaluated in double.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void inv3x3(const float* K, double* o) {
+    const double a = K[0], b = K[1], c = K[2], d = K[3], e = K[4], f = K[5], g = K[6], h = K[7], i = K[8];
+    const double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+    const double det = a * A + b * B + c * C, r = 1.0 / det;
+    o[0] = A * r, o[1] = -(b * i - c * h) * r, o[2] = (b * f - c * e) * r;
+    o[3] = B * r, o[4] = (a * i - c * g) * r, o[5] = -(a * f - c * d) * r;
+    o[6] = C * r, o[7] = -(a * h - b * g) * r, o[8] = (a * e - b * d) * r;
+}
+
+__global__ void camera_setup_kernel(int n, const float* __restrict__ extr, const float* __restrict__ intr,
+                                    const float* __restrict__ near, const float* __restrict__ far, int scale_invariant,
+                                    float* __restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const float* E = extr + 16 * v;
+    const float* K = intr + 9 * v;
+    float* o = out + (size_t)GGRT_CAMERA_FLOATS * v;
+    const float scale = scale_invariant ? fdiv(1.0f, near[v]) : 1.0f;
+    const float nr = fmul(near[v], scale), fr = fmul(far[v], scale);
+    // camera-to-world with the translation rescaled (cuda_splatting.py:68-69); its inverse, transposed = viewmatrix
+    double M[16];
+    for (int k = 0; k < 16; ++k) M[k] = E[k];
+    for (int r = 0; r < 3; ++r) M[4 * r + 3] = (double)fmul(E[4 * r + 3], scale);
+    // general 4x4 inverse by cofactors (the reference calls .inverse(); poses are rigid but nothing here assumes it)
+    double inv[16];
+    {
+        const double* m = M;
+        inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+        inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+        inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+        inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+        inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+        inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+        inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+        inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+        inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+        inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+        inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+        inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+        inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+        inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+        inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+        inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+        const double det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12], r = 1.0 / det;
+        for (int k = 0; k < 16; ++k) inv[k] *= r;
+    }
+    float V[16];  // viewmatrix = inverse(extrinsics)^T, float32 as the reference holds it
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) V[4 * r + c] = (float)inv[4 * c + r];
+    // projection (get_projection_matrix, cuda_splatting.py:18-46) from the intrinsics of VIEW 0 (reference quirk)
+    const float* K0 = intr;
+    float Pm[16];
+    for (int k = 0; k < 16; ++k) Pm[k] = 0.0f;
+    Pm[0] = fmul(fmul(2.0f, nr), K0[0]);
+    Pm[5] = fmul(fmul(2.0f, nr), K0[4]);
+    Pm[2] = fsub(fmul(2.0f, K0[2]), 1.0f);
+    Pm[6] = fsub(fmul(2.0f, K0[5]), 1.0f);
+    Pm[14] = 1.0f;
+    Pm[10] = fdiv(fr, fsub(fr, nr));
+    Pm[11] = fdiv(-fmul(fr, nr), fsub(fr, nr));
+    // full = view @ projection^T (row-vector convention), float32 accumulation in index order as torch's matmul of
+    // a [4,4] pair does for these sizes (differences are at the last ulp and inside the parity tolerance)
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            float acc = 0.0f;
+            for (int k = 0; k < 4; ++k) acc = fmaf(V[4 * r + k], Pm[4 * c + k], acc);
+            o[16 + 4 * r + c] = acc;
+        }
+    for (int k = 0; k < 16; ++k) o[k] = V[k];
+    for (int r = 0; r < 3; ++r) o[32 + r] = fmul(E[4 * r + 3], scale);  // campos = rescaled camera-to-world translation
+    // get_fov (ggrt/geometry/projection.py:233-247) of THIS view: angle between the un-projected mid-points of
+    // opposite image edges
+    double Ki[9];
+    inv3x3(K, Ki);
+    const double px[4][3] = {{0, 0.5, 1}, {1, 0.5, 1}, {0.5, 0, 1}, {0.5, 1, 1}};
+    double ray[4][3];
+    for (int p = 0; p < 4; ++p) {
+        double nrm = 0;
+        for (int r = 0; r < 3; ++r) {
+            ray[p][r] = Ki[3 * r] * px[p][0] + Ki[3 * r + 1] * px[p][1] + Ki[3 * r + 2] * px[p][2];
+            nrm += ray[p][r] * ray[p][r];
+        }
+        nrm = sqrt(nrm);
+        for (int r = 0; r < 3; ++r) ray[p][r] /= nrm;
+    }
+    const double cx_ = ray[0][0] * ray[1][0] + ray[0][1] * ray[1][1] + ray[0][2] * ray[1][2];
+    const double cy_ = ray[2][0] * ray[3][0] + ray[2][1] * ray[3][1] + ray[2][2] * ray[3][2];
+    const float fovx = (float)acos(fmin(1.0, fmax(-1.0, cx_))), fovy = (float)acos(fmin(1.0, fmax(-1.0, cy_)));
+    o[35] = tanf(fmul(0.5f, fovx));
+    o[36] = tanf(fmul(0.5f, fovy));
+    o[37] = scale;
+    o[38] = nr, o[39] = fr;
+    for (int k = 40; k < GGRT_CAMERA_FLOATS; ++k) o[k] = 0.0f;
+}
+
+void launch_camera_setup(int n, const float* extr, const float* intr, const float* near, const float* far,
+                         int scale_invariant, float* out, cudaStream_t s) {
+    if (n <= 0) return;
+    camera_setup_kernel<<<(n + 31) / 32, 32, 0, s>>>(n, extr, intr, near, far, scale_invariant, out);
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means, const float* __restrict__ V,

@@ -64,6 +64,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     if (threadIdx.x < 16) sV[threadIdx.x] = v.view[threadIdx.x];
     else if (threadIdx.x < 32) sM[threadIdx.x - 16] = v.proj[threadIdx.x - 16];
 
+    resolve_device_params(v);
     // signalled exchange: this step pushes into half (epoch & 1) of every sink
     const long long poff = sinks.epoch != nullptr
                                ? (long long)(*reinterpret_cast<volatile uint32_t*>(sinks.epoch) & 1u) * sinks.parity_stride
@@ -112,7 +113,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             n_ga = *reinterpret_cast<const float4*>(gs);
             n_gb = *reinterpret_cast<const float4*>(gs + 4);
             n_gc = gs[8];
-            if (AUX && daux) n_gx = gs[G_AUX];
+            if (AUX && (daux || v.aux_mode)) n_gx = gs[G_AUX];
         }
     };
     prefetch(blockIdx.x);
@@ -217,8 +218,11 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
         const float z1 = 1.0f / q.tz, z2 = z1 * z1, z3 = z2 * z1;
         const float dtx = xmul * -v.fx * z2 * dJ02;
         const float dty = ymul * -v.fy * z2 * dJ12;
-        const float dtz = -v.fx * z2 * dJ00 - v.fy * z2 * dJ11 + (2.0f * v.fx * q.cx) * z3 * dJ02 +
-                          (2.0f * v.fy * q.cy) * z3 * dJ12;
+        float dtz = -v.fx * z2 * dJ00 - v.fy * z2 * dJ11 + (2.0f * v.fx * q.cx) * z3 * dJ02 +
+                    (2.0f * v.fy * q.cy) * z3 * dJ12;
+        // GGRt's depth channel is a function of the view depth: its gradient enters through t.z (the final scene-scale
+        // chain rule below turns d/d(scaled mean) into d/d(mean))
+        if (AUX && v.aux_mode == 1 && ggrt_depth_channel(q.tz, v.scale) > 0.0f) dtz += gaux * GGRT_SH_C0 / v.scale;
         // NDC mean -> mean3D through the full projection
         const float mw = q.pw;
         const float mul1 = q.hx * mw * mw, mul2 = q.hy * mw * mw;
@@ -469,7 +473,7 @@ void launch_preprocess_backward(const View& v, const float* means, const float* 
     const bool cm = v.sh_ks == 1 && v.K > 1;
     if (dcam) {  // camera gradients are rare: one instantiation per SH layout, aux always compiled in
         if (cm) GGRT_LAUNCH_PB(true, true, true) else GGRT_LAUNCH_PB(true, false, true)
-    } else if (daux) {
+    } else if (daux || v.aux_mode) {
         if (cm) GGRT_LAUNCH_PB(true, true, false) else GGRT_LAUNCH_PB(true, false, false)
     } else {
         if (cm) GGRT_LAUNCH_PB(false, true, false) else GGRT_LAUNCH_PB(false, false, false)

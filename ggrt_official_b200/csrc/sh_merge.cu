@@ -22,9 +22,18 @@
 
 namespace ggrt {
 
+#ifndef GGRT_MERGE_STAGES
+#define GGRT_MERGE_STAGES 2
+#endif
+#ifndef GGRT_MERGE_GROUP
+#define GGRT_MERGE_GROUP 8
+#endif
+#ifndef GGRT_MERGE_MINBLOCKS
+#define GGRT_MERGE_MINBLOCKS 3
+#endif
 constexpr int MERGE_THREADS = 128;
-constexpr int MERGE_STAGES = 2;
-constexpr int MERGE_GROUP = 8;  // views whose loads are in flight together
+constexpr int MERGE_STAGES = GGRT_MERGE_STAGES;
+constexpr int MERGE_GROUP = GGRT_MERGE_GROUP;  // views whose loads are in flight together
 
 struct MergeViews {
     const float* drgb[GGRT_RASTER_MAX_MERGE_VIEWS];    // [P,3] each (device or peer memory)
@@ -45,7 +54,7 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 
 template <int DEG, bool CMAJOR>
-__global__ void __launch_bounds__(MERGE_THREADS, 3)
+__global__ void __launch_bounds__(MERGE_THREADS, GGRT_MERGE_MINBLOCKS)
 sh_gradient_merge_kernel(int P, float scale, const float* __restrict__ means, MergeViews mv, float* __restrict__ dsh,
                          int num_slabs, MergeSignal sig) {
     constexpr int K = (DEG + 1) * (DEG + 1);
@@ -168,7 +177,7 @@ static void launch_merge_deg(int P, float scale, bool cmajor, const float* means
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int per_sm = max(1, min(3, (int)((220 * 1024) / (smem + 1024))));
+    const int per_sm = max(1, min(GGRT_MERGE_MINBLOCKS, (int)((220 * 1024) / (smem + 1024))));
     const int grid = min(num_slabs, per_sm * sms);
     if (cmajor && K > 1) {
         if (smem > 32 * 1024)

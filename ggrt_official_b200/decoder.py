@@ -11,7 +11,7 @@ import torch
 from torch import Tensor, nn
 
 from .render import (DepthRenderingMode, render_color_and_depth_cuda, render_cuda, render_depth_cuda,
-                     render_views_fast)
+                     render_views_device, render_views_fast)
 
 
 @dataclass
@@ -34,20 +34,35 @@ def _per_view(t: Tensor, v: int) -> Tensor:
 
 
 class DecoderSplattingCUDA(nn.Module):
-    def __init__(self, background_color=(0.0, 0.0, 0.0), fused_depth: bool = False, fast_glue: bool = False) -> None:
+    def __init__(self, background_color=(0.0, 0.0, 0.0), fused_depth: bool = False, fast_glue: bool = False,
+                 device_glue: bool = False) -> None:
         """fused_depth: render colour and depth in one rasterization (same outputs as the reference's two
         passes; roughly half the rasterizer work when a depth mode is requested).
         fast_glue: additionally skip the reference glue's per-view replication / rescale / gather / permute
-        copies and its per-view host syncs (render_views_fast); implies fused_depth."""
+        copies and its per-view host syncs (render_views_fast); implies fused_depth.
+        device_glue: additionally set up all cameras in one kernel and keep them on the device -- no host
+        synchronisation at all, the depth channel evaluated inside the rasterizer (render_views_device; depth modes
+        other than "depth" fall back to fast_glue); implies fast_glue."""
         super().__init__()
         self.background_color = torch.tensor(background_color, dtype=torch.float32)
-        self.fused_depth = fused_depth or fast_glue
-        self.fast_glue = fast_glue
+        self.fused_depth = fused_depth or fast_glue or device_glue
+        self.fast_glue = fast_glue or device_glue
+        self.device_glue = device_glue
+        self._bg = {}
 
     def forward(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
                 image_shape: tuple, depth_mode: Optional[DepthRenderingMode] = None) -> DecoderOutput:
         b, v = extrinsics.shape[:2]
-        bg = self.background_color.to(far.device)[None].expand(b * v, 3)
+        key = (far.device, b * v)
+        if key not in self._bg:  # cached: one host-to-device copy per (device, view count), not per call
+            self._bg[key] = self.background_color.to(far.device)[None].expand(b * v, 3).contiguous()
+        bg = self._bg[key]
+        if self.device_glue and depth_mode in (None, "depth"):
+            color, depth = render_views_device(
+                extrinsics.flatten(0, 1), intrinsics.flatten(0, 1), near.flatten(), far.flatten(), image_shape, bg,
+                gaussians.means, gaussians.covariances, gaussians.harmonics, gaussians.opacities,
+                view_to_scene=[i // v for i in range(b * v)], depth=depth_mode is not None)
+            return DecoderOutput(color.unflatten(0, (b, v)), None if depth is None else depth.unflatten(0, (b, v)))
         if self.fast_glue:
             color, depth = render_views_fast(
                 extrinsics.flatten(0, 1), intrinsics.flatten(0, 1), near.flatten(), far.flatten(), image_shape, bg,

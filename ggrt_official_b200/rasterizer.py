@@ -36,6 +36,9 @@ class GaussianRasterizationSettings(NamedTuple):
     campos: torch.Tensor
     prefiltered: bool
     debug: bool = False
+    # extensions GGRt never passes (sync-free render glue, render.render_views_device):
+    device_params: Optional[torch.Tensor] = None  # [3] CUDA {tanfovx, tanfovy, scene_scale}: replaces the host floats
+    aux_mode: int = 0  # 1: third output = GGRt's depth pass, max(0, C0 z + 0.5) blended, differentiable w.r.t. means3D
 
 
 def _debug_enabled(rs) -> bool:
@@ -213,7 +216,18 @@ class _Call:
         self.bg = _f32c(rs.bg, "bg", dev).reshape(3)
         s = _cabi.Settings()
         s.image_height, s.image_width = self.H, self.W
-        s.tanfovx, s.tanfovy = float(rs.tanfovx), float(rs.tanfovy)
+        self.device_params = _f32c(getattr(rs, "device_params", None), "device_params", dev)
+        self.aux_mode = int(getattr(rs, "aux_mode", 0) or 0)
+        if self.device_params is not None:
+            if self.device_params.numel() != 3:
+                raise ValueError("device_params must hold {tanfovx, tanfovy, scene_scale}")
+            s.device_params = self.device_params.data_ptr()
+            s.tanfovx = s.tanfovy = 0.0
+        else:
+            s.tanfovx, s.tanfovy = float(rs.tanfovx), float(rs.tanfovy)
+        s.aux_mode = self.aux_mode
+        if self.aux_mode and self.aux is not None:
+            raise ValueError("aux_mode=1 computes the aux channel itself: do not pass aux_precomp as well")
         s.scale_modifier = float(rs.scale_modifier)
         s.sh_degree = self.deg
         s.prefiltered = int(bool(rs.prefiltered))
@@ -365,7 +379,7 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
         sp = C.c_void_p(stream.cuda_stream)
         g = _f32c(grad_color, "grad_color", dev)
         ga = _f32c(grad_aux, "grad_aux", dev)
-        if ga is not None and c.aux is None:
+        if ga is not None and c.aux is None and not c.aux_mode:
             raise RuntimeError("the third output is only differentiable when aux_precomp was given")
         f32 = dict(dtype=torch.float32, device=dev)
         ws = state.get("workspace")
@@ -387,7 +401,7 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
             dcov3D=buf("dcov3D", (c.P, 3, 3) if c.cov9 else (c.P, 6)),
             dsh=buf("dsh", tuple(c.sh.shape)) if c.sh is not None and not compact else None,
             dcolors=buf("dcolors", (c.P, 3)) if c.sh is None or (compact and sinks is None) else None,
-            daux=buf("daux", (c.P,)) if ga is not None else None,
+            daux=buf("daux", (c.P,)) if ga is not None and not c.aux_mode else None,
             dcamera=torch.zeros(35, **f32) if want_camera else None,
         )
         lay = C.byref(c.layout) if c.layout is not None else None
@@ -475,7 +489,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.raster_settings = raster_settings
         ctx.sh_shape = None if sh is None else tuple(sh.shape)
         ctx.opacity_shape = tuple(opacities.shape)
-        ctx.has_aux = aux is not None
+        ctx.has_aux = aux is not None or bool(getattr(raster_settings, "aux_mode", 0))
         ctx.aux_shape = None if aux is None else tuple(aux.shape)
         if ctx.has_aux:  # the third output blends the caller's channel and is differentiable
             ctx.mark_non_differentiable(st["radii"])
@@ -508,7 +522,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             full[:, : dsh.shape[1]] = dsh
             dsh = full
         daux = g.get("daux")
-        if daux is not None:
+        if daux is not None and ctx.aux_shape is not None:
             daux = daux.reshape(ctx.aux_shape)
         dview = dproj = dcampos = None
         if want_cam:

@@ -192,6 +192,68 @@ def render_views_fast(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far:
     return torch.stack(colors), (torch.stack(depths) if depth_mode is not None else None)
 
 
+def camera_setup(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
+                 scale_invariant: bool = True) -> Tensor:
+    """[n, 48] float32 camera blocks for n views -- viewmatrix [0:16], projmatrix [16:32], campos [32:35],
+    {tanfovx, tanfovy, scene_scale} [35:38] -- computed by ONE kernel (ggrt_camera_setup) with no host read-back:
+    the device-side twin of the ~60 small PyTorch operations and two .item() synchronisations per view of
+    cuda_splatting.py:64-89,104-105.  The cameras are constants (the reference detaches poses)."""
+    import ctypes as C
+
+    from . import _cabi
+
+    if not extrinsics.is_cuda:
+        raise RuntimeError("extrinsics must be a CUDA tensor: the rasterizer has no CPU path")
+    dev = extrinsics.device
+    f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+    E, K, nr, fr = f(extrinsics), f(intrinsics), f(near).reshape(-1), f(far).reshape(-1)
+    n = E.shape[0]
+    if tuple(E.shape) != (n, 4, 4) or tuple(K.shape) != (n, 3, 3) or nr.numel() != n or fr.numel() != n:
+        raise ValueError(f"camera_setup: need extrinsics [n,4,4], intrinsics [n,3,3], near / far [n]; got "
+                         f"{tuple(E.shape)}, {tuple(K.shape)}, {tuple(nr.shape)}, {tuple(fr.shape)}")
+    out = torch.empty((n, _cabi.CAMERA_FLOATS), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _cabi.check(_cabi.lib().ggrt_camera_setup(n, p(E), p(K), p(nr), p(fr), int(bool(scale_invariant)), p(out), sp),
+                    "camera_setup")
+    return out
+
+
+def render_views_device(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple,
+                        background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
+                        gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor, view_to_scene: Sequence[int],
+                        scale_invariant: bool = True, depth: bool = False):
+    """render_views_fast without any host synchronisation and with (almost) no PyTorch glue: the cameras of all views
+    are set up by one kernel (camera_setup), the rasterizer reads tan(fov/2) and the scene scale from the device
+    (GaussianRasterizationSettings.device_params), reads pixelSplat's own tensor layout, and -- with depth=True --
+    evaluates GGRt's depth channel (mode "depth") inside its kernels (aux_mode=1), its gradient flowing straight
+    into the means.  The views' kernels are enqueued back to back; nothing is read back.  Same outputs as
+    render_cuda (+ render_depth_cuda) within the parity tolerance (the camera matrices may differ from the PyTorch
+    glue's in the last ulp).  Returns (color [n,3,h,w], depth [n,h,w] or None)."""
+    nb = extrinsics.shape[0]
+    h, w = image_shape
+    degree = isqrt(gaussian_sh_coefficients.shape[-1]) - 1
+    cams = camera_setup(extrinsics, intrinsics, near, far, scale_invariant)
+    harm = gaussian_sh_coefficients.contiguous()
+    cov = gaussian_covariances.contiguous()
+    layout = dict(scene_scale=1.0, cov_full3x3=True, sh_channel_major=True)  # the scale itself is read on the device
+    colors, depths = [], []
+    for i in range(nb):
+        s_ = view_to_scene[i]
+        c = cams[i]
+        settings = GaussianRasterizationSettings(
+            image_height=h, image_width=w, tanfovx=0.0, tanfovy=0.0, bg=background_color[i], scale_modifier=1.0,
+            viewmatrix=c[0:16], projmatrix=c[16:32], sh_degree=degree, campos=c[32:35], prefiltered=False,
+            device_params=c[35:38], aux_mode=1 if depth else 0)
+        image, _, d = GaussianRasterizer(settings)(
+            means3D=gaussian_means[s_], means2D=None, shs=harm[s_], opacities=gaussian_opacities[s_],
+            cov3D_precomp=cov[s_], layout=layout)
+        colors.append(image)
+        depths.append(d)
+    return torch.stack(colors), (torch.stack(depths) if depth else None)
+
+
 def render_depth_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple,
                       gaussian_means: Tensor, gaussian_covariances: Tensor, gaussian_opacities: Tensor,
                       scale_invariant: bool = True, mode: DepthRenderingMode = "depth") -> Tensor:

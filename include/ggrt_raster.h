@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GGRT_RASTER_ABI_VERSION 7
+#define GGRT_RASTER_ABI_VERSION 8
 #define GGRT_RASTER_TILE 16 /* tile edge in pixels (tile ids are part of the contract) */
 #define GGRT_RASTER_SUBS 16 /* pair counters per tile (contention spreading) */
 #define GGRT_RASTER_MAX_MERGE_VIEWS 16 /* views per ggrt_raster_sh_gradient_merge call */
@@ -67,7 +67,30 @@ typedef struct GgrtRasterSettings {
     const float* projmatrix; /* [4,4] device: viewmatrix @ projection^T */
     const float* campos;     /* [3]   device */
     const float* bg;         /* [3]   device */
+    /* Extensions for the sync-free render glue; zero / NULL = the upstream behaviour. */
+    const float* device_params; /* [3] device: {tanfovx, tanfovy, scene_scale}.  When non-NULL these replace the host
+                                   fields tanfovx / tanfovy above and GgrtRasterInputLayout.scene_scale, so that a caller
+                                   whose camera lives on the device (ggrt_camera_setup) never reads it back -- the
+                                   reference glue synchronises twice per view for them, cuda_splatting.py:104-105 */
+    int32_t aux_mode;           /* 0: the aux channel is the `aux` argument (or the view depth).  1: GGRt's depth pass
+                                   (cuda_splatting.py:240-268 with mode "depth"): aux = max(0, C0 * z + 0.5), z the
+                                   camera-space depth of the UNSCALED scene, computed in the kernels; its gradient
+                                   (dL_dout_aux) flows into dL_dmeans3D, dL_daux stays NULL */
+    int32_t reserved;
 } GgrtRasterSettings;
+
+/*
+ * Camera set-up of GGRt's render glue for n views in ONE kernel and without a host read-back: replaces the ~60
+ * small PyTorch operations and the two .item() synchronisations per view of cuda_splatting.py:64-89,104-105
+ * (scale-invariant rescale by 1/near, get_fov, get_projection_matrix -- including its quirk of taking the
+ * intrinsics of view 0 for every view, :39-42 -- the inverse of the camera-to-world matrix and the full projection).
+ * extrinsics [n,4,4] camera-to-world, intrinsics [n,3,3] normalised, near / far [n]; all device float32.
+ * Writes GGRT_CAMERA_FLOATS floats per view: [0,16) viewmatrix, [16,32) projmatrix (both as GgrtRasterSettings wants
+ * them), [32,35) campos, [35,38) {tanfovx, tanfovy, scene_scale} = device_params, [38] near, [39] far after the rescale.
+ */
+#define GGRT_CAMERA_FLOATS 48
+int ggrt_camera_setup(int32_t num_views, const float* extrinsics, const float* intrinsics, const float* near,
+                      const float* far, int32_t scale_invariant, float* cameras_out, ggrt_stream_t stream);
 
 /*
  * Optional description of how the caller stores the Gaussians, so that the copies GGRt's glue makes before

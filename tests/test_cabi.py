@@ -13,7 +13,7 @@ HEADER = (ROOT / "include" / "ggrt_raster.h").read_text()
 
 
 def declared_functions():
-    names = set(re.findall(r"\b(ggrt_(?:raster|adapter)_\w+)\s*\(", HEADER))
+    names = set(re.findall(r"\b(ggrt_(?:raster|adapter|camera)_\w+)\s*\(", HEADER))
     return sorted(names)
 
 
@@ -91,7 +91,7 @@ def test_ctypes_signatures_have_the_arity_the_header_declares():
     """Every prototype of include/ggrt_raster.h against the argtypes the ctypes binding registers."""
     lib = _cabi.lib()
     text = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
-    protos = re.findall(r"\b(ggrt_(?:raster|adapter)_\w+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S)
+    protos = re.findall(r"\b(ggrt_(?:raster|adapter|camera)_\w+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S)
     assert len(protos) >= 16
     checked = 0
     for name, params in protos:

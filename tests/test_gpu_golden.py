@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 GOLDEN = sorted((Path(__file__).resolve().parent / "golden").glob("decoder_*.npz"))
 
 
-@pytest.mark.parametrize("fused", [False, True, "fast"], ids=["two_pass", "fused_depth", "fast_glue"])
+@pytest.mark.parametrize("fused", [False, True, "fast", "device"], ids=["two_pass", "fused_depth", "fast_glue", "device_glue"])
 @pytest.mark.parametrize("path", GOLDEN, ids=lambda p: p.stem)
 def test_cuda_decoder_matches_reference_decoder_golden(path, fused):
     z = np.load(path)
@@ -21,7 +21,7 @@ def test_cuda_decoder_matches_reference_decoder_golden(path, fused):
     t = {k[3:]: torch.tensor(z[k], device=dev) for k in z.files if k.startswith("in_") and k != "in_image_shape"}
     leaves = {k: t[k].clone().requires_grad_() for k in ("means", "covariances", "harmonics", "opacities")}
     shape = tuple(int(x) for x in z["in_image_shape"])
-    res = DecoderSplattingCUDA(fused_depth=bool(fused), fast_glue=(fused == "fast"))(Gaussians(**leaves), t["extrinsics"], t["intrinsics"], t["near"], t["far"], shape,
+    res = DecoderSplattingCUDA(fused_depth=bool(fused), fast_glue=(fused == "fast"), device_glue=(fused == "device"))(Gaussians(**leaves), t["extrinsics"], t["intrinsics"], t["near"], t["far"], shape,
                                  depth_mode=str(z["depth_mode"]))
     wc, wd = torch.tensor(z["out_w_color"], device=dev), torch.tensor(z["out_w_depth"], device=dev)
     ((res.color * wc).sum() + (res.depth * wd).sum()).backward()
