@@ -258,6 +258,7 @@ render_backward_classic(int W, int H, int gx, const uint2* __restrict__ ranges, 
 }
 
 int make_view(const GgrtRasterSettings* s, int P, View* v) {
+    *v = View{};  // dparams = NULL, aux_mode = 0: host-side scalars, plain depth channel
     v->W = s->image_width, v->H = s->image_height;
     v->gx = (v->W + TILE - 1) / TILE, v->gy = (v->H + TILE - 1) / TILE;
     v->P = P, v->deg = s->sh_degree, v->K = (s->sh_degree + 1) * (s->sh_degree + 1);
