@@ -3,38 +3,50 @@
 // issues ~10 global float atomics per contributing Gaussian.
 //
 // Work decomposition ("Gaussian-parallel"): one CTA per 16x16 tile, warp w owns the 8x4
-// pixel block (w&1, w>>1) as in the forward.  A batch of up to 512 Gaussian records is
-// staged into shared memory; each warp culls it against its pixel block (exact ellipse vs
-// rectangle test on {alpha >= 1/255}) into a back-to-front queue and then consumes the queue
-// 8 Gaussians at a time with LANES = (pixel slot q, Gaussian slot gl).  Per step a lane evaluates
-// ITS Gaussian at the TWO pixels (q, row) and (q + 4, row) of one row of the block, so the warp covers
-// 8 Gaussians x 8 pixels; a segmented warp scan over the associative maps
-// (T, R) -> (aT, R + bT) recovers each Gaussian's transmittance T_i and the colour
-// accumulated behind it, and every lane accumulates the 9 partial gradients of ITS Gaussian
-// in registers.  There is no per-Gaussian reduction over 32 pixel lanes (the upstream
-// bottleneck): the pixel-slot partials are folded once per chunk and committed with
-// vector RED.ADD.F32 (2 x v4 + 1 scalar per Gaussian per warp).
-//   dL/dalpha_i = [ T_i (c_i . g) - sum_{j behind i, j included} w_j (c_j . g) - T_final (bg . g) ] / (1 - alpha_i)
+// pixel block (w&1, w>>1) as in the forward.  A batch of Gaussian records is staged into shared
+// memory with cp.async; each warp culls it against its pixel block (exact ellipse vs rectangle
+// test on {alpha >= 1/255}) into a back-to-front queue and then consumes the queue 16 Gaussians
+// at a time.  LANES = (Gaussian pair k = lane >> 2, pixel slot q = lane & 3): per step (one row of
+// the block) a lane evaluates ITS two Gaussians (queue entries 2k, 2k+1) at ITS two pixels
+// (q, row) and (q + 4, row), so the warp covers 16 Gaussians x 8 pixels.
+//
+//  * Alpha-blend replay as a prefix scan ("warp-shuffle prefix scans for the alpha-blend", north_star).  Going back
+//    to front each Gaussian maps the running pair (T, -R) to (a T, -R + nb T), a = 1/(1-alpha),
+//    nb = -alpha (c.g)/(1-alpha).  These maps compose associatively: a lane composes its two Gaussians in
+//    registers, ONE 3-level warp scan over the 8 pairs (shuffle distance 4, 8, 16) yields every pair's inclusive
+//    prefix, and the prefix of the pair's back Gaussian follows by undoing the front one (multiply by 1 - alpha).
+//    Lanes without a partner at some level blend in the identity map through per-lane 0/1 masks (no selects).
+//        dL/dalpha_i = [ T_i (c_i . g) - sum_{j behind i, j included} w_j (c_j . g) - T_final (bg . g) ] / (1 - alpha_i)
+//  * Gradient accumulation on the tensor pipe.  The nine sums a Gaussian needs over the pixels of the block,
+//        sum_p q_ip {1, x_p, y_p, x_p^2, x_p y_p, y_p^2}   (q = G dL/dalpha: opacity, mean and conic gradients)
+//        sum_p w_ip {g_r, g_g, g_b, g_aux}_p               (w = alpha T: colour gradients)
+//    are [16 Gaussians x 8 pixels] . [8 pixels x 8 features] products: mma.sync.m16n8k8 (tf32 inputs, fp32
+//    accumulate; SASS HMMA.1688.F32.TF32), whose A fragment is exactly this lane layout.  Pixel coordinates are taken
+//    relative to the block centre (+-3.5, +-1.5 and their products: exact in tf32); q, w and the pixel gradients are
+//    split into a tf32 head and a remainder (x = hi + lo, two MMAs), so the sums carry ~22 mantissa bits.  The D
+//    fragments replace the per-lane register accumulators AND the per-chunk shuffle fold of the first version; they
+//    are converted to gradients w.r.t. the Gaussian's own centre once per chunk (binomial shift by u = gx - xc) by
+//    16 lanes and committed with vector RED.ADD.F32 (2 x v4 + 1 scalar per Gaussian per warp).
 // Per-pixel running state {T behind, -(sum behind)} lives in shared memory between chunks.
 //
-// The kernel is instruction-issue bound (ncu round 1: 140 M warp instructions, DRAM 3 %).  Two things cut the
-// instruction count of the pixel step almost in half:
-//   * the two pixels of a lane share dy and their dx differ by the constant 4, so dx, dx^2 and the dx^2 term of
-//     the exponent are per-CHUNK constants, and the y moments are accumulated once for the pair;
-//   * everything else runs on packed FP32 pairs (FFMA2 / FMUL2 / FADD2, f32x2.cuh): one issue slot per two
-//     float operations, including the scan's combine step.
+// The kernel is instruction-issue bound (ncu: DRAM 3 %).  Everything per-pixel-pair runs on packed FP32 pairs
+// (FFMA2 / FMUL2 / FADD2, f32x2.cuh): the two pixels of a lane share dy and their dx differ by the constant 4.
 // Signs are arranged so that no negation is ever issued: the opacity is negated once per chunk (n_alpha = -alpha
 // falls out of the multiply), the state carries -R, and the colour sums come out negated and are fixed at commit.
+// History and measurements: DESIGN.md section 4 (K7).
 #include "f32x2.cuh"
 #include "render_common.cuh"
 
 namespace ggrt {
 
+#ifndef GGRT_BWD_MMA
+#define GGRT_BWD_MMA 1
+#endif
 #ifndef GGRT_BWD_BATCH
-#define GGRT_BWD_BATCH 512
+#define GGRT_BWD_BATCH (GGRT_BWD_MMA ? 384 : 512)
 #endif
 #ifndef GGRT_BWD_MINBLOCKS
-#define GGRT_BWD_MINBLOCKS 4
+#define GGRT_BWD_MINBLOCKS (GGRT_BWD_MMA ? 3 : 4)
 #endif
 constexpr int BWD_BATCH = GGRT_BWD_BATCH;
 constexpr int NWARPS = BWD_WARPS;
@@ -42,7 +54,7 @@ constexpr int NWARPS = BWD_WARPS;
 #define GGRT_BWD_ROW_UNROLL 2
 #endif
 constexpr int ROW_UNROLL = GGRT_BWD_ROW_UNROLL;
-constexpr int GL = 8;  // Gaussians per warp step
+constexpr int GL = 8;  // (first version) Gaussians per warp step
 constexpr int QL = 4;  // pixel slots per warp step (each slot = the pixel pair (q, q + 4) of one row)
 
 __device__ __forceinline__ void red_add(float* addr, float v) {
@@ -63,10 +75,13 @@ __device__ __forceinline__ void lds_2f2(uint32_t a, f2& x, f2& y) {
 __device__ __forceinline__ void sts_2f2(uint32_t a, f2 x, f2 y) {
     asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(a), "l"(x.v), "l"(y.v) : "memory");
 }
+__device__ __forceinline__ void sts_f2(uint32_t a, f2 x) {
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(x.v) : "memory");
+}
 
 // One level of the segmented scan over the GL = 8 Gaussian slots (consecutive lanes): (A, nB) <- (A Ap, nB Ap + nBp)
 // where (Ap, nBp) come from the lane d slots further back; lanes without such a lane keep their values (the shuffle's
-// in-range predicate drives the two packed operations, no compare, no select).
+// in-range predicate drives the two packed operations, no compare, no select).  [first version]
 __device__ __forceinline__ void scan_step(f2& A, f2& nB, int d, int gl) {
     asm volatile(
         "{\n\t"
@@ -89,9 +104,116 @@ __device__ __forceinline__ void scan_step(f2& A, f2& nB, int d, int gl) {
         : "r"(d), "r"(gl));
 }
 
-// Per-warp pixel tables, indexed by pair slot j = row * 4 + q (pixels (q, row) = "A" and (q + 4, row) = "B"):
-//   spix[j] = {g_r A, g_r B, g_g A, g_g B | g_b A, g_b B, last A (bits), last B (bits) |
-//              T behind A, T behind B, -(sum behind) A, -(sum behind) B}          sga[j] = {g_aux A, g_aux B}
+}  // namespace ggrt
+
+#if !GGRT_BWD_MMA
+#include "render_bwd_v1.cuh"
+#else
+
+namespace ggrt {
+
+constexpr int GC = 16;            // Gaussians per warp step / chunk
+constexpr int STAGE_STRIDE = 20;  // floats per Gaussian row of the per-warp D staging area (16 used, 80-byte rows)
+constexpr uint32_t TF32_MASK = 0xffffe000u;
+
+// D[16x8] += A[16x8] . B[8x8], tf32 inputs (the low 13 mantissa bits of the registers are ignored), fp32 accumulate.
+// A: a0 = (row g, col c), a1 = (g + 8, c), a2 = (g, c + 4), a3 = (g + 8, c + 4); B: b0 = (c, g), b1 = (c + 4, g);
+// D: d0, d1 = (g, 2c), (g, 2c + 1); d2, d3 = (g + 8, 2c), (g + 8, 2c + 1); with g = lane >> 2, c = lane & 3.
+__device__ __forceinline__ void mma_tf32(float (&d)[4], float a0, float a1, float a2, float a3, float b0, float b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(a2)), "r"(__float_as_uint(a3)),
+          "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+__device__ __forceinline__ float tf32_head(float x) { return __uint_as_float(__float_as_uint(x) & TF32_MASK); }
+__device__ __forceinline__ f2 tf32_head2(f2 x) { return pk(tf32_head(lo(x)), tf32_head(hi(x))); }
+// remainder of a packed pair after its tf32 heads h: x - h, exact
+__device__ __forceinline__ f2 tf32_tail2(f2 x, f2 h) { return fma2(h, bc(-1.0f), x); }
+
+// One level of the scan over the 8 Gaussian pairs (lane distance 4 d): (A, nB) <- (A Ap, nB Ap + nBp) with (Ap, nBp)
+// from the lane d pairs further back; m = 1 where such a lane exists, else 0 (om = 1 - m): the identity map.
+__device__ __forceinline__ void pair_scan_step(f2& A, f2& nB, int delta, f2 m, f2 om) {
+    f2 ap, bp;
+    ap.v = __shfl_up_sync(0xffffffffu, A.v, delta);
+    bp.v = __shfl_up_sync(0xffffffffu, nB.v, delta);
+    ap = fma2(ap, m, om);
+    bp = mul2(bp, m);
+    nB = fma2(nB, ap, bp);
+    A = mul2(A, ap);
+}
+
+struct GaussReg {  // per-chunk constants of one of a lane's two Gaussians
+    f2 dx2, pa2;     // dx at the lane's two pixels; ea dx^2
+    float eb, ec, gyr, ncw;
+    float cr, cg, cb, cx;
+    uint32_t pos;
+};
+
+struct Eval {  // one Gaussian at the lane's pixel pair of one row
+    f2 G2, nal2, om2, io2, sdot2;
+    bool acta, actb;
+};
+
+template <bool AUX>
+__device__ __forceinline__ void load_gauss(GaussReg& r, uint32_t sbase, uint32_t jj, bool valid, uint32_t boff, float xq,
+                                           float by0f) {
+    const uint32_t src = sbase + jj * REC_BYTES;
+    const float2 gxy = lds64(src);
+    float4 con = lds128(src + 16);
+    const float4 col = lds128(src + 32);
+    if (!valid) con.w = 0.f;  // zero opacity: never active
+    r.pos = valid ? boff + jj : 0xffffffffu;  // 0-based list position (never "behind" a pixel's last)
+    asm volatile("" : "+r"(r.pos));           // keep the select: otherwise `valid` is re-tested in every pixel step
+    // exponent of the Gaussian in base 2 with the -1/2 folded in: G = 2^(ea dx^2 + eb dx dy + ec dy^2)
+    const float ea = -0.5f * LOG2E * con.x;
+    r.eb = -LOG2E * con.y, r.ec = -0.5f * LOG2E * con.z;
+    r.ncw = -con.w;
+    const float dxa = gxy.x - xq;
+    r.dx2 = pk(dxa, dxa - 4.0f);
+    r.pa2 = mul2(bc(ea), mul2(r.dx2, r.dx2));
+    r.gyr = gxy.y - by0f;
+    r.cr = col.x, r.cg = col.y, r.cb = col.z, r.cx = AUX ? col.w : 0.f;
+}
+
+template <bool AUX>
+__device__ __forceinline__ void eval_gauss(Eval& e, const GaussReg& r, float rowf, f2 gr2, f2 gg2, f2 gb2, f2 ga2,
+                                           f2 last2) {
+    const float dy = r.gyr - rowf;
+    // log2 of the Gaussian at both pixels: ea dx^2 + (eb dx + ec dy) dy
+    const f2 pw2 = fma2(fma2(bc(r.eb), r.dx2, bc(r.ec * dy)), bc(dy), r.pa2);
+    const float pwa = lo(pw2), pwb = hi(pw2);
+    e.G2 = pk(ex2_approx(pwa), ex2_approx(pwb));
+    const f2 arn2 = mul2(bc(r.ncw), e.G2);  // -(opacity * G)
+    const float arna = fmaxf(-ALPHA_MAX, lo(arn2)), arnb = fmaxf(-ALPHA_MAX, hi(arn2));
+    e.acta = (r.pos < __float_as_uint(lo(last2))) && (pwa <= 0.0f) && (arna <= -ALPHA_MIN);
+    e.actb = (r.pos < __float_as_uint(hi(last2))) && (pwb <= 0.0f) && (arnb <= -ALPHA_MIN);
+    e.nal2 = pk(e.acta ? arna : 0.f, e.actb ? arnb : 0.f);  // -alpha
+    e.om2 = add2(bc(1.0f), e.nal2);                          // 1 - alpha
+    e.io2 = pk(rcp_approx(lo(e.om2)), rcp_approx(hi(e.om2)));
+    e.sdot2 = fma2(bc(r.cb), gb2, fma2(bc(r.cg), gg2, mul2(bc(r.cr), gr2)));
+    if (AUX) e.sdot2 = fma2(bc(r.cx), ga2, e.sdot2);
+}
+
+// Per-warp shared memory (one block per warp, so that two base registers + immediate offsets reach everything):
+//   pix[j], j = row * 4 + q (pixels (q, row) = "A" and (q + 4, row) = "B"):
+//          {g_r A, g_r B, g_g A, g_g B | g_b A, g_b B, last A (bits), last B (bits) |
+//           T behind A, T behind B, -(sum behind) A, -(sum behind) B}
+//   ga[j] = {g_aux A, g_aux B}
+//   fcm[row][lane] = {c0, c1, m0, m1}: the lane's two B fragments for that row.  {c0, c1}: pixel-gradient feature
+//          n = lane >> 2 at pixels q = lane & 3 and q + 4 (n = 0..3: tf32 heads of g_r, g_g, g_b, g_aux, n = 4..7: their
+//          remainders); {m0, m1}: coordinate monomial n of {1, x, y, x^2, xy, y^2, 0, 0} at the same pixels,
+//          x = column - 3.5, y = row - 1.5
+//   stage[16][STAGE_STRIDE]: the chunk's D fragments as per-Gaussian rows;  queue: the culled batch, back to front
+struct WarpShared {
+    float pix[16][12];
+    float ga[16][2];
+    float fcm[4][32][4];
+    float stage[GC][STAGE_STRIDE];
+    unsigned short queue[BWD_BATCH];
+};
+static_assert(sizeof(WarpShared) % 16 == 0, "per-warp blocks stay 16-byte aligned");
+
 // AUX: the 4th blended channel (out_depth) also carries an upstream gradient.
 template <bool AUX>
 __global__ void __launch_bounds__(BWD_THREADS, GGRT_BWD_MINBLOCKS * 8 / BWD_WARPS)
@@ -100,20 +222,37 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
                        const uint32_t* __restrict__ points, const float* __restrict__ final_T,
                        const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dout,
                        const float* __restrict__ dL_dout_aux, float* __restrict__ scratch) {
-    __shared__ __align__(16) unsigned char srec[BWD_BATCH * REC_BYTES];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];  // WarpShared[NWARPS] | records of the batch
     __shared__ uint32_t sid[BWD_BATCH];
-    __shared__ unsigned short squeue[NWARPS][BWD_BATCH];
-    __shared__ __align__(16) float spix[NWARPS][16][12];  // per pair slot: sg0 | sg1 | sst (48 B, one base register)
-    __shared__ __align__(8) float sga[AUX ? NWARPS : 1][16][2];
+    __shared__ __align__(16) float sdummy[16][12];  // sink of the state stores of the lanes that do not own the state
     __shared__ uint32_t block_last_s;
 
-    const uint32_t sbase = smem_addr(srec);
+    WarpShared* const wsm = reinterpret_cast<WarpShared*>(dyn_smem);
+    const uint32_t sbase = smem_addr(dyn_smem + NWARPS * sizeof(WarpShared));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    WarpShared& ws = wsm[warp];
     const int tile = blockIdx.y * v.gx + blockIdx.x;
     const int wt = warp + blockIdx.z * BWD_WARPS;  // warp pixel block of the tile (8 per tile)
     const int bx0 = blockIdx.x * TILE + (wt & 1) * 8, by0 = blockIdx.y * TILE + (wt >> 1) * 4;
     const float bx0f = (float)bx0, by0f = (float)by0;
-    const uint32_t start = starts[tile];
+    const uint32_t start = starts[tile], tile_cnt = starts[tile + 1] - start;
+
+    // Records of a batch of list entries [boff, boff + cnt) -> shared memory with cp.async (SASS LDGSTS), one group
+    auto gather = [&](uint32_t boff, uint32_t cnt) {
+        for (uint32_t k = tid; k < cnt; k += BWD_THREADS) {
+            const uint32_t id = points[start + boff + k];
+            sid[k] = id;
+            const uint32_t dst = sbase + k * REC_BYTES;
+            cp_async16(dst, rec0 + id);
+            cp_async16(dst + 16, rec1 + id);
+            cp_async16(dst + 32, rec2 + id);
+        }
+        cp_async_commit();
+    };
+    // The batches are consumed back to front and the first one is normally the tile's last (unless every pixel
+    // saturated early): start its gather now, so that it overlaps the per-pixel loads and the reduction below.
+    const uint32_t spec_b = tile_cnt ? (tile_cnt - 1) / BWD_BATCH : 0;
+    gather(spec_b * BWD_BATCH, tile_cnt - spec_b * BWD_BATCH);
 
     // ---- per-pixel constants / initial state (lane = pixel here) -------------------------------
     uint32_t last = 0;
@@ -133,12 +272,35 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
         // pixels with a zero upstream gradient contribute nothing (crop training leaves most tiles empty)
         if (d0 == 0.f && d1 == 0.f && d2 == 0.f && da == 0.f) last = 0;
         const float bg_dot = v.bg[0] * d0 + v.bg[1] * d1 + v.bg[2] * d2;
-        const int j = ly * 4 + (lx & 3), h = lx >> 2;  // pair slot, half (0 = A, 1 = B)
-        float* sp = spix[warp][j];
+        const int qq = lx & 3, h = lx >> 2;  // pixel slot, half (0 = A, 1 = B)
+        const int j = ly * 4 + qq;
+        float* sp = ws.pix[j];
         sp[h] = d0, sp[2 + h] = d1;
         sp[4 + h] = d2, sp[6 + h] = __uint_as_float(last);
         sp[8 + h] = Tfin, sp[10 + h] = -(Tfin * bg_dot);
-        if (AUX) sga[warp][j][h] = da;
+        ws.ga[j][h] = da;
+        // B fragments of the pixel-gradient features: lane n * 4 + qq of row ly holds feature n at pixels qq, qq + 4
+        const float f[4] = {d0, d1, d2, da};
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            const float head = tf32_head(f[n]);
+            ws.fcm[ly][n * 4 + qq][h] = head;
+            ws.fcm[ly][(n + 4) * 4 + qq][h] = f[n] - head;
+        }
+        {  // coordinate monomials relative to the block centre (this lane's fragment): x^ex y^ey, n -> (ex, ey)
+            const int n = lane >> 2;
+            const int ex = (n == 1 || n == 4) ? 1 : (n == 3 ? 2 : 0), ey = (n == 2 || n == 4) ? 1 : (n == 5 ? 2 : 0);
+            const float keep = n < 6 ? 1.f : 0.f;
+            const float xa = (float)(lane & 3) - 3.5f, xb = xa + 4.0f;
+            const float fxa = keep * (ex == 0 ? 1.f : ex == 1 ? xa : xa * xa), fxb = keep * (ex == 0 ? 1.f : ex == 1 ? xb : xb * xb);
+#pragma unroll
+            for (int row = 0; row < 4; ++row) {
+                const float y = (float)row - 1.5f;
+                const float fy = ey == 0 ? 1.f : ey == 1 ? y : y * y;
+                ws.fcm[row][lane][2] = fxa * fy;
+                ws.fcm[row][lane][3] = fxb * fy;
+            }
+        }
     }
     if (tid == 0) block_last_s = 0;
     __syncthreads();
@@ -146,29 +308,36 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
     if (lane == 0 && warp_last > 0) atomicMax(&block_last_s, warp_last);
     __syncthreads();
     const uint32_t block_last = block_last_s;
-    if (block_last == 0) return;
+    if (block_last == 0) {
+        cp_async_wait<0>();  // nothing may still be in flight into this CTA's shared memory when it exits
+        return;
+    }
     const uint32_t pmask = __ballot_sync(0xffffffffu, last > 0);  // pixels of this warp that matter (bit = ly*8 + lx)
 
     const float neg_half_w = -0.5f * (float)v.W, neg_half_h = -0.5f * (float)v.H;
-    const int gl = lane & (GL - 1), q = lane / GL;
-    const uint32_t paddr = smem_addr(&spix[warp][q][0]);  // + row * 192 (4 pair slots of 48 B per row)
-    const float* aux_g = &sga[AUX ? warp : 0][q][0];
+    const int q = lane & 3, kp = lane >> 2;
+    // Base addresses, opaque to the compiler (it would otherwise rebuild them from the thread index in every row):
+    //   pq: pix[q] (+ row * 192; ga[q] follows at a fixed distance)    pl: fcm[0][lane] (+ row * 512)
+    //   pst: where this lane's state store goes -- the real state for the frontmost pair, a sink for the others
+    uint32_t pq = smem_addr(&ws.pix[q][0]), pl = smem_addr(&ws.fcm[0][lane][0]);
+    uint32_t pst = kp == 7 ? pq + 32u : smem_addr(&sdummy[q][8]);
+    uint32_t stage_w = smem_addr(&ws.stage[2 * kp][2 * q]);  // this lane's D elements: rows 2 kp, 2 kp + 1
+    asm volatile("" : "+r"(pq), "+r"(pl), "+r"(pst), "+r"(stage_w));
+    const uint32_t pga = pq + (uint32_t)(offsetof(WarpShared, ga) - offsetof(WarpShared, pix)) - 40u * (uint32_t)q;  // ga[q]
     const float xq = bx0f + (float)q;  // x of this lane's pixel A; pixel B is 4 to the right
+    // identity masks of the pair scan: level d needs a lane 4 d below
+    const f2 m1 = bc(kp >= 1 ? 1.f : 0.f), m2 = bc(kp >= 2 ? 1.f : 0.f), m4 = bc(kp >= 4 ? 1.f : 0.f);
+    const f2 om1 = bc(kp >= 1 ? 0.f : 1.f), om2 = bc(kp >= 2 ? 0.f : 1.f), om4 = bc(kp >= 4 ? 0.f : 1.f);
 
     const int nb = (int)((block_last + BWD_BATCH - 1) / BWD_BATCH);
     for (int bi = nb - 1; bi >= 0; --bi) {
         const uint32_t boff = (uint32_t)bi * BWD_BATCH;
         const uint32_t cnt = min((uint32_t)BWD_BATCH, block_last - boff);
-        __syncthreads();  // every warp is done with the previous batch before the refill
-        for (uint32_t k = tid; k < cnt; k += BWD_THREADS) {  // gather the batch's records with cp.async (LDGSTS)
-            const uint32_t id = points[start + boff + k];
-            sid[k] = id;
-            const uint32_t dst = sbase + k * REC_BYTES;
-            cp_async16(dst, rec0 + id);
-            cp_async16(dst + 16, rec1 + id);
-            cp_async16(dst + 32, rec2 + id);
+        if (bi != nb - 1 || (uint32_t)bi != spec_b) {  // (the speculative gather above covers the first batch)
+            __syncthreads();  // every warp is done with the previous batch before the refill
+            if (bi == nb - 1) cp_async_wait<0>();  // the unused speculative batch has landed before it is overwritten
+            gather(boff, cnt);
         }
-        cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
         if (warp_last <= boff) continue;
@@ -185,129 +354,125 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
                 hit = ellipse_hits_rect(a.x, a.y, a.z, c.x, c.y, c.z, bx0f, by0f, 7.0f, 3.0f);
             }
             const uint32_t m = __ballot_sync(0xffffffffu, hit);
-            if (hit) squeue[warp][qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
+            if (hit) ws.queue[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
             qn += __popc(m);
         }
+        if (lane == 0 && (qn & 1u)) ws.queue[qn] = 0;  // the pair read below never sees stale bits
         __syncwarp();
 
-        // ---- 8 queued Gaussians at a time; lane = (pixel slot q, Gaussian slot gl) ------------------
-        const unsigned short* queue = squeue[warp];
-        for (uint32_t c0 = 0; c0 < qn; c0 += GL) {
-            const bool valid = c0 + gl < qn;
-            const uint32_t jj = valid ? queue[c0 + gl] : 0u;
-            const uint32_t src = sbase + jj * REC_BYTES;
-            const float2 gxy = lds64(src);
-            float4 con = lds128(src + 16);
-            const float4 col = lds128(src + 32);
-            if (!valid) con.w = 0.f;  // zero opacity: never active
-            uint32_t pos = valid ? boff + jj : 0xffffffffu;  // 0-based list position (never "behind" a pixel's last)
-            asm volatile("" : "+r"(pos));  // keep the select: otherwise `valid` is re-tested in every pixel step
-            // exponent of the Gaussian in base 2 with the -1/2 folded in: G = 2^(ea dx^2 + eb dx dy + ec dy^2)
-            const float ea = -0.5f * LOG2E * con.x, eb = -LOG2E * con.y, ec = -0.5f * LOG2E * con.z;
-            const float ncw = -con.w;
-            // per-chunk constants of this lane's pixel pair: dx (B is 4 px to the right of A), dx^2, ea dx^2
-            const float dxa = gxy.x - xq;
-            const f2 dx2 = pk(dxa, dxa - 4.0f);
-            const f2 pa2 = mul2(bc(ea), mul2(dx2, dx2));
-            const float gyr = gxy.y - by0f;
-            f2 a_op2 = bc(0.f), a_mx2 = bc(0.f), a_A2 = bc(0.f), a_B2 = bc(0.f);
-            f2 a_r2 = bc(0.f), a_g2 = bc(0.f), a_b2 = bc(0.f), a_x2 = bc(0.f);  // colour sums come out NEGATED
-            float a_my = 0.f, a_C = 0.f;
+        // ---- 16 queued Gaussians at a time; lane = (Gaussian pair kp, pixel slot q) ------------------
+        const uint32_t qaddr = smem_addr(&ws.queue[2 * kp]);
+        for (uint32_t c0 = 0; c0 < qn; c0 += GC) {
+            uint32_t jpair = 0;
+            const bool valid_e = c0 + 2 * kp < qn, valid_o = c0 + 2 * kp + 1 < qn;
+            if (valid_e) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(jpair) : "r"(qaddr + c0 * 2) : "memory");
+            GaussReg ge, go;  // e: the pair's back Gaussian (queue entry 2 kp), o: the one in front of it
+            load_gauss<AUX>(ge, sbase, jpair & 0xffffu, valid_e, boff, xq, by0f);
+            load_gauss<AUX>(go, sbase, jpair >> 16, valid_o, boff, xq, by0f);
+            float Dm[4] = {0.f, 0.f, 0.f, 0.f}, Dc[4] = {0.f, 0.f, 0.f, 0.f};
 
 #pragma unroll
             for (int row = 0; row < 4; ++row) {
                 if (((pmask >> (row * 8)) & 0xffu) == 0) continue;  // no pixel of the row matters
-                const uint32_t off = paddr + (uint32_t)row * 192u;  // an immediate offset once the loop is unrolled
-                f2 gr2, gg2, gb2, last2, Tb2, nRb2;
+                const uint32_t off = pq + (uint32_t)row * 192u;  // an immediate offset once the loop is unrolled
+                f2 gr2, gg2, gb2, last2, Tb2, nRb2, ga2 = bc(0.f);
                 lds_2f2(off, gr2, gg2);
                 lds_2f2(off + 16, gb2, last2);
                 lds_2f2(off + 32, Tb2, nRb2);
-                const float dy = gyr - (float)row;
-                // log2 of the Gaussian at both pixels: ea dx^2 + (eb dx + ec dy) dy
-                const f2 pw2 = fma2(fma2(bc(eb), dx2, bc(ec * dy)), bc(dy), pa2);
-                const float pwa = lo(pw2), pwb = hi(pw2);
-                const float Ga = ex2_approx(pwa), Gb = ex2_approx(pwb);
-                const f2 G2 = pk(Ga, Gb);
-                const f2 arn2 = mul2(bc(ncw), G2);  // -(opacity * G)
-                const float arna = fmaxf(-ALPHA_MAX, lo(arn2)), arnb = fmaxf(-ALPHA_MAX, hi(arn2));
-                const bool acta = (pos < __float_as_uint(lo(last2))) && (pwa <= 0.0f) && (arna <= -ALPHA_MIN);
-                const bool actb = (pos < __float_as_uint(hi(last2))) && (pwb <= 0.0f) && (arnb <= -ALPHA_MIN);
-                const f2 nal2 = pk(acta ? arna : 0.f, actb ? arnb : 0.f);  // -alpha
-                const f2 om2 = add2(bc(1.0f), nal2);
-                const f2 io2 = pk(rcp_approx(lo(om2)), rcp_approx(hi(om2)));  // 1 / (1 - alpha)
-                f2 sdot2 = fma2(bc(col.z), gb2, fma2(bc(col.y), gg2, mul2(bc(col.x), gr2)));
-                f2 ga2 = bc(0.f);
-                if (AUX) {
-                    ga2 = lds_f2(smem_addr(aux_g) + (uint32_t)row * 32u);
-                    sdot2 = fma2(bc(col.w), ga2, sdot2);
-                }
-                // Going back to front each Gaussian maps the running pair (T, -R) to (a T, -R + nb T) with
-                // a = 1/(1-alpha), nb = -alpha (c.g)/(1-alpha).  These maps compose associatively, so ONE
-                // segmented warp scan (slot 0 = backmost) yields every lane's transmittance and the sum behind it.
-                f2 A2 = io2, nB2 = mul2(mul2(nal2, sdot2), io2);
-#pragma unroll
-                for (int d = 1; d < GL; d <<= 1) scan_step(A2, nB2, d, gl);
-                const f2 Ti2 = mul2(Tb2, A2);            // transmittance in front of this Gaussian
-                const f2 nRt2 = fma2(Tb2, nB2, nRb2);    // -(sum behind, this Gaussian included)
-                const f2 dLa2 = mul2(fma2(Ti2, sdot2, nRt2), io2);  // dL/dalpha
-                const f2 qg2 = mul2(G2, dLa2);
-                const f2 qv2 = pk(acta ? lo(qg2) : 0.f, actb ? hi(qg2) : 0.f);
-                const f2 tq2 = mul2(bc(con.w), qv2);
-                const f2 nw2 = mul2(nal2, Ti2);          // -(blend weight)
-                a_op2 = add2(a_op2, qv2);
-                const f2 inc2 = mul2(tq2, dx2);          // first x moment; the conic is applied once per chunk below
-                a_mx2 = add2(a_mx2, inc2);
-                a_B2 = fma2(inc2, bc(dy), a_B2);
-                a_A2 = fma2(inc2, dx2, a_A2);
-                const float sd = (lo(tq2) + hi(tq2)) * dy;  // the pair shares dy: y moments once for both pixels
-                a_my += sd;
-                a_C = fmaf(sd, dy, a_C);
-                a_r2 = fma2(nw2, gr2, a_r2);
-                a_g2 = fma2(nw2, gg2, a_g2);
-                a_b2 = fma2(nw2, gb2, a_b2);
-                if (AUX) a_x2 = fma2(nw2, ga2, a_x2);
-                if (gl == GL - 1) sts_2f2(off + 32, Ti2, nRt2);  // frontmost slot: state behind the next chunk
+                if (AUX) ga2 = lds_f2(pga + (uint32_t)row * 32u);
+                Eval e, o;
+                eval_gauss<AUX>(e, ge, (float)row, gr2, gg2, gb2, ga2, last2);
+                eval_gauss<AUX>(o, go, (float)row, gr2, gg2, gb2, ga2, last2);
+                // the pair as one map (o in front of e), then the inclusive scan over the pairs
+                const f2 nBe = mul2(mul2(e.nal2, e.sdot2), e.io2), nBo = mul2(mul2(o.nal2, o.sdot2), o.io2);
+                f2 A2 = mul2(e.io2, o.io2), nB2 = fma2(nBo, e.io2, nBe);  // (a_o a_e, nb_o a_e + nb_e)
+                pair_scan_step(A2, nB2, 4, m1, om1);
+                pair_scan_step(A2, nB2, 8, m2, om2);
+                pair_scan_step(A2, nB2, 16, m4, om4);
+                // prefix through o = the scan's result (A, nB) = (a_o A', nb_o A' + nB'); prefix through e = (A', nB'):
+                // undo o with 1 / a_o = 1 - alpha_o
+                const f2 Ae = mul2(A2, o.om2), nBi = fma2(mul2(nBo, bc(-1.0f)), Ae, nB2);
+                const f2 Ti_o = mul2(Tb2, A2), nRt_o = fma2(Tb2, nB2, nRb2);  // transmittance in front of o; -(sum behind, o incl.)
+                const f2 Ti_e = mul2(Tb2, Ae), nRt_e = fma2(Tb2, nBi, nRb2);
+                sts_2f2(pst + (uint32_t)row * 192u, Ti_o, nRt_o);  // frontmost pair: the state behind the next chunk
+                const f2 dq_e = mul2(fma2(Ti_e, e.sdot2, nRt_e), e.io2), dq_o = mul2(fma2(Ti_o, o.sdot2, nRt_o), o.io2);  // dL/dalpha
+                // A fragments {e at A, o at A, e at B, o at B}: built with scalar operations, so that each lands in the
+                // register the MMA wants (pairing the packed results would cost a move per element)
+                const float qAe = e.acta ? lo(e.G2) * lo(dq_e) : 0.f, qAo = o.acta ? lo(o.G2) * lo(dq_o) : 0.f;  // G dL/dalpha
+                const float qBe = e.actb ? hi(e.G2) * hi(dq_e) : 0.f, qBo = o.actb ? hi(o.G2) * hi(dq_o) : 0.f;
+                const float wAe = lo(e.nal2) * lo(Ti_e), wAo = lo(o.nal2) * lo(Ti_o);  // -(blend weight)
+                const float wBe = hi(e.nal2) * hi(Ti_e), wBo = hi(o.nal2) * hi(Ti_o);
+                // tf32 heads (masked explicitly: the result does not depend on how the tensor pipe treats the low bits)
+                const f2 qA = pk(qAe, qAo), qB = pk(qBe, qBo), wA = pk(wAe, wAo), wB = pk(wBe, wBo);
+                const f2 qhA = tf32_head2(qA), qhB = tf32_head2(qB), whA = tf32_head2(wA), whB = tf32_head2(wB);
+                const f2 qtA = tf32_tail2(qA, qhA), qtB = tf32_tail2(qB, qhB), wtA = tf32_tail2(wA, whA), wtB = tf32_tail2(wB, whB);
+                const float4 fb = lds128(pl + (uint32_t)row * 512u);  // {colour b0, b1, monomial b0, b1}
+                mma_tf32(Dm, lo(qhA), hi(qhA), lo(qhB), hi(qhB), fb.z, fb.w);
+                mma_tf32(Dm, lo(qtA), hi(qtA), lo(qtB), hi(qtB), fb.z, fb.w);
+                mma_tf32(Dc, lo(whA), hi(whA), lo(whB), hi(whB), fb.x, fb.y);
+                mma_tf32(Dc, lo(wtA), hi(wtA), lo(wtB), hi(wtB), fb.x, fb.y);
             }
+            // ---- D fragments -> per-Gaussian rows {S1, Sx, Sy, Sxx, Sxy, Syy, -, - | head sums r g b x | tail sums} ----
+            sts_f2(stage_w, pk(Dm[0], Dm[1]));
+            sts_f2(stage_w + STAGE_STRIDE * 4, pk(Dm[2], Dm[3]));
+            sts_f2(stage_w + 32, pk(Dc[0], Dc[1]));
+            sts_f2(stage_w + STAGE_STRIDE * 4 + 32, pk(Dc[2], Dc[3]));
             __syncwarp();
-            // fold the pair, then the QL pixel-slot partials of each Gaussian (lanes gl, gl+GL, ...)
-            float a_op = lo(a_op2) + hi(a_op2), a_mx = lo(a_mx2) + hi(a_mx2), a_A = lo(a_A2) + hi(a_A2),
-                  a_B = lo(a_B2) + hi(a_B2), a_r = lo(a_r2) + hi(a_r2), a_g = lo(a_g2) + hi(a_g2),
-                  a_b = lo(a_b2) + hi(a_b2), a_x = lo(a_x2) + hi(a_x2);
-#pragma unroll
-            for (int d = GL; d < 32; d <<= 1) {
-                a_op += __shfl_xor_sync(0xffffffffu, a_op, d);
-                a_mx += __shfl_xor_sync(0xffffffffu, a_mx, d);
-                a_my += __shfl_xor_sync(0xffffffffu, a_my, d);
-                a_A += __shfl_xor_sync(0xffffffffu, a_A, d);
-                a_B += __shfl_xor_sync(0xffffffffu, a_B, d);
-                a_C += __shfl_xor_sync(0xffffffffu, a_C, d);
-                a_r += __shfl_xor_sync(0xffffffffu, a_r, d);
-                a_g += __shfl_xor_sync(0xffffffffu, a_g, d);
-                a_b += __shfl_xor_sync(0xffffffffu, a_b, d);
-                if (AUX) a_x += __shfl_xor_sync(0xffffffffu, a_x, d);
-            }
-            if (valid && q == 0) {
+            if (lane < GC && c0 + lane < qn) {
+                const uint32_t jj = ws.queue[c0 + lane];
+                const uint32_t src = sbase + jj * REC_BYTES;
+                const float2 gxy = lds64(src);
+                const float4 con = lds128(src + 16);
+                const uint32_t stage_r = smem_addr(&ws.stage[lane][0]);
+                const float4 s0 = lds128(stage_r), s1 = lds128(stage_r + 16), ch = lds128(stage_r + 32),
+                             ct = lds128(stage_r + 48);
+                // moments about the block centre -> about the Gaussian's centre: d = u - x with u = g - centre
+                const float u = gxy.x - (bx0f + 3.5f), w = gxy.y - (by0f + 1.5f);
+                const float S1 = s0.x, Sx = s0.y, Sy = s0.z, Sxx = s0.w, Sxy = s1.x, Syy = s1.y;
+                const float mx = fmaf(u, S1, -Sx), my = fmaf(w, S1, -Sy);                 // sum q dx, sum q dy
+                const float mA = fmaf(u, mx, fmaf(-u, Sx, Sxx));                          // sum q dx^2
+                const float mB = fmaf(w, mx, fmaf(-u, Sy, Sxy));                          // sum q dx dy
+                const float mC = fmaf(w, my, fmaf(-w, Sy, Syy));                          // sum q dy^2
+                const float a_mx = con.w * mx, a_my = con.w * my;
                 float* dst = scratch + (size_t)sid[jj] * GRAD_STRIDE;
                 // scratch rows are 48 B (16-B aligned): slots {mx,my,A,B} {C,op,r,g} {b}
                 const float gmx = fmaf(con.x, a_mx, con.y * a_my), gmy = fmaf(con.z, a_my, con.y * a_mx);
-                red_add_v4(dst + G_MX, gmx * neg_half_w, gmy * neg_half_h, -0.5f * a_A, -0.5f * a_B);
-                red_add_v4(dst + G_CC, -0.5f * a_C, a_op, -a_r, -a_g);
-                red_add(dst + G_B, -a_b);
-                if (AUX) red_add(dst + G_AUX, -a_x);
+                const float hw = -0.5f * con.w;
+                red_add_v4(dst + G_MX, gmx * neg_half_w, gmy * neg_half_h, hw * mA, hw * mB);
+                red_add_v4(dst + G_CC, hw * mC, S1, -(ch.x + ct.x), -(ch.y + ct.y));
+                red_add(dst + G_B, -(ch.z + ct.z));
+                if (AUX) red_add(dst + G_AUX, -(ch.w + ct.w));
             }
+            __syncwarp();
         }
     }
 }
 
+}  // namespace ggrt
+#endif  // GGRT_BWD_MMA
+
+namespace ggrt {
+
 void launch_render_backward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, const float* dL_dout,
                             const float* dL_dout_aux, float* scratch, cudaStream_t s) {
     dim3 grid(v.gx, v.gy, 8 / BWD_WARPS);
+#if GGRT_BWD_MMA
+    constexpr size_t dyn = NWARPS * sizeof(WarpShared) + (size_t)BWD_BATCH * REC_BYTES;
+    static const bool opted_in = [] {  // static + dynamic shared memory exceeds the 48 KB default (per device, cheap)
+        cudaFuncSetAttribute(render_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        cudaFuncSetAttribute(render_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        return true;
+    }();
+    (void)opted_in;
+#else
+    constexpr size_t dyn = 0;
+#endif
     if (dL_dout_aux)
-        render_backward_kernel<true><<<grid, BWD_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
+        render_backward_kernel<true><<<grid, BWD_THREADS, dyn, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
                                                                      im.final_T, im.n_contrib, dL_dout, dL_dout_aux,
                                                                      scratch);
     else
-        render_backward_kernel<false><<<grid, BWD_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
+        render_backward_kernel<false><<<grid, BWD_THREADS, dyn, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
                                                                       im.final_T, im.n_contrib, dL_dout, nullptr, scratch);
 }
 

@@ -42,6 +42,18 @@ __global__ void kern(float* out, long long* cyc, float a, float b) {
                 if ((i & 3) == 0) x[i] = __shfl_up_sync(0xffffffffu, x[i], 1, 8);
             }
             if (MODE == 8) x[i] = fminf(x[i] + a, b);                                    // FADD + FMNMX (fma + alu pipe)
+            if (MODE == 10) {                                                            // HMMA.1688.F32.TF32, 8 independent accumulators
+                asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                             : "+f"(x[i]), "+f"(x[(i + 1) % UNROLL]), "+f"(x[(i + 2) % UNROLL]), "+f"(x[(i + 3) % UNROLL])
+                             : "r"(z[i]), "r"(z[(i + 1) % UNROLL]), "r"(z[(i + 2) % UNROLL]), "r"(z[(i + 3) % UNROLL]), "r"(z[(i + 4) % UNROLL]), "r"(z[(i + 5) % UNROLL]));
+            }
+            if (MODE == 11) {                                                            // 1 HMMA per 16 FFMA2 (the K7 mix)
+                if (i == 0) asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                             : "+f"(x[0]), "+f"(x[1]), "+f"(x[2]), "+f"(x[3])
+                             : "r"(z[0]), "r"(z[1]), "r"(z[2]), "r"(z[3]), "r"(z[4]), "r"(z[5]));
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(y[i]) : "l"(y[(i + 1) % UNROLL]), "l"(y[(i + 3) % UNROLL]));
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(y[i]) : "l"(y[(i + 2) % UNROLL]), "l"(y[(i + 5) % UNROLL]));
+            }
             if (MODE == 9) {                                                             // 2 FFMA vs. the same on FFMA2: compare 0 with 2
                 x[i] = fmaf(x[i], a, b);
                 x[i] = fmaf(x[i], b, a);
@@ -87,6 +99,8 @@ int main() {
     run<7>("ffma+shfl 4:1 (per 1.25)", 1, out, cyc);
     run<8>("fadd+fmnmx(per 2)", 2, out, cyc);
     run<9>("2xffma dependent(per 2)", 2, out, cyc);
+    run<10>("hmma_1688_tf32 (4 overlapping accumulator quads)", 1, out, cyc);
+    run<11>("1 hmma + 16 ffma2 (per 17/8 per unroll slot)", 2, out, cyc);
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
