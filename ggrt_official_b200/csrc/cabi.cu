@@ -147,6 +147,7 @@ void compute_layout(int P, int H, int W, long long N, GgrtRasterLayout* L) {
     off = 0;
     L->bin_keys = off; off = align_up(off + n * sizeof(unsigned long long));
     L->bin_points = off; off = align_up(off + n * sizeof(uint32_t));
+    L->bin_masks = off; off = align_up(off + n * sizeof(uint8_t));
     L->bin_bytes = off > 0 ? off : 256;
 }
 
@@ -186,6 +187,7 @@ BinPtrs bin_ptrs(void* base, long long N) {
     BinPtrs p;
     p.keys = reinterpret_cast<unsigned long long*>(b + L.bin_keys);
     p.points = reinterpret_cast<uint32_t*>(b + L.bin_points);
+    p.masks = reinterpret_cast<uint8_t*>(b + L.bin_masks);
     return p;
 }
 

@@ -64,6 +64,7 @@ struct ImagePtrs {
 struct BinPtrs {
     unsigned long long* keys;
     uint32_t* points;
+    uint8_t* masks;  // per list entry: which of the tile's 8 warp pixel blocks the Gaussian reaches (render kernels)
 };
 
 // destinations of the compact colour gradients: [P,3] rows of dL/drgb, plus (with_campos) a row P holding the

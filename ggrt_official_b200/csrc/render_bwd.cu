@@ -4,8 +4,9 @@
 //
 // Work decomposition ("Gaussian-parallel"): one CTA per 16x16 tile, warp w owns the 8x4
 // pixel block (w&1, w>>1) as in the forward.  A batch of Gaussian records is staged into shared
-// memory with cp.async; each warp culls it against its pixel block (exact ellipse vs rectangle
-// test on {alpha >= 1/255}) into a back-to-front queue and then consumes the queue 16 Gaussians
+// memory with cp.async together with the forward kernel's cull result (one bit per warp pixel
+// block: exact ellipse vs rectangle test on {alpha >= 1/255}); each warp compacts the entries
+// that reach its block into a back-to-front queue and then consumes the queue 16 Gaussians
 // at a time.  LANES = (Gaussian pair k = lane >> 2, pixel slot q = lane & 3): per step (one row of
 // the block) a lane evaluates ITS two Gaussians (queue entries 2k, 2k+1) at ITS two pixels
 // (q, row) and (q + 4, row), so the warp covers 16 Gaussians x 8 pixels.
@@ -219,11 +220,13 @@ template <bool AUX>
 __global__ void __launch_bounds__(BWD_THREADS, GGRT_BWD_MINBLOCKS * 8 / BWD_WARPS)
 render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __restrict__ rec1,
                        const float4* __restrict__ rec2, const uint32_t* __restrict__ starts,
-                       const uint32_t* __restrict__ points, const float* __restrict__ final_T,
-                       const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dout,
-                       const float* __restrict__ dL_dout_aux, float* __restrict__ scratch) {
+                       const uint32_t* __restrict__ points, const uint8_t* __restrict__ masks,
+                       const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
+                       const float* __restrict__ dL_dout, const float* __restrict__ dL_dout_aux,
+                       float* __restrict__ scratch) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];  // WarpShared[NWARPS] | records of the batch
     __shared__ uint32_t sid[BWD_BATCH];
+    __shared__ uint8_t smask[BWD_BATCH];  // the forward kernel's cull result per staged record (bit = warp pixel block)
     __shared__ __align__(16) float sdummy[16][12];  // sink of the state stores of the lanes that do not own the state
     __shared__ uint32_t block_last_s;
 
@@ -242,6 +245,7 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
         for (uint32_t k = tid; k < cnt; k += BWD_THREADS) {
             const uint32_t id = points[start + boff + k];
             sid[k] = id;
+            smask[k] = masks[start + boff + k];
             const uint32_t dst = sbase + k * REC_BYTES;
             cp_async16(dst, rec0 + id);
             cp_async16(dst + 16, rec1 + id);
@@ -342,17 +346,13 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
         __syncthreads();
         if (warp_last <= boff) continue;
 
-        // ---- cull the batch against this warp's pixel block into a back-to-front queue -----------
+        // ---- the entries that reach this warp's pixel block (the forward kernel's exact ellipse-vs-rectangle cull,
+        // one bit per block), compacted into a back-to-front queue ---------------------------------------------
         uint32_t qn = 0;
         const uint32_t lim = min(cnt, warp_last - boff);  // entries at or beyond warp_last never contribute here
         for (int r = (int)((lim - 1) & ~31u); r >= 0; r -= 32) {
             const uint32_t j = (uint32_t)r + 31 - lane;  // lane 0 tests the backmost entry of the round
-            bool hit = false;
-            if (j < lim) {
-                const float4 a = lds128(sbase + j * REC_BYTES);
-                const float4 c = lds128(sbase + j * REC_BYTES + 16);
-                hit = ellipse_hits_rect(a.x, a.y, a.z, c.x, c.y, c.z, bx0f, by0f, 7.0f, 3.0f);
-            }
+            const bool hit = j < lim && ((smask[j] >> wt) & 1u);
             const uint32_t m = __ballot_sync(0xffffffffu, hit);
             if (hit) ws.queue[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
             qn += __popc(m);
@@ -464,16 +464,19 @@ void launch_render_backward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, 
         return true;
     }();
     (void)opted_in;
+#define BWD_MASKS b.masks,
 #else
     constexpr size_t dyn = 0;
+#define BWD_MASKS
 #endif
     if (dL_dout_aux)
         render_backward_kernel<true><<<grid, BWD_THREADS, dyn, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
-                                                                     im.final_T, im.n_contrib, dL_dout, dL_dout_aux,
-                                                                     scratch);
+                                                                       BWD_MASKS im.final_T, im.n_contrib, dL_dout,
+                                                                       dL_dout_aux, scratch);
     else
         render_backward_kernel<false><<<grid, BWD_THREADS, dyn, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
-                                                                      im.final_T, im.n_contrib, dL_dout, nullptr, scratch);
+                                                                        BWD_MASKS im.final_T, im.n_contrib, dL_dout,
+                                                                        nullptr, scratch);
 }
 
 }  // namespace ggrt

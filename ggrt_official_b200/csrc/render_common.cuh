@@ -78,4 +78,38 @@ __device__ __forceinline__ bool ellipse_hits_rect(float gx, float gy, float tau_
     return qmin <= tau_c;
 }
 
+
+// The same test for all 8 warp pixel blocks of a tile at once (block w: columns 8 (w & 1) .. + 7, rows 4 (w >> 1) .. + 3
+// from the tile origin), run by ONE thread per staged Gaussian: bit w of the result is set if the ellipse reaches block
+// w.  The per-column and per-row terms are shared, so a block costs ~12 instructions.  min(q on the facing vertical
+// edge, q on the facing horizontal edge) is the minimum over the rectangle in every case: with the centre inside the
+// rectangle's x range the "vertical edge" degenerates to the line x = 0 through the centre, whose minimum over the
+// row range is not above the other candidate (and 0 when the centre is inside).
+__device__ __forceinline__ uint32_t block_mask8(float gx, float gy, float tau_c, float A, float B, float C, float tx0,
+                                                float ty0) {
+    const float iA = rcp_approx(A), iC = rcp_approx(C), B2 = 2.0f * B;
+    float lox[2], hix[2], dxe[2], qxe[2], dy0[2], bxe[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        lox[c] = tx0 + 8.0f * c - gx, hix[c] = lox[c] + 7.0f;
+        dxe[c] = fminf(fmaxf(0.f, lox[c]), hix[c]);
+        qxe[c] = A * dxe[c] * dxe[c], bxe[c] = B2 * dxe[c], dy0[c] = -B * dxe[c] * iC;
+    }
+    uint32_t mask = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float loy = ty0 + 4.0f * r - gy, hiy = loy + 3.0f;
+        const float dye = fminf(fmaxf(0.f, loy), hiy);
+        const float qye = C * dye * dye, bye = B2 * dye, dx0 = -B * dye * iA;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float dy = fminf(fmaxf(dy0[c], loy), hiy), dx = fminf(fmaxf(dx0, lox[c]), hix[c]);
+            const float qv = fmaf(fmaf(C, dy, bxe[c]), dy, qxe[c]);  // A dxe^2 + 2 B dxe dy + C dy^2
+            const float qh = fmaf(fmaf(A, dx, bye), dx, qye);        // C dye^2 + 2 B dye dx + A dx^2
+            if (fminf(qv, qh) <= tau_c) mask |= 1u << (2 * r + c);
+        }
+    }
+    return mask;
+}
+
 }  // namespace ggrt

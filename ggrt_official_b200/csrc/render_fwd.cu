@@ -3,10 +3,11 @@
 //
 // One CTA per 16x16 tile; warp w owns the 8x4 pixel block (w&1, w>>1) so each warp's
 // output rows are 32-byte contiguous.  A batch of 256 Gaussian records (48 B each) is
-// staged into shared memory; each warp first culls the batch against its pixel block with
-// one bounding-box test per lane (the records carry the {alpha >= 1/255} extent) and then
-// walks only the surviving bits of the ballot masks, in list order.  GGRt's splats are a
-// few pixels wide, so most (warp, Gaussian) pairs of a tile are culled.
+// staged into shared memory; the thread that staged a record culls it against all 8 warp
+// pixel blocks of the tile (exact ellipse-vs-rectangle test on {alpha >= 1/255}, block_mask8)
+// and publishes the 8-bit result in shared memory and, for the backward kernel, in the pair
+// buffer; each warp then ballots its bit and walks only the surviving entries, in list order.
+// GGRt's splats are a few pixels wide, so most (warp, Gaussian) pairs of a tile are culled.
 #include "render_common.cuh"
 
 namespace ggrt {
@@ -23,9 +24,11 @@ template <bool ASYNC>
 __global__ void __launch_bounds__(FWD_THREADS, 1024 / FWD_THREADS)
 render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __restrict__ rec1,
                       const float4* __restrict__ rec2, const uint32_t* __restrict__ starts,
-                      const uint32_t* __restrict__ points, uint32_t capacity, float* __restrict__ out_color,
-                      float* __restrict__ out_depth, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
+                      const uint32_t* __restrict__ points, uint8_t* __restrict__ masks, uint32_t capacity,
+                      float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ final_T,
+                      uint32_t* __restrict__ n_contrib) {
     __shared__ __align__(16) unsigned char srec[(ASYNC ? 2 : 1) * FWD_BATCH * REC_BYTES];
+    __shared__ __align__(4) uint8_t smask[FWD_BATCH];  // per staged record: the warp pixel blocks it reaches
     uint32_t sbase = smem_addr(srec);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.y * v.gx + blockIdx.x;
@@ -34,7 +37,7 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
     const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
     const bool inside = px < v.W && py < v.H;
     const float pxf = (float)px, pyf = (float)py;
-    const float bx0f = (float)bx0, by0f = (float)by0;
+    const float tx0f = (float)(blockIdx.x * TILE), ty0f = (float)(blockIdx.y * TILE);
     const uint32_t start = min(starts[tile], capacity), end = min(starts[tile + 1], capacity);
 
     // The sign of T carries the per-pixel "done" flag (T > 0: live, T < 0: terminated with final transmittance |T|;
@@ -69,8 +72,14 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
             sbase = smem_addr(srec) + half * (FWD_BATCH * REC_BYTES);
             gather(base + FWD_BATCH, half ^ 1u);   // the next batch streams in under this one's blend loop
             cp_async_wait<1>();                    // this thread's copies of the current batch have landed ...
-            if (tid < cnt) {                       // ... rescale its record's conic for the ex2 exponent, in place
+            if (tid < cnt) {  // ... cull it against the tile's 8 warp pixel blocks (ONE exact test per record and block for
+                              // the whole CTA; the backward kernel reuses the result) and rescale its conic for the ex2
+                              // exponent, in place
+                const float4 a = lds128(sbase + tid * REC_BYTES);
                 float4 c = lds128(sbase + tid * REC_BYTES + 16);
+                const uint32_t m = block_mask8(a.x, a.y, a.z, c.x, c.y, c.z, tx0f, ty0f);
+                smask[tid] = (uint8_t)m;
+                masks[base + tid] = (uint8_t)m;
                 c.x *= -0.5f * LOG2E, c.y *= -LOG2E, c.z *= -0.5f * LOG2E;
                 sts128(sbase + tid * REC_BYTES + 16, c);
             }
@@ -78,9 +87,13 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
             for (uint32_t k = tid; k < cnt; k += FWD_THREADS) {
                 const uint32_t id = points[base + k];
                 const uint32_t dst = sbase + k * REC_BYTES;
+                const float4 a = rec0[id];
                 float4 c = rec1[id];
+                const uint32_t m = block_mask8(a.x, a.y, a.z, c.x, c.y, c.z, tx0f, ty0f);
+                smask[k] = (uint8_t)m;
+                masks[base + k] = (uint8_t)m;
                 c.x *= -0.5f * LOG2E, c.y *= -LOG2E, c.z *= -0.5f * LOG2E;
-                sts128(dst, rec0[id]);
+                sts128(dst, a);
                 sts128(dst + 16, c);
                 sts128(dst + 32, rec2[id]);
             }
@@ -90,14 +103,7 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
         for (uint32_t r = 0; r < cnt; r += 32) {
             // lane l tests list entry r + 31 - l: bit b of the ballot is entry r + 31 - b, the highest bit comes first
             const uint32_t j = r + 31 - lane;
-            bool hit = false;
-            if (j < cnt) {
-                const float4 a = lds128(sbase + j * REC_BYTES);
-                const float4 c = lds128(sbase + j * REC_BYTES + 16);
-                constexpr float UNSCALE = -2.0f / LOG2E;  // back to (A, 2B, C) for the cull
-                hit = ellipse_hits_rect(a.x, a.y, a.z, c.x * UNSCALE, c.y * (0.5f * UNSCALE), c.z * UNSCALE, bx0f, by0f,
-                                        7.0f, 3.0f);
-            }
+            const bool hit = j < cnt && ((smask[j] >> wt) & 1u);
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
             const uint32_t top = sbase + (r + 31) * REC_BYTES;       // record of bit 0 ... minus b records for bit b
             const uint32_t last_top = (base - start) + r + 32;       // 1-based list position of bit 0's entry ... - b
@@ -144,8 +150,8 @@ void launch_render_forward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, u
                            float* out_depth, cudaStream_t s) {
     dim3 grid(v.gx, v.gy, 8 / FWD_WARPS);
     render_forward_kernel<GGRT_FWD_ASYNC != 0><<<grid, FWD_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
-                                                                             capacity, out_color, out_depth, im.final_T,
-                                                                             im.n_contrib);
+                                                                             b.masks, capacity, out_color, out_depth,
+                                                                             im.final_T, im.n_contrib);
 }
 
 }  // namespace ggrt

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GGRT_RASTER_ABI_VERSION 8
+#define GGRT_RASTER_ABI_VERSION 9
 #define GGRT_RASTER_TILE 16 /* tile edge in pixels (tile ids are part of the contract) */
 #define GGRT_RASTER_SUBS 16 /* pair counters per tile (contention spreading) */
 #define GGRT_RASTER_MAX_MERGE_VIEWS 16 /* views per ggrt_raster_sh_gradient_merge call */
@@ -157,6 +157,9 @@ typedef struct GgrtRasterLayout {
     /* binning buffer, per pair */
     size_t bin_keys;    /* uint64[N]  (depth_bits << 32 | gaussian_idx), sorted ascending inside each tile segment */
     size_t bin_points;  /* uint32[N]  gaussian idx, tile-major then depth then idx */
+    size_t bin_masks;   /* uint8[N]   per list entry: bit w set if the Gaussian's {alpha >= 1/255} ellipse reaches warp pixel
+                           block w of its tile (8x4 pixels; w & 1 = column, w >> 1 = row); written by the forward render
+                           kernel for the entries it consumed, read by the backward render kernel */
     size_t bin_bytes;
 } GgrtRasterLayout;
 
