@@ -257,7 +257,7 @@ def run_ours(args, rank, world, local_rank):
     del st0
     launch, cap, cap_err = args.launch, None, None
     if launch == "auto":
-        launch = "graph" if world == 1 else "eager"
+        launch = "graph"
     if launch == "graph" and arena is None:
         try:
             cap = CapturedStep(means, shs, None, opac, cov, rs, grad_img, exchange=exch, want_camera=args.pose_grads)
@@ -629,8 +629,8 @@ def main():
                     help="multi-GPU gradient exchange (N>1 only), see run_ours")
     ap.add_argument("--launch", default="auto", choices=["auto", "graph", "eager"],
                     help="how the timed step is issued: one CUDA graph replay, or eager kernel launches with the "
-                         "pair-buffer check deferred; auto (default) = graph at N=1, eager at N>1 (measured on 8xB200, "
-                         "DESIGN.md section 6: 0.355 vs 0.369 ms at N=1, 0.470 vs 0.438 ms at N=8)")
+                         "pair-buffer check deferred; auto (default) = graph (measured on 8xB200, DESIGN.md section 6: "
+                         "0.319 vs 0.331 ms at N=1, 0.433 vs 0.453 ms at N=8)")
     ap.add_argument("--no-extras", action="store_true", help="skip the depth-pass / through-the-caller lines (N=1)")
     ap.add_argument("--pose-grads", action="store_true",
                     help="also compute dL/d(viewmatrix, projmatrix, campos) in the backward (BASELINE config 3)")

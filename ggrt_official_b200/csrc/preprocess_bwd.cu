@@ -20,14 +20,14 @@
 namespace ggrt {
 
 #ifndef GGRT_PB_THREADS
-#define GGRT_PB_THREADS 128
+#define GGRT_PB_THREADS 32
 #endif
 #ifndef GGRT_PB_STAGES
 #define GGRT_PB_STAGES 2
 #endif
 constexpr int PB_THREADS = GGRT_PB_THREADS;
 #ifndef GGRT_PB_MINBLOCKS
-#define GGRT_PB_MINBLOCKS 3
+#define GGRT_PB_MINBLOCKS 10
 #endif
 
 constexpr int PB_STAGES = GGRT_PB_STAGES;

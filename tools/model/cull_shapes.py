@@ -31,6 +31,6 @@ def frac(bw,bh):
             tot += (q<=tau).sum()
     nb = (16//bw)*(16//bh)
     return tot/(N*nb), tot/N*bw*bh
-for bw,bh in [(16,16),(8,8),(8,4),(4,4),(8,2),(4,2),(2,2),(16,2),(16,1),(8,1)]:
+for bw,bh in [(16,16),(16,8),(8,8),(16,4),(8,4),(4,4),(8,2),(4,2),(2,2),(16,2),(16,1),(8,1)]:
     f,pp = frac(bw,bh)
     print(f"block {bw}x{bh}: survive frac {f:.3f}; evaluated px per pair {pp:.1f}; surviving (block,pair) per pair {pp/(bw*bh):.2f}")
