@@ -630,7 +630,7 @@ def main():
     ap.add_argument("--launch", default="auto", choices=["auto", "graph", "eager"],
                     help="how the timed step is issued: one CUDA graph replay, or eager kernel launches with the "
                          "pair-buffer check deferred; auto (default) = graph (measured on 8xB200, DESIGN.md section 6: "
-                         "0.319 vs 0.331 ms at N=1, 0.433 vs 0.453 ms at N=8)")
+                         "0.355 vs 0.367 ms at N=1, 0.433 vs 0.453 ms at N=8)")
     ap.add_argument("--no-extras", action="store_true", help="skip the depth-pass / through-the-caller lines (N=1)")
     ap.add_argument("--pose-grads", action="store_true",
                     help="also compute dL/d(viewmatrix, projmatrix, campos) in the backward (BASELINE config 3)")
