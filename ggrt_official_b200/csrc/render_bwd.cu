@@ -226,7 +226,8 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
                        float* __restrict__ scratch) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];  // WarpShared[NWARPS] | records of the batch
     __shared__ uint32_t sid[BWD_BATCH];
-    __shared__ uint8_t smask[BWD_BATCH];  // the forward kernel's cull result per staged record (bit = warp pixel block)
+    static_assert(BWD_BATCH % 4 == 0, "the compaction reads the masks four at a time");
+    __shared__ __align__(4) uint8_t smask[BWD_BATCH];  // the forward kernel's cull result per staged record (bit = warp pixel block)
     __shared__ __align__(16) float sdummy[16][12];  // sink of the state stores of the lanes that do not own the state
     __shared__ uint32_t block_last_s;
 
@@ -238,6 +239,21 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
     const int wt = warp + blockIdx.z * BWD_WARPS;  // warp pixel block of the tile (8 per tile)
     const int bx0 = blockIdx.x * TILE + (wt & 1) * 8, by0 = blockIdx.y * TILE + (wt >> 1) * 4;
     const float bx0f = (float)bx0, by0f = (float)by0;
+    // The per-pixel loads are issued first: they do not depend on the tile's list range, so their latency overlaps
+    // the dependent chain  tile range -> list entries -> records  of the speculative gather below.
+    const int lx = lane & 7, ly = lane >> 3;
+    const int px = bx0 + lx, py = by0 + ly;
+    uint32_t last = 0;
+    float Tfin = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, da = 0.f;
+    if (px < v.W && py < v.H) {
+        const size_t pix = (size_t)py * v.W + px, hw = (size_t)v.H * v.W;
+        Tfin = final_T[pix];
+        last = n_contrib[pix];
+        d0 = dL_dout[pix];
+        d1 = dL_dout[hw + pix];
+        d2 = dL_dout[2 * hw + pix];
+        if (AUX) da = dL_dout_aux[pix];
+    }
     const uint32_t start = starts[tile], tile_cnt = starts[tile + 1] - start;
 
     // Records of a batch of list entries [boff, boff + cnt) -> shared memory with cp.async (SASS LDGSTS), one group
@@ -259,20 +275,7 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
     gather(spec_b * BWD_BATCH, tile_cnt - spec_b * BWD_BATCH);
 
     // ---- per-pixel constants / initial state (lane = pixel here) -------------------------------
-    uint32_t last = 0;
     {
-        const int lx = lane & 7, ly = lane >> 3;
-        const int px = bx0 + lx, py = by0 + ly;
-        float Tfin = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, da = 0.f;
-        if (px < v.W && py < v.H) {
-            const size_t pix = (size_t)py * v.W + px, hw = (size_t)v.H * v.W;
-            Tfin = final_T[pix];
-            last = n_contrib[pix];
-            d0 = dL_dout[pix];
-            d1 = dL_dout[hw + pix];
-            d2 = dL_dout[2 * hw + pix];
-            if (AUX) da = dL_dout_aux[pix];
-        }
         // pixels with a zero upstream gradient contribute nothing (crop training leaves most tiles empty)
         if (d0 == 0.f && d1 == 0.f && d2 == 0.f && da == 0.f) last = 0;
         const float bg_dot = v.bg[0] * d0 + v.bg[1] * d1 + v.bg[2] * d2;
@@ -350,12 +353,23 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
         // one bit per block), compacted into a back-to-front queue ---------------------------------------------
         uint32_t qn = 0;
         const uint32_t lim = min(cnt, warp_last - boff);  // entries at or beyond warp_last never contribute here
-        for (int r = (int)((lim - 1) & ~31u); r >= 0; r -= 32) {
-            const uint32_t j = (uint32_t)r + 31 - lane;  // lane 0 tests the backmost entry of the round
-            const bool hit = j < lim && ((smask[j] >> wt) & 1u);
-            const uint32_t m = __ballot_sync(0xffffffffu, hit);
-            if (hit) ws.queue[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
-            qn += __popc(m);
+        for (int R = (int)((lim - 1) & ~127u); R >= 0; R -= 128) {  // 128 entries per round: four mask bytes per lane
+            const uint32_t e0 = (uint32_t)R + 4u * (31u - (uint32_t)lane);  // lane 0 holds the round's backmost four
+            uint32_t w = 0;
+            if (e0 < lim) {
+                w = (*reinterpret_cast<const uint32_t*>(&smask[e0]) >> wt) & 0x01010101u;
+                const uint32_t nv = lim - e0;
+                if (nv < 4u) w &= (1u << (8u * nv)) - 1u;
+            }
+            const uint32_t b3 = __ballot_sync(0xffffffffu, w & 0x01000000u), b2 = __ballot_sync(0xffffffffu, w & 0x00010000u),
+                           b1 = __ballot_sync(0xffffffffu, w & 0x00000100u), b0 = __ballot_sync(0xffffffffu, w & 0x00000001u);
+            const uint32_t lt = (1u << lane) - 1u;
+            uint32_t pos = qn + __popc(b3 & lt) + __popc(b2 & lt) + __popc(b1 & lt) + __popc(b0 & lt);
+            if (w & 0x01000000u) ws.queue[pos++] = (unsigned short)(e0 + 3u);
+            if (w & 0x00010000u) ws.queue[pos++] = (unsigned short)(e0 + 2u);
+            if (w & 0x00000100u) ws.queue[pos++] = (unsigned short)(e0 + 1u);
+            if (w & 0x00000001u) ws.queue[pos++] = (unsigned short)e0;
+            qn += __popc(b3) + __popc(b2) + __popc(b1) + __popc(b0);
         }
         if (lane == 0 && (qn & 1u)) ws.queue[qn] = 0;  // the pair read below never sees stale bits
         __syncwarp();
