@@ -12,6 +12,9 @@
 
 namespace ggrt {
 
+#ifndef GGRT_SORT_Q
+#define GGRT_SORT_Q 1
+#endif
 constexpr int EMIT_THREADS = 256;
 constexpr int SORT_THREADS = 256;
 
@@ -217,6 +220,169 @@ sort_tiles_reg_kernel(int T, const uint32_t* __restrict__ starts, unsigned long 
     (void)lane;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Quantised variant of the register sort (default): the network runs on 32-bit composites
+//     (depth_bits - tile_min) >> shift  |  position of the key in the emitted segment
+// instead of the 64-bit keys, so a compare-exchange is ONE shuffle + ONE VIMNMX (min or max chosen by a predicate)
+// instead of two shuffles, a 64-bit compare and two selects -- a third of the instructions.  View depths are positive
+// floats, so their bit patterns are monotone integers and the shift-quantisation is exactly monotone; the tile's
+// own [min, max] range is spread over 32 - log2(capacity) bits (21 for tiles up to 2048 pairs).  Entries whose
+// quantised depths collide (about 2 % of the tiles have one such pair at C2) come out adjacent and are ranked
+// inside their run with the exact 64-bit keys (re-read from the unsorted segment through the position the composite
+// carries), so the result is still the reference order, bit for bit.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void cx32(uint32_t& a, uint32_t& b) {
+    const uint32_t lo = min(a, b), hi = max(a, b);
+    a = lo, b = hi;
+}
+__device__ __forceinline__ void local_tail32(uint32_t (&v)[SORT_E]) {  // distances 4, 2, 1
+    cx32(v[0], v[4]), cx32(v[1], v[5]), cx32(v[2], v[6]), cx32(v[3], v[7]);
+    cx32(v[0], v[2]), cx32(v[1], v[3]), cx32(v[4], v[6]), cx32(v[5], v[7]);
+    cx32(v[0], v[1]), cx32(v[2], v[3]), cx32(v[4], v[5]), cx32(v[6], v[7]);
+}
+__device__ __forceinline__ uint32_t keep32(uint32_t mine, uint32_t other, bool lower) {
+    return lower ? min(mine, other) : max(mine, other);
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
+sort_tiles_q_kernel(int T, const uint32_t* __restrict__ starts, unsigned long long* __restrict__ keys,
+                    uint32_t* __restrict__ points, uint32_t capacity) {
+    constexpr int CAP = 256 * WARPS;
+    constexpr int IDXB = WARPS == 1 ? 8 : WARPS == 2 ? 9 : WARPS == 4 ? 10 : WARPS == 8 ? 11 : WARPS == 16 ? 12 : 13;  // log2(CAP)
+    constexpr uint32_t IDXM = (1u << IDXB) - 1u;
+    __shared__ uint32_t xch[CAP];             // cross-warp exchange; afterwards the sorted composites
+    __shared__ uint32_t smin[WARPS], smax[WARPS];
+    const int tile = blockIdx.x;
+    if (tile >= T) return;
+    const uint32_t s = min(starts[tile], capacity), n = min(starts[tile + 1], capacity) - s;
+    if (n == 0) return;
+    unsigned long long* seg = keys + s;
+    if (n > (uint32_t)CAP) {  // larger than the (hinted) register capacity: the 64-bit network in place in global memory
+        bitonic_sort(seg, n, 32 * WARPS);
+        for (uint32_t i = threadIdx.x; i < n; i += 32 * WARPS) points[s + i] = (uint32_t)seg[i];
+        return;
+    }
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, i0 = tid * SORT_E;
+    int L = 3;  // log2 of the padded size (>= 8)
+    while ((1u << L) < n) ++L;
+    const bool active = warp * 256u < (1u << L);  // warps beyond the padded size only keep the barriers company
+
+    uint32_t d[SORT_E], dmin = 0xffffffffu, dmax = 0u;
+#pragma unroll
+    for (int e = 0; e < SORT_E; ++e) {
+        d[e] = 0u;
+        if (i0 + e < n) {
+            d[e] = (uint32_t)(seg[i0 + e] >> 32);
+            dmin = min(dmin, d[e]), dmax = max(dmax, d[e]);
+        }
+    }
+    dmin = __reduce_min_sync(0xffffffffu, dmin), dmax = __reduce_max_sync(0xffffffffu, dmax);
+    if (WARPS > 1) {
+        if ((tid & 31u) == 0) smin[warp] = dmin, smax[warp] = dmax;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) dmin = min(dmin, smin[w]), dmax = max(dmax, smax[w]);
+    }
+    const int range_bits = 32 - __clz(dmax - dmin);  // 0 when all depths are equal
+    const int shift = max(0, range_bits - (32 - IDXB));
+    uint32_t v[SORT_E];
+#pragma unroll
+    for (int e = 0; e < SORT_E; ++e)
+        v[e] = (i0 + e < n) ? ((((d[e] - dmin) >> shift) << IDXB) | (i0 + e)) : 0xffffffffu;
+
+    if (active) {  // levels 1..3 (blocks of 2, 4, 8 keys) are entirely thread-local
+        cx32(v[0], v[1]), cx32(v[2], v[3]), cx32(v[4], v[5]), cx32(v[6], v[7]);
+        cx32(v[0], v[3]), cx32(v[1], v[2]), cx32(v[4], v[7]), cx32(v[5], v[6]);
+        cx32(v[0], v[1]), cx32(v[2], v[3]), cx32(v[4], v[5]), cx32(v[6], v[7]);
+        cx32(v[0], v[7]), cx32(v[1], v[6]), cx32(v[2], v[5]), cx32(v[3], v[4]);
+        cx32(v[0], v[2]), cx32(v[1], v[3]), cx32(v[4], v[6]), cx32(v[5], v[7]);
+        cx32(v[0], v[1]), cx32(v[2], v[3]), cx32(v[4], v[5]), cx32(v[6], v[7]);
+    }
+    for (int lk = 4; lk <= L; ++lk) {
+        {  // flip step: key i pairs with i ^ (2^lk - 1): local slot e <-> 7-e in thread tid ^ (2^(lk-3) - 1)
+            const bool lower = ((tid >> (lk - 4)) & 1u) == 0;  // bit lk-1 of the key index
+            uint32_t o[SORT_E];
+            if (WARPS == 1 || lk <= 8) {
+                if (active) {
+                    const int m = (1 << (lk - 3)) - 1;
+#pragma unroll
+                    for (int e = 0; e < SORT_E; ++e) o[e] = __shfl_xor_sync(0xffffffffu, v[SORT_E - 1 - e], m);
+#pragma unroll
+                    for (int e = 0; e < SORT_E; ++e) v[e] = keep32(v[e], o[e], lower);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < SORT_E; ++e) xch[i0 + e] = v[e];
+                __syncthreads();
+                const uint32_t m = (1u << lk) - 1u;
+#pragma unroll
+                for (int e = 0; e < SORT_E; ++e) o[e] = xch[(i0 + e) ^ m];
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < SORT_E; ++e) v[e] = keep32(v[e], o[e], lower);
+            }
+        }
+        // half-cleaners with distance 2^lj, lj = lk-2 .. 3 (cross-thread), then the local tail (4, 2, 1)
+        for (int lj = lk - 2; lj >= 3; --lj) {
+            const bool lower = ((tid >> (lj - 3)) & 1u) == 0;  // bit lj of the key index
+            uint32_t o[SORT_E];
+            if (WARPS == 1 || lj < 8) {
+                if (active) {
+                    const int m = 1 << (lj - 3);
+#pragma unroll
+                    for (int e = 0; e < SORT_E; ++e) o[e] = __shfl_xor_sync(0xffffffffu, v[e], m);
+#pragma unroll
+                    for (int e = 0; e < SORT_E; ++e) v[e] = keep32(v[e], o[e], lower);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < SORT_E; ++e) xch[i0 + e] = v[e];
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < SORT_E; ++e) o[e] = xch[(i0 + e) ^ (1u << lj)];
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < SORT_E; ++e) v[e] = keep32(v[e], o[e], lower);
+            }
+        }
+        if (active) local_tail32(v);
+    }
+    // sorted composites -> shared memory; the exact keys are read back from the (still unsorted) segment through the
+    // position each composite carries, and entries whose quantised depth collides with a neighbour's are ranked inside
+    // their run with those exact keys.  All reads of the segment happen before the barrier, all writes after it.
+#pragma unroll
+    for (int e = 0; e < SORT_E; ++e) xch[i0 + e] = v[e];
+    if (WARPS > 1) __syncthreads(); else __syncwarp();
+    unsigned long long key[SORT_E];
+    uint32_t pos[SORT_E];
+#pragma unroll
+    for (int e = 0; e < SORT_E; ++e) {
+        const uint32_t p = i0 + e;
+        pos[e] = p, key[e] = 0ull;
+        if (p >= n) continue;
+        const uint32_t qd = v[e] >> IDXB;
+        key[e] = seg[v[e] & IDXM];
+        const bool tie_l = p > 0 && (xch[p - 1] >> IDXB) == qd, tie_r = p + 1 < n && (xch[p + 1] >> IDXB) == qd;
+        if (tie_l || tie_r) {
+            uint32_t a = p, b = p + 1;
+            while (a > 0 && (xch[a - 1] >> IDXB) == qd) --a;
+            while (b < n && (xch[b] >> IDXB) == qd) ++b;
+            uint32_t rank = 0;
+            for (uint32_t r = a; r < b; ++r) rank += seg[xch[r] & IDXM] < key[e] ? 1u : 0u;
+            pos[e] = a + rank;
+        }
+    }
+    if (WARPS > 1) __syncthreads(); else __syncwarp();
+#pragma unroll
+    for (int e = 0; e < SORT_E; ++e)
+        if (i0 + e < n) {
+            seg[pos[e]] = key[e];
+            points[s + pos[e]] = (uint32_t)key[e];
+        }
+}
+
 void launch_emit(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, uint32_t capacity, cudaStream_t s) {
     if (v.P == 0) return;
     emit_kernel<<<(v.P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, s>>>(v, g, im.cursor, b.keys, capacity);
@@ -225,6 +391,14 @@ void launch_emit(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, uint32_t ca
 void launch_sort_tiles(const View& v, ImagePtrs im, BinPtrs b, uint32_t max_tile_pairs, uint32_t capacity,
                        cudaStream_t s) {
     const int T = v.gx * v.gy;
+#if GGRT_SORT_Q
+    if (max_tile_pairs <= 256) return (void)sort_tiles_q_kernel<1><<<T, 32, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
+    if (max_tile_pairs <= 512) return (void)sort_tiles_q_kernel<2><<<T, 64, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
+    if (max_tile_pairs <= 1024) return (void)sort_tiles_q_kernel<4><<<T, 128, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
+    if (max_tile_pairs <= 2048) return (void)sort_tiles_q_kernel<8><<<T, 256, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
+    if (max_tile_pairs <= 4096) return (void)sort_tiles_q_kernel<16><<<T, 512, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
+    if (max_tile_pairs <= 8192) return (void)sort_tiles_q_kernel<32><<<T, 1024, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
+#endif
     if (max_tile_pairs <= 256) {
         sort_tiles_reg_kernel<1><<<T, 32, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
         return;

@@ -93,3 +93,30 @@ def test_non_contiguous_float64_and_wide_sh_table():
     img.sum().backward()
     assert sh16.grad.shape == (P, 16, 3) and float(sh16.grad[:, 9:].abs().max()) == 0.0
     assert float(sh16.grad[:, :9].abs().max()) > 0.0 and means2D.grad.shape == (P, 3)
+
+
+@pytest.mark.parametrize("P,planes", [(3000, 3), (20000, 40), (60000, 1)])
+def test_depth_ties_keep_the_reference_order(P, planes):
+    """Many Gaussians with bit-identical view depths in one tile (all means snapped onto a few planes of constant
+    camera z): the per-tile sort must order them by (depth bits, Gaussian index) exactly as the reference's 64-bit
+    radix sort does -- the quantised sort keys collide massively here and the exact-key ranking of the runs
+    decides (binning.cu: sort_tiles_q_kernel; 60000 on ONE plane also drives the larger sort tiers)."""
+    H, W = 64, 96
+    sc, ri = small_case(P, H, W, 1, seed=77, behind_fraction=0.0)
+    # camera-space z of every mean -> snapped to `planes` distinct values; x, y kept
+    V = ri.viewmatrix.astype(np.float64)  # column-major 4x4 as the rasterizer reads it: p_view = p_world^T V
+    hom = np.concatenate([ri.means3D.astype(np.float64), np.ones((P, 1))], axis=1)
+    cam = hom @ V.reshape(4, 4)
+    levels = np.linspace(2.0, 6.0, planes)
+    cam[:, 2] = levels[np.random.default_rng(5).integers(0, planes, P)]
+    world = cam @ np.linalg.inv(V.reshape(4, 4))
+    ri.means3D = np.ascontiguousarray(world[:, :3].astype(np.float32))
+    st = G.run_cuda_forward(ri)
+    _, f = G.oracle_forward(ri)
+    res = G.compare_forward(st, f)
+    depth_bits = f["pre"]["depth"][f["pre"]["radii"] > 0].view(np.uint32)
+    assert len(np.unique(depth_bits)) < 0.2 * depth_bits.size  # the ties really exist after the float32 round trip
+    for k in ("radii_mismatch", "tiles_mismatch", "starts_mismatch", "point_list_mismatch", "key_depth_mismatch",
+              "key_idx_mismatch"):
+        assert res.get(k, 0) == 0, (k, res)
+    assert res["N"][0] == res["N"][1] > 0
