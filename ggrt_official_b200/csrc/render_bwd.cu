@@ -43,6 +43,9 @@ namespace ggrt {
 #ifndef GGRT_BWD_MMA
 #define GGRT_BWD_MMA 1
 #endif
+#ifndef GGRT_BWD_ROWPAIR
+#define GGRT_BWD_ROWPAIR 0
+#endif
 #ifndef GGRT_BWD_BATCH
 #define GGRT_BWD_BATCH (GGRT_BWD_MMA ? 384 : 512)
 #endif
@@ -385,27 +388,30 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
             load_gauss<AUX>(go, sbase, jpair >> 16, valid_o, boff, xq, by0f);
             float Dm[4] = {0.f, 0.f, 0.f, 0.f}, Dc[4] = {0.f, 0.f, 0.f, 0.f};
 
-#pragma unroll
-            for (int row = 0; row < 4; ++row) {
-                if (((pmask >> (row * 8)) & 0xffu) == 0) continue;  // no pixel of the row matters
+            // One row step in three parts, so that GGRT_BWD_ROWPAIR can interleave the dependent shuffle chains of two rows
+            struct RowState {
+                Eval e, o;
+                f2 A2, nB2, nBo, Tb2, nRb2;
+            };
+            auto row_front = [&](int row, RowState& r) {  // loads, both Gaussians' evaluations, the pair as one map
                 const uint32_t off = pq + (uint32_t)row * 192u;  // an immediate offset once the loop is unrolled
-                f2 gr2, gg2, gb2, last2, Tb2, nRb2, ga2 = bc(0.f);
+                f2 gr2, gg2, gb2, last2, ga2 = bc(0.f);
                 lds_2f2(off, gr2, gg2);
                 lds_2f2(off + 16, gb2, last2);
-                lds_2f2(off + 32, Tb2, nRb2);
+                lds_2f2(off + 32, r.Tb2, r.nRb2);
                 if (AUX) ga2 = lds_f2(pga + (uint32_t)row * 32u);
-                Eval e, o;
-                eval_gauss<AUX>(e, ge, (float)row, gr2, gg2, gb2, ga2, last2);
-                eval_gauss<AUX>(o, go, (float)row, gr2, gg2, gb2, ga2, last2);
-                // the pair as one map (o in front of e), then the inclusive scan over the pairs
-                const f2 nBe = mul2(mul2(e.nal2, e.sdot2), e.io2), nBo = mul2(mul2(o.nal2, o.sdot2), o.io2);
-                f2 A2 = mul2(e.io2, o.io2), nB2 = fma2(nBo, e.io2, nBe);  // (a_o a_e, nb_o a_e + nb_e)
-                pair_scan_step(A2, nB2, 4, m1, om1);
-                pair_scan_step(A2, nB2, 8, m2, om2);
-                pair_scan_step(A2, nB2, 16, m4, om4);
+                eval_gauss<AUX>(r.e, ge, (float)row, gr2, gg2, gb2, ga2, last2);
+                eval_gauss<AUX>(r.o, go, (float)row, gr2, gg2, gb2, ga2, last2);
+                const f2 nBe = mul2(mul2(r.e.nal2, r.e.sdot2), r.e.io2);
+                r.nBo = mul2(mul2(r.o.nal2, r.o.sdot2), r.o.io2);
+                r.A2 = mul2(r.e.io2, r.o.io2), r.nB2 = fma2(r.nBo, r.e.io2, nBe);  // (a_o a_e, nb_o a_e + nb_e)
+            };
+            auto row_back = [&](int row, RowState& r) {
+                const Eval &e = r.e, &o = r.o;
+                const f2 A2 = r.A2, nB2 = r.nB2, Tb2 = r.Tb2, nRb2 = r.nRb2;
                 // prefix through o = the scan's result (A, nB) = (a_o A', nb_o A' + nB'); prefix through e = (A', nB'):
                 // undo o with 1 / a_o = 1 - alpha_o
-                const f2 Ae = mul2(A2, o.om2), nBi = fma2(mul2(nBo, bc(-1.0f)), Ae, nB2);
+                const f2 Ae = mul2(A2, o.om2), nBi = fma2(mul2(r.nBo, bc(-1.0f)), Ae, nB2);
                 const f2 Ti_o = mul2(Tb2, A2), nRt_o = fma2(Tb2, nB2, nRb2);  // transmittance in front of o; -(sum behind, o incl.)
                 const f2 Ti_e = mul2(Tb2, Ae), nRt_e = fma2(Tb2, nBi, nRb2);
                 sts_2f2(pst + (uint32_t)row * 192u, Ti_o, nRt_o);  // frontmost pair: the state behind the next chunk
@@ -425,7 +431,36 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
                 mma_tf32(Dm, lo(qtA), hi(qtA), lo(qtB), hi(qtB), fb.z, fb.w);
                 mma_tf32(Dc, lo(whA), hi(whA), lo(whB), hi(whB), fb.x, fb.y);
                 mma_tf32(Dc, lo(wtA), hi(wtA), lo(wtB), hi(wtB), fb.x, fb.y);
+            };
+#if GGRT_BWD_ROWPAIR
+#pragma unroll
+            for (int rp = 0; rp < 4; rp += 2) {
+                if (((pmask >> (rp * 8)) & 0xffffu) == 0) continue;  // no pixel of the two rows matters
+                RowState r0, r1;
+                row_front(rp, r0);
+                row_front(rp + 1, r1);
+                pair_scan_step(r0.A2, r0.nB2, 4, m1, om1);
+                pair_scan_step(r1.A2, r1.nB2, 4, m1, om1);
+                pair_scan_step(r0.A2, r0.nB2, 8, m2, om2);
+                pair_scan_step(r1.A2, r1.nB2, 8, m2, om2);
+                pair_scan_step(r0.A2, r0.nB2, 16, m4, om4);
+                pair_scan_step(r1.A2, r1.nB2, 16, m4, om4);
+                row_back(rp, r0);
+                row_back(rp + 1, r1);
             }
+#else
+#pragma unroll
+            for (int row = 0; row < 4; ++row) {
+                if (((pmask >> (row * 8)) & 0xffu) == 0) continue;  // no pixel of the row matters
+                RowState r;
+                row_front(row, r);
+                // the inclusive scan over the pairs
+                pair_scan_step(r.A2, r.nB2, 4, m1, om1);
+                pair_scan_step(r.A2, r.nB2, 8, m2, om2);
+                pair_scan_step(r.A2, r.nB2, 16, m4, om4);
+                row_back(row, r);
+            }
+#endif
             // ---- D fragments -> per-Gaussian rows {S1, Sx, Sy, Sxx, Sxy, Syy, -, - | head sums r g b x | tail sums} ----
             sts_f2(stage_w, pk(Dm[0], Dm[1]));
             sts_f2(stage_w + STAGE_STRIDE * 4, pk(Dm[2], Dm[3]));
