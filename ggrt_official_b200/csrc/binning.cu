@@ -26,12 +26,28 @@ emit_kernel(View v, GeomPtrs g, uint32_t* __restrict__ cursor, unsigned long lon
     if (g.tiles[i] == 0) return;
     const ushort4 r = g.rect[i];
     const unsigned long long key = ((unsigned long long)__float_as_uint(g.rec0[i].w) << 32) | (uint32_t)i;
-    const int sub = i & (SUBS - 1);
-    // The (tile, sub-counter) segment start doubles as its allocation cursor: one returning atomic per pair.  The
-    // kernel is pure L2-atomic latency, so the claims of a Gaussian are issued TOGETHER, four at a time (GGRt's
-    // splats touch 1-4 tiles; 2x2 is the common rect), and only then the dependent stores: four round trips in
-    // flight per thread instead of one.
     const int w = r.z - r.x, n = w * (r.w - r.y);
+    if (n <= RANKED_TILES) {
+        // small splat: the geometry kernel's counting atomics already returned this pair's rank inside its
+        // (tile, sub-counter) segment -- slot = segment start + rank, no atomic, nothing to wait for but two loads
+        const int sub = i & (SUB_LANES - 1);
+        const uint4 rk = g.ranks[i];
+        const uint32_t rank[RANKED_TILES] = {rk.x, rk.y, rk.z, rk.w};
+        uint32_t slot[RANKED_TILES];
+#pragma unroll
+        for (int u = 0; u < RANKED_TILES; ++u) {
+            slot[u] = 0xffffffffu;
+            if (u < n) slot[u] = cursor[(((r.y + u / w) * v.gx + r.x + u % w) << SUBS_LOG2) + sub] + rank[u];
+        }
+#pragma unroll
+        for (int u = 0; u < RANKED_TILES; ++u)
+            if (slot[u] < capacity) keys[slot[u]] = key;  // a too-small (speculative) buffer is detected and redone by the host
+        return;
+    }
+    // Larger splats: the (tile, sub-counter) segment start of the second counter bank doubles as its allocation cursor,
+    // one returning atomic per pair.  The claims are issued four at a time and only then the dependent stores: four round
+    // trips in flight per thread instead of one.
+    const int sub = SUB_LANES + (i & (SUB_LANES - 1));
     for (int t0 = 0; t0 < n; t0 += 4) {
         uint32_t slot[4];
 #pragma unroll

@@ -129,6 +129,7 @@ void compute_layout(int P, int H, int W, long long N, GgrtRasterLayout* L) {
     L->geom_rect = off; off = align_up(off + p * sizeof(ushort4));
     L->geom_tiles = off; off = align_up(off + p * sizeof(uint32_t));
     L->geom_flags = off; off = align_up(off + p * sizeof(uint8_t));
+    L->geom_ranks = off; off = align_up(off + p * sizeof(uint4));
     L->geom_bytes = off > 0 ? off : 256;
 
     const size_t gx = (size_t)(W + TILE - 1) / TILE, gy = (size_t)(H + TILE - 1) / TILE, T = gx * gy;
@@ -162,6 +163,7 @@ GeomPtrs geom_ptrs(void* base, int P) {
     g.rect = reinterpret_cast<ushort4*>(b + L.geom_rect);
     g.tiles = reinterpret_cast<uint32_t*>(b + L.geom_tiles);
     g.flags = reinterpret_cast<uint8_t*>(b + L.geom_flags);
+    g.ranks = reinterpret_cast<uint4*>(b + L.geom_ranks);
     return g;
 }
 

@@ -17,11 +17,16 @@ constexpr float ALPHA_MAX = 0.99f;
 constexpr float T_EPS = 0.0001f;
 constexpr float RADIUS_CAP = 1.0e6f;
 constexpr int GRAD_STRIDE = 12;     // floats per Gaussian in the backward scratch
-// Each tile owns SUBS pair counters (sub-counter = Gaussian index mod SUBS): same-address
-// atomics serialise in L2, so spreading a tile's ~300 increments over 16 addresses cuts the
-// binning kernels' critical path ~16x.  Sub-segments are contiguous inside the tile segment.
-constexpr int SUBS = 16;
-constexpr int SUBS_LOG2 = 4;
+// Each tile owns SUBS pair counters: same-address atomics serialise in L2, so a tile's ~300 increments are spread
+// over 16 addresses by the Gaussian index (idx mod 16), which cuts the binning kernels' critical path ~16x.
+// The counters come in two banks of 16.  Bank 0 counts the pairs of Gaussians that touch at most RANKED_TILES tiles:
+// the geometry kernel increments it with RETURNING atomics and keeps the returned ranks (GeomPtrs::ranks), so that
+// `emit` places those pairs without any atomic (segment start + rank).  Bank 1 counts the pairs of larger Gaussians,
+// which `emit` places with allocation atomics as before.  Sub-segments are contiguous inside the tile segment.
+constexpr int SUBS = 32;
+constexpr int SUBS_LOG2 = 5;
+constexpr int SUB_LANES = 16;     // counters per bank
+constexpr int RANKED_TILES = 4;   // Gaussians touching at most this many tiles get their slots ranked by geometry
 
 // grad_scratch slot meaning (A.4): NDC-mean x,y | conic A, B(half convention), C | opacity | colour r,g,b
 enum GradSlot { G_MX = 0, G_MY = 1, G_CA = 2, G_CB = 3, G_CC = 4, G_OP = 5, G_R = 6, G_G = 7, G_B = 8, G_AUX = 9 };
@@ -47,6 +52,7 @@ struct GeomPtrs {
     ushort4* rect;     // tile rect
     uint32_t* tiles;   // tiles touched
     uint8_t* flags;    // clamp bits
+    uint4* ranks;      // per Gaussian touching <= RANKED_TILES tiles: its rank in the (tile, sub-counter) segment of each
 };
 
 constexpr int SCAN_BLOCK = 256;      // tiles per CTA of the tile scan

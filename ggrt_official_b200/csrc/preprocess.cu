@@ -41,6 +41,7 @@ geometry_kernel(View v, const float* __restrict__ means, const float* __restrict
     ushort4 rect = make_ushort4(0, 0, 0, 0);
     float4 r0 = make_float4(0.f, 0.f, -1.0f, 0.f);
     float4 r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint4 rk = make_uint4(0u, 0u, 0u, 0u);
 
     Geo q;
     if (geometry(v, sV, sM, px, py, pz, cv, q)) {
@@ -70,11 +71,25 @@ geometry_kernel(View v, const float* __restrict__ means, const float* __restrict
             if (tau > 0.0f) tau_c = tau * 1.001f + 0.02f;
             r0 = make_float4(pxx, pxy, tau_c, q.tz);
             r1 = make_float4(cA, cB, cC, o);
-            const int sub = i & (SUBS - 1);
-            for (int y = y0; y < y1; ++y)
-                for (int x = x0; x < x1; ++x) atomicAdd(&counts[((y * v.gx + x) << SUBS_LOG2) + sub], 1u);
+            if (area <= RANKED_TILES) {
+                // small splat (the common case: 1, 2 or 2x2 tiles): count with RETURNING atomics, all of them in flight
+                // together, and keep the ranks -- emit then needs no atomic for these pairs
+                const int sub = i & (SUB_LANES - 1), w = x1 - x0;
+                uint32_t r[RANKED_TILES];
+#pragma unroll
+                for (int u = 0; u < RANKED_TILES; ++u) {
+                    r[u] = 0u;
+                    if (u < area) r[u] = atomicAdd(&counts[(((y0 + u / w) * v.gx + x0 + u % w) << SUBS_LOG2) + sub], 1u);
+                }
+                rk = make_uint4(r[0], r[1], r[2], r[3]);
+            } else {
+                const int sub = SUB_LANES + (i & (SUB_LANES - 1));  // the bank emit allocates from with atomics
+                for (int y = y0; y < y1; ++y)
+                    for (int x = x0; x < x1; ++x) atomicAdd(&counts[((y * v.gx + x) << SUBS_LOG2) + sub], 1u);
+            }
         }
     }
+    g.ranks[i] = rk;
     radii[i] = radius;
     g.tiles[i] = tiles;
     g.rect[i] = rect;

@@ -231,7 +231,6 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
     __shared__ uint32_t sid[BWD_BATCH];
     static_assert(BWD_BATCH % 4 == 0, "the compaction reads the masks four at a time");
     __shared__ __align__(4) uint8_t smask[BWD_BATCH];  // the forward kernel's cull result per staged record (bit = warp pixel block)
-    __shared__ __align__(16) float sdummy[16][12];  // sink of the state stores of the lanes that do not own the state
     __shared__ uint32_t block_last_s;
 
     WarpShared* const wsm = reinterpret_cast<WarpShared*>(dyn_smem);
@@ -328,11 +327,12 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
     const int q = lane & 3, kp = lane >> 2;
     // Base addresses, opaque to the compiler (it would otherwise rebuild them from the thread index in every row):
     //   pq: pix[q] (+ row * 192; ga[q] follows at a fixed distance)    pl: fcm[0][lane] (+ row * 512)
-    //   pst: where this lane's state store goes -- the real state for the frontmost pair, a sink for the others
+    //   front: non-zero in the lanes of the frontmost pair, which own the state stores (kept as a register: the
+    //   compiler would otherwise re-derive the predicate from the thread index in every row)
     uint32_t pq = smem_addr(&ws.pix[q][0]), pl = smem_addr(&ws.fcm[0][lane][0]);
-    uint32_t pst = kp == 7 ? pq + 32u : smem_addr(&sdummy[q][8]);
+    uint32_t front = kp == 7 ? 1u : 0u;
     uint32_t stage_w = smem_addr(&ws.stage[2 * kp][2 * q]);  // this lane's D elements: rows 2 kp, 2 kp + 1
-    asm volatile("" : "+r"(pq), "+r"(pl), "+r"(pst), "+r"(stage_w));
+    asm volatile("" : "+r"(pq), "+r"(pl), "+r"(front), "+r"(stage_w));
     const uint32_t pga = pq + (uint32_t)(offsetof(WarpShared, ga) - offsetof(WarpShared, pix)) - 40u * (uint32_t)q;  // ga[q]
     const float xq = bx0f + (float)q;  // x of this lane's pixel A; pixel B is 4 to the right
     // identity masks of the pair scan: level d needs a lane 4 d below
@@ -414,7 +414,7 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
                 const f2 Ae = mul2(A2, o.om2), nBi = fma2(mul2(r.nBo, bc(-1.0f)), Ae, nB2);
                 const f2 Ti_o = mul2(Tb2, A2), nRt_o = fma2(Tb2, nB2, nRb2);  // transmittance in front of o; -(sum behind, o incl.)
                 const f2 Ti_e = mul2(Tb2, Ae), nRt_e = fma2(Tb2, nBi, nRb2);
-                sts_2f2(pst + (uint32_t)row * 192u, Ti_o, nRt_o);  // frontmost pair: the state behind the next chunk
+                if (front) sts_2f2(pq + 32u + (uint32_t)row * 192u, Ti_o, nRt_o);  // frontmost pair: the state behind the next chunk
                 const f2 dq_e = mul2(fma2(Ti_e, e.sdot2, nRt_e), e.io2), dq_o = mul2(fma2(Ti_o, o.sdot2, nRt_o), o.io2);  // dL/dalpha
                 // A fragments {e at A, o at A, e at B, o at B}: built with scalar operations, so that each lands in the
                 // register the MMA wants (pairing the packed results would cost a move per element)

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GGRT_RASTER_ABI_VERSION 9
+#define GGRT_RASTER_ABI_VERSION 10
 #define GGRT_RASTER_TILE 16 /* tile edge in pixels (tile ids are part of the contract) */
 #define GGRT_RASTER_SUBS 16 /* pair counters per tile (contention spreading) */
 #define GGRT_RASTER_MAX_MERGE_VIEWS 16 /* views per ggrt_raster_sh_gradient_merge call */
@@ -143,11 +143,14 @@ typedef struct GgrtRasterLayout {
     size_t geom_rect;   /* uint16x4[P] {tile_x0, tile_y0, tile_x1, tile_y1} */
     size_t geom_tiles;  /* uint32[P]  tiles touched */
     size_t geom_flags;  /* uint8[P]   bit c: colour channel c was clamped at 0 */
+    size_t geom_ranks;  /* uint32x4[P] Gaussians touching <= 4 tiles: rank of each of their pairs inside its (tile, sub-counter)
+                           segment, returned by the geometry kernel's counting atomics and consumed by the emit kernel */
     size_t geom_bytes;
     /* image buffer, per tile / per pixel */
-    size_t img_counts;  /* uint32[T*16] pairs per (tile, sub-counter); sub-counter = gaussian idx % 16 */
+    size_t img_counts;  /* uint32[T*32] pairs per (tile, sub-counter); sub-counter = gaussian idx % 16 (+ 16 for Gaussians that
+                           touch more than 4 tiles) */
     size_t img_partials;/* uint64[ceil(T/256)] per-scan-block {flag, max, total} (directly after img_counts, zeroed with it) */
-    size_t img_cursor;  /* uint32[T*16] exclusive scan of img_counts (per (tile, sub-counter) segment starts); consumed as
+    size_t img_cursor;  /* uint32[T*32] exclusive scan of img_counts (per (tile, sub-counter) segment starts); consumed as
                            allocation cursors by the emit kernel */
     size_t img_starts;  /* uint32[T+1]  exclusive scan of the per-tile totals; tile t owns [starts[t], starts[t+1]); [T] == N */
     size_t img_header;  /* uint32[4]   {N, max pairs in a tile, 0, 0} */

@@ -47,7 +47,7 @@ def unpack_state(st):
         rect=_view(g, L.geom_rect, torch.int16, 4 * P).reshape(P, 4),
         tiles=_view(g, L.geom_tiles, torch.int32, P),
         flags=_view(g, L.geom_flags, torch.uint8, P),
-        counts=_view(im, L.img_counts, torch.int32, T * 16).reshape(T, 16).sum(dim=1),
+        counts=_view(im, L.img_counts, torch.int32, T * 32).reshape(T, 32).sum(dim=1),
         starts=_view(im, L.img_starts, torch.int32, T + 1),
         header=_view(im, L.img_header, torch.int32, 4),
         final_T=_view(im, L.img_final_T, torch.float32, H * W).reshape(H, W),

@@ -37,11 +37,11 @@ def test_abi_version_and_layout():
     L = _cabi.layout(P, H, W, N)
     T = ((W + 15) // 16) * ((H + 15) // 16)
     assert L.geom_bytes == lib.ggrt_raster_geom_bytes(P) >= P * (48 + 8 + 4 + 1)
-    assert L.img_bytes == lib.ggrt_raster_image_bytes(H, W) >= 8 * H * W + 4 * (T + 1) + 2 * 4 * 16 * T
+    assert L.img_bytes == lib.ggrt_raster_image_bytes(H, W) >= 8 * H * W + 4 * (T + 1) + 2 * 4 * 32 * T
     assert L.bin_bytes == lib.ggrt_raster_binning_bytes(N) >= 12 * N
-    offs = [L.geom_rec0, L.geom_rec1, L.geom_rec2, L.geom_rect, L.geom_tiles, L.geom_flags]
+    offs = [L.geom_rec0, L.geom_rec1, L.geom_rec2, L.geom_rect, L.geom_tiles, L.geom_flags, L.geom_ranks]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
-    assert L.img_partials == L.img_counts + 4 * 16 * T and L.img_cursor > L.img_partials
+    assert L.img_partials == L.img_counts + 4 * 32 * T and L.img_cursor > L.img_partials
     assert lib.ggrt_raster_binning_bytes(0) > 0  # never a zero-sized allocation
 
 
