@@ -55,7 +55,10 @@ struct GeomPtrs {
     uint4* ranks;      // per Gaussian touching <= RANKED_TILES tiles: its rank in the (tile, sub-counter) segment of each
 };
 
-constexpr int SCAN_BLOCK = 256;      // tiles per CTA of the tile scan
+#ifndef GGRT_SCAN_BLOCK
+#define GGRT_SCAN_BLOCK 256
+#endif
+constexpr int SCAN_BLOCK = GGRT_SCAN_BLOCK;  // tiles per CTA of the tile scan
 
 struct ImagePtrs {
     uint32_t* counts;
