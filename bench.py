@@ -604,6 +604,41 @@ def measure_extras(args, ri, g_np, dev, flush_l2):
                 dstep()
             ms = time_loop(dstep, n, dev)
             res[name] = {"value": 1e3 * n / sum(ms), "unit": "frames/s", "ms_per_step": sum(ms) / n}
+        # several target views of the same Gaussians in one decoder call (GGRt renders 1-4 target views per step): the
+        # sync-free glue with the views queued on one stream, on two streams, and with the pair-buffer check deferred
+        try:
+            nv = 4
+            rng = np.random.default_rng(SEED + 5)
+            from ggrt_official_b200.synthetic import small_se3
+
+            E4 = np.stack([sc.extrinsics.astype(np.float64) @ small_se3(rng).astype(np.float64) for _ in range(nv)]).astype(np.float32)
+            extr4, intr4 = t(E4)[None], t(np.stack([sc.intrinsics] * nv))[None]
+            near4, far4 = torch.full((1, nv), sc.near, device=dev), torch.full((1, nv), sc.far, device=dev)
+            wc4 = t(g_np)[None, None].expand(1, nv, 3, H, W)
+            wd4 = wd.expand(1, nv, H, W)
+            multi = {}
+            for name, streams, check in (("one_stream", 1, "sync"), ("two_streams", 2, "sync"),
+                                         ("one_stream_lazy_check", 1, "lazy"), ("two_streams_lazy_check", 2, "lazy")):
+                dec = DecoderSplattingCUDA(device_glue=True, view_streams=streams)
+                R.AUTOGRAD_CHECK = check
+
+                def mstep():
+                    for v in leaves.values():
+                        v.grad = None
+                    r = dec(Gaussians(**leaves), extr4, intr4, near4, far4, (H, W), depth_mode="depth")
+                    ((r.color * wc4).sum() + (r.depth * wd4).sum()).backward()
+
+                for _ in range(3):
+                    mstep()
+                ms = time_loop(mstep, 10, dev)
+                R.check_pending(block=True)
+                multi[name] = {"value": 1e3 * 10 * nv / sum(ms), "unit": "frames/s", "ms_per_call": sum(ms) / 10}
+            R.AUTOGRAD_CHECK = "sync"
+            multi["what"] = f"{nv} target views of the same Gaussians per decoder call (colour + depth, fwd+bwd through autograd)"
+            res["multi_view_device_glue"] = multi
+        except Exception as e:  # noqa: BLE001
+            R.AUTOGRAD_CHECK = "sync"
+            res["multi_view_device_glue"] = {"error": repr(e)[:300]}
         res["what"] = ("DecoderSplattingCUDA (mirror of decoder_splatting_cuda.py:29-85 driving render_cuda / "
                        "render_depth_cuda, same host syncs and copies as the reference glue), 1 view, fwd+bwd through "
                        "autograd, inputs resident, no L2 flush")

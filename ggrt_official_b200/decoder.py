@@ -35,19 +35,22 @@ def _per_view(t: Tensor, v: int) -> Tensor:
 
 class DecoderSplattingCUDA(nn.Module):
     def __init__(self, background_color=(0.0, 0.0, 0.0), fused_depth: bool = False, fast_glue: bool = False,
-                 device_glue: bool = False) -> None:
+                 device_glue: bool = False, view_streams: int = 1) -> None:
         """fused_depth: render colour and depth in one rasterization (same outputs as the reference's two
         passes; roughly half the rasterizer work when a depth mode is requested).
         fast_glue: additionally skip the reference glue's per-view replication / rescale / gather / permute
         copies and its per-view host syncs (render_views_fast); implies fused_depth.
         device_glue: additionally set up all cameras in one kernel and keep them on the device -- no host
         synchronisation at all, the depth channel evaluated inside the rasterizer (render_views_device; depth modes
-        other than "depth" fall back to fast_glue); implies fast_glue."""
+        other than "depth" fall back to fast_glue); implies fast_glue.
+        view_streams (with device_glue): issue the (batch x view) rasterizations round-robin on this many CUDA streams so
+        that independent views overlap on the GPU (render_views_device)."""
         super().__init__()
         self.background_color = torch.tensor(background_color, dtype=torch.float32)
         self.fused_depth = fused_depth or fast_glue or device_glue
         self.fast_glue = fast_glue or device_glue
         self.device_glue = device_glue
+        self.view_streams = int(view_streams)
         self._bg = {}
 
     def forward(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
@@ -61,7 +64,7 @@ class DecoderSplattingCUDA(nn.Module):
             color, depth = render_views_device(
                 extrinsics.flatten(0, 1), intrinsics.flatten(0, 1), near.flatten(), far.flatten(), image_shape, bg,
                 gaussians.means, gaussians.covariances, gaussians.harmonics, gaussians.opacities,
-                view_to_scene=[i // v for i in range(b * v)], depth=depth_mode is not None)
+                view_to_scene=[i // v for i in range(b * v)], depth=depth_mode is not None, streams=self.view_streams)
             return DecoderOutput(color.unflatten(0, (b, v)), None if depth is None else depth.unflatten(0, (b, v)))
         if self.fast_glue:
             color, depth = render_views_fast(

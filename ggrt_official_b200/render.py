@@ -223,14 +223,20 @@ def camera_setup(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tens
 def render_views_device(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple,
                         background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
                         gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor, view_to_scene: Sequence[int],
-                        scale_invariant: bool = True, depth: bool = False):
+                        scale_invariant: bool = True, depth: bool = False, streams: int = 1):
     """render_views_fast without any host synchronisation and with (almost) no PyTorch glue: the cameras of all views
     are set up by one kernel (camera_setup), the rasterizer reads tan(fov/2) and the scene scale from the device
     (GaussianRasterizationSettings.device_params), reads pixelSplat's own tensor layout, and -- with depth=True --
     evaluates GGRt's depth channel (mode "depth") inside its kernels (aux_mode=1), its gradient flowing straight
     into the means.  The views' kernels are enqueued back to back; nothing is read back.  Same outputs as
     render_cuda (+ render_depth_cuda) within the parity tolerance (the camera matrices may differ from the PyTorch
-    glue's in the last ulp).  Returns (color [n,3,h,w], depth [n,h,w] or None)."""
+    glue's in the last ulp).
+    `streams` > 1 (multi-view calls): the views are issued round-robin on that many CUDA streams (the caller's + cached
+    side streams), forward AND -- because autograd runs a node's backward on its forward stream -- backward.  The views
+    are independent (cuda_splatting.py:93-127), and the rasterizer alternates between latency-bound kernels (binning),
+    issue-bound ones (the two render kernels) and HBM-bound ones (colour, per-Gaussian backward), so two views in
+    flight fill each other's gaps instead of queueing 8 kernels per view one after another.
+    Returns (color [n,3,h,w], depth [n,h,w] or None)."""
     nb = extrinsics.shape[0]
     h, w = image_shape
     degree = isqrt(gaussian_sh_coefficients.shape[-1]) - 1
@@ -238,20 +244,44 @@ def render_views_device(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, fa
     harm = gaussian_sh_coefficients.contiguous()
     cov = gaussian_covariances.contiguous()
     layout = dict(scene_scale=1.0, cov_full3x3=True, sh_channel_major=True)  # the scale itself is read on the device
+    dev = extrinsics.device
+    main = torch.cuda.current_stream(dev)
+    pool = [main] + _side_streams(dev, max(0, min(int(streams), nb) - 1))
+    for st in pool[1:]:
+        st.wait_stream(main)  # the inputs (and the camera kernel) were produced on the caller's stream
     colors, depths = [], []
     for i in range(nb):
         s_ = view_to_scene[i]
         c = cams[i]
-        settings = GaussianRasterizationSettings(
-            image_height=h, image_width=w, tanfovx=0.0, tanfovy=0.0, bg=background_color[i], scale_modifier=1.0,
-            viewmatrix=c[0:16], projmatrix=c[16:32], sh_degree=degree, campos=c[32:35], prefiltered=False,
-            device_params=c[35:38], aux_mode=1 if depth else 0)
-        image, _, d = GaussianRasterizer(settings)(
-            means3D=gaussian_means[s_], means2D=None, shs=harm[s_], opacities=gaussian_opacities[s_],
-            cov3D_precomp=cov[s_], layout=layout)
+        st = pool[i % len(pool)]
+        with torch.cuda.stream(st):
+            settings = GaussianRasterizationSettings(
+                image_height=h, image_width=w, tanfovx=0.0, tanfovy=0.0, bg=background_color[i], scale_modifier=1.0,
+                viewmatrix=c[0:16], projmatrix=c[16:32], sh_degree=degree, campos=c[32:35], prefiltered=False,
+                device_params=c[35:38], aux_mode=1 if depth else 0)
+            image, _, d = GaussianRasterizer(settings)(
+                means3D=gaussian_means[s_], means2D=None, shs=harm[s_], opacities=gaussian_opacities[s_],
+                cov3D_precomp=cov[s_], layout=layout)
+        if st is not main:  # the outputs are consumed on the caller's stream: keep the allocator from recycling them early
+            image.record_stream(main)
+            d.record_stream(main)
         colors.append(image)
         depths.append(d)
+    for st in pool[1:]:
+        main.wait_stream(st)
     return torch.stack(colors), (torch.stack(depths) if depth else None)
+
+
+_SIDE_STREAMS: dict = {}
+
+
+def _side_streams(device, n: int) -> list:
+    """n cached side streams of `device` for render_views_device(streams=...)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    have = _SIDE_STREAMS.setdefault(key, [])
+    while len(have) < n:
+        have.append(torch.cuda.Stream(device=device))
+    return have[:n]
 
 
 def render_depth_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple,

@@ -104,3 +104,32 @@ def test_device_glue_decoder_equals_fast_glue_for_two_views():
     for k in la:
         ref, got = la[k].grad, lb[k].grad
         assert float((got - ref).abs().max()) <= 1e-3 * float(ref.abs().max()), k
+
+
+@pytest.mark.parametrize("streams", [2, 3])
+def test_views_on_several_streams_equal_the_sequential_views(streams):
+    """render_views_device(streams=n): the views of a call issued round-robin on n CUDA streams (forward and, through
+    autograd, backward) must give what the sequential loop gives -- images bit for bit (the forward is deterministic),
+    gradients up to the summation order of the float atomics."""
+    sc, E, K, near, far = _views(5, seed=11)
+    H, W = sc.image_shape
+    t = lambda a: torch.tensor(np.asarray(a), device=DEV)
+    out = {}
+    for name, kw in (("seq", dict(device_glue=True)), ("par", dict(device_glue=True, view_streams=streams))):
+        leaves = dict(means=t(sc.means)[None].requires_grad_(), covariances=t(sc.covariances)[None].requires_grad_(),
+                      harmonics=t(sc.harmonics)[None].requires_grad_(), opacities=t(sc.opacities)[None].requires_grad_())
+        for _ in range(2):  # twice: the second pass reuses cached streams and allocator blocks
+            for v in leaves.values():
+                v.grad = None
+            r = DecoderSplattingCUDA(**kw)(Gaussians(**leaves), E[None], K[None], near[None], far[None], (H, W),
+                                           depth_mode="depth")
+            torch.manual_seed(0)
+            wc, wd = torch.randn_like(r.color), torch.randn_like(r.depth)
+            ((r.color * wc).sum() + (r.depth * wd).sum()).backward()
+        torch.cuda.synchronize()
+        out[name] = (r, leaves)
+    (ra, la), (rb, lb) = out["seq"], out["par"]
+    assert torch.equal(ra.color, rb.color) and torch.equal(ra.depth, rb.depth)
+    for k in la:
+        ref, got = la[k].grad, lb[k].grad
+        assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max()), k
