@@ -497,7 +497,7 @@ def run_ours(args, rank, world, local_rank):
         cfg["views_per_step"] = world
         n_exch = 0 if exch is None else exch.kernels_per_step()
         line = {
-            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "impl": "ours", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg,
