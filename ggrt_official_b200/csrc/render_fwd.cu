@@ -8,6 +8,7 @@
 // and publishes the 8-bit result in shared memory and, for the backward kernel, in the pair
 // buffer; each warp then ballots its bit and walks only the surviving entries, in list order.
 // GGRt's splats are a few pixels wide, so most (warp, Gaussian) pairs of a tile are culled.
+#include "f32x2.cuh"
 #include "render_common.cuh"
 
 namespace ggrt {
@@ -210,8 +211,174 @@ render_forward_kernel(View v, const float4* __restrict__ rec0, const float4* __r
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Pixel-pair variant (GGRT_FWD_PAIR, default): one CTA of 4 warps per tile, warp w owns the 8x8 pixel block
+// (w & 1, w >> 1) and every lane TWO pixels of it, (x, y) and (x, y + 4), which share dx and whose dy differ by the
+// constant 4 -- so the blend body runs on packed f32x2 pairs (FFMA2 / FMUL2: one issue slot, two pixels).  The kernel
+// is instruction-issue bound and the body is 75 % of its instructions: per list entry 1.21 8x8 blocks survive the cull
+// and cost ~45 instructions each, against 1.78 8x4 blocks at 34 (CPU model tools/model/cull_shapes.py).  Each packed
+// operation performs exactly the two scalar operations of the single-pixel kernel, so the image is bit-identical.
+// Batches of 128 records (one per thread), cp.async double buffer and the 8-bit cull masks for the backward kernel as
+// above; a warp's own cull bit is the OR of the two 8x4 blocks it covers.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef GGRT_FWD_PAIR_RPT
+#define GGRT_FWD_PAIR_RPT 1
+#endif
+constexpr int F2_WARPS = 4, F2_THREADS = 32 * F2_WARPS;
+constexpr int F2_RPT = GGRT_FWD_PAIR_RPT;  // records staged per thread and batch
+constexpr int F2_BATCH = F2_THREADS * F2_RPT;
+#ifndef GGRT_FWD_PAIR
+#define GGRT_FWD_PAIR 1
+#endif
+#ifndef GGRT_FWD_PAIR_MINBLOCKS
+#define GGRT_FWD_PAIR_MINBLOCKS 8
+#endif
+
+__global__ void __launch_bounds__(F2_THREADS, GGRT_FWD_PAIR_MINBLOCKS)
+render_forward_pair_kernel(View v, const float4* __restrict__ rec0, const float4* __restrict__ rec1,
+                           const float4* __restrict__ rec2, const uint32_t* __restrict__ starts,
+                           const uint32_t* __restrict__ points, uint8_t* __restrict__ masks, uint32_t capacity,
+                           float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ final_T,
+                           uint32_t* __restrict__ n_contrib) {
+    __shared__ __align__(16) unsigned char srec[2 * F2_BATCH * REC_BYTES];
+    __shared__ __align__(4) uint8_t smask[F2_BATCH];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.y * v.gx + blockIdx.x;
+    const int bx0 = blockIdx.x * TILE + (warp & 1) * 8, by0 = blockIdx.y * TILE + (warp >> 1) * 8;
+    const int px = bx0 + (lane & 7), pya = by0 + (lane >> 3), pyb = pya + 4;
+    const bool ina = px < v.W && pya < v.H, inb = px < v.W && pyb < v.H;
+    const float pxf = (float)px, pyaf = (float)pya;
+    const float tx0f = (float)(blockIdx.x * TILE), ty0f = (float)(blockIdx.y * TILE);
+    // the two 8x4 blocks of the cull mask that make up this warp's 8x8 block: rows 2 (w >> 1) and 2 (w >> 1) + 1
+    const uint32_t wbits = (1u << (4 * (warp >> 1) + (warp & 1))) | (1u << (4 * (warp >> 1) + 2 + (warp & 1)));
+    const uint32_t start = min(starts[tile], capacity), end = min(starts[tile + 1], capacity);
+
+    // sign of T = per-pixel "done" flag, as in the single-pixel kernel
+    f2 T2 = pk(ina ? 1.0f : -1.0f, inb ? 1.0f : -1.0f), C0 = bc(0.f), C1 = bc(0.f), C2 = bc(0.f), D = bc(0.f);
+    uint32_t lasta = 0, lastb = 0;
+
+    uint32_t nid[F2_RPT];
+    auto gather = [&](uint32_t b, uint32_t h) {
+#pragma unroll
+        for (int u = 0; u < F2_RPT; ++u) {
+            const uint32_t k = tid + u * F2_THREADS;
+            if (b + k < end) {
+                const uint32_t dst = smem_addr(srec) + h * (F2_BATCH * REC_BYTES) + k * REC_BYTES;
+                cp_async16(dst, rec0 + nid[u]);
+                cp_async16(dst + 16, rec1 + nid[u]);
+                cp_async16(dst + 32, rec2 + nid[u]);
+            }
+        }
+        cp_async_commit();
+#pragma unroll
+        for (int u = 0; u < F2_RPT; ++u) {
+            const uint32_t nn = b + F2_BATCH + tid + u * F2_THREADS;
+            if (nn < end) nid[u] = points[nn];
+        }
+    };
+#pragma unroll
+    for (int u = 0; u < F2_RPT; ++u) {
+        nid[u] = 0;
+        if (start + tid + u * F2_THREADS < end) nid[u] = points[start + tid + u * F2_THREADS];
+    }
+    gather(start, 0);
+    uint32_t half = 0;
+    for (uint32_t base = start; base < end; base += F2_BATCH, half ^= 1u) {
+        const bool done = lo(T2) < 0.0f && hi(T2) < 0.0f;
+        if (__syncthreads_and(done)) break;  // also orders the previous batch's reads before the refill
+        const uint32_t cnt = min((uint32_t)F2_BATCH, end - base);
+        const uint32_t sbase = smem_addr(srec) + half * (F2_BATCH * REC_BYTES);
+        gather(base + F2_BATCH, half ^ 1u);  // the next batch streams in under this one's blend loop
+        cp_async_wait<1>();
+#pragma unroll
+        for (int u = 0; u < F2_RPT; ++u) {
+            const uint32_t k = tid + u * F2_THREADS;
+            if (k < cnt) {  // cull against the tile's 8 warp pixel blocks (8x4; the backward kernel's granularity), rescale
+                const float4 a = lds128(sbase + k * REC_BYTES);
+                float4 c = lds128(sbase + k * REC_BYTES + 16);
+                const uint32_t m = block_mask8(a.x, a.y, a.z, c.x, c.y, c.z, tx0f, ty0f);
+                smask[k] = (uint8_t)m;
+                masks[base + k] = (uint8_t)m;
+                c.x *= -0.5f * LOG2E, c.y *= -LOG2E, c.z *= -0.5f * LOG2E;
+                sts128(sbase + k * REC_BYTES + 16, c);
+            }
+        }
+        __syncthreads();
+        if (__all_sync(0xffffffffu, lo(T2) < 0.0f && hi(T2) < 0.0f)) continue;
+        for (uint32_t r = 0; r < cnt; r += 32) {
+            // lane l tests list entry r + 31 - l: bit b of the ballot is entry r + 31 - b, the highest bit comes first
+            const uint32_t j = r + 31 - lane;
+            const bool hit = j < cnt && (smask[j] & wbits);
+            uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            const uint32_t top = sbase + (r + 31) * REC_BYTES;       // record of bit 0 ... minus b records for bit b
+            const uint32_t last_top = (base - start) + r + 32;       // 1-based list position of bit 0's entry ... - b
+            while (mask) {
+                uint32_t b, src;  // opaque to the optimiser, which otherwise rebuilds the index from 31 - clz
+                asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(mask));
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(src) : "r"(b), "r"(0u - (uint32_t)REC_BYTES), "r"(top));
+                mask ^= 1u << b;
+                const float2 xy = lds64(src);
+                const float4 c = lds128(src + 16);
+                const float4 col = lds128(src + 32);
+                const float dx = xy.x - pxf, dya = xy.y - pyaf;
+                const f2 dy2 = pk(dya, dya - 4.0f);
+                // power2 = fma(dx, fma(c.x, dx, c.y * dy), (c.z * dy) * dy), both pixels at once
+                const f2 power2 = fma2(bc(dx), fma2(bc(c.x), bc(dx), mul2(bc(c.y), dy2)), mul2(mul2(bc(c.z), dy2), dy2));
+                const float pa = lo(power2), pb = hi(power2);
+                const f2 raw2 = mul2(bc(c.w), pk(ex2_approx(pa), ex2_approx(pb)));
+                const float ala = fminf(ALPHA_MAX, lo(raw2)), alb = fminf(ALPHA_MAX, hi(raw2));
+                const bool acta = (pa <= 0.0f) && (ala >= ALPHA_MIN), actb = (pb <= 0.0f) && (alb >= ALPHA_MIN);
+                const f2 al2 = pk(ala, alb);
+                const f2 Tn2 = mul2(T2, fma2(al2, bc(-1.0f), bc(1.0f)));  // T (1 - alpha)
+                const float Ta = lo(T2), Tb = hi(T2), Tna = lo(Tn2), Tnb = hi(Tn2);
+                const bool bla = acta && (Tna >= T_EPS), blb = actb && (Tnb >= T_EPS);
+                const f2 aT2 = mul2(al2, T2);
+                const f2 w2 = pk(bla ? lo(aT2) : 0.0f, blb ? hi(aT2) : 0.0f);
+                C0 = fma2(bc(col.x), w2, C0);
+                C1 = fma2(bc(col.y), w2, C1);
+                C2 = fma2(bc(col.z), w2, C2);
+                D = fma2(bc(col.w), w2, D);
+                const float Tsa = acta ? -fabsf(Ta) : Ta, Tsb = actb ? -fabsf(Tb) : Tb;  // live pixel that cannot blend stops
+                T2 = pk(bla ? Tna : Tsa, blb ? Tnb : Tsb);
+                const uint32_t pos = last_top - b;
+                lasta = bla ? pos : lasta;
+                lastb = blb ? pos : lastb;
+            }
+            if (__all_sync(0xffffffffu, lo(T2) < 0.0f && hi(T2) < 0.0f)) break;
+        }
+    }
+    cp_async_wait<0>();  // nothing may still be in flight into this CTA's shared memory when it exits
+    const size_t hw = (size_t)v.H * v.W;
+    if (ina) {
+        const float Tf = fabsf(lo(T2));
+        const size_t pix = (size_t)pya * v.W + px;
+        out_color[pix] = fmaf(Tf, v.bg[0], lo(C0));
+        out_color[hw + pix] = fmaf(Tf, v.bg[1], lo(C1));
+        out_color[2 * hw + pix] = fmaf(Tf, v.bg[2], lo(C2));
+        out_depth[pix] = lo(D);
+        final_T[pix] = Tf;
+        n_contrib[pix] = lasta;
+    }
+    if (inb) {
+        const float Tf = fabsf(hi(T2));
+        const size_t pix = (size_t)pyb * v.W + px;
+        out_color[pix] = fmaf(Tf, v.bg[0], hi(C0));
+        out_color[hw + pix] = fmaf(Tf, v.bg[1], hi(C1));
+        out_color[2 * hw + pix] = fmaf(Tf, v.bg[2], hi(C2));
+        out_depth[pix] = hi(D);
+        final_T[pix] = Tf;
+        n_contrib[pix] = lastb;
+    }
+}
+
 void launch_render_forward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, uint32_t capacity, float* out_color,
                            float* out_depth, cudaStream_t s) {
+#if GGRT_FWD_PAIR
+    render_forward_pair_kernel<<<dim3(v.gx, v.gy, 1), F2_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points, b.masks,
+                                                                          capacity, out_color, out_depth, im.final_T,
+                                                                          im.n_contrib);
+    return;
+#endif
     dim3 grid(v.gx, v.gy, 8 / FWD_WARPS);
     render_forward_kernel<GGRT_FWD_ASYNC != 0><<<grid, FWD_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
                                                                              b.masks, capacity, out_color, out_depth,
