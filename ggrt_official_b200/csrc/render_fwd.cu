@@ -10,6 +10,7 @@
 // GGRt's splats are a few pixels wide, so most (warp, Gaussian) pairs of a tile are culled.
 #include "f32x2.cuh"
 #include "render_common.cuh"
+#include "tma.cuh"
 
 namespace ggrt {
 
@@ -371,8 +372,280 @@ render_forward_pair_kernel(View v, const float4* __restrict__ rec0, const float4
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Warp-specialised persistent variant (GGRT_FWD_WS): the pixel-pair kernel above spends ~23 % of its warp time in the
+// per-tile prologue -- three dependent global round trips (tile range -> list entries -> records) and the cull-mask pass,
+// with all four warps waiting.  Here every CTA is persistent (tiles blockIdx.x, + gridDim.x, ...), has ONE producer warp
+// and four consumer warps, and a 3-stage shared-memory ring between them (mbarrier full / empty pairs):
+//   producer: for each tile and batch of 128 list entries: wait for a free stage, load the entries, gather their records
+//             with cp.async, cull them against the tile's 8 warp pixel blocks (block_mask8; also written to the pair
+//             buffer for the backward kernel), rescale the conics, publish {tile, offset, count, last} and arrive on `full`;
+//   consumers: wait on `full`, blend the batch exactly as the pixel-pair kernel does, arrive on `empty`; the image is
+//             written when a tile's last batch has been consumed.
+// The producer runs up to three batches -- usually two tiles -- ahead, so its latencies never stall a consumer.  When all
+// pixels of a tile have terminated the consumers say so (done_tile) and the producer closes the tile with an empty batch.
+// ---------------------------------------------------------------------------------------------------------------------
+// Measured on B200 at C2 (round 2): 99 us against 77 us for the pixel-pair kernel (101 us with a producer that
+// completed one batch before gathering the next) -- the consumers wait less, but there are only 24 of them per SM
+// instead of 32 (64 registers x 160 threads), the four waiters of a stage spin on the mbarrier, and 3024 tiles over
+// 888 persistent CTAs quantise to 4 tile times where 3.4 would be ideal.  Kept for A/B builds (-DGGRT_FWD_WS=1).
+#ifndef GGRT_FWD_WS
+#define GGRT_FWD_WS 0
+#endif
+#ifndef GGRT_FWD_WS_MINBLOCKS
+#define GGRT_FWD_WS_MINBLOCKS 6
+#endif
+#ifndef GGRT_FWD_WS_STAGES
+#define GGRT_FWD_WS_STAGES 3
+#endif
+constexpr int WS_CONS = 4, WS_THREADS = 32 * (WS_CONS + 1), WS_BATCH = 128, WS_STAGES = GGRT_FWD_WS_STAGES;
+struct __align__(16) WsMeta {
+    int tile;       // -1: no more work
+    uint32_t off;   // list offset of the batch inside its tile
+    uint32_t cnt;   // records staged (0: empty tile, or a tile closed early)
+    int last;       // the tile ends with this batch
+};
+
+__device__ __forceinline__ bool consumers_all(bool pred) {  // barrier 1 over the four consumer warps, AND-reduction
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 q, %1, 0;\n\t"
+        "barrier.red.and.pred p, 1, %2, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(r)
+        : "r"((uint32_t)pred), "n"(32 * WS_CONS)
+        : "memory");
+    return r != 0;
+}
+
+__global__ void __launch_bounds__(WS_THREADS, GGRT_FWD_WS_MINBLOCKS)
+render_forward_ws_kernel(View v, const float4* __restrict__ rec0, const float4* __restrict__ rec1,
+                         const float4* __restrict__ rec2, const uint32_t* __restrict__ starts,
+                         const uint32_t* __restrict__ points, uint8_t* __restrict__ masks, uint32_t capacity,
+                         float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ final_T,
+                         uint32_t* __restrict__ n_contrib) {
+    __shared__ __align__(16) unsigned char srec[WS_STAGES * WS_BATCH * REC_BYTES];
+    __shared__ __align__(4) uint8_t smask[WS_STAGES][WS_BATCH];
+    __shared__ WsMeta smeta[WS_STAGES];
+    __shared__ __align__(8) unsigned long long full_bar[WS_STAGES], empty_bar[WS_STAGES];
+    __shared__ int done_tile_s;
+    volatile int* done_tile = &done_tile_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = v.gx * v.gy;
+    if (tid == 0) {
+        for (int st = 0; st < WS_STAGES; ++st) mbar_init(smem_u32(&full_bar[st]), 1), mbar_init(smem_u32(&empty_bar[st]), WS_CONS);
+        done_tile_s = -1;
+    }
+    __syncthreads();
+    uint32_t stage = 0, phase = 0;
+
+    if (warp == WS_CONS) {
+        // ------------------------------------------------ producer ------------------------------------------------
+        // Two batches in flight: the gather of item i+1 (list entries, then cp.async of the records) is issued before
+        // the cull pass of item i, so the producer's own round trips overlap; the next tile's range is loaded a tile ahead.
+        int tile = blockIdx.x;
+        uint32_t start = 0, end = 0, base = 0, nstart = 0, nend = 0;
+        auto load_next_range = [&](int t) {
+            if (t < T) nstart = min(starts[t], capacity), nend = min(starts[t + 1], capacity);
+        };
+        if (tile < T) start = min(starts[tile], capacity), end = min(starts[tile + 1], capacity);
+        base = start;
+        load_next_range(tile + (int)gridDim.x);
+        // an issued item: its ring stage, meta data, list position and tile origin
+        uint32_t p_stage[2] = {0u, 0u}, p_gbase[2] = {0u, 0u};
+        WsMeta p_meta[2];
+        uint32_t istage = 0, iphase = 0;  // ring position of the next issue (stage / phase above: next publish)
+        int np = 0, head = 0;
+        bool more = tile < T, sentinel = false;
+        for (;;) {
+            while (np < 2 && (more || !sentinel)) {
+                mbar_wait(smem_u32(&empty_bar[istage]), iphase ^ 1u);
+                const int slot = (head + np) & 1;
+                p_stage[slot] = istage;
+                if (!more) {  // all tiles issued: the end marker
+                    p_meta[slot] = WsMeta{-1, 0u, 0u, 1};
+                    p_gbase[slot] = 0u;
+                    sentinel = true;
+                } else {
+                    // consumers report a tile whose pixels have all terminated: close it with an empty batch
+                    const bool stop = base > start && __shfl_sync(0xffffffffu, *done_tile == tile ? 1 : 0, 0);
+                    const uint32_t cnt = (stop || base >= end) ? 0u : min((uint32_t)WS_BATCH, end - base);
+                    const bool last = stop || base + WS_BATCH >= end;
+                    p_meta[slot] = WsMeta{tile, base - start, cnt, last ? 1 : 0};
+                    p_gbase[slot] = base;
+                    const uint32_t sb = smem_addr(srec) + istage * (WS_BATCH * REC_BYTES);
+                    uint32_t id[WS_BATCH / 32];
+#pragma unroll
+                    for (int u = 0; u < WS_BATCH / 32; ++u) {
+                        const uint32_t k = lane + 32u * u;
+                        id[u] = k < cnt ? points[base + k] : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < WS_BATCH / 32; ++u) {
+                        const uint32_t k = lane + 32u * u;
+                        if (k < cnt) {
+                            cp_async16(sb + k * REC_BYTES, rec0 + id[u]);
+                            cp_async16(sb + k * REC_BYTES + 16, rec1 + id[u]);
+                            cp_async16(sb + k * REC_BYTES + 32, rec2 + id[u]);
+                        }
+                    }
+                    if (last) {
+                        tile += (int)gridDim.x;
+                        start = nstart, end = nend, base = start;
+                        more = tile < T;
+                        load_next_range(tile + (int)gridDim.x);
+                    } else {
+                        base += WS_BATCH;
+                    }
+                }
+                cp_async_commit();  // one group per issued item (possibly empty)
+                if (++istage == (uint32_t)WS_STAGES) istage = 0, iphase ^= 1u;
+                ++np;
+            }
+            if (np == 0) break;
+            // complete the oldest item in flight: its records have landed once at most one younger group is pending
+            if (np == 2) cp_async_wait<1>(); else cp_async_wait<0>();
+            const WsMeta m = p_meta[head];
+            const uint32_t st = p_stage[head], sb = smem_addr(srec) + st * (WS_BATCH * REC_BYTES);
+            if (m.cnt) {
+                const float tx0f = (float)((m.tile % v.gx) * TILE), ty0f = (float)((m.tile / v.gx) * TILE);
+#pragma unroll
+                for (int u = 0; u < WS_BATCH / 32; ++u) {
+                    const uint32_t k = lane + 32u * u;
+                    if (k < m.cnt) {
+                        const float4 a = lds128(sb + k * REC_BYTES);
+                        float4 c = lds128(sb + k * REC_BYTES + 16);
+                        const uint32_t mk = block_mask8(a.x, a.y, a.z, c.x, c.y, c.z, tx0f, ty0f);
+                        smask[st][k] = (uint8_t)mk;
+                        masks[p_gbase[head] + k] = (uint8_t)mk;
+                        c.x *= -0.5f * LOG2E, c.y *= -LOG2E, c.z *= -0.5f * LOG2E;
+                        sts128(sb + k * REC_BYTES + 16, c);
+                    }
+                }
+            }
+            if (lane == 0) smeta[st] = m;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&full_bar[st]));
+            head ^= 1, --np;
+            if (m.tile < 0) break;
+        }
+        return;
+    }
+
+    // -------------------------------------------------- consumers --------------------------------------------------
+    const uint32_t wbits = (1u << (4 * (warp >> 1) + (warp & 1))) | (1u << (4 * (warp >> 1) + 2 + (warp & 1)));
+    const size_t hw = (size_t)v.H * v.W;
+    int cur_tile = -1, px = 0, pya = 0, pyb = 0;
+    bool ina = false, inb = false, tile_done = false;
+    float pxf = 0.f, pyaf = 0.f;
+    f2 T2 = bc(-1.0f), C0 = bc(0.f), C1 = bc(0.f), C2 = bc(0.f), D = bc(0.f);
+    uint32_t lasta = 0, lastb = 0;
+    for (;;) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        const WsMeta m = smeta[stage];
+        if (m.tile < 0) break;
+        if (m.tile != cur_tile) {  // first batch of a tile: this warp's 8x8 block, fresh pixel state
+            cur_tile = m.tile, tile_done = false;
+            const int bx0 = (m.tile % v.gx) * TILE + (warp & 1) * 8, by0 = (m.tile / v.gx) * TILE + (warp >> 1) * 8;
+            px = bx0 + (lane & 7), pya = by0 + (lane >> 3), pyb = pya + 4;
+            ina = px < v.W && pya < v.H, inb = px < v.W && pyb < v.H;
+            pxf = (float)px, pyaf = (float)pya;
+            T2 = pk(ina ? 1.0f : -1.0f, inb ? 1.0f : -1.0f), C0 = C1 = C2 = D = bc(0.f);
+            lasta = lastb = 0;
+        }
+        const uint32_t cnt = tile_done ? 0u : m.cnt;
+        const uint32_t sbase = smem_addr(srec) + stage * (WS_BATCH * REC_BYTES);
+        if (cnt && !__all_sync(0xffffffffu, lo(T2) < 0.0f && hi(T2) < 0.0f)) {
+            for (uint32_t r = 0; r < cnt; r += 32) {
+                // lane l tests list entry r + 31 - l: bit b of the ballot is entry r + 31 - b, the highest bit comes first
+                const uint32_t j = r + 31 - lane;
+                const bool hit = j < cnt && (smask[stage][j] & wbits);
+                uint32_t mask = __ballot_sync(0xffffffffu, hit);
+                const uint32_t top = sbase + (r + 31) * REC_BYTES;  // record of bit 0 ... minus b records for bit b
+                const uint32_t last_top = m.off + r + 32;           // 1-based list position of bit 0's entry ... - b
+                while (mask) {
+                    uint32_t b, src;  // opaque to the optimiser, which otherwise rebuilds the index from 31 - clz
+                    asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(mask));
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(src) : "r"(b), "r"(0u - (uint32_t)REC_BYTES), "r"(top));
+                    mask ^= 1u << b;
+                    const float2 xy = lds64(src);
+                    const float4 c = lds128(src + 16);
+                    const float4 col = lds128(src + 32);
+                    const float dx = xy.x - pxf, dya = xy.y - pyaf;
+                    const f2 dy2 = pk(dya, dya - 4.0f);
+                    const f2 power2 = fma2(bc(dx), fma2(bc(c.x), bc(dx), mul2(bc(c.y), dy2)), mul2(mul2(bc(c.z), dy2), dy2));
+                    const float pa = lo(power2), pb = hi(power2);
+                    const f2 raw2 = mul2(bc(c.w), pk(ex2_approx(pa), ex2_approx(pb)));
+                    const float ala = fminf(ALPHA_MAX, lo(raw2)), alb = fminf(ALPHA_MAX, hi(raw2));
+                    const bool acta = (pa <= 0.0f) && (ala >= ALPHA_MIN), actb = (pb <= 0.0f) && (alb >= ALPHA_MIN);
+                    const f2 al2 = pk(ala, alb);
+                    const f2 Tn2 = mul2(T2, fma2(al2, bc(-1.0f), bc(1.0f)));  // T (1 - alpha)
+                    const float Ta = lo(T2), Tb = hi(T2), Tna = lo(Tn2), Tnb = hi(Tn2);
+                    const bool bla = acta && (Tna >= T_EPS), blb = actb && (Tnb >= T_EPS);
+                    const f2 aT2 = mul2(al2, T2);
+                    const f2 w2 = pk(bla ? lo(aT2) : 0.0f, blb ? hi(aT2) : 0.0f);
+                    C0 = fma2(bc(col.x), w2, C0);
+                    C1 = fma2(bc(col.y), w2, C1);
+                    C2 = fma2(bc(col.z), w2, C2);
+                    D = fma2(bc(col.w), w2, D);
+                    const float Tsa = acta ? -fabsf(Ta) : Ta, Tsb = actb ? -fabsf(Tb) : Tb;
+                    T2 = pk(bla ? Tna : Tsa, blb ? Tnb : Tsb);
+                    const uint32_t pos = last_top - b;
+                    lasta = bla ? pos : lasta;
+                    lastb = blb ? pos : lastb;
+                }
+                if (__all_sync(0xffffffffu, lo(T2) < 0.0f && hi(T2) < 0.0f)) break;
+            }
+        }
+        if (!m.last && !tile_done) {  // (uniform over the consumers) have all pixels of the tile terminated?
+            tile_done = consumers_all(lo(T2) < 0.0f && hi(T2) < 0.0f);
+            if (tile_done && tid == 0) *done_tile = m.tile;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));
+        if (++stage == (uint32_t)WS_STAGES) stage = 0, phase ^= 1u;
+        if (m.last) {
+            if (ina) {
+                const float Tf = fabsf(lo(T2));
+                const size_t pix = (size_t)pya * v.W + px;
+                out_color[pix] = fmaf(Tf, v.bg[0], lo(C0));
+                out_color[hw + pix] = fmaf(Tf, v.bg[1], lo(C1));
+                out_color[2 * hw + pix] = fmaf(Tf, v.bg[2], lo(C2));
+                out_depth[pix] = lo(D);
+                final_T[pix] = Tf;
+                n_contrib[pix] = lasta;
+            }
+            if (inb) {
+                const float Tf = fabsf(hi(T2));
+                const size_t pix = (size_t)pyb * v.W + px;
+                out_color[pix] = fmaf(Tf, v.bg[0], hi(C0));
+                out_color[hw + pix] = fmaf(Tf, v.bg[1], hi(C1));
+                out_color[2 * hw + pix] = fmaf(Tf, v.bg[2], hi(C2));
+                out_depth[pix] = hi(D);
+                final_T[pix] = Tf;
+                n_contrib[pix] = lastb;
+            }
+        }
+    }
+}
+
 void launch_render_forward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, uint32_t capacity, float* out_color,
                            float* out_depth, cudaStream_t s) {
+#if GGRT_FWD_WS
+    {
+        static int sms = 0;  // persistent CTAs: as many as stay resident (per device the same on one box)
+        if (sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        const int T = v.gx * v.gy, grid = T < sms * GGRT_FWD_WS_MINBLOCKS ? T : sms * GGRT_FWD_WS_MINBLOCKS;
+        render_forward_ws_kernel<<<grid, WS_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points, b.masks, capacity,
+                                                             out_color, out_depth, im.final_T, im.n_contrib);
+        return;
+    }
+#endif
 #if GGRT_FWD_PAIR
     render_forward_pair_kernel<<<dim3(v.gx, v.gy, 1), F2_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points, b.masks,
                                                                           capacity, out_color, out_depth, im.final_T,
