@@ -23,15 +23,17 @@ emit_kernel(View v, GeomPtrs g, uint32_t* __restrict__ cursor, unsigned long lon
             uint32_t capacity) {
     const int i = blockIdx.x * EMIT_THREADS + threadIdx.x;
     if (i >= v.P) return;
-    if (g.tiles[i] == 0) return;
+    // all three per-Gaussian loads are issued together (a culled Gaussian has an empty rect: no separate look at
+    // tiles_touched, which would put one more dependent round trip in front of everything else)
     const ushort4 r = g.rect[i];
+    const uint4 rk = g.ranks[i];
     const unsigned long long key = ((unsigned long long)__float_as_uint(g.rec0[i].w) << 32) | (uint32_t)i;
     const int w = r.z - r.x, n = w * (r.w - r.y);
+    if (n == 0) return;
     if (n <= RANKED_TILES) {
         // small splat: the geometry kernel's counting atomics already returned this pair's rank inside its
         // (tile, sub-counter) segment -- slot = segment start + rank, no atomic, nothing to wait for but two loads
         const int sub = i & (SUB_LANES - 1);
-        const uint4 rk = g.ranks[i];
         const uint32_t rank[RANKED_TILES] = {rk.x, rk.y, rk.z, rk.w};
         uint32_t slot[RANKED_TILES];
 #pragma unroll

@@ -60,17 +60,7 @@ geometry_kernel(View v, const float* __restrict__ means, const float* __restrict
         const int y1 = min(v.gy, max(0, f2i_sat(fdiv(fadd(fadd(pxy, radf), (float)(TILE - 1)), (float)TILE))));
         const int area = (x1 - x0) * (y1 - y0);
         if (area > 0) {
-            radius = (int)radf;
-            tiles = (uint32_t)area;
-            rect = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
-            // {alpha >= 1/255} <=> q(d) = A dx^2 + 2B dx dy + C dy^2 <= tau = 2 ln(255 o).  The render kernels cull
-            // (warp pixel block, Gaussian) pairs with an exact ellipse-vs-rectangle test against tau, slightly
-            // inflated so that float rounding of the per-pixel power can never contradict the cull.
-            float tau_c = -1.0f;  // opacity below 1/255: never visible
-            const float tau = 2.0f * logf(255.0f * o);
-            if (tau > 0.0f) tau_c = tau * 1.001f + 0.02f;
-            r0 = make_float4(pxx, pxy, tau_c, q.tz);
-            r1 = make_float4(cA, cB, cC, o);
+            // (the counting atomics go first: their round trips overlap the conic / threshold arithmetic below)
             if (area <= RANKED_TILES) {
                 // small splat (the common case: 1, 2 or 2x2 tiles): count with RETURNING atomics, all of them in flight
                 // together, and keep the ranks -- emit then needs no atomic for these pairs
@@ -87,14 +77,25 @@ geometry_kernel(View v, const float* __restrict__ means, const float* __restrict
                 for (int y = y0; y < y1; ++y)
                     for (int x = x0; x < x1; ++x) atomicAdd(&counts[((y * v.gx + x) << SUBS_LOG2) + sub], 1u);
             }
+            radius = (int)radf;
+            tiles = (uint32_t)area;
+            rect = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+            // {alpha >= 1/255} <=> q(d) = A dx^2 + 2B dx dy + C dy^2 <= tau = 2 ln(255 o).  The render kernels cull
+            // (warp pixel block, Gaussian) pairs with an exact ellipse-vs-rectangle test against tau, slightly
+            // inflated so that float rounding of the per-pixel power can never contradict the cull.
+            float tau_c = -1.0f;  // opacity below 1/255: never visible
+            const float tau = 2.0f * logf(255.0f * o);
+            if (tau > 0.0f) tau_c = tau * 1.001f + 0.02f;
+            r0 = make_float4(pxx, pxy, tau_c, q.tz);
+            r1 = make_float4(cA, cB, cC, o);
         }
     }
-    g.ranks[i] = rk;
     radii[i] = radius;
     g.tiles[i] = tiles;
     g.rect[i] = rect;
     g.rec0[i] = r0;
     g.rec1[i] = r1;
+    g.ranks[i] = rk;  // last: the only store that has to wait for the atomics' results (issue is in order)
 }
 
 // ---------------------------------------------------------------------------------------
