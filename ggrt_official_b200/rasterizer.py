@@ -543,6 +543,22 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
                                      raster_settings.projmatrix, raster_settings.campos)
 
 
+def covariance_from_scaling_rotation(scales: torch.Tensor, rotations: torch.Tensor, scale_modifier: float = 1.0):
+    """[P,3] scales + [P,4] quaternions (r, x, y, z) -> [P,6] upper-triangular world covariances (xx, xy, xz, yy, yz, zz),
+    as upstream's computeCov3D does inside its preprocess kernel."""
+    if scales.dim() != 2 or scales.shape[1] != 3 or rotations.dim() != 2 or rotations.shape[1] != 4 or \
+            scales.shape[0] != rotations.shape[0]:
+        raise ValueError(f"scales must be [P,3] and rotations [P,4], got {tuple(scales.shape)} / {tuple(rotations.shape)}")
+    r, x, y, z = rotations.float().unbind(dim=1)
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                     2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                     2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], dim=1).reshape(-1, 3, 3)
+    M = R * (scales.float() * scale_modifier)[:, None, :]  # R S
+    cov = M @ M.transpose(1, 2)                            # R S S^T R^T
+    iu = torch.triu_indices(3, 3, device=cov.device)
+    return cov[:, iu[0], iu[1]].contiguous()
+
+
 class GaussianRasterizer(nn.Module):
     def __init__(self, raster_settings: GaussianRasterizationSettings):
         super().__init__()
@@ -577,7 +593,10 @@ class GaussianRasterizer(nn.Module):
                 (scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
         if cov3D_precomp is None:
-            raise NotImplementedError(
-                "scales/rotations are not supported: GGRt always passes cov3D_precomp (cuda_splatting.py:124)")
+            # GGRt always passes cov3D_precomp (cuda_splatting.py:124).  For callers of the stock 3DGS interface the
+            # covariance is built here with differentiable PyTorch operations (upstream computeCov3D: Sigma = R S^2 R^T,
+            # S = scale_modifier * diag(scales), R from the quaternion (r, x, y, z) as given -- not re-normalised) and
+            # handed to the same kernels; gradients reach scales / rotations through autograd.
+            cov3D_precomp = covariance_from_scaling_rotation(scales, rotations, float(self.raster_settings.scale_modifier))
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
                                    self.raster_settings, aux_precomp, layout)

@@ -44,9 +44,37 @@ def test_exactly_one_of_checks():
     with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
         r(means3D=m, means2D=m, opacities=o, shs=torch.zeros(P, 1, 3), scales=torch.zeros(P, 3),
           rotations=torch.zeros(P, 4), cov3D_precomp=c6)
-    with pytest.raises(NotImplementedError):
+    # scales / rotations (the stock 3DGS interface; GGRt never uses it): accepted, the covariance is built with PyTorch
+    # and the call then fails only for the same reason every CPU call does
+    with pytest.raises(RuntimeError, match="no CPU path"):
         r(means3D=m, means2D=m, opacities=o, shs=torch.zeros(P, 1, 3), scales=torch.zeros(P, 3),
           rotations=torch.zeros(P, 4))
+    with pytest.raises(ValueError, match="scales must be"):
+        r(means3D=m, means2D=m, opacities=o, shs=torch.zeros(P, 1, 3), scales=torch.zeros(P, 2),
+          rotations=torch.zeros(P, 4))
+
+
+def test_covariance_from_scaling_rotation_is_upstreams_formula():
+    """Sigma = R S^2 R^T with R from the quaternion (r, x, y, z), upper triangle in (xx, xy, xz, yy, yz, zz) order."""
+    import numpy as np
+
+    from ggrt_official_b200.rasterizer import covariance_from_scaling_rotation
+
+    rng = np.random.default_rng(0)
+    q = rng.normal(size=(50, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    s = rng.uniform(0.1, 2.0, size=(50, 3))
+    got = covariance_from_scaling_rotation(torch.tensor(s, dtype=torch.float32), torch.tensor(q, dtype=torch.float32), 1.5)
+    for i in range(50):
+        r_, x, y, z = q[i]
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - r_ * z), 2 * (x * z + r_ * y)],
+                      [2 * (x * y + r_ * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r_ * x)],
+                      [2 * (x * z - r_ * y), 2 * (y * z + r_ * x), 1 - 2 * (x * x + y * y)]])
+        assert abs(np.linalg.det(R) - 1) < 1e-9                      # a proper rotation for unit quaternions
+        S = np.diag(1.5 * s[i])
+        cov = R @ S @ S.T @ R.T
+        ref = cov[np.triu_indices(3)]
+        assert np.allclose(got[i].numpy(), ref, rtol=1e-5, atol=1e-6)
 
 
 def test_no_cpu_fallback():

@@ -120,3 +120,29 @@ def test_depth_ties_keep_the_reference_order(P, planes):
               "key_idx_mismatch"):
         assert res.get(k, 0) == 0, (k, res)
     assert res["N"][0] == res["N"][1] > 0
+
+
+def test_scales_rotations_interface_equals_precomputed_covariance():
+    """The stock 3DGS interface (scales + rotations instead of cov3D_precomp; GGRt never uses it): same image as
+    passing the covariance upstream's computeCov3D would build, and gradients reach scales / rotations."""
+    from ggrt_official_b200.rasterizer import covariance_from_scaling_rotation
+
+    P, H, W = 1500, 64, 80
+    _, ri = small_case(P, H, W, 2, seed=21)
+    rng = np.random.default_rng(4)
+    q = rng.normal(size=(P, 4)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    s = rng.uniform(0.01, 0.08, size=(P, 3)).astype(np.float32)
+    rs = G.settings_from(ri, DEV)._replace(scale_modifier=1.3)
+    scales, rots = _t(s).requires_grad_(), _t(q).requires_grad_()
+    means, shs, opac = _t(ri.means3D), _t(ri.shs), _t(ri.opacities)
+    img_a, radii_a, _ = GaussianRasterizer(rs)(means3D=means, means2D=None, opacities=opac, shs=shs, scales=scales,
+                                               rotations=rots)
+    cov = covariance_from_scaling_rotation(_t(s), _t(q), 1.3)
+    img_b, radii_b, _ = GaussianRasterizer(rs)(means3D=means, means2D=None, opacities=opac, shs=shs, cov3D_precomp=cov)
+    assert torch.equal(radii_a, radii_b) and torch.equal(img_a, img_b)
+    assert int((radii_a > 0).sum()) > P // 4
+    img_a.square().sum().backward()
+    assert scales.grad is not None and rots.grad is not None
+    assert torch.isfinite(scales.grad).all() and torch.isfinite(rots.grad).all()
+    assert float(scales.grad.abs().max()) > 0 and float(rots.grad.abs().max()) > 0
