@@ -10,7 +10,7 @@ from pathlib import Path
 
 from . import build as _build
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 _lib = None
 
 
@@ -33,6 +33,7 @@ class Settings(C.Structure):
         ("device_params", C.c_void_p),
         ("aux_mode", C.c_int32),
         ("reserved", C.c_int32),
+        ("zero_scratch", C.c_void_p),
     ]
 
 
@@ -62,7 +63,7 @@ class Layout(C.Structure):
     """struct GgrtRasterLayout"""
 
     _fields_ = [(n, C.c_size_t) for n in (
-        "geom_rec0", "geom_rec1", "geom_rec2", "geom_rect", "geom_tiles", "geom_flags", "geom_ranks", "geom_bytes",
+        "geom_rec0", "geom_rec1", "geom_rec2", "geom_rect", "geom_tiles", "geom_flags", "geom_ranks", "geom_jac", "geom_bytes",
         "img_counts", "img_partials", "img_cursor", "img_starts", "img_header", "img_final_T", "img_ncontrib", "img_bytes",
         "bin_keys", "bin_points", "bin_masks", "bin_bytes")]
 

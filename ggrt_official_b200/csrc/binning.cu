@@ -21,6 +21,7 @@ constexpr int SORT_THREADS = 256;
 __global__ void __launch_bounds__(EMIT_THREADS)
 emit_kernel(View v, GeomPtrs g, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ keys,
             uint32_t capacity) {
+    pdl_enter();
     const int i = blockIdx.x * EMIT_THREADS + threadIdx.x;
     if (i >= v.P) return;
     // all three per-Gaussian loads are issued together (a culled Gaussian has an empty rect: no separate look at
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(1024)
 sort_tiles_kernel(int T, const uint32_t* __restrict__ starts, unsigned long long* __restrict__ keys,
                   uint32_t* __restrict__ points, uint32_t smem_cap, uint32_t capacity) {
     extern __shared__ __align__(16) unsigned long long sk[];
+    pdl_enter();
     const int tile = blockIdx.x;
     if (tile >= T) return;
     const uint32_t s = min(starts[tile], capacity), e = min(starts[tile + 1], capacity), n = e - s;
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(32 * WARPS)
 sort_tiles_reg_kernel(int T, const uint32_t* __restrict__ starts, unsigned long long* __restrict__ keys,
                       uint32_t* __restrict__ points, uint32_t capacity) {
     __shared__ unsigned long long xch[WARPS > 1 ? 256 * WARPS : 1];
+    pdl_enter();
     const int tile = blockIdx.x;
     if (tile >= T) return;
     const uint32_t s = min(starts[tile], capacity), n = min(starts[tile + 1], capacity) - s;
@@ -272,6 +275,7 @@ sort_tiles_q_kernel(int T, const uint32_t* __restrict__ starts, unsigned long lo
     constexpr uint32_t IDXM = (1u << IDXB) - 1u;
     __shared__ uint32_t xch[CAP];             // cross-warp exchange; afterwards the sorted composites
     __shared__ uint32_t smin[WARPS], smax[WARPS];
+    pdl_enter();
     const int tile = blockIdx.x;
     if (tile >= T) return;
     const uint32_t s = min(starts[tile], capacity), n = min(starts[tile + 1], capacity) - s;
@@ -403,34 +407,34 @@ sort_tiles_q_kernel(int T, const uint32_t* __restrict__ starts, unsigned long lo
 
 void launch_emit(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, uint32_t capacity, cudaStream_t s) {
     if (v.P == 0) return;
-    emit_kernel<<<(v.P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, s>>>(v, g, im.cursor, b.keys, capacity);
+    launch_chain(emit_kernel, dim3((v.P + EMIT_THREADS - 1) / EMIT_THREADS), dim3(EMIT_THREADS), 0, s, v, g, im.cursor, b.keys, capacity);
 }
 
 void launch_sort_tiles(const View& v, ImagePtrs im, BinPtrs b, uint32_t max_tile_pairs, uint32_t capacity,
                        cudaStream_t s) {
     const int T = v.gx * v.gy;
 #if GGRT_SORT_Q
-    if (max_tile_pairs <= 256) return (void)sort_tiles_q_kernel<1><<<T, 32, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
-    if (max_tile_pairs <= 512) return (void)sort_tiles_q_kernel<2><<<T, 64, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
-    if (max_tile_pairs <= 1024) return (void)sort_tiles_q_kernel<4><<<T, 128, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
-    if (max_tile_pairs <= 2048) return (void)sort_tiles_q_kernel<8><<<T, 256, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
-    if (max_tile_pairs <= 4096) return (void)sort_tiles_q_kernel<16><<<T, 512, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
-    if (max_tile_pairs <= 8192) return (void)sort_tiles_q_kernel<32><<<T, 1024, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
+    if (max_tile_pairs <= 256) return launch_chain(sort_tiles_q_kernel<1>, dim3(T), dim3(32), 0, s, T, im.starts, b.keys, b.points, capacity);
+    if (max_tile_pairs <= 512) return launch_chain(sort_tiles_q_kernel<2>, dim3(T), dim3(64), 0, s, T, im.starts, b.keys, b.points, capacity);
+    if (max_tile_pairs <= 1024) return launch_chain(sort_tiles_q_kernel<4>, dim3(T), dim3(128), 0, s, T, im.starts, b.keys, b.points, capacity);
+    if (max_tile_pairs <= 2048) return launch_chain(sort_tiles_q_kernel<8>, dim3(T), dim3(256), 0, s, T, im.starts, b.keys, b.points, capacity);
+    if (max_tile_pairs <= 4096) return launch_chain(sort_tiles_q_kernel<16>, dim3(T), dim3(512), 0, s, T, im.starts, b.keys, b.points, capacity);
+    if (max_tile_pairs <= 8192) return launch_chain(sort_tiles_q_kernel<32>, dim3(T), dim3(1024), 0, s, T, im.starts, b.keys, b.points, capacity);
 #endif
     if (max_tile_pairs <= 256) {
-        sort_tiles_reg_kernel<1><<<T, 32, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
+        launch_chain(sort_tiles_reg_kernel<1>, dim3(T), dim3(32), 0, s, T, im.starts, b.keys, b.points, capacity);
         return;
     }
     if (max_tile_pairs <= 512) {
-        sort_tiles_reg_kernel<2><<<T, 64, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
+        launch_chain(sort_tiles_reg_kernel<2>, dim3(T), dim3(64), 0, s, T, im.starts, b.keys, b.points, capacity);
         return;
     }
     if (max_tile_pairs <= 1024) {
-        sort_tiles_reg_kernel<4><<<T, 128, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
+        launch_chain(sort_tiles_reg_kernel<4>, dim3(T), dim3(128), 0, s, T, im.starts, b.keys, b.points, capacity);
         return;
     }
     if (max_tile_pairs <= 2048) {
-        sort_tiles_reg_kernel<8><<<T, 256, 0, s>>>(T, im.starts, b.keys, b.points, capacity);
+        launch_chain(sort_tiles_reg_kernel<8>, dim3(T), dim3(256), 0, s, T, im.starts, b.keys, b.points, capacity);
         return;
     }
     // shared-memory capacity tier from the largest tile (reported by scan_tiles)
@@ -441,7 +445,7 @@ void launch_sort_tiles(const View& v, ImagePtrs im, BinPtrs b, uint32_t max_tile
         cudaFuncSetAttribute(sort_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
     // a tile beyond the shared-memory tier is sorted in place in global memory by its CTA: give it the largest CTA
     const int threads = max_tile_pairs > 16384 ? 1024 : SORT_THREADS;
-    sort_tiles_kernel<<<v.gx * v.gy, threads, smem, s>>>(v.gx * v.gy, im.starts, b.keys, b.points, cap, capacity);
+    launch_chain(sort_tiles_kernel, dim3(v.gx * v.gy), dim3(threads), smem, s, v.gx * v.gy, im.starts, b.keys, b.points, cap, capacity);
 }
 
 }  // namespace ggrt

@@ -21,6 +21,14 @@ static const char* const kStageNames[GGRT_STAGE_COUNT] = {"geometry",       "sca
                                                           "emit",           "sort_tiles",      "render_forward",
                                                           "render_backward", "preprocess_backward"};
 
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("GGRT_RASTER_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -76,6 +84,7 @@ struct StageTimer {  // RAII: records start/stop events around one launch when p
 struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t fork_b = nullptr, join_b = nullptr;  // backward: the dL/dsh writer beside the per-Gaussian kernel
     bool pending = false;
     unsigned long long capture_id = 0;  // stream-capture sequence the join event was last recorded in (0: none)
 };
@@ -110,7 +119,9 @@ static SideStream* side_stream() {
     if (!ss->stream) {
         if (cudaStreamCreateWithFlags(&ss->stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&ss->fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ss->join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&ss->join, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ss->fork_b, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ss->join_b, cudaEventDisableTiming) != cudaSuccess) {
             cudaGetLastError();
             ss->stream = nullptr;
             return nullptr;
@@ -130,6 +141,7 @@ void compute_layout(int P, int H, int W, long long N, GgrtRasterLayout* L) {
     L->geom_tiles = off; off = align_up(off + p * sizeof(uint32_t));
     L->geom_flags = off; off = align_up(off + p * sizeof(uint8_t));
     L->geom_ranks = off; off = align_up(off + p * sizeof(uint4));
+    L->geom_jac = off; off = align_up(off + 9 * p * sizeof(float));
     L->geom_bytes = off > 0 ? off : 256;
 
     const size_t gx = (size_t)(W + TILE - 1) / TILE, gy = (size_t)(H + TILE - 1) / TILE, T = gx * gy;
@@ -164,6 +176,8 @@ GeomPtrs geom_ptrs(void* base, int P) {
     g.tiles = reinterpret_cast<uint32_t*>(b + L.geom_tiles);
     g.flags = reinterpret_cast<uint8_t*>(b + L.geom_flags);
     g.ranks = reinterpret_cast<uint4*>(b + L.geom_ranks);
+    g.jac = reinterpret_cast<float*>(b + L.geom_jac);
+    g.jac_plane = (size_t)(P > 0 ? P : 0);
     return g;
 }
 
@@ -334,6 +348,10 @@ int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, const GgrtRa
         launch_color(v, means3D, shs, colors_precomp, aux, radii, g, ss->stream);
         nvtxRangePop();
         GGRT_TRY(check_launch("color", 0, ss->stream));
+        // the backward's scratch is zeroed here, off the critical path (GgrtRasterSettings.zero_scratch)
+        if (settings->zero_scratch &&
+            cudaMemsetAsync(settings->zero_scratch, 0, (size_t)P * GRAD_STRIDE * sizeof(float), ss->stream) != cudaSuccess)
+            return check_launch("memset grad scratch", 0, ss->stream);
         if (cudaEventRecord(ss->join, ss->stream) != cudaSuccess) return check_launch("color join", 0, s);
         ss->pending = true;
         ss->capture_id = capture_id_of(s);
@@ -346,6 +364,9 @@ int ggrt_raster_forward_prepare(const GgrtRasterSettings* settings, const GgrtRa
     if (!ss) {
         { StageTimer t_(GGRT_STAGE_COLOR, s); launch_color(v, means3D, shs, colors_precomp, aux, radii, g, s); }
         GGRT_TRY(check_launch("color", dbg, s));
+        if (settings->zero_scratch && P > 0 &&
+            cudaMemsetAsync(settings->zero_scratch, 0, (size_t)P * GRAD_STRIDE * sizeof(float), s) != cudaSuccess)
+            return check_launch("memset grad scratch", 0, s);
     }
     return GGRT_OK;
 }
@@ -478,7 +499,8 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
     GeomPtrs g = geom_ptrs(const_cast<void*>(geom_buffer), P);
     ImagePtrs im = image_ptrs(const_cast<void*>(image_buffer), v.H, v.W);
     BinPtrs b = bin_ptrs(const_cast<void*>(binning_buffer), num_rendered);
-    if (cudaMemsetAsync(grad_scratch, 0, (size_t)P * GRAD_STRIDE * sizeof(float), s) != cudaSuccess)
+    if (settings->zero_scratch != grad_scratch &&  // (else forward_prepare has zeroed it already)
+        cudaMemsetAsync(grad_scratch, 0, (size_t)P * GRAD_STRIDE * sizeof(float), s) != cudaSuccess)
         return check_launch("memset grad scratch", 0, s);
     if (dL_dcamera && cudaMemsetAsync(dL_dcamera, 0, 35 * sizeof(float), s) != cudaSuccess)
         return check_launch("memset camera gradient", 0, s);
@@ -487,9 +509,18 @@ int ggrt_raster_backward(const GgrtRasterSettings* settings, const GgrtRasterInp
         GGRT_TRY(check_launch("render_backward", dbg, s));
     }
     {
+        // with a full SH gradient to write, its streaming kernel runs on the side stream beside the per-Gaussian kernel
+        SideStream* ss = (overlap_enabled() && !g_prof.on && !dbg && shs != nullptr && dL_dsh != nullptr) ? side_stream() : nullptr;
+        if (ss && !(cudaEventRecord(ss->fork_b, s) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork_b, 0) == cudaSuccess)) {
+            cudaGetLastError();
+            ss = nullptr;
+        }
         StageTimer t_(GGRT_STAGE_PREPROCESS_BACKWARD, s);
         launch_preprocess_backward(v, means3D, cov3D_precomp, shs, radii, g, grad_scratch, dL_dmeans2D, dL_dopacity,
-                                   dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dcolors, dL_daux, dL_dcamera, sinks, s);
+                                   dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dcolors, dL_daux, dL_dcamera, sinks, s,
+                                   ss ? ss->stream : nullptr);
+        if (ss && !(cudaEventRecord(ss->join_b, ss->stream) == cudaSuccess && cudaStreamWaitEvent(s, ss->join_b, 0) == cudaSuccess))
+            return check_launch("dL/dsh join", 0, s);
     }
     GGRT_TRY(check_launch("preprocess_backward", dbg, s));
     return GGRT_OK;

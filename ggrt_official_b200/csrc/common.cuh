@@ -53,6 +53,9 @@ struct GeomPtrs {
     uint32_t* tiles;   // tiles touched
     uint8_t* flags;    // clamp bits
     uint4* ranks;      // per Gaussian touching <= RANKED_TILES tiles: its rank in the (tile, sub-counter) segment of each
+    float* jac;        // 9 planes of P floats: d(SH colour c)/d(scaled mean j) at plane 3c + j, written by the colour kernel
+                       // (which has the SH rows in shared memory anyway) so that the backward never re-reads the SH table
+    size_t jac_plane;  // floats per plane
 };
 
 #ifndef GGRT_SCAN_BLOCK
@@ -117,6 +120,28 @@ __device__ __forceinline__ bool last_cta_done(uint32_t* done_counter) {
     return true;
 }
 
+// ---- programmatic dependent launch (PDL) along the chain scan -> emit -> sort -> render fwd -> render bwd -> per-Gaussian
+// bwd.  Each of these kernels calls pdl_enter() before its first global access: it lets the NEXT kernel of the stream be
+// scheduled as soon as every CTA of this one has started (the dependents then sit in freed SM slots during this kernel's
+// tail), and waits until the PREVIOUS kernel has completed and its memory is visible.  launch_chain() launches with
+// programmatic stream serialisation, so the launch latency and the CTA ramp of each kernel hide under its predecessor;
+// without the attribute (GGRT_RASTER_PDL=0, or a predecessor that is not a kernel) both instructions are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = pdl_enabled() ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 void compute_layout(int P, int H, int W, long long N, GgrtRasterLayout* L);
@@ -140,7 +165,7 @@ void launch_render_backward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, 
 void launch_preprocess_backward(const View& v, const float* means, const float* cov3d, const float* shs,
                                 const int* radii, GeomPtrs g, const float* scratch, float* dmeans2D, float* dopacity,
                                 float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, float* daux, float* dcam,
-                                const ColorSinks& sinks, cudaStream_t s);
+                                const ColorSinks& sinks, cudaStream_t s, cudaStream_t sh_stream = nullptr);
 struct MergeSignal {  // signalled exchange: wait for world * *epoch arrivals, read half (*epoch - 1) & 1
     const uint32_t* epoch = nullptr;
     const uint32_t* arrive = nullptr;
@@ -289,6 +314,57 @@ __device__ __forceinline__ int f2i_sat(float x) {
 #define GGRT_SH_C4_6 0.47308734787878004f
 #define GGRT_SH_C4_7 -1.7701307697799304f
 #define GGRT_SH_C4_8 0.6258357354491761f
+
+// The real SH basis up to degree 4 as a list of terms T(k, B_k, dB_k/dx, dB_k/dy, dB_k/dz) at the direction (x, y, z)
+// (derivatives of the polynomials; the normalisation of the direction is differentiated separately).  The users define
+// T and need xx, yy, zz, xy, yz, xz in scope; B_k is the same expression as sh_basis() below.
+#define GGRT_SH_TERMS_0(T) T(0, GGRT_SH_C0, GGRT_Z, GGRT_Z, GGRT_Z)
+#define GGRT_SH_TERMS_1(T)                                   \
+    T(1, -GGRT_SH_C1 * y, GGRT_Z, -GGRT_SH_C1, GGRT_Z)             \
+    T(2, GGRT_SH_C1 * z, GGRT_Z, GGRT_Z, GGRT_SH_C1)               \
+    T(3, -GGRT_SH_C1 * x, -GGRT_SH_C1, GGRT_Z, GGRT_Z)
+#define GGRT_SH_TERMS_2(T)                                                                                         \
+    T(4, GGRT_SH_C2_0 * xy, GGRT_SH_C2_0 * y, GGRT_SH_C2_0 * x, GGRT_Z)                                              \
+    T(5, GGRT_SH_C2_1 * yz, GGRT_Z, GGRT_SH_C2_1 * z, GGRT_SH_C2_1 * y)                                              \
+    T(6, GGRT_SH_C2_2 * (2.0f * zz - xx - yy), GGRT_SH_C2_2 * -2.0f * x, GGRT_SH_C2_2 * -2.0f * y,                \
+      GGRT_SH_C2_2 * 4.0f * z)                                                                                    \
+    T(7, GGRT_SH_C2_3 * xz, GGRT_SH_C2_3 * z, GGRT_Z, GGRT_SH_C2_3 * x)                                              \
+    T(8, GGRT_SH_C2_4 * (xx - yy), GGRT_SH_C2_4 * 2.0f * x, GGRT_SH_C2_4 * -2.0f * y, GGRT_Z)
+#define GGRT_SH_TERMS_3(T)                                                                                         \
+    T(9, GGRT_SH_C3_0 * y * (3.0f * xx - yy), GGRT_SH_C3_0 * 6.0f * xy, GGRT_SH_C3_0 * (3.0f * xx - 3.0f * yy), GGRT_Z) \
+    T(10, GGRT_SH_C3_1 * xy * z, GGRT_SH_C3_1 * yz, GGRT_SH_C3_1 * xz, GGRT_SH_C3_1 * xy)                          \
+    T(11, GGRT_SH_C3_2 * y * (4.0f * zz - xx - yy), GGRT_SH_C3_2 * -2.0f * xy,                                    \
+      GGRT_SH_C3_2 * (4.0f * zz - xx - 3.0f * yy), GGRT_SH_C3_2 * 8.0f * yz)                                      \
+    T(12, GGRT_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy), GGRT_SH_C3_3 * -6.0f * xz,                      \
+      GGRT_SH_C3_3 * -6.0f * yz, GGRT_SH_C3_3 * (6.0f * zz - 3.0f * xx - 3.0f * yy))                              \
+    T(13, GGRT_SH_C3_4 * x * (4.0f * zz - xx - yy), GGRT_SH_C3_4 * (4.0f * zz - 3.0f * xx - yy),                  \
+      GGRT_SH_C3_4 * -2.0f * xy, GGRT_SH_C3_4 * 8.0f * xz)                                                        \
+    T(14, GGRT_SH_C3_5 * z * (xx - yy), GGRT_SH_C3_5 * 2.0f * xz, GGRT_SH_C3_5 * -2.0f * yz,                      \
+      GGRT_SH_C3_5 * (xx - yy))                                                                                   \
+    T(15, GGRT_SH_C3_6 * x * (xx - 3.0f * yy), GGRT_SH_C3_6 * (3.0f * xx - 3.0f * yy), GGRT_SH_C3_6 * -6.0f * xy, GGRT_Z)
+#define GGRT_SH_TERMS_4(T)                                                                                         \
+    T(16, GGRT_SH_C4_0 * xy * (xx - yy), GGRT_SH_C4_0 * y * (3.0f * xx - yy), GGRT_SH_C4_0 * x * (xx - 3.0f * yy), GGRT_Z) \
+    T(17, GGRT_SH_C4_1 * yz * (3.0f * xx - yy), GGRT_SH_C4_1 * 6.0f * xy * z,                                     \
+      GGRT_SH_C4_1 * z * (3.0f * xx - 3.0f * yy), GGRT_SH_C4_1 * y * (3.0f * xx - yy))                            \
+    T(18, GGRT_SH_C4_2 * xy * (7.0f * zz - 1.0f), GGRT_SH_C4_2 * y * (7.0f * zz - 1.0f),                          \
+      GGRT_SH_C4_2 * x * (7.0f * zz - 1.0f), GGRT_SH_C4_2 * 14.0f * xy * z)                                       \
+    T(19, GGRT_SH_C4_3 * yz * (7.0f * zz - 3.0f), GGRT_Z, GGRT_SH_C4_3 * z * (7.0f * zz - 3.0f),                     \
+      GGRT_SH_C4_3 * y * (21.0f * zz - 3.0f))                                                                     \
+    T(20, GGRT_SH_C4_4 * (zz * (35.0f * zz - 30.0f) + 3.0f), GGRT_Z, GGRT_Z, GGRT_SH_C4_4 * (140.0f * zz * z - 60.0f * z)) \
+    T(21, GGRT_SH_C4_5 * xz * (7.0f * zz - 3.0f), GGRT_SH_C4_5 * z * (7.0f * zz - 3.0f), GGRT_Z,                     \
+      GGRT_SH_C4_5 * x * (21.0f * zz - 3.0f))                                                                     \
+    T(22, GGRT_SH_C4_6 * (xx - yy) * (7.0f * zz - 1.0f), GGRT_SH_C4_6 * 2.0f * x * (7.0f * zz - 1.0f),            \
+      GGRT_SH_C4_6 * -2.0f * y * (7.0f * zz - 1.0f), GGRT_SH_C4_6 * (xx - yy) * 14.0f * z)                        \
+    T(23, GGRT_SH_C4_7 * xz * (xx - 3.0f * yy), GGRT_SH_C4_7 * z * (3.0f * xx - 3.0f * yy),                       \
+      GGRT_SH_C4_7 * -6.0f * xy * z, GGRT_SH_C4_7 * x * (xx - 3.0f * yy))                                         \
+    T(24, GGRT_SH_C4_8 * (xx * (xx - 3.0f * yy) - yy * (3.0f * xx - yy)),                                         \
+      GGRT_SH_C4_8 * (4.0f * xx * x - 12.0f * x * yy), GGRT_SH_C4_8 * (-12.0f * xx * y + 4.0f * yy * y), GGRT_Z)
+// acc += coefficient * s; GGRT_Z marks the identically-zero derivatives of the term list, whose FMA is dropped at
+// compile time by overload resolution (fmaf(0, s, acc) itself could not be: s may be Inf / NaN)
+struct ShZero {};
+#define GGRT_Z (ShZero{})
+__device__ __forceinline__ void sh_fma(ShZero, float, float&) {}
+__device__ __forceinline__ void sh_fma(float coef, float s, float& acc) { acc = fmaf(coef, s, acc); }
 
 // Real SH basis of degree `deg` at unit direction (x,y,z) -> b[0..K)
 __device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float* b) {

@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_tiles_kernel(int T, const uin
     __shared__ uint32_t gmax_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = blockIdx.x * SCAN_BLOCK + tid;
+    pdl_enter();
     const uint4* c4 = reinterpret_cast<const uint4*>(counts) + (size_t)t * (SUBS / 4);
     uint4 c[SUBS / 4];
     unsigned long long ts = 0;
@@ -199,7 +200,9 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_tiles_kernel(int T, const uin
             counts_host[1] = mx;
             counts_host[2] = hi;
             counts_host[3] = 0u;
+#ifndef GGRT_SCAN_NO_SYSFENCE
             __threadfence_system();
+#endif
         }
     }
 }
@@ -229,7 +232,7 @@ __device__ __forceinline__ void fill_slab_generic(float* slab, const float* src,
     }
 }
 
-template <int DEG, bool CMAJOR>
+template <int DEG, bool CMAJOR, bool JAC>
 __global__ void __launch_bounds__(COLOR_THREADS, 3)
 color_kernel(View v, const float* __restrict__ means, const float* __restrict__ shs, const float* __restrict__ colors,
              const float* __restrict__ aux, const int* __restrict__ radii, GeomPtrs g, int num_slabs) {
@@ -308,18 +311,44 @@ color_kernel(View v, const float* __restrict__ means, const float* __restrict__ 
                 if (shs == nullptr) {
                     rgb[0] = colors[3 * i], rgb[1] = colors[3 * i + 1], rgb[2] = colors[3 * i + 2];
                 } else {
-                    float dx = mx - cpx, dy = my_ - cpy, dz = mz - cpz;
-                    const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-                    dx *= inv, dy *= inv, dz *= inv;
-                    float b[25];
-                    sh_basis(DEG, dx, dy, dz, b);
+                    const float vx = mx - cpx, vy = my_ - cpy, vz = mz - cpz;
+                    const float len2 = vx * vx + vy * vy + vz * vz;
+                    const float inv = 1.0f / sqrtf(len2);
+                    const float x = vx * inv, y = vy * inv, z = vz * inv;
+                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
                     const float* my = slab + threadIdx.x * row;
                     rgb[0] = rgb[1] = rgb[2] = 0.5f;
+                    // d(colour c)/d(direction) accumulates beside the colour: the SH row is in shared memory here, and
+                    // with this 3x3 Jacobian stored the backward pass never reads the 12K-byte row again
+                    float jx[3] = {0.f, 0.f, 0.f}, jy[3] = {0.f, 0.f, 0.f}, jz[3] = {0.f, 0.f, 0.f};
+#define GGRT_COLOR_TERM(k, B, BX, BY, BZ)                                                       \
+    {                                                                                           \
+        const float b_ = (B);                                                                   \
+        _Pragma("unroll") for (int c = 0; c < 3; ++c) {                                         \
+            const float s_ = my[(k) * ks + c * cs];                                             \
+            rgb[c] = fmaf(b_, s_, rgb[c]);                                                      \
+            if (JAC) {                                                                          \
+                sh_fma(BX, s_, jx[c]);                                                            \
+                sh_fma(BY, s_, jy[c]);                                                            \
+                sh_fma(BZ, s_, jz[c]);                                                            \
+            }                                                                                   \
+        }                                                                                       \
+    }
+                    GGRT_SH_TERMS_0(GGRT_COLOR_TERM)
+                    if (DEG > 0) { GGRT_SH_TERMS_1(GGRT_COLOR_TERM) }
+                    if (DEG > 1) { GGRT_SH_TERMS_2(GGRT_COLOR_TERM) }
+                    if (DEG > 2) { GGRT_SH_TERMS_3(GGRT_COLOR_TERM) }
+                    if (DEG > 3) { GGRT_SH_TERMS_4(GGRT_COLOR_TERM) }
+#undef GGRT_COLOR_TERM
+                    if (JAC) {  // through normalize(): (I |v|^2 - v v^T) / |v|^3, one row of the Jacobian per channel
+                        const float inv3 = inv * inv * inv;
 #pragma unroll
-                    for (int k = 0; k < KK; ++k) {
-                        rgb[0] = fmaf(b[k], my[k * ks], rgb[0]);
-                        rgb[1] = fmaf(b[k], my[k * ks + cs], rgb[1]);
-                        rgb[2] = fmaf(b[k], my[k * ks + 2 * cs], rgb[2]);
+                        for (int c = 0; c < 3; ++c) {
+                            const float dot = vx * jx[c] + vy * jy[c] + vz * jz[c];
+                            g.jac[(size_t)(3 * c + 0) * g.jac_plane + i] = (len2 * jx[c] - vx * dot) * inv3;
+                            g.jac[(size_t)(3 * c + 1) * g.jac_plane + i] = (len2 * jy[c] - vy * dot) * inv3;
+                            g.jac[(size_t)(3 * c + 2) * g.jac_plane + i] = (len2 * jz[c] - vz * dot) * inv3;
+                        }
                     }
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
@@ -469,8 +498,8 @@ void launch_geometry(const View& v, const float* means, const float* cov3d, cons
 
 void launch_scan_tiles(const View& v, ImagePtrs im, uint32_t* counts_host, cudaStream_t s) {
     const int T = v.gx * v.gy;
-    scan_tiles_kernel<<<(T + SCAN_BLOCK - 1) / SCAN_BLOCK, SCAN_BLOCK, 0, s>>>(T, im.counts, im.starts, im.cursor, im.partials,
-                                                                              im.header, counts_host);
+    launch_chain(scan_tiles_kernel, dim3((T + SCAN_BLOCK - 1) / SCAN_BLOCK), dim3(SCAN_BLOCK), 0, s, T, im.counts, im.starts,
+                 im.cursor, im.partials, im.header, counts_host);
 }
 
 void launch_color(const View& v, const float* means, const float* shs, const float* colors, const float* aux,
@@ -483,11 +512,16 @@ void launch_color(const View& v, const float* means, const float* shs, const flo
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int per_sm = smem ? max(1, min(8, (int)((220 * 1024) / (smem + 1024)))) : 8;
     const int grid = min(num_slabs, per_sm * sms);  // persistent CTAs, each streams slabs through its ring
+    // (the direction Jacobian for the backward is stored whenever there is an SH table of degree > 0 to differentiate)
 #define GGRT_LAUNCH_COLOR2(D, CM)                                                                                   \
     {                                                                                                               \
+        constexpr bool JC = (D) > 0;                                                                                \
         if (smem > 32 * 1024)                                                                                       \
-            cudaFuncSetAttribute(color_kernel<D, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-        color_kernel<D, CM><<<grid, COLOR_THREADS, smem, s>>>(v, means, shs, colors, aux, radii, g, num_slabs);     \
+            cudaFuncSetAttribute(color_kernel<D, CM, JC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        if (shs != nullptr)                                                                                         \
+            color_kernel<D, CM, JC><<<grid, COLOR_THREADS, smem, s>>>(v, means, shs, colors, aux, radii, g, num_slabs); \
+        else                                                                                                        \
+            color_kernel<0, false, false><<<grid, COLOR_THREADS, smem, s>>>(v, means, shs, colors, aux, radii, g, num_slabs); \
     }
 #define GGRT_LAUNCH_COLOR(D)                                                                                        \
     case D:                                                                                                         \

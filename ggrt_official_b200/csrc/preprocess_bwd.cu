@@ -4,16 +4,17 @@
 // 8a row a13, fused into one pass.  Every output element is written (zeros for culled
 // Gaussians) so the caller needs no memset of the 300 B/Gaussian SH gradient.
 //
-// HBM-bound (about 700 B per Gaussian at SH degree 4).  Persistent CTAs, 2 per SM; the SH
-// slab of PB_THREADS Gaussians (contiguous in HBM) is pulled into a 2-stage shared-memory
-// ring by the TMA engine (cp.async.bulk + mbarrier), overwritten in place with dL/dsh by the
-// threads (one row each, odd stride), and written back with a TMA bulk store
+// HBM-bound (about 480 B per Gaussian at SH degree 4, 300 of them the dL/dsh row it writes).  The SH table is NOT
+// read: the only use the backward has for the coefficients is d(colour)/d(view direction), a 3x3 matrix per
+// Gaussian that the forward's colour kernel stores while the row is on chip (GeomPtrs::jac, 36 B instead of
+// 12K B).  Persistent CTAs; the dL/dsh slab of PB_THREADS Gaussians (contiguous in HBM) is assembled in a
+// shared-memory ring by the threads (one row each, odd stride) and written with TMA bulk stores
 // (cp.async.bulk.global.shared) while the next slab is processed.
 //
 // Compact mode (shs given, dsh == NULL, dcolors != NULL): dL/dsh of one view is the outer product
 // basis(dir) x dL/drgb, so for the view-sharded multi-GPU path only the masked colour gradient [P,3] is
 // written (12 B instead of 12K B per Gaussian) and the SH gradient of ALL views is rebuilt after the exchange
-// by sh_gradient_merge_kernel (sh_merge.cu).  The SH slab is still read: dL/dmean3D needs it.
+// by sh_gradient_merge_kernel (sh_merge.cu).  No shared-memory ring at all in this mode.
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -27,10 +28,13 @@ namespace ggrt {
 #endif
 constexpr int PB_THREADS = GGRT_PB_THREADS;
 #ifndef GGRT_PB_MINBLOCKS
-#define GGRT_PB_MINBLOCKS 10
+#define GGRT_PB_MINBLOCKS 16  // 128 registers (4 bytes of spill): 16 one-warp CTAs per SM hide the kernel's dependent chains
 #endif
 
 constexpr int PB_STAGES = GGRT_PB_STAGES;
+#ifndef GGRT_PB_SPLIT_BLOCKS
+#define GGRT_PB_SPLIT_BLOCKS 16
+#endif
 
 // float4 / scalar stores of the compact colour gradients: plain (local or peer memory) or NVLS multicast
 __device__ __forceinline__ void sink_store4(float* dst, float4 v, bool multimem) {
@@ -52,15 +56,16 @@ template <bool AUX, bool CMAJOR, bool POSE>
 __global__ void __launch_bounds__(PB_THREADS, GGRT_PB_MINBLOCKS)
 preprocess_backward_kernel(View v, const float* __restrict__ means, const float* __restrict__ cov3d,
                            const float* __restrict__ shs, const int* __restrict__ radii,
-                           const uint8_t* __restrict__ flags, const float* __restrict__ scratch,
+                           const uint8_t* __restrict__ flags, const float* __restrict__ jac, size_t jac_plane,
+                           const float* __restrict__ scratch,
                            float* __restrict__ dmeans2D, float* __restrict__ dopacity, float* __restrict__ dmeans3D,
                            float* __restrict__ dcov3D, float* __restrict__ dsh, float* __restrict__ dcolors,
                            float* __restrict__ daux, float* __restrict__ dcam, ColorSinks sinks, int num_slabs) {
     extern __shared__ __align__(128) float slab_ring[];
     __shared__ __align__(16) float sdc[PB_THREADS * 3];  // compact mode: the slab's colour gradients, staged for
                                                           // coalesced 16-byte (possibly remote / multicast) stores
-    __shared__ __align__(8) unsigned long long full_bar[PB_STAGES];
     __shared__ float sV[16], sM[16];
+    pdl_enter();
     if (threadIdx.x < 16) sV[threadIdx.x] = v.view[threadIdx.x];
     else if (threadIdx.x < 32) sM[threadIdx.x - 16] = v.proj[threadIdx.x - 16];
 
@@ -71,27 +76,12 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
                                : 0ll;
     const int row = v.K * 3;
     const bool compact = shs != nullptr && dsh == nullptr;  // uniform: write dL/drgb instead of dL/dsh
+    const bool push = compact && sinks.n > 0;               // (no sink: dL/dsh is written by sh_gradient_kernel)
     const int ks = CMAJOR ? 1 : 3, cs = CMAJOR ? v.K : 1;  // SH element (k, c) at k*ks + c*cs of the row
     const int slab_floats = PB_THREADS * row;
-    const bool tma_ok = shs != nullptr && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&
-                        (reinterpret_cast<uintptr_t>(dsh) & 15) == 0;  // (a NULL dsh is "aligned": no store is issued)
-    if (shs != nullptr && threadIdx.x == 0) {
-        for (int st = 0; st < PB_STAGES; ++st) mbar_init(smem_u32(&full_bar[st]), 1);
-        fence_mbar_init();
-    }
-    __syncthreads();  // publishes sV / sM and the barriers
-    if (threadIdx.x == 0 && tma_ok) {  // prologue: fill the ring
-        for (int st = 0; st < PB_STAGES; ++st) {
-            const int sl = blockIdx.x + st * gridDim.x;
-            if (sl >= num_slabs) break;
-            const uint32_t bytes = (uint32_t)min(PB_THREADS, v.P - sl * PB_THREADS) * row * 4u;
-            if ((bytes & 15u) == 0) {
-                mbar_expect_tx(smem_u32(&full_bar[st]), bytes);
-                bulk_g2s(smem_u32(slab_ring + st * slab_floats), shs + (size_t)sl * slab_floats, bytes,
-                         smem_u32(&full_bar[st]));
-            }
-        }
-    }
+    const bool use_jac = shs != nullptr && v.deg > 0;   // uniform
+    const bool tma_ok = shs != nullptr && !compact && (reinterpret_cast<uintptr_t>(dsh) & 15) == 0;
+    __syncthreads();  // publishes sV / sM
 
     // per-Gaussian inputs of the NEXT slab are prefetched into registers (one DRAM latency, overlapped with
     // the evaluation of the current slab) instead of being loaded behind data-dependent branches
@@ -100,6 +90,7 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     float n_mean[3] = {0.f, 0.f, 0.f}, n_cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float4 n_ga = make_float4(0.f, 0.f, 0.f, 0.f), n_gb = n_ga;
     float n_gc = 0.f, n_gx = 0.f;
+    float n_jac[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     auto prefetch = [&](int sl) {
         const int i = sl * PB_THREADS + threadIdx.x;
         n_radius = 0;
@@ -114,6 +105,10 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             n_gb = *reinterpret_cast<const float4*>(gs + 4);
             n_gc = gs[8];
             if (AUX && (daux || v.aux_mode)) n_gx = gs[G_AUX];
+            if (use_jac && n_radius > 0) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) n_jac[k] = jac[(size_t)k * jac_plane + i];
+            }
         }
     };
     prefetch(blockIdx.x);
@@ -129,7 +124,6 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     int it = 0;
     for (int sl = blockIdx.x; sl < num_slabs; sl += gridDim.x, ++it) {
     const int st = it % PB_STAGES;
-    const uint32_t parity = (uint32_t)(it / PB_STAGES) & 1u;
     float* slab = slab_ring + st * slab_floats;
     const int base = sl * PB_THREADS;
     const int cnt = min(PB_THREADS, v.P - base);
@@ -146,25 +140,16 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     scale_cov6(v, cv);
     const float4 ga = n_ga, gb = n_gb;
     const float gc = n_gc, gaux = n_gx;
+    float jc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) jc[k] = n_jac[k];
     prefetch(sl + gridDim.x);
 
-    // the CTA's SH slab (staged by TMA, or cooperatively when ragged); it is overwritten in place with dL/dsh
-    if (shs != nullptr) {
-        if (slab_tma) {
-            mbar_wait(smem_u32(&full_bar[st]), parity);
-        } else {
-            const float* src = shs + (size_t)base * row;
-            if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-                const float4* s4 = reinterpret_cast<const float4*>(src);
-                float4* d4 = reinterpret_cast<float4*>(slab);
-                const int n4 = nfl >> 2;
-                for (int k = threadIdx.x; k < n4; k += PB_THREADS) d4[k] = __ldcs(s4 + k);
-                for (int k = (n4 << 2) + threadIdx.x; k < nfl; k += PB_THREADS) slab[k] = src[k];
-            } else {
-                for (int k = threadIdx.x; k < nfl; k += PB_THREADS) slab[k] = src[k];
-            }
-            __syncthreads();
-        }
+    // the stage this slab's dL/dsh rows are assembled in must have been drained by the bulk store issued
+    // PB_STAGES slabs ago
+    if (shs != nullptr && !compact) {
+        if (threadIdx.x == 0) bulk_wait_read<PB_STAGES - 1>();
+        __syncthreads();
     }
 
     float dmean[3] = {0.f, 0.f, 0.f};
@@ -261,84 +246,33 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
             if (fl & 1) dR = 0.f;
             if (fl & 2) dG = 0.f;
             if (fl & 4) dB = 0.f;
-            const float vx = mean_x - cpx, vy = mean_y - cpy, vz = mean_z - cpz;
-            const float len2 = vx * vx + vy * vy + vz * vz;
-            const float inv = rsqrtf(len2);
-            const float x = vx * inv, y = vy * inv, z = vz * inv;
-            float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-            // one SH term: accumulate dL/ddir from the stored coefficients, then overwrite them with dL/dsh
-#define GGRT_TERM(k, B, BX, BY, BZ)                                                        \
-    {                                                                                      \
-        const float s_ = my[(k) * ks] * dR + my[(k) * ks + cs] * dG + my[(k) * ks + 2 * cs] * dB; \
-        ddx = fmaf((BX), s_, ddx), ddy = fmaf((BY), s_, ddy), ddz = fmaf((BZ), s_, ddz);   \
-        if (!compact) {                                                                    \
-            const float b_ = (B);                                                          \
-            my[(k) * ks] = b_ * dR, my[(k) * ks + cs] = b_ * dG, my[(k) * ks + 2 * cs] = b_ * dB; \
-        }                                                                                  \
+            if (use_jac) {  // colour -> mean through the view direction: the forward's Jacobian times dL/dcolour
+                const float m0 = jc[0] * dR + jc[3] * dG + jc[6] * dB, m1 = jc[1] * dR + jc[4] * dG + jc[7] * dB,
+                            m2 = jc[2] * dR + jc[5] * dG + jc[8] * dB;
+                dmean[0] += m0, dmean[1] += m1, dmean[2] += m2;
+                if (POSE) camC[0] -= m0, camC[1] -= m1, camC[2] -= m2;  // dir = p - campos
+            }
+            if (!compact) {  // dL/dsh row = basis(dir) (x) dL/dcolour
+                const float vx = mean_x - cpx, vy = mean_y - cpy, vz = mean_z - cpz;
+                const float inv = 1.0f / sqrtf(vx * vx + vy * vy + vz * vz);  // as the colour kernel normalises
+                const float x = vx * inv, y = vy * inv, z = vz * inv;
+#define GGRT_TERM(k, B, BX, BY, BZ)                                                               \
+    {                                                                                             \
+        const float b_ = (B);                                                                     \
+        my[(k) * ks] = b_ * dR, my[(k) * ks + cs] = b_ * dG, my[(k) * ks + 2 * cs] = b_ * dB;     \
     }
-            GGRT_TERM(0, GGRT_SH_C0, 0.f, 0.f, 0.f)
-            if (v.deg > 0) {
-                GGRT_TERM(1, -GGRT_SH_C1 * y, 0.f, -GGRT_SH_C1, 0.f)
-                GGRT_TERM(2, GGRT_SH_C1 * z, 0.f, 0.f, GGRT_SH_C1)
-                GGRT_TERM(3, -GGRT_SH_C1 * x, -GGRT_SH_C1, 0.f, 0.f)
-            }
-            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-            if (v.deg > 1) {
-                GGRT_TERM(4, GGRT_SH_C2_0 * xy, GGRT_SH_C2_0 * y, GGRT_SH_C2_0 * x, 0.f)
-                GGRT_TERM(5, GGRT_SH_C2_1 * yz, 0.f, GGRT_SH_C2_1 * z, GGRT_SH_C2_1 * y)
-                GGRT_TERM(6, GGRT_SH_C2_2 * (2.0f * zz - xx - yy), GGRT_SH_C2_2 * -2.0f * x, GGRT_SH_C2_2 * -2.0f * y,
-                          GGRT_SH_C2_2 * 4.0f * z)
-                GGRT_TERM(7, GGRT_SH_C2_3 * xz, GGRT_SH_C2_3 * z, 0.f, GGRT_SH_C2_3 * x)
-                GGRT_TERM(8, GGRT_SH_C2_4 * (xx - yy), GGRT_SH_C2_4 * 2.0f * x, GGRT_SH_C2_4 * -2.0f * y, 0.f)
-            }
-            if (v.deg > 2) {
-                GGRT_TERM(9, GGRT_SH_C3_0 * y * (3.0f * xx - yy), GGRT_SH_C3_0 * 6.0f * xy,
-                          GGRT_SH_C3_0 * (3.0f * xx - 3.0f * yy), 0.f)
-                GGRT_TERM(10, GGRT_SH_C3_1 * xy * z, GGRT_SH_C3_1 * yz, GGRT_SH_C3_1 * xz, GGRT_SH_C3_1 * xy)
-                GGRT_TERM(11, GGRT_SH_C3_2 * y * (4.0f * zz - xx - yy), GGRT_SH_C3_2 * -2.0f * xy,
-                          GGRT_SH_C3_2 * (4.0f * zz - xx - 3.0f * yy), GGRT_SH_C3_2 * 8.0f * yz)
-                GGRT_TERM(12, GGRT_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy), GGRT_SH_C3_3 * -6.0f * xz,
-                          GGRT_SH_C3_3 * -6.0f * yz, GGRT_SH_C3_3 * (6.0f * zz - 3.0f * xx - 3.0f * yy))
-                GGRT_TERM(13, GGRT_SH_C3_4 * x * (4.0f * zz - xx - yy), GGRT_SH_C3_4 * (4.0f * zz - 3.0f * xx - yy),
-                          GGRT_SH_C3_4 * -2.0f * xy, GGRT_SH_C3_4 * 8.0f * xz)
-                GGRT_TERM(14, GGRT_SH_C3_5 * z * (xx - yy), GGRT_SH_C3_5 * 2.0f * xz, GGRT_SH_C3_5 * -2.0f * yz,
-                          GGRT_SH_C3_5 * (xx - yy))
-                GGRT_TERM(15, GGRT_SH_C3_6 * x * (xx - 3.0f * yy), GGRT_SH_C3_6 * (3.0f * xx - 3.0f * yy),
-                          GGRT_SH_C3_6 * -6.0f * xy, 0.f)
-            }
-            if (v.deg > 3) {
-                GGRT_TERM(16, GGRT_SH_C4_0 * xy * (xx - yy), GGRT_SH_C4_0 * y * (3.0f * xx - yy),
-                          GGRT_SH_C4_0 * x * (xx - 3.0f * yy), 0.f)
-                GGRT_TERM(17, GGRT_SH_C4_1 * yz * (3.0f * xx - yy), GGRT_SH_C4_1 * 6.0f * xy * z,
-                          GGRT_SH_C4_1 * z * (3.0f * xx - 3.0f * yy), GGRT_SH_C4_1 * y * (3.0f * xx - yy))
-                GGRT_TERM(18, GGRT_SH_C4_2 * xy * (7.0f * zz - 1.0f), GGRT_SH_C4_2 * y * (7.0f * zz - 1.0f),
-                          GGRT_SH_C4_2 * x * (7.0f * zz - 1.0f), GGRT_SH_C4_2 * 14.0f * xy * z)
-                GGRT_TERM(19, GGRT_SH_C4_3 * yz * (7.0f * zz - 3.0f), 0.f, GGRT_SH_C4_3 * z * (7.0f * zz - 3.0f),
-                          GGRT_SH_C4_3 * y * (21.0f * zz - 3.0f))
-                GGRT_TERM(20, GGRT_SH_C4_4 * (zz * (35.0f * zz - 30.0f) + 3.0f), 0.f, 0.f,
-                          GGRT_SH_C4_4 * (140.0f * zz * z - 60.0f * z))
-                GGRT_TERM(21, GGRT_SH_C4_5 * xz * (7.0f * zz - 3.0f), GGRT_SH_C4_5 * z * (7.0f * zz - 3.0f), 0.f,
-                          GGRT_SH_C4_5 * x * (21.0f * zz - 3.0f))
-                GGRT_TERM(22, GGRT_SH_C4_6 * (xx - yy) * (7.0f * zz - 1.0f), GGRT_SH_C4_6 * 2.0f * x * (7.0f * zz - 1.0f),
-                          GGRT_SH_C4_6 * -2.0f * y * (7.0f * zz - 1.0f), GGRT_SH_C4_6 * (xx - yy) * 14.0f * z)
-                GGRT_TERM(23, GGRT_SH_C4_7 * xz * (xx - 3.0f * yy), GGRT_SH_C4_7 * z * (3.0f * xx - 3.0f * yy),
-                          GGRT_SH_C4_7 * -6.0f * xy * z, GGRT_SH_C4_7 * x * (xx - 3.0f * yy))
-                GGRT_TERM(24, GGRT_SH_C4_8 * (xx * (xx - 3.0f * yy) - yy * (3.0f * xx - yy)),
-                          GGRT_SH_C4_8 * (4.0f * xx * x - 12.0f * x * yy), GGRT_SH_C4_8 * (-12.0f * xx * y + 4.0f * yy * y),
-                          0.f)
-            }
+                GGRT_SH_TERMS_0(GGRT_TERM)
+                if (v.deg > 0) { GGRT_SH_TERMS_1(GGRT_TERM) }
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                if (v.deg > 1) { GGRT_SH_TERMS_2(GGRT_TERM) }
+                if (v.deg > 2) { GGRT_SH_TERMS_3(GGRT_TERM) }
+                if (v.deg > 3) { GGRT_SH_TERMS_4(GGRT_TERM) }
 #undef GGRT_TERM
-            // through normalize(): (I |v|^2 - v v^T) / |v|^3
-            const float inv3 = inv * inv * inv;
-            const float dot = vx * ddx + vy * ddy + vz * ddz;
-            const float m0 = (len2 * ddx - vx * dot) * inv3, m1 = (len2 * ddy - vy * dot) * inv3,
-                        m2 = (len2 * ddz - vz * dot) * inv3;
-            dmean[0] += m0, dmean[1] += m1, dmean[2] += m2;
-            if (POSE) camC[0] -= m0, camC[1] -= m1, camC[2] -= m2;  // dir = p - campos
+            }
         } else if (valid && !compact) {
             for (int k = 0; k < row; ++k) my[k] = 0.f;
         }
-        if (compact) {  // masked colour gradient (zero for culled Gaussians and clamped channels)
+        if (push) {  // masked colour gradient (zero for culled Gaussians and clamped channels)
             if (valid) sdc[3 * threadIdx.x] = dR, sdc[3 * threadIdx.x + 1] = dG, sdc[3 * threadIdx.x + 2] = dB;
             __syncthreads();
             const int n3 = cnt * 3, n4 = n3 >> 2;
@@ -353,41 +287,32 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
                     for (int k = threadIdx.x; k < n3; k += PB_THREADS) sink_store1(dstc + k, sdc[k], mm);
                 }
             }
-            // (the barrier in the slab write-out / refill code below orders these reads before the next slab's writes)
         }
         // write-out of the dL/dsh slab: TMA bulk store, or coalesced stores when ragged / unaligned
-        float* dst = compact ? nullptr : dsh + (size_t)base * row;
-        if (slab_tma) {
-            if (!compact) fence_proxy_async();  // this thread's generic writes -> visible to the async proxy
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                if (!compact) {
+        if (!compact) {
+            float* dst = dsh + (size_t)base * row;
+            if (slab_tma) {
+                fence_proxy_async();  // this thread's generic writes -> visible to the async proxy
+                __syncthreads();
+                if (threadIdx.x == 0) {
                     bulk_s2g(dst, smem_u32(slab), (uint32_t)nfl * 4u);
                     bulk_commit();
                 }
-                const int nsl = sl + PB_STAGES * gridDim.x;
-                if (nsl < num_slabs) {
-                    const uint32_t nbytes = (uint32_t)min(PB_THREADS, v.P - nsl * PB_THREADS) * row * 4u;
-                    if ((nbytes & 15u) == 0) {
-                        if (!compact) bulk_wait_read0();  // the store has drained this stage before it is refilled
-                        mbar_expect_tx(smem_u32(&full_bar[st]), nbytes);
-                        bulk_g2s(smem_u32(slab), shs + (size_t)nsl * slab_floats, nbytes, smem_u32(&full_bar[st]));
-                    }
-                }
-            }
-        } else {
-            __syncthreads();
-            if (compact) {
-            } else if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-                float4* d4 = reinterpret_cast<float4*>(dst);
-                const float4* s4 = reinterpret_cast<const float4*>(slab);
-                const int n4 = nfl >> 2;
-                for (int k = threadIdx.x; k < n4; k += PB_THREADS) __stcs(d4 + k, s4[k]);
-                for (int k = (n4 << 2) + threadIdx.x; k < nfl; k += PB_THREADS) dst[k] = slab[k];
             } else {
-                for (int k = threadIdx.x; k < nfl; k += PB_THREADS) dst[k] = slab[k];
+                __syncthreads();
+                if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                    float4* d4 = reinterpret_cast<float4*>(dst);
+                    const float4* s4 = reinterpret_cast<const float4*>(slab);
+                    const int n4 = nfl >> 2;
+                    for (int k = threadIdx.x; k < n4; k += PB_THREADS) __stcs(d4 + k, s4[k]);
+                    for (int k = (n4 << 2) + threadIdx.x; k < nfl; k += PB_THREADS) dst[k] = slab[k];
+                } else {
+                    for (int k = threadIdx.x; k < nfl; k += PB_THREADS) dst[k] = slab[k];
+                }
+                // (the barrier at the top of the slab loop orders these reads before the stage is written again)
             }
-            __syncthreads();  // stage free again
+        } else if (push) {
+            __syncthreads();  // the staged colour gradients have been read before the next slab overwrites them
         }
     } else if (valid) {
         dcolors[3 * i] = dR, dcolors[3 * i + 1] = dG, dcolors[3 * i + 2] = dB;
@@ -447,28 +372,156 @@ preprocess_backward_kernel(View v, const float* __restrict__ means, const float*
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// dL/dsh writer.  dL/dsh[i] = basis(dir_i) (x) dL/dcolour_i is 88 % of the bytes the per-Gaussian backward moves
+// and needs none of its arithmetic -- only the Gaussian's mean, its clamp flags and the three colour sums of the
+// scratch row -- so it is a kernel of its own (40 registers, 128-thread CTAs, a store-only shared-memory ring
+// drained by TMA bulk stores) that ggrt_raster_backward runs BESIDE the register-heavy, latency-bound kernel above
+// on the library's side stream: together they keep HBM busy where one fused kernel could not (36.9 us fused).
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef GGRT_SG_THREADS
+#define GGRT_SG_THREADS 64
+#endif
+#ifndef GGRT_SG_PER_SM
+#define GGRT_SG_PER_SM 4
+#endif
+#ifndef GGRT_SG_STAGES
+#define GGRT_SG_STAGES 2
+#endif
+constexpr int SG_THREADS = GGRT_SG_THREADS;
+constexpr int SG_STAGES = GGRT_SG_STAGES;
+
+template <bool CMAJOR>
+__global__ void __launch_bounds__(SG_THREADS)
+sh_gradient_kernel(View v, const float* __restrict__ means, const int* __restrict__ radii,
+                   const uint8_t* __restrict__ flags, const float* __restrict__ scratch, float* __restrict__ dsh,
+                   int num_slabs) {
+    extern __shared__ __align__(128) float slab_ring[];
+    resolve_device_params(v);
+    const int row = v.K * 3;
+    const int ks = CMAJOR ? 1 : 3, cs = CMAJOR ? v.K : 1;
+    const int slab_floats = SG_THREADS * row;
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(dsh) & 15) == 0;
+    const float cpx = v.campos[0], cpy = v.campos[1], cpz = v.campos[2];
+
+    int n_radius = 0;
+    uint32_t n_flags = 0;
+    float n_mean[3] = {0.f, 0.f, 0.f}, n_d[3] = {0.f, 0.f, 0.f};
+    auto prefetch = [&](int sl) {
+        const int i = sl * SG_THREADS + threadIdx.x;
+        n_radius = 0;
+        if (sl < num_slabs && i < v.P) {
+            n_radius = radii[i];
+            n_flags = flags[i];
+            const float* gs = scratch + (size_t)i * GRAD_STRIDE;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) n_mean[k] = means[3 * (size_t)i + k], n_d[k] = gs[G_R + k];
+        }
+    };
+    prefetch(blockIdx.x);
+
+    int it = 0;
+    for (int sl = blockIdx.x; sl < num_slabs; sl += gridDim.x, ++it) {
+        float* slab = slab_ring + (it % SG_STAGES) * slab_floats;
+        const int base = sl * SG_THREADS;
+        const int cnt = min(SG_THREADS, v.P - base);
+        const int nfl = cnt * row;
+        const bool valid = threadIdx.x < cnt, vis = valid && n_radius > 0;
+        const uint32_t fl = n_flags;
+        const float vx = fmul(n_mean[0], v.scale) - cpx, vy = fmul(n_mean[1], v.scale) - cpy,
+                    vz = fmul(n_mean[2], v.scale) - cpz;
+        const float dR = (fl & 1) ? 0.f : n_d[0], dG = (fl & 2) ? 0.f : n_d[1], dB = (fl & 4) ? 0.f : n_d[2];
+        prefetch(sl + gridDim.x);
+        // the bulk store issued SG_STAGES slabs ago has drained this stage
+        if (threadIdx.x == 0) bulk_wait_read<SG_STAGES - 1>();
+        __syncthreads();
+        float* my = slab + threadIdx.x * row;
+        if (vis) {
+            const float inv = 1.0f / sqrtf(vx * vx + vy * vy + vz * vz);  // as the colour kernel normalises
+            const float x = vx * inv, y = vy * inv, z = vz * inv;
+#define GGRT_TERM(k, B, BX, BY, BZ)                                                               \
+    {                                                                                             \
+        const float b_ = (B);                                                                     \
+        my[(k) * ks] = b_ * dR, my[(k) * ks + cs] = b_ * dG, my[(k) * ks + 2 * cs] = b_ * dB;     \
+    }
+            GGRT_SH_TERMS_0(GGRT_TERM)
+            if (v.deg > 0) { GGRT_SH_TERMS_1(GGRT_TERM) }
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            if (v.deg > 1) { GGRT_SH_TERMS_2(GGRT_TERM) }
+            if (v.deg > 2) { GGRT_SH_TERMS_3(GGRT_TERM) }
+            if (v.deg > 3) { GGRT_SH_TERMS_4(GGRT_TERM) }
+#undef GGRT_TERM
+        } else if (valid) {
+            for (int k = 0; k < row; ++k) my[k] = 0.f;
+        }
+        float* dst = dsh + (size_t)base * row;
+        if (tma_ok && ((nfl * 4) & 15) == 0) {
+            fence_proxy_async();  // this thread's generic writes -> visible to the async proxy
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                bulk_s2g(dst, smem_u32(slab), (uint32_t)nfl * 4u);
+                bulk_commit();
+            }
+        } else {  // ragged / unaligned slab: coalesced stores (the barrier at the top of the loop protects the stage)
+            __syncthreads();
+            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                float4* d4 = reinterpret_cast<float4*>(dst);
+                const float4* s4 = reinterpret_cast<const float4*>(slab);
+                const int n4 = nfl >> 2;
+                for (int k = threadIdx.x; k < n4; k += SG_THREADS) __stcs(d4 + k, s4[k]);
+                for (int k = (n4 << 2) + threadIdx.x; k < nfl; k += SG_THREADS) dst[k] = slab[k];
+            } else {
+                for (int k = threadIdx.x; k < nfl; k += SG_THREADS) dst[k] = slab[k];
+            }
+        }
+    }
+    if (threadIdx.x == 0) bulk_wait0();  // all bulk stores of this CTA have completed
+}
+
 void launch_preprocess_backward(const View& v, const float* means, const float* cov3d, const float* shs,
                                 const int* radii, GeomPtrs g, const float* scratch, float* dmeans2D, float* dopacity,
                                 float* dmeans3D, float* dcov3D, float* dsh, float* dcolors, float* daux, float* dcam,
-                                const ColorSinks& sinks, cudaStream_t s) {
+                                const ColorSinks& sinks, cudaStream_t s, cudaStream_t sh_stream) {
     if (v.P == 0) return;
-    const size_t smem = shs ? (size_t)PB_STAGES * PB_THREADS * v.K * 3 * sizeof(float) : 0;
-    const int num_slabs = (v.P + PB_THREADS - 1) / PB_THREADS;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#ifndef GGRT_PB_FUSED_DSH
+    if (shs != nullptr && dsh != nullptr) {
+        // dL/dsh goes through its own streaming kernel (on `sh_stream`, which the caller has ordered after the render
+        // backward and joins afterwards -- or on `s` itself); the kernel below then runs without any SH work
+        const size_t smem = (size_t)SG_STAGES * SG_THREADS * v.K * 3 * sizeof(float);
+        const int num_slabs = (v.P + SG_THREADS - 1) / SG_THREADS;
+        const int per_sm = max(1, min(GGRT_SG_PER_SM, (int)((200 * 1024) / (smem + 1024))));
+        const int grid = min(num_slabs, per_sm * sms);
+        cudaStream_t st = sh_stream ? sh_stream : s;
+        if (v.sh_ks == 1 && v.K > 1) {
+            if (smem > 32 * 1024)
+                cudaFuncSetAttribute(sh_gradient_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            sh_gradient_kernel<true><<<grid, SG_THREADS, smem, st>>>(v, means, radii, g.flags, scratch, dsh, num_slabs);
+        } else {
+            if (smem > 32 * 1024)
+                cudaFuncSetAttribute(sh_gradient_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            sh_gradient_kernel<false><<<grid, SG_THREADS, smem, st>>>(v, means, radii, g.flags, scratch, dsh, num_slabs);
+        }
+        dsh = nullptr;  // (shs != NULL, no dsh, no sinks: the "compact" code path with nothing to push)
+    }
+#endif
+    const size_t smem = (shs && dsh) ? (size_t)PB_STAGES * PB_THREADS * v.K * 3 * sizeof(float) : 0;  // dL/dsh ring
+    const int num_slabs = (v.P + PB_THREADS - 1) / PB_THREADS;
     // persistent CTAs: as many per SM as shared memory AND the register budget of __launch_bounds__ allow
-    const int per_sm = smem ? max(1, min(GGRT_PB_MINBLOCKS, (int)((220 * 1024) / (smem + 1024)))) : 8;
+    // (without a ring: GGRT_PB_SPLIT_BLOCKS one-warp CTAs per SM.  Measured at C2 with the dL/dsh writer beside it, whole
+    // step: 9 CTAs x 166 registers 0.2923 ms, 13 x 128 0.2921, 16 x 128 0.2911, 17 x 96 0.2948)
+    const int per_sm = smem ? max(1, min(GGRT_PB_MINBLOCKS, (int)((220 * 1024) / (smem + 1024)))) : GGRT_PB_SPLIT_BLOCKS;
     const int grid = min(num_slabs, per_sm * sms);
 #define GGRT_LAUNCH_PB(AX, CM, PO)                                                                                      \
     {                                                                                                                   \
         if (smem > 32 * 1024)                                                                                           \
             cudaFuncSetAttribute(preprocess_backward_kernel<AX, CM, PO>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                  (int)smem);                                                                            \
-        preprocess_backward_kernel<AX, CM, PO><<<grid, PB_THREADS, smem, s>>>(v, means, cov3d, shs, radii, g.flags,     \
-                                                                              scratch, dmeans2D, dopacity, dmeans3D,    \
-                                                                              dcov3D, dsh, dcolors, daux, dcam,         \
-                                                                              sinks, num_slabs);                               \
+        launch_chain(preprocess_backward_kernel<AX, CM, PO>, dim3(grid), dim3(PB_THREADS), smem, s, v, means, cov3d, shs,  \
+                     radii, (const uint8_t*)g.flags, (const float*)g.jac, g.jac_plane, scratch, dmeans2D, dopacity,     \
+                     dmeans3D, dcov3D, dsh, dcolors, daux, dcam, sinks, num_slabs);                                     \
     }
     const bool cm = v.sh_ks == 1 && v.K > 1;
     if (dcam) {  // camera gradients are rare: one instantiation per SH layout, aux always compiled in

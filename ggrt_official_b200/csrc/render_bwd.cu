@@ -247,6 +247,7 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
     const int px = bx0 + lx, py = by0 + ly;
     uint32_t last = 0;
     float Tfin = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, da = 0.f;
+    pdl_enter();  // (programmatic dependent launch: the CTA is resident before the forward render kernel has drained)
     if (px < v.W && py < v.H) {
         const size_t pix = (size_t)py * v.W + px, hw = (size_t)v.H * v.W;
         Tfin = final_T[pix];
@@ -519,13 +520,11 @@ void launch_render_backward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, 
 #define BWD_MASKS
 #endif
     if (dL_dout_aux)
-        render_backward_kernel<true><<<grid, BWD_THREADS, dyn, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
-                                                                       BWD_MASKS im.final_T, im.n_contrib, dL_dout,
-                                                                       dL_dout_aux, scratch);
+        launch_chain(render_backward_kernel<true>, grid, dim3(BWD_THREADS), dyn, s, v, g.rec0, g.rec1, g.rec2, im.starts,
+                     b.points, BWD_MASKS im.final_T, im.n_contrib, dL_dout, dL_dout_aux, scratch);
     else
-        render_backward_kernel<false><<<grid, BWD_THREADS, dyn, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points,
-                                                                        BWD_MASKS im.final_T, im.n_contrib, dL_dout,
-                                                                        nullptr, scratch);
+        launch_chain(render_backward_kernel<false>, grid, dim3(BWD_THREADS), dyn, s, v, g.rec0, g.rec1, g.rec2, im.starts,
+                     b.points, BWD_MASKS im.final_T, im.n_contrib, dL_dout, (const float*)nullptr, scratch);
 }
 
 }  // namespace ggrt

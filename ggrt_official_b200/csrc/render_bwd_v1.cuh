@@ -28,6 +28,7 @@ render_backward_kernel(View v, const float4* __restrict__ rec0, const float4* __
     const int wt = warp + blockIdx.z * BWD_WARPS;  // warp pixel block of the tile (8 per tile)
     const int bx0 = blockIdx.x * TILE + (wt & 1) * 8, by0 = blockIdx.y * TILE + (wt >> 1) * 4;
     const float bx0f = (float)bx0, by0f = (float)by0;
+    pdl_enter();
     const uint32_t start = starts[tile];
 
     // ---- per-pixel constants / initial state (lane = pixel here) -------------------------------

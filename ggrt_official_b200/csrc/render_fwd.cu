@@ -252,6 +252,7 @@ render_forward_pair_kernel(View v, const float4* __restrict__ rec0, const float4
     const float tx0f = (float)(blockIdx.x * TILE), ty0f = (float)(blockIdx.y * TILE);
     // the two 8x4 blocks of the cull mask that make up this warp's 8x8 block: rows 2 (w >> 1) and 2 (w >> 1) + 1
     const uint32_t wbits = (1u << (4 * (warp >> 1) + (warp & 1))) | (1u << (4 * (warp >> 1) + 2 + (warp & 1)));
+    pdl_enter();  // (everything above is index arithmetic: it runs while the sort kernel drains)
     const uint32_t start = min(starts[tile], capacity), end = min(starts[tile + 1], capacity);
 
     // sign of T = per-pixel "done" flag, as in the single-pixel kernel
@@ -647,9 +648,8 @@ void launch_render_forward(const View& v, GeomPtrs g, ImagePtrs im, BinPtrs b, u
     }
 #endif
 #if GGRT_FWD_PAIR
-    render_forward_pair_kernel<<<dim3(v.gx, v.gy, 1), F2_THREADS, 0, s>>>(v, g.rec0, g.rec1, g.rec2, im.starts, b.points, b.masks,
-                                                                          capacity, out_color, out_depth, im.final_T,
-                                                                          im.n_contrib);
+    launch_chain(render_forward_pair_kernel, dim3(v.gx, v.gy, 1), dim3(F2_THREADS), 0, s, v, g.rec0, g.rec1, g.rec2, im.starts,
+                 b.points, b.masks, capacity, out_color, out_depth, im.final_T, im.n_contrib);
     return;
 #endif
     dim3 grid(v.gx, v.gy, 8 / FWD_WARPS);

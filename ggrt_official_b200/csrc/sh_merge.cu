@@ -51,11 +51,6 @@ __device__ __forceinline__ float ld_sys(const float* p) {
     return v;
 }
 
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-
 template <int DEG, bool CMAJOR>
 __global__ void __launch_bounds__(MERGE_THREADS, GGRT_MERGE_MINBLOCKS)
 sh_gradient_merge_kernel(int P, float scale, const float* __restrict__ means, MergeViews mv, float* __restrict__ dsh,

@@ -239,7 +239,7 @@ class _Call:
 
 def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: GaussianRasterizationSettings,
                 aux=None, layout: Optional[dict] = None, workspace: Optional[Workspace] = None,
-                check: str = "sync") -> dict:
+                check: str = "sync", prezero_scratch: bool = False) -> dict:
     """Runs the forward through the C ABI and returns outputs plus the opaque state buffers.
     `aux` [P]: optional extra per-Gaussian channel blended into the third output instead of the view depth.
     `layout`: optional {scene_scale, cov_full3x3, sh_channel_major} (struct GgrtRasterInputLayout).
@@ -248,7 +248,10 @@ def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: Gauss
       "sync"  wait for N inside this call and redo the binning if a speculative buffer was too small (exact, default);
       "lazy"  do not wait: the host returns at once and can queue further work; the check happens at the next
               forward of this thread (or check_pending()) and raises BinningOverflow after the fact;
-      "none"  no check is scheduled (a captured CUDA graph: the owner reads workspace.counts after replays)."""
+      "none"  no check is scheduled (a captured CUDA graph: the owner reads workspace.counts after replays).
+    `prezero_scratch`: a backward of this frame will follow -- its [P,12] scratch is allocated now and zeroed on the
+      library's side stream under the binning kernels (GgrtRasterSettings.zero_scratch) instead of between the two
+      render kernels.  Always on with a workspace (which owns the scratch)."""
     if check not in ("sync", "lazy", "none"):
         raise ValueError(f"check must be 'sync', 'lazy' or 'none', got {check!r}")
     L = _cabi.lib()
@@ -273,6 +276,13 @@ def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: Gauss
             counts = _pinned_counts()
         else:
             radii, geom, img, color, depth, counts = ws.radii, ws.geom, ws.img, ws.color, ws.depth, ws.counts
+        scratch = None
+        if ws is not None:
+            scratch = ws.scratch
+        elif prezero_scratch and c.P > 0:
+            scratch = torch.empty((c.P, 12), dtype=torch.float32, device=dev)
+        if scratch is not None:
+            c.settings.zero_scratch = scratch.data_ptr()
         lay = C.byref(c.layout) if c.layout is not None else None
         _cabi.check(L.ggrt_raster_forward_prepare(C.byref(c.settings), lay, c.P, _ptr(c.means3D), _ptr(c.cov3D),
                                                   _ptr(c.opacities), _ptr(c.sh), _ptr(c.colors), _ptr(c.aux),
@@ -334,7 +344,7 @@ def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: Gauss
             L.ggrt_raster_join(sp)
             raise
     return dict(call=c, color=color, depth=depth, radii=radii, geom=geom, img=img, binning=binning, N=N,
-                capacity=cap, max_tile_pairs=max_pairs, workspace=ws)
+                capacity=cap, max_tile_pairs=max_pairs, workspace=ws, scratch=scratch)
 
 
 def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = None,
@@ -382,8 +392,13 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
         if ga is not None and c.aux is None and not c.aux_mode:
             raise RuntimeError("the third output is only differentiable when aux_precomp was given")
         f32 = dict(dtype=torch.float32, device=dev)
-        ws = state.get("workspace")
-        scratch = ws.scratch if ws is not None else torch.empty((c.P, 12), **f32)
+        # the scratch the forward zeroed for this frame (settings.zero_scratch still names it), else a fresh one
+        # that the library zeroes itself
+        scratch = state.get("scratch") if c.settings.zero_scratch else None
+        if scratch is None:
+            ws = state.get("workspace")
+            scratch = ws.scratch if ws is not None else torch.empty((c.P, 12), **f32)
+            c.settings.zero_scratch = None
         given = out or {}
 
         def buf(name, shape):
@@ -413,6 +428,7 @@ def backward_raw(state: dict, grad_color: torch.Tensor, out: Optional[dict] = No
                                            _ptr(out["dcolors"]), _ptr(out["daux"]), _ptr(out["dcamera"]),
                                            C.byref(sinks) if sinks is not None else None, sp),
                     "backward")
+        c.settings.zero_scratch = None  # used up: a second backward of this frame has the library zero the scratch
     return out
 
 
@@ -478,14 +494,14 @@ class _RasterizeGaussians(torch.autograd.Function):
         # inputs lets autograd deliver camera gradients when (and only when) they require grad
         try:
             st = forward_raw(means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings, aux, layout,
-                             check=AUTOGRAD_CHECK)
+                             check=AUTOGRAD_CHECK, prezero_scratch=any(ctx.needs_input_grad))
         except Exception:
             if _debug_enabled(raster_settings):
                 _dump("snapshot_fw.dump", (means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings))
             raise
         # keep only what backward needs; the outputs must not be referenced from ctx (that would be a
         # grad_fn <-> output reference cycle and the buffers would wait for the garbage collector)
-        ctx.state = {k: st[k] for k in ("call", "radii", "geom", "img", "binning", "N", "capacity")}
+        ctx.state = {k: st[k] for k in ("call", "radii", "geom", "img", "binning", "N", "capacity", "scratch")}
         ctx.raster_settings = raster_settings
         ctx.sh_shape = None if sh is None else tuple(sh.shape)
         ctx.opacity_shape = tuple(opacities.shape)

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GGRT_RASTER_ABI_VERSION 10
+#define GGRT_RASTER_ABI_VERSION 11
 #define GGRT_RASTER_TILE 16 /* tile edge in pixels (tile ids are part of the contract) */
 #define GGRT_RASTER_SUBS 16 /* pair counters per tile (contention spreading) */
 #define GGRT_RASTER_MAX_MERGE_VIEWS 16 /* views per ggrt_raster_sh_gradient_merge call */
@@ -77,6 +77,12 @@ typedef struct GgrtRasterSettings {
                                    camera-space depth of the UNSCALED scene, computed in the kernels; its gradient
                                    (dL_dout_aux) flows into dL_dmeans3D, dL_daux stays NULL */
     int32_t reserved;
+    float* zero_scratch;        /* NULL, or the [P,12] grad_scratch buffer the caller will pass to ggrt_raster_backward for
+                                   this frame: forward_prepare then zeroes it on the library's side stream, beside the
+                                   colour kernel and under the binning kernels, and a backward that is given the same
+                                   pointer in both places skips its own memset (which otherwise sits between the two
+                                   render kernels on the critical path).  The caller must not touch the buffer between
+                                   the two calls and must clear this field for a second backward of the same frame */
 } GgrtRasterSettings;
 
 /*
@@ -145,6 +151,9 @@ typedef struct GgrtRasterLayout {
     size_t geom_flags;  /* uint8[P]   bit c: colour channel c was clamped at 0 */
     size_t geom_ranks;  /* uint32x4[P] Gaussians touching <= 4 tiles: rank of each of their pairs inside its (tile, sub-counter)
                            segment, returned by the geometry kernel's counting atomics and consumed by the emit kernel */
+    size_t geom_jac;    /* float[9][P] (SH inputs of degree > 0 only) plane 3c + j: d(colour channel c)/d(scaled mean j) through
+                           the view direction, stored by the colour kernel while the SH row is on chip; the per-Gaussian
+                           backward kernel multiplies it with dL/dcolour instead of reading the SH table a second time */
     size_t geom_bytes;
     /* image buffer, per tile / per pixel */
     size_t img_counts;  /* uint32[T*32] pairs per (tile, sub-counter); sub-counter = gaussian idx % 16 (+ 16 for Gaussians that
@@ -223,7 +232,7 @@ int ggrt_raster_join(ggrt_stream_t stream);
 /*
  * Backward.  dL_dout_color [3,H,W]; dL_dout_aux [H,W] or NULL (gradient of out_depth; only
  * meaningful when aux was given to prepare).  grad_scratch is [P,12] float32 scratch (zeroed
- * by the callee).  Outputs, all overwritten: dL_dmeans2D [P,3] (gradient w.r.t. NDC
+ * by the callee -- here, or already by forward_prepare, see GgrtRasterSettings.zero_scratch).  Outputs, all overwritten: dL_dmeans2D [P,3] (gradient w.r.t. NDC
  * xy, z = 0), dL_dopacity [P], dL_dmeans3D [P,3], dL_dcov3D [P,6], either dL_dsh [P,K,3]
  * (when shs was given) or dL_dcolors [P,3] (the unused one is NULL), and dL_daux [P] (NULL
  * unless dL_dout_aux is given).  dL_dcamera (NULL, or 35 floats: dL/dviewmatrix [4,4] |

@@ -28,7 +28,7 @@ def _camera(rs, deg):
 
 
 def fake_forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs, aux=None, layout=None,
-                     workspace=None, check="sync"):
+                     workspace=None, check="sync", prezero_scratch=False):
     CALLS.append(dict(means3D=means3D, sh=sh, colors_precomp=colors_precomp, opacities=opacities,
                       cov3D_precomp=cov3D_precomp, settings=rs, aux=aux, layout=layout))
     deg = int(rs.sh_degree)
@@ -54,7 +54,7 @@ def fake_forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs, 
                            device=means3D.device, campos=rs.campos)
     return dict(call=call, color=torch.from_numpy(f["color"].copy()), depth=torch.from_numpy(f["depth"].copy()),
                 radii=torch.from_numpy(f["radii"].copy()), geom=None, img=None, binning=None, N=f["bin"]["N"],
-                capacity=f["bin"]["N"], max_tile_pairs=0, workspace=None, _oracle=(cam, inp, f))
+                capacity=f["bin"]["N"], max_tile_pairs=0, workspace=None, scratch=None, _oracle=(cam, inp, f))
 
 
 def fake_backward_raw(state, grad_color, out=None, grad_aux=None, want_camera=False):
