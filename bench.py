@@ -45,11 +45,12 @@ def alg_bytes(P, N, H, W, K=25):
     T = ((W + 15) // 16) * ((H + 15) // 16)
     HW = H * W
     return {
-        "geometry+color": P * (40 + 12 * K) + 52 * P,
+        "geometry+color": P * (40 + 12 * K) + 52 * P + 36 * P,  # + the colour Jacobian kept for the backward
         "binning": 12 * N + 24 * N + 8 * T,  # emit + one read/one write of the pairs + ranges
         "render_forward": 4 * N + 36 * P + 8 * T + 20 * HW,
         "render_backward": 4 * N + 36 * P + 20 * HW + 44 * P,
-        "preprocess_backward": P * (44 + 40 + 12 * K + 4) + P * (36 + 12 * K),
+        # round 2: the SH table (12K B) is no longer read here, the 36-byte colour Jacobian of the forward replaces it
+        "preprocess_backward": P * (44 + 40 + 36 + 4) + P * (36 + 12 * K),
     }
 
 
@@ -634,6 +635,24 @@ def measure_extras(args, ri, g_np, dev, flush_l2):
                 R.check_pending(block=True)
                 multi[name] = {"value": 1e3 * 10 * nv / sum(ms), "unit": "frames/s", "ms_per_call": sum(ms) / 10}
             R.AUTOGRAD_CHECK = "sync"
+            # the same call as ONE captured CUDA-graph launch (graph.CapturedViews: compact per-view colour gradients,
+            # one SH-gradient merge for all views, views on two streams inside the graph; fixed loss gradients)
+            try:
+                from ggrt_official_b200.graph import CapturedViews
+
+                for name, streams in (("captured_graph_one_stream", 1), ("captured_graph_two_streams", 2)):
+                    cap = CapturedViews(extr4[0], intr4[0], near4[0], far4[0], (H, W), torch.zeros(nv, 3, device=dev),
+                                        leaves["means"][0], leaves["covariances"][0], leaves["harmonics"][0],
+                                        leaves["opacities"][0], grad_color=wc4[0].contiguous(),
+                                        grad_depth=wd4[0].contiguous(), streams=streams)
+                    for _ in range(3):
+                        cap.replay()
+                    ms = time_loop(cap.replay, 10, dev)
+                    cap.check()
+                    multi[name] = {"value": 1e3 * 10 * nv / sum(ms), "unit": "frames/s", "ms_per_call": sum(ms) / 10}
+                    del cap
+            except Exception as e:  # noqa: BLE001
+                multi["captured_graph"] = {"error": repr(e)[:300]}
             multi["what"] = f"{nv} target views of the same Gaussians per decoder call (colour + depth, fwd+bwd through autograd)"
             res["multi_view_device_glue"] = multi
         except Exception as e:  # noqa: BLE001

@@ -21,12 +21,18 @@ static const char* const kStageNames[GGRT_STAGE_COUNT] = {"geometry",       "sca
                                                           "emit",           "sort_tiles",      "render_forward",
                                                           "render_backward", "preprocess_backward"};
 
-bool pdl_enabled() {
+bool pdl_enabled(cudaStream_t s) {
     static const bool on = [] {
         const char* e = getenv("GGRT_RASTER_PDL");
         return !(e && e[0] == '0');
     }();
-    return on;
+    if (!on) return false;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return st == cudaStreamCaptureStatusActive;
 }
 
 void set_error(const char* fmt, ...) {

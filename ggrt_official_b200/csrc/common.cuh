@@ -125,12 +125,16 @@ __device__ __forceinline__ bool last_cta_done(uint32_t* done_counter) {
 // scheduled as soon as every CTA of this one has started (the dependents then sit in freed SM slots during this kernel's
 // tail), and waits until the PREVIOUS kernel has completed and its memory is visible.  launch_chain() launches with
 // programmatic stream serialisation, so the launch latency and the CTA ramp of each kernel hide under its predecessor;
-// without the attribute (GGRT_RASTER_PDL=0, or a predecessor that is not a kernel) both instructions are no-ops.
+// without the attribute both instructions are no-ops.  The attribute is only used while the stream is being CAPTURED
+// into a CUDA graph (graph.CapturedStep / CapturedViews, where it becomes a programmatic graph edge: 0.3030 -> 0.3001 ms
+// per step at C2): on a live stream that also carries the side-stream event waits, launches with the attribute cost the
+// HOST 0.33 ms more per frame (measured: decoder-level call 0.87 -> 1.20 ms), and an eagerly launched frame is host
+// bound already.  GGRT_RASTER_PDL=0 switches it off everywhere.
 __device__ __forceinline__ void pdl_enter() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
-bool pdl_enabled();
+bool pdl_enabled(cudaStream_t s);
 template <typename... KArgs, typename... Args>
 inline void launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -138,7 +142,7 @@ inline void launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at, cfg.numAttrs = pdl_enabled() ? 1u : 0u;
+    cfg.attrs = at, cfg.numAttrs = pdl_enabled(s) ? 1u : 0u;
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

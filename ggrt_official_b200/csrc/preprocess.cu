@@ -7,6 +7,9 @@
 namespace ggrt {
 
 constexpr int GEO_THREADS = 256;
+#ifndef GGRT_GEO_MINBLOCKS
+#define GGRT_GEO_MINBLOCKS 4
+#endif
 #ifndef GGRT_COLOR_THREADS
 #define GGRT_COLOR_THREADS 128
 #endif
@@ -20,7 +23,7 @@ constexpr int COLOR_THREADS = GGRT_COLOR_THREADS;
 // Pair counting goes straight into the per-tile counters (no per-Gaussian prefix sum:
 // tile segments are allocated per tile, see binning.cu).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEO_THREADS)
+__global__ void __launch_bounds__(GEO_THREADS, GGRT_GEO_MINBLOCKS)
 geometry_kernel(View v, const float* __restrict__ means, const float* __restrict__ cov3d,
                 const float* __restrict__ opac, int* __restrict__ radii, GeomPtrs g, uint32_t* __restrict__ counts) {
     __shared__ float sV[16], sM[16];

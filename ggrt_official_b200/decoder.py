@@ -87,6 +87,22 @@ class DecoderSplattingCUDA(nn.Module):
             depth = self.render_depth(gaussians, extrinsics, intrinsics, near, far, image_shape, depth_mode)
         return DecoderOutput(color, depth)
 
+    def capture(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
+                image_shape: tuple, grad_color: Tensor, grad_depth: Optional[Tensor] = None, streams: int = 2):
+        """A training loop that renders the same shapes every step: all v target views of ONE scene (b = 1) -- forward,
+        depth channel and backward -- frozen into one CUDA-graph launch (graph.CapturedViews).  `grad_color` [v,3,h,w] /
+        `grad_depth` [v,h,w] are the buffers the loss writes dL/dimage into; the Gaussians and cameras are read from the
+        given tensors at every replay."""
+        from .graph import CapturedViews
+
+        b, v = extrinsics.shape[:2]
+        if b != 1:
+            raise ValueError("capture() takes one scene (b = 1); build one CapturedViews per scene")
+        bg = self.background_color.to(far.device)[None].expand(v, 3).contiguous()
+        return CapturedViews(extrinsics[0], intrinsics[0], near[0], far[0], image_shape, bg, gaussians.means[0],
+                             gaussians.covariances[0], gaussians.harmonics[0], gaussians.opacities[0],
+                             grad_color=grad_color, grad_depth=grad_depth, streams=streams)
+
     def render_depth(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
                      image_shape: tuple, mode: DepthRenderingMode = "depth") -> Tensor:
         b, v = extrinsics.shape[:2]

@@ -193,7 +193,7 @@ def render_views_fast(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far:
 
 
 def camera_setup(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
-                 scale_invariant: bool = True) -> Tensor:
+                 scale_invariant: bool = True, out: Optional[Tensor] = None) -> Tensor:
     """[n, 48] float32 camera blocks for n views -- viewmatrix [0:16], projmatrix [16:32], campos [32:35],
     {tanfovx, tanfovy, scene_scale} [35:38] -- computed by ONE kernel (ggrt_camera_setup) with no host read-back:
     the device-side twin of the ~60 small PyTorch operations and two .item() synchronisations per view of
@@ -211,7 +211,10 @@ def camera_setup(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tens
     if tuple(E.shape) != (n, 4, 4) or tuple(K.shape) != (n, 3, 3) or nr.numel() != n or fr.numel() != n:
         raise ValueError(f"camera_setup: need extrinsics [n,4,4], intrinsics [n,3,3], near / far [n]; got "
                          f"{tuple(E.shape)}, {tuple(K.shape)}, {tuple(nr.shape)}, {tuple(fr.shape)}")
-    out = torch.empty((n, _cabi.CAMERA_FLOATS), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((n, _cabi.CAMERA_FLOATS), dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (n, _cabi.CAMERA_FLOATS) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
+        raise ValueError(f"camera_setup: out must be a contiguous float32 [{n},{_cabi.CAMERA_FLOATS}] tensor on {dev}")
     with torch.cuda.device(dev):
         sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         p = lambda t: C.c_void_p(t.data_ptr())
@@ -270,6 +273,12 @@ def render_views_device(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, fa
     for st in pool[1:]:
         main.wait_stream(st)
     return torch.stack(colors), (torch.stack(depths) if depth else None)
+
+
+def _cabi_camera_floats() -> int:
+    from . import _cabi
+
+    return _cabi.CAMERA_FLOATS
 
 
 _SIDE_STREAMS: dict = {}

@@ -133,3 +133,53 @@ def test_views_on_several_streams_equal_the_sequential_views(streams):
     for k in la:
         ref, got = la[k].grad, lb[k].grad
         assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max()), k
+
+
+@pytest.mark.parametrize("with_depth,streams", [(True, 2), (False, 1), (True, 3)])
+def test_captured_views_equal_the_autograd_decoder_call(with_depth, streams):
+    """graph.CapturedViews -- all views of a call as one CUDA-graph launch, compact per-view colour gradients and ONE
+    SH-gradient merge -- against the same call through DecoderSplattingCUDA(device_glue=True) and autograd: images
+    bit for bit, gradients (summed over the views) up to float summation order; also after several replays and after
+    the cameras were changed in place."""
+    from ggrt_official_b200.graph import CapturedViews
+
+    sc, E, K, near, far = _views(4, seed=21)
+    H, W = sc.image_shape
+    t = lambda a: torch.tensor(np.asarray(a), device=DEV)
+    torch.manual_seed(1)
+    wc = torch.randn(4, 3, H, W, device=DEV)
+    wd = torch.randn(4, H, W, device=DEV) if with_depth else None
+    bg = torch.zeros(4, 3, device=DEV)
+    cap = CapturedViews(E, K, near, far, (H, W), bg, t(sc.means), t(sc.covariances), t(sc.harmonics), t(sc.opacities),
+                        grad_color=wc, grad_depth=wd, streams=streams)
+
+    def reference(E_):
+        leaves = dict(means=t(sc.means)[None].requires_grad_(), covariances=t(sc.covariances)[None].requires_grad_(),
+                      harmonics=t(sc.harmonics)[None].requires_grad_(), opacities=t(sc.opacities)[None].requires_grad_())
+        r = DecoderSplattingCUDA(device_glue=True)(Gaussians(**leaves), E_[None], K[None], near[None], far[None], (H, W),
+                                                   depth_mode="depth" if with_depth else None)
+        loss = (r.color[0] * wc).sum()
+        if with_depth:
+            loss = loss + (r.depth[0] * wd).sum()
+        loss.backward()
+        return r, {k: v.grad[0] for k, v in leaves.items()}
+
+    for trial in range(2):
+        if trial == 1:  # move the cameras in place: the captured camera kernel must pick the new poses up
+            rng = np.random.default_rng(5)
+            E2 = torch.tensor(np.stack([E[i].cpu().numpy().astype(np.float64) @ small_se3(rng, rot_deg=5.0, trans=0.1)
+                                        for i in range(4)]).astype(np.float32), device=DEV)
+            cap.cam_in[0].copy_(E2)
+        for _ in range(3):
+            cap.replay()
+        cap.check()
+        r, g = reference(cap.cam_in[0].clone())
+        assert torch.equal(cap.color, r.color[0])
+        if with_depth:
+            assert torch.equal(cap.depth, r.depth[0])
+        got = cap.grads
+        for k, name in (("means", "dmeans"), ("covariances", "dcovariances"), ("harmonics", "dharmonics"),
+                        ("opacities", "dopacities")):
+            ref = g[k]
+            assert got[name].shape == ref.shape, (name, got[name].shape, ref.shape)
+            assert float((got[name] - ref).abs().max()) <= 3e-5 * float(ref.abs().max()), name
