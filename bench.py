@@ -523,9 +523,10 @@ def run_ours(args, rank, world, local_rank):
             },
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": n_e2e},
-            # this library's kernels per step: 8 of the fwd+bwd path + the exchange's; torch / NCCL kernels
-            # (collectives, L2 flush) are not counted
-            "gpu_launches": (8 + n_exch) * args.steps,
+            # this library's kernels per step: 8 of the fwd+bwd path, the dL/dsh writer beside the per-Gaussian backward
+            # when one GPU writes the full SH gradient itself (with an exchange the merge kernel writes it), + the
+            # exchange's; torch / NCCL kernels (collectives, L2 flush) are not counted
+            "gpu_launches": (8 + (1 if exch is None else 0) + n_exch) * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "gpu_baseline": gpu_base,

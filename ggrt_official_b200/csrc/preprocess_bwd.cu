@@ -52,8 +52,9 @@ __device__ __forceinline__ void sink_store1(float* dst, float v, bool multimem) 
         *dst = v;
 }
 
+// (the camera-gradient instantiation carries 27 more accumulators: it keeps the 10-CTA register budget instead of spilling)
 template <bool AUX, bool CMAJOR, bool POSE>
-__global__ void __launch_bounds__(PB_THREADS, GGRT_PB_MINBLOCKS)
+__global__ void __launch_bounds__(PB_THREADS, POSE ? (GGRT_PB_MINBLOCKS < 10 ? GGRT_PB_MINBLOCKS : 10) : GGRT_PB_MINBLOCKS)
 preprocess_backward_kernel(View v, const float* __restrict__ means, const float* __restrict__ cov3d,
                            const float* __restrict__ shs, const int* __restrict__ radii,
                            const uint8_t* __restrict__ flags, const float* __restrict__ jac, size_t jac_plane,
@@ -512,7 +513,7 @@ void launch_preprocess_backward(const View& v, const float* means, const float* 
     // persistent CTAs: as many per SM as shared memory AND the register budget of __launch_bounds__ allow
     // (without a ring: GGRT_PB_SPLIT_BLOCKS one-warp CTAs per SM.  Measured at C2 with the dL/dsh writer beside it, whole
     // step: 9 CTAs x 166 registers 0.2923 ms, 13 x 128 0.2921, 16 x 128 0.2911, 17 x 96 0.2948)
-    const int per_sm = smem ? max(1, min(GGRT_PB_MINBLOCKS, (int)((220 * 1024) / (smem + 1024)))) : GGRT_PB_SPLIT_BLOCKS;
+    const int per_sm = dcam ? 10 : smem ? max(1, min(GGRT_PB_MINBLOCKS, (int)((220 * 1024) / (smem + 1024)))) : GGRT_PB_SPLIT_BLOCKS;
     const int grid = min(num_slabs, per_sm * sms);
 #define GGRT_LAUNCH_PB(AX, CM, PO)                                                                                      \
     {                                                                                                                   \

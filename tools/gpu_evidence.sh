@@ -1,6 +1,6 @@
 #!/bin/bash
 # Evidence session (1 GPU): parity suite, bench lines (C2 with baselines, reference arm, C3, C3+pose, C4, C5 sweep), ncu launch
-# list + full capture of one step (all 8 kernels) with source pages, adapter bench + ncu.   bash tools/gpu_evidence.sh [tag]
+# list + full capture of one step (all 9 kernels) with source pages, adapter bench + ncu.   bash tools/gpu_evidence.sh [tag]
 tag=${1:-ev}
 out=gpurun_out/$tag
 mkdir -p $out
@@ -19,8 +19,8 @@ timeout 600 python bench.py --impl reference --steps 10 --warmup 1 > $out/bench_
 ts "ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $out/launches.csv python bench.py --launch eager --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-extras > $out/ncu_bench.log 2>&1
 ts "ncu full: one step"
-K='regex:geometry_kernel|scan_tiles|color_kernel|emit_kernel|sort_tiles|render_forward|render_backward|preprocess_backward'
-timeout 900 ncu --set full --clock-control none --import-source on -k "$K" -s 16 -c 8 -f -o $out/step python tools/profile_step.py c2 2 > $out/ncu_full.log 2>&1
+K='regex:geometry_kernel|scan_tiles|color_kernel|emit_kernel|sort_tiles|render_forward|render_backward|preprocess_backward|sh_gradient_kernel'
+timeout 900 ncu --set full --clock-control none --import-source on -k "$K" -s 18 -c 9 -f -o $out/step python tools/profile_step.py c2 2 > $out/ncu_full.log 2>&1
 ncu -i $out/step.ncu-rep --page raw --csv > $out/raw.csv 2> $out/raw.err
 ncu -i $out/step.ncu-rep --page source --csv -k regex:render_backward > $out/source_render_backward.csv 2>> $out/raw.err
 ncu -i $out/step.ncu-rep --page source --csv -k regex:render_forward > $out/source_render_forward.csv 2>> $out/raw.err
@@ -33,11 +33,13 @@ ts sweep
 for n in 50000 100000 300000 600000 1000000 2000000; do
   timeout 300 python bench.py --gaussians $n --steps 30 --no-cpu-baseline --no-gpu-baseline --no-extras > $out/sweep_$n.json 2> $out/sweep_$n.err
 done
+if [ "$2" != "noadapter" ]; then
 ts adapter
 timeout 300 python tools/bench_adapter.py > $out/bench_adapter.json 2> $out/bench_adapter.err
 timeout 600 ncu --set full --clock-control none -k regex:adapter_ -s 4 -c 2 -f -o $out/adapter python tools/bench_adapter.py > $out/ncu_adapter.log 2>&1
 ncu -i $out/adapter.ncu-rep --page raw --csv > $out/adapter_raw.csv 2>> $out/raw.err
 rm -f $out/adapter.ncu-rep
+fi
 ts done
 python - <<'PY' $out
 import json, sys, glob, os
