@@ -17,5 +17,6 @@ for (P, H, W, deg, cs, seed) in [(3000, 100, 75, 4, 9.0, 2), (1400, 32, 32, 1, 6
     st = G.run_cuda_forward(ri)
     g = torch.tensor(np.random.default_rng(0).standard_normal((3, H, W)).astype(np.float32), device="cuda:0")
     out = R.backward_raw(st, g)
+    comp = R.backward_raw(st, g, compact=True)  # the compact (multi-GPU / multi-view) mode of the per-Gaussian kernel
     torch.cuda.synchronize()
     print("case", P, H, W, deg, "N", st["N"], "max", st["max_tile_pairs"], float(out["dmeans3D"].abs().sum()))
