@@ -34,7 +34,10 @@ namespace ggrt {
 #ifndef GGRT_MERGE_MINBLOCKS
 #define GGRT_MERGE_MINBLOCKS 4
 #endif
-constexpr int MERGE_THREADS = 128;
+#ifndef GGRT_MERGE_THREADS
+#define GGRT_MERGE_THREADS 128
+#endif
+constexpr int MERGE_THREADS = GGRT_MERGE_THREADS;
 constexpr int MERGE_STAGES = GGRT_MERGE_STAGES;
 constexpr int MERGE_GROUP = GGRT_MERGE_GROUP;  // views whose loads are in flight together
 
