@@ -36,10 +36,10 @@ def test_abi_version_and_layout():
     P, H, W, N = 1000, 100, 75, 2500
     L = _cabi.layout(P, H, W, N)
     T = ((W + 15) // 16) * ((H + 15) // 16)
-    assert L.geom_bytes == lib.ggrt_raster_geom_bytes(P) >= P * (48 + 8 + 4 + 1)
+    assert L.geom_bytes == lib.ggrt_raster_geom_bytes(P) >= P * (48 + 8 + 4 + 1 + 16 + 36) and L.geom_bytes >= L.geom_jac + 36 * P
     assert L.img_bytes == lib.ggrt_raster_image_bytes(H, W) >= 8 * H * W + 4 * (T + 1) + 2 * 4 * 32 * T
     assert L.bin_bytes == lib.ggrt_raster_binning_bytes(N) >= 12 * N
-    offs = [L.geom_rec0, L.geom_rec1, L.geom_rec2, L.geom_rect, L.geom_tiles, L.geom_flags, L.geom_ranks]
+    offs = [L.geom_rec0, L.geom_rec1, L.geom_rec2, L.geom_rect, L.geom_tiles, L.geom_flags, L.geom_ranks, L.geom_jac]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
     assert L.img_partials == L.img_counts + 4 * 32 * T and L.img_cursor > L.img_partials
     assert lib.ggrt_raster_binning_bytes(0) > 0  # never a zero-sized allocation
@@ -102,3 +102,40 @@ def test_ctypes_signatures_have_the_arity_the_header_declares():
             assert len(fn.argtypes) == n, (name, len(fn.argtypes), n)
             checked += 1
     assert checked >= 12
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """sizeof / offsetof of every struct in include/ggrt_raster.h, as gcc lays them out, against the ctypes mirrors in
+    _cabi.py (a field added on one side only would shift everything behind it silently)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    structs = {"GgrtRasterSettings": _cabi.Settings, "GgrtRasterInputLayout": _cabi.InputLayout,
+               "GgrtRasterGradSinks": _cabi.GradSinks, "GgrtAdapterParams": _cabi.AdapterParams,
+               "GgrtRasterLayout": _cabi.Layout}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include" / "ggrt_raster.h"}"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", str(src), "-o", str(exe)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, field, val = line.split()
+        cls = structs[cname]
+        expect = C.sizeof(cls) if field == "size" else getattr(cls, field).offset
+        assert int(val) == expect, (cname, field, int(val), expect)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in structs.values())
+    # the header's constants the binding repeats
+    assert f"#define GGRT_RASTER_ABI_VERSION {_cabi.ABI_VERSION}" in HEADER
+    assert f"#define GGRT_RASTER_MAX_MERGE_VIEWS {_cabi.MAX_MERGE_VIEWS}" in HEADER
+    assert f"#define GGRT_CAMERA_FLOATS {_cabi.CAMERA_FLOATS}" in HEADER and f"#define GGRT_STAGE_COUNT {_cabi.STAGE_COUNT}" in HEADER
