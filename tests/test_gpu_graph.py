@@ -57,3 +57,21 @@ def test_captured_step_equals_the_eager_calls(P, H, W, deg, cs, seed, aux, pose)
                 continue
             # (the 35 camera sums go through a few thousand float atomics: looser)
             assert _close(cap.grads[k], v, 1e-3 if k == "dcamera" else 3e-5), (trial, k, float((cap.grads[k] - v).abs().max()), float(v.abs().max()))
+
+
+@pytest.mark.parametrize("env", [{"GGRT_RASTER_OVERLAP": "0"}, {"GGRT_RASTER_PDL": "0"}])
+def test_library_switches_keep_the_results(env):
+    """GGRT_RASTER_OVERLAP=0 (every kernel and the scratch memset on the caller's stream) and GGRT_RASTER_PDL=0 (no
+    programmatic dependent launch under capture) are read once per process: the captured-step and oracle-parity tests
+    are re-run in a child process with the switch set."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-x", "tests/test_gpu_graph.py", "-k",
+                          "(captured_step and (3000 or 20000)) or test_gpu_parity", "tests/test_gpu_parity.py"], cwd=root, capture_output=True,
+                         text=True, timeout=900, env=dict(os.environ, **env))
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+    assert " passed" in res.stdout
