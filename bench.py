@@ -579,6 +579,29 @@ def measure_extras(args, ri, g_np, dev, flush_l2):
     except Exception as e:  # noqa: BLE001
         out["depth_pass"] = {"error": repr(e)[:300]}
     try:
+        # crop training (finetune_ggrt_stable.py:126-142): dL/dimage is zero outside one crop -- here one quadrant -- so the
+        # backward render kernel skips three quarters of the tiles; same Gaussians, same forward
+        from ggrt_official_b200.synthetic import image_gradient
+
+        shs = t(ri.shs)
+        rs4 = rs0._replace(sh_degree=ri.sh_degree)
+        gq = t(image_gradient(H, W, seed=SEED, quadrant_only=True))
+
+        def crop_step():
+            st = R.forward_raw(means, shs, None, opac, cov, rs4, check="lazy", prezero_scratch=True)
+            R.backward_raw(st, gq)
+
+        R.forward_raw(means, shs, None, opac, cov, rs4)
+        for _ in range(3):
+            crop_step()
+        ms = time_loop(crop_step, n, dev, before=flush_l2)
+        R.check_pending(block=True)
+        out["crop_gradient"] = {"value": 1e3 * n / sum(ms), "unit": "frames/s", "ms_per_step": sum(ms) / n,
+                                "what": "the metric's workload with dL/dimage non-zero in one quadrant only (crop training), "
+                                        "fwd+bwd, C ABI, eager launches, L2 flushed"}
+    except Exception as e:  # noqa: BLE001
+        out["crop_gradient"] = {"error": repr(e)[:300]}
+    try:
         sc = make_scene(P, H, W, sh_degree=SH_DEGREE, seed=SEED)
         leaves = dict(means=t(sc.means)[None].requires_grad_(), covariances=t(sc.covariances)[None].requires_grad_(),
                       harmonics=t(sc.harmonics)[None].requires_grad_(), opacities=t(sc.opacities)[None].requires_grad_())
