@@ -49,10 +49,21 @@ def _debug_enabled(rs) -> bool:
 
 _tls = threading.local()
 
-# (device, P, H, W) -> (N, max pairs per tile) of the most recent forward of that shape (see forward_raw)
+# (device, P, H, W) -> (N, max pairs per tile) estimate for the next forward of that shape (see forward_raw): a
+# slowly decaying high-water mark of the pair counts seen, so that a loop alternating between sparse and dense frames
+# of one shape (other scenes, other crops) does not overflow its speculative pair buffer on every dense frame
 _capacity_cache: dict = {}
 SPECULATIVE_BINNING = True
 CAPACITY_SLACK = 1.25
+CAPACITY_DECAY = 0.97  # per forward; ~100 sparse frames forget a 20x denser one
+
+
+def _remember_counts(key, N: int, max_pairs: int) -> None:
+    prev = _capacity_cache.get(key)
+    if prev is not None:
+        N = max(int(N), int(prev[0] * CAPACITY_DECAY))
+        max_pairs = max(int(max_pairs), int(prev[1] * CAPACITY_DECAY))
+    _capacity_cache[key] = (int(N), int(max_pairs))
 # how GaussianRasterizer (the autograd path) verifies the speculative pair buffer: "sync" (exact: one host wait per
 # forward, like the reference, whose caller synchronises twice per view anyway) or "lazy" (no host wait; an overflow
 # surfaces as BinningOverflow in backward / the next forward).  GGRT_RASTER_CHECK=lazy selects the latter.
@@ -139,7 +150,7 @@ def check_pending(block: bool = True) -> None:
         p.pop(0)
         N, mx = counts.read()
         if key is not None:
-            _capacity_cache[key] = (N, mx)
+            _remember_counts(key, N, mx)
         if N > cap:
             bad = (N, cap)
     if bad:
@@ -337,7 +348,7 @@ def forward_raw(means3D, sh, colors_precomp, opacities, cov3D_precomp, rs: Gauss
                     if check == "lazy":
                         _pending().append((ev, counts, cap, key))
             if check == "sync":
-                _capacity_cache[key] = (N, max_pairs)
+                _remember_counts(key, N, max_pairs)
         except Exception:
             # the colour kernel forked by `prepare` may still be running on the library's side stream: order the
             # caller's stream (and with it the release of geom / radii to the caching allocator) after it

@@ -118,3 +118,23 @@ def test_debug_mode_from_settings_or_environment(monkeypatch):
     assert R._debug_enabled(rs)
     monkeypatch.delenv("GGRT_RASTER_DEBUG")
     assert R._debug_enabled(rs._replace(debug=True))
+
+
+def test_capacity_estimate_is_a_decaying_high_water_mark():
+    """The pair-buffer estimate a shape's next forward is sized from: the largest recent pair count, forgotten slowly --
+    a loop alternating between sparse and dense frames must not overflow its speculative buffer on every dense frame."""
+    from ggrt_official_b200 import rasterizer as R
+
+    key = ("test", 1, 2, 3)
+    R._capacity_cache.pop(key, None)
+    R._remember_counts(key, 1000, 40)
+    assert R._capacity_cache[key] == (1000, 40)
+    R._remember_counts(key, 5000, 90)          # a denser frame raises the mark at once
+    assert R._capacity_cache[key] == (5000, 90)
+    R._remember_counts(key, 1000, 40)          # a sparse frame lowers it by a few per cent only
+    n, m = R._capacity_cache[key]
+    assert 0.95 * 5000 <= n < 5000 and 0.95 * 90 <= m <= 90
+    for _ in range(400):                        # ... but a long sparse phase forgets the dense frame
+        R._remember_counts(key, 1000, 40)
+    assert R._capacity_cache[key] == (1000, 40)
+    R._capacity_cache.pop(key, None)
