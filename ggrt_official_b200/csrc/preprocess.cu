@@ -212,7 +212,9 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_tiles_kernel(int T, const uin
 
 // ---------------------------------------------------------------------------------------
 // colour: SH degree 0..4 -> RGB (+0.5, clamp at 0, remember clamp bits).  HBM-bound: 12 K
-// bytes per Gaussian (300 B at degree 4) are read exactly once.
+// bytes per Gaussian (300 B at degree 4) are read exactly once -- in the whole step: while the row
+// is on chip the kernel also contracts it with the basis derivatives into d(colour)/d(mean)
+// (GeomPtrs::jac, 3x3 floats), which is all the backward needs the coefficients for.
 //
 // Persistent CTAs (2 per SM); each walks slabs of COLOR_THREADS Gaussians.  A slab's SH block
 // is contiguous in HBM (COLOR_THREADS x K x 3 floats) and is pulled into a 2-stage shared

@@ -15,9 +15,11 @@
  * Plain C: raw device pointers, sizes and a CUDA stream handle.  No torch / pybind
  * types cross this boundary.  The library never allocates or frees device memory and
  * keeps no data between calls; the caller owns every buffer (sizes from the
- * ggrt_raster_*_bytes functions).  The only internal objects are one side stream and two
- * events per (host thread, device): forward_prepare forks the SH colour kernel onto it so that
- * it overlaps the binning kernels, forward_render joins it in front of the render kernel
+ * ggrt_raster_*_bytes functions).  The only internal objects are one side stream and four
+ * events per (host thread, device): forward_prepare forks the SH colour kernel (and the zeroing
+ * of the backward's scratch, GgrtRasterSettings.zero_scratch) onto it so that it overlaps the
+ * binning kernels, forward_render joins it in front of the render kernel; ggrt_raster_backward
+ * runs the dL/dsh writer on it beside the per-Gaussian kernel and joins before it returns
  * (GGRT_RASTER_OVERLAP=0 in the environment keeps every kernel on the caller's stream).
  * Consequently the inputs of forward_prepare must stay valid and unmodified until the matching
  * forward_render has been enqueued.  All float data is float32, all pointers are device
