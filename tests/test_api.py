@@ -138,3 +138,20 @@ def test_capacity_estimate_is_a_decaying_high_water_mark():
         R._remember_counts(key, 1000, 40)
     assert R._capacity_cache[key] == (1000, 40)
     R._capacity_cache.pop(key, None)
+
+
+def test_decoder_capture_takes_one_scene():
+    """DecoderSplattingCUDA.capture freezes the views of ONE scene into a CUDA graph; a batch of scenes is refused
+    before anything touches the device."""
+    import pytest
+    import torch
+
+    from ggrt_official_b200.decoder import DecoderSplattingCUDA, Gaussians
+
+    g = Gaussians(means=torch.zeros(2, 5, 3), covariances=torch.zeros(2, 5, 3, 3), harmonics=torch.zeros(2, 5, 3, 9),
+                  opacities=torch.zeros(2, 5))
+    E = torch.eye(4).expand(2, 3, 4, 4)
+    K = torch.eye(3).expand(2, 3, 3, 3)
+    with pytest.raises(ValueError, match="one scene"):
+        DecoderSplattingCUDA().capture(g, E, K, torch.ones(2, 3), torch.ones(2, 3) * 10, (16, 16),
+                                       grad_color=torch.zeros(3, 3, 16, 16))
