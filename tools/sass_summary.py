@@ -1,6 +1,7 @@
 """Per-kernel SASS mnemonic counts of libggrt_raster.so (cuobjdump -sass): the evidence for which hardware paths each
 kernel uses (UBLKCP = TMA bulk copy, LDGSTS = cp.async, HMMA = mma.sync tensor pipe, FFMA2/FMUL2/FADD2 = packed fp32,
-REDG/ATOMG = global reductions / atomics, SYNCS = mbarrier, MULTIMEM via *.MMEM*).  python tools/sass_summary.py [out.json]"""
+REDG/ATOMG = global reductions / atomics, SYNCS = mbarrier, PREEXIT / ACQBULK = programmatic dependent launch
+(griddepcontrol.launch_dependents / .wait), MULTIMEM via *.MMEM*).  python tools/sass_summary.py [out.json]"""
 import collections
 import json
 import re
@@ -10,7 +11,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / "ggrt_official_b200" / "lib" / "libggrt_raster.so"
-KEY = ("UBLKCP", "UTMA", "LDGSTS", "HMMA", "FFMA2", "FMUL2", "FADD2", "REDG", "RED", "ATOMG", "ATOM", "SYNCS", "SHFL", "MUFU", "VOTE",
+KEY = ("UBLKCP", "UTMA", "PREEXIT", "ACQBULK", "LDGSTS", "HMMA", "FFMA2", "FMUL2", "FADD2", "REDG", "RED", "ATOMG", "ATOM", "SYNCS", "SHFL", "MUFU", "VOTE",
        "VIMNMX", "LDS", "STS", "LDG", "STG", "BAR", "MATCH", "REDUX")
 
 
