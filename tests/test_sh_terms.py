@@ -74,3 +74,23 @@ def test_term_list_matches_the_oracle_basis_and_its_derivatives():
             dv = eval(_py(e), {}, env)
             dv = dv if torch.is_tensor(dv) else torch.full_like(x, float(dv))
             assert torch.allclose(dv, g[:, axis], atol=1e-10), (k, "xyz"[axis], e)
+
+
+def test_direction_is_invariant_under_the_per_view_scene_scale():
+    """graph.CapturedViews merges views whose scene scale s_v lives on the device (scale-invariant rendering: s_v = 1 /
+    near_v) with ONE host-side scale of 1: basis(normalize(s m - c)) == basis(normalize(m - c / s)) for s > 0, so the
+    camera centres are divided by their view's scale instead."""
+    torch.manual_seed(3)
+    m = torch.randn(200, 3, dtype=torch.float64) * 3
+    acc_a = acc_b = 0
+    for v in range(4):
+        s = 0.3 + 1.7 * torch.rand((), dtype=torch.float64)
+        c = torch.randn(3, dtype=torch.float64)
+        d = torch.randn(200, 3, dtype=torch.float64)
+        da = s * m - c
+        db = m - c / s
+        ba = sh_basis(4, da / da.norm(dim=1, keepdim=True))
+        bb = sh_basis(4, db / db.norm(dim=1, keepdim=True))
+        acc_a = acc_a + ba[:, :, None] * d[:, None, :]
+        acc_b = acc_b + bb[:, :, None] * d[:, None, :]
+    assert torch.allclose(acc_a, acc_b, atol=1e-12)
