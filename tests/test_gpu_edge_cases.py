@@ -146,3 +146,27 @@ def test_scales_rotations_interface_equals_precomputed_covariance():
     assert scales.grad is not None and rots.grad is not None
     assert torch.isfinite(scales.grad).all() and torch.isfinite(rots.grad).all()
     assert float(scales.grad.abs().max()) > 0 and float(rots.grad.abs().max()) > 0
+
+
+@pytest.mark.parametrize("P,deg,offset_floats", [(517, 4, 1), (1031, 3, 2), (640, 4, 1), (333, 1, 3)])
+def test_sh_gradient_into_an_unaligned_output(P, deg, offset_floats):
+    """dL/dsh written into a caller-supplied buffer that is not 16-byte aligned (a view into a gradient arena at an odd
+    offset): the dL/dsh writer leaves the TMA bulk-store path for plain stores; same values as the aligned default, also
+    for ragged last slabs."""
+    H, W = 48, 64
+    _, ri = small_case(P, H, W, deg, seed=11, cov_scale=4.0)
+    st = G.run_cuda_forward(ri)
+    g = _t(np.random.default_rng(2).standard_normal((3, H, W)).astype(np.float32))
+    ref = R.backward_raw(st, g)
+    K = (deg + 1) ** 2
+    arena = torch.full((P * K * 3 + 8,), float("nan"), device=DEV)
+    view = arena[offset_floats: offset_floats + P * K * 3].view(P, K, 3)
+    assert view.data_ptr() % 16 != 0
+    got = R.backward_raw(st, g, out={"dsh": view})
+    torch.cuda.synchronize()
+    assert got["dsh"].data_ptr() == view.data_ptr()
+    assert bool(torch.isnan(arena[:offset_floats]).all()) and bool(torch.isnan(arena[offset_floats + P * K * 3:]).all())
+    tol = 3e-5 * float(ref["dsh"].abs().max())
+    assert float((view - ref["dsh"]).abs().max()) <= tol
+    for k in ("dmeans3D", "dcov3D", "dopacity"):
+        assert float((got[k] - ref[k]).abs().max()) <= 3e-5 * float(ref[k].abs().max()), k
